@@ -1,0 +1,168 @@
+/*
+ * vsrdec.h — C ABI of the B200-native role-shift captioning decoder (libvsrdec.so).
+ *
+ * The reference (mad-red/VSR-guided-CIC) has no FFI/plugin layer: its boundary for this
+ * path is the Python class surface `ControllableCaptioningModel` / `CaptioningModel`
+ * (models/controllable_captioning.py:10-303, models/CaptioningModel.py:8-294).  The
+ * drop-in `models` package in this repo keeps that surface and forwards every hot call
+ * to the entry points below through ctypes.  Each entry point cites the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross this boundary;
+ *   - unless marked [host], every pointer is a DEVICE pointer on the handle's device,
+ *     fp32 tensors contiguous row-major, index tensors int64 (torch.long);
+ *   - the library BORROWS caller pointers for the duration of a call only, except the
+ *     inputs given to vsr_prologue(), which must stay alive and unchanged until the last
+ *     decode call that uses that prologue has been enqueued AND executed (they are read
+ *     by the step kernels);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *     default stream); no entry point synchronises the host with the device except
+ *     vsr_create / vsr_destroy / vsr_set_verb_table;
+ *   - every function returns 0 on success or a negative VSR_E* code; the message is
+ *     available from vsr_last_error() (thread-local).  Nothing throws across the ABI;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef VSRDEC_H_
+#define VSRDEC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSR_ABI_VERSION 1
+
+#define VSR_OK 0
+#define VSR_EINVAL (-1)  /* bad argument / unsupported size                       */
+#define VSR_ECUDA (-2)   /* CUDA runtime error (message has the cudaError string) */
+#define VSR_ENOMEM (-3)  /* device allocation failed                              */
+#define VSR_ESTATE (-4)  /* call order violated (e.g. decode before prologue)     */
+
+#define VSR_MAX_BEAM 8   /* largest beam_size supported by the fused top-k        */
+#define VSR_NUM_WEIGHTS 28
+
+/* dtype tags for the `verbs` tensor (eval_coco.py:240 hands float64 from numpy) */
+#define VSR_DT_F64 0
+#define VSR_DT_F32 1
+#define VSR_DT_I64 2
+
+typedef struct VsrHandle_* vsr_handle;
+
+/* Constructor arguments of ControllableCaptioningModel (controllable_captioning.py:11-12). */
+typedef struct VsrDims {
+  int32_t seq_len;
+  int32_t vocab_size;
+  int32_t bos_idx;
+  int32_t det_feat_size;       /* must be a multiple of 4 (128-bit feature loads) */
+  int32_t input_encoding_size;
+  int32_t rnn_size;
+  int32_t att_size;
+  int32_t h2_first_lstm;       /* bool */
+  int32_t img_second_lstm;     /* bool */
+} VsrDims;
+
+/* Optional per-step trace buffers (parity tests / trajectory replay).  Any pointer may be NULL.
+ * Rows of step t are caption-major (row = caption*cur_beam + beam, cur_beam = 1 at t = 0). */
+typedef struct VsrTrace {
+  float* step_out;            /* [T][b*beam][V]  word log-probs returned by step t          */
+  float* step_gate;           /* [T][b*beam][2]  gate log-probs returned by step t          */
+  const int32_t* forced_beam; /* [T][b][beam]    replay these selections instead of top-k   */
+  const int32_t* forced_word; /* [T][b][beam]                                               */
+  const int32_t* forced_gate; /* [T][b][beam]                                               */
+} VsrTrace;
+
+const char* vsr_last_error(void);
+int32_t vsr_abi_version(void);
+
+/* Replaces ControllableCaptioningModel.__init__ + state_dict ownership
+ * (controllable_captioning.py:11-70).  `weights` [host array of 28 device pointers] follows
+ * the state_dict registration order:
+ *   0 embed.weight (V,E)            1 W1_is.weight (H,in1)       2 W1_is.bias (H)
+ *   3 W1_hs.weight (H,H)            4 W1_hs.bias (H)             5 att_va.weight (A,F)
+ *   6 att_ha.weight (A,H)           7 att_a.weight (1,A)         8 att_sa.weight (A,H)
+ *   9 att_s.weight (1,A)           10 lstm_cell_1.weight_ih (4H,in1)
+ *  11 lstm_cell_1.weight_hh (4H,H) 12 lstm_cell_1.bias_ih (4H)  13 lstm_cell_1.bias_hh (4H)
+ *  14 lstm_cell_2.weight_ih (4H,in2) 15 lstm_cell_2.weight_hh (4H,H)
+ *  16 lstm_cell_2.bias_ih (4H)     17 lstm_cell_2.bias_hh (4H)  18 out_fc.weight (V,H)
+ *  19 out_fc.bias (V)              20 s_fc.weight (F,H)         21 s_fc.bias (F)
+ *  22 W1_ig.weight (H,in1)         23 W1_ig.bias (H)            24 W1_hg.weight (H,H)
+ *  25 W1_hg.bias (H)               26 att_ga.weight (A,H)       27 att_g.weight (1,A)
+ * with in1 = [H if h2_first_lstm] + F + E  (column order [h2 | img | xt], :228) and
+ * in2 = H + F [+ F if img_second_lstm]     (column order [h1 | att | img], :254-257).
+ * The library keeps its own packed (stacked / K-padded) copy; the caller keeps ownership
+ * of the originals. */
+int vsr_create(const VsrDims* dims, const float* const* weights, vsr_handle* out);
+
+/* Re-pack after load_state_dict()/.to(): replaces nn.Module.load_state_dict coherence. */
+int vsr_load_weights(vsr_handle h, const float* const* weights, void* stream);
+
+void vsr_destroy(vsr_handle h);
+
+/* Replaces the verb_2_vob_all JSON dict (controllable_captioning.py:25-34, 283-292) with a
+ * CSR table: keys [host, n_keys, strictly increasing], offsets [host, n_keys+1],
+ * vocab_idx [host, offsets[n_keys]].  n_keys = 0 clears the table. */
+int vsr_set_verb_table(vsr_handle h, const int64_t* keys, const int32_t* offsets,
+                       const int32_t* vocab_idx, int32_t n_keys);
+
+/* Time-invariant part of step()/step_v() hoisted out of the loop
+ * (controllable_captioning.py:126-128 / 203-205 image descriptor; :159/:240 validity of the
+ * region rows; :161/:242 att_va projection of every slot tile; the img columns of
+ * W1_is / lstm_cell_1.weight_ih / W1_ig (:151-152,181) and of lstm_cell_2.weight_ih (:174)).
+ *   det       (b, D, F) fp32; det_batch_stride in elements, 0 when the caller expanded one
+ *             image over all captions (eval_coco.py:243)
+ *   det_seqs  (b, L, R, F) fp32 slot tiles (feedback: statics[1]; teacher forcing: seqs[1], L=T)
+ *   verbs     (b, L) or NULL; verbs_dtype one of VSR_DT_*; value -1 = no verb in that slot */
+int vsr_prologue(vsr_handle h, const float* det, int64_t det_batch_stride, int32_t D,
+                 const float* det_seqs, int32_t b, int32_t L, int32_t R,
+                 const void* verbs, int32_t verbs_dtype, void* stream);
+
+/* One decoder step for the b prologue captions, one row per caption
+ * (ControllableCaptioningModel.step / step_v, controllable_captioning.py:117-190 / 192-297).
+ *   h1,c1,h2,c2 (b,H) state in;  slot (b) int64 = slot index the row attends to (feedback:
+ *   clamp(ctrl_det_idxs + prev_gate) as in :139-140; teacher forcing: t);  word (b) int64 input
+ *   token (bos at t = 0, :136);  use_verbs/gt select step_v semantics.
+ *   Outputs: h1o,c1o,h2o,c2o (b,H);  out_logp (b,V);  gate_logp (b,2). */
+int vsr_step(vsr_handle h, const float* h1, const float* c1, const float* h2, const float* c2,
+             const int64_t* slot, const int64_t* word, int32_t use_verbs, int32_t gt,
+             float* h1o, float* c1o, float* h2o, float* c2o,
+             float* out_logp, float* gate_logp, void* stream);
+
+/* Whole beam search over the prologue batch without host synchronisation
+ * (CaptioningModel.beam_search / beam_search_v, CaptioningModel.py:116-195 / 197-294).
+ *   out_words,out_gates (b,out_size,T) int64;  lp_words,lp_gates (b,out_size,T) fp32
+ *   eos_idxs[2] [host];  trace may be NULL. */
+int vsr_beam_search(vsr_handle h, int32_t beam_size, int32_t out_size, const int64_t* eos_idxs,
+                    int32_t use_verbs, int32_t gt,
+                    int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
+                    const VsrTrace* trace, void* stream);
+
+/* Per-step selections of the last vsr_beam_search on this handle, each [T][b][beam]
+ * (int32 parent slot / word / gate, fp32 accumulated score).  Any pointer may be NULL. */
+int vsr_get_history(vsr_handle h, int32_t* parent, int32_t* word, int32_t* gate, float* score,
+                    void* stream);
+
+/* Teacher-forced unroll over the prologue batch (CaptioningModel.forward,
+ * CaptioningModel.py:22-36; the prologue's det_seqs is seqs[1] with L = T).
+ *   captions (b,T) int64;  out (b,T,V);  gate (b,T,2). */
+int vsr_forward_teacher(vsr_handle h, const int64_t* captions, int32_t T,
+                        float* out, float* gate, void* stream);
+
+/* Greedy decode (CaptioningModel.test, CaptioningModel.py:38-52): argmax of both heads.
+ *   out_words,out_gates (b,T) int64. */
+int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* stream);
+
+/* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t vsr_launch_count(vsr_handle h);
+
+/* Per-phase device time of the last decode when enabled (CUDA events around each phase of each
+ * step; adds event overhead, off by default).  names/ms are [host] arrays of capacity cap;
+ * returns the number of phases written, or a negative error. */
+int vsr_set_profiling(vsr_handle h, int32_t enabled);
+int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* launches, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSRDEC_H_ */

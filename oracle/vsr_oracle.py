@@ -325,7 +325,7 @@ class BeamTrace:
 def beam_search(W, d: Dims, statics, eos_idxs: Sequence[int], beam_size: int, out_size: int = 1,
                 use_verbs: bool = False, gt: bool = False, verb_table=None,
                 trace: Optional[BeamTrace] = None, keep_step_outputs: bool = False,
-                keep_cand_scores: bool = False, forced: Optional[BeamTrace] = None):
+                keep_cand_scores: bool = False, forced: Optional[BeamTrace] = None, step_hook=None):
     """Joint (word, gate) beam search.
 
     ``use_verbs=False`` follows ``beam_search`` (CaptioningModel.py:116-195);
@@ -337,6 +337,8 @@ def beam_search(W, d: Dims, statics, eos_idxs: Sequence[int], beam_size: int, ou
 
     ``forced``: replay the given selections instead of the sorted top-k (trajectory replay for
     per-step parity tests); scores are still taken from this run's own candidates.
+    ``step_hook(t, out, gate, flat_candidate_scores)`` is called once per step (streaming checks
+    that would not fit in memory as a stored trace).
     """
     k = beam_size
     b = statics[0].size(0)
@@ -369,6 +371,8 @@ def beam_search(W, d: Dims, statics, eos_idxs: Sequence[int], beam_size: int, ou
             full = torch.clamp(seq_masks[0] + seq_masks[1], 0, 1).view(b, cur, 1, 1)
             cand = full * cand + old * (1 - full)
         flat = cand.view(b, -1)
+        if step_hook is not None:
+            step_hook(t, out, gate, flat)
         if forced is None:
             sorted_lp, sorted_idx = torch.sort(flat, -1, descending=True)
             top_lp, top_idx = sorted_lp[:, :k], sorted_idx[:, :k]

@@ -36,3 +36,83 @@ def rel_close(a, b, rel=1e-3, abs_floor=1e-4):
 def max_rel_err(a, b, abs_floor=1e-4):
     a, b = a.double(), b.double()
     return float(((a - b).abs() / (b.abs() + abs_floor)).max())
+
+
+# ----------------------------------------------------------------------------- tie-aware beam check
+class BeamVerdict:
+    def __init__(self):
+        self.decisions = 0          # (step, caption) pairs checked
+        self.in_band = 0            # pairs whose k-th / (k+1)-th oracle candidates are closer than the band
+        self.set_mismatch = 0       # pairs where the device's selected set differs from the oracle's top-k set
+        self.violations = []        # hard failures (outside the tie band)
+        self.max_score_err = 0.0
+        self.max_out_rel = 0.0      # per-step word log-prob error (relative, abs floor 1e-4)
+        self.max_gate_rel = 0.0
+        self.max_out_abs = 0.0
+        self.max_gate_abs = 0.0
+
+    def summary(self):
+        return (f"decisions={self.decisions} in_tie_band={self.in_band} set_mismatch={self.set_mismatch} "
+                f"violations={len(self.violations)} max_score_err={self.max_score_err:.3e} "
+                f"out_err(rel/abs)={self.max_out_rel:.3e}/{self.max_out_abs:.3e} "
+                f"gate_err(rel/abs)={self.max_gate_rel:.3e}/{self.max_gate_abs:.3e}")
+
+
+def verify_device_beam(W, d, statics, eos, k, hist, use_verbs=False, gt=False, verb_table=None,
+                       step_out=None, step_gate=None, band_abs=2e-3, band_rel=2e-5):
+    """Replay the DEVICE's beam trajectory (hist = parent, word, gate, score each (T,b,k), CPU)
+    through the oracle and check, at every step and caption, that the device's selection is a
+    valid top-k of the ORACLE's candidate scores up to a tie band:
+      * every selected candidate scores >= (oracle k-th best) - band,
+      * every candidate scoring > (oracle k-th best) + band was selected,
+      * the device's accumulated scores equal the oracle's at the selected candidates (<= band).
+    Optionally also compares the per-step log-probs (step_out (T,b*k,V), step_gate (T,b*k,2)).
+    band = band_abs + band_rel*|score|  (fp32 accumulated scores reach ~ -200: 1 ulp = 1.5e-5).
+    """
+    parent, word, gate, score = [x.cpu() for x in hist]
+    T, b, _ = parent.shape
+    V = d.vocab_size
+    forced = O.BeamTrace([parent[t].long() for t in range(T)], [word[t].long() for t in range(T)],
+                         [gate[t].long() for t in range(T)], [], [], [], [])
+    v = BeamVerdict()
+
+    def hook(t, out, gate_lp, flat):
+        cur = flat.size(1) // (2 * V)
+        sel = parent[t].long() * (2 * V) + word[t].long() * 2 + gate[t].long()      # (b,k)
+        sel_sc = torch.gather(flat, 1, sel)
+        top = torch.topk(flat, k + 1, dim=1).values
+        kth, nxt = top[:, k - 1], top[:, k]
+        band = band_abs + band_rel * kth.abs()
+        v.decisions += b
+        v.in_band += int(((kth - nxt) <= band).sum())
+        oracle_sel = torch.topk(flat, k, dim=1).indices
+        v.set_mismatch += int((oracle_sel.sort(1).values != sel.sort(1).values).any(1).sum())
+        low = sel_sc < (kth - band).unsqueeze(1)
+        for c in torch.nonzero(low.any(1)).flatten().tolist():
+            v.violations.append(f"t={t} caption={c}: selected score {sel_sc[c].tolist()} below k-th {float(kth[c])}")
+        must = flat > (kth + band).unsqueeze(1)                                   # decisive candidates
+        picked = torch.zeros_like(must)
+        picked.scatter_(1, sel, True)
+        miss = (must & ~picked).any(1)
+        for c in torch.nonzero(miss).flatten().tolist():
+            v.violations.append(f"t={t} caption={c}: a decisive candidate was not selected")
+        err = (score[t] - sel_sc).abs()
+        v.max_score_err = max(v.max_score_err, float(err.max()))
+        bad = err > (band_abs + band_rel * sel_sc.abs())
+        for c in torch.nonzero(bad.any(1)).flatten().tolist():
+            v.violations.append(f"t={t} caption={c}: device score {score[t, c].tolist()} vs oracle {sel_sc[c].tolist()}")
+        if step_out is not None:
+            n = out.size(0)
+            dv = step_out[t, :n].cpu()
+            v.max_out_abs = max(v.max_out_abs, float((dv - out).abs().max()))
+            v.max_out_rel = max(v.max_out_rel, max_rel_err(dv, out))
+        if step_gate is not None:
+            n = gate_lp.size(0)
+            dg = step_gate[t, :n].cpu()
+            v.max_gate_abs = max(v.max_gate_abs, float((dg - gate_lp).abs().max()))
+            v.max_gate_rel = max(v.max_gate_rel, max_rel_err(dg, gate_lp))
+
+    with torch.no_grad():
+        outs, lps = O.beam_search(W, d, statics, eos, k, k, use_verbs=use_verbs, gt=gt, verb_table=verb_table,
+                                  forced=forced, step_hook=hook)
+    return v, outs, lps

@@ -1,0 +1,206 @@
+"""Parity of the sm_100a decoder (through the drop-in model -> ctypes -> libvsrdec C ABI) against
+the CPU oracle and the committed golden vectors of the reference.  Needs a GPU."""
+import pytest
+import torch
+
+from oracle import vsr_oracle as O
+from common import load_golden, verify_device_beam, rel_close, max_rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+# north-star tolerance on per-step log-probs: 1e-3 relative (fp32-accumulated), abs floor 1e-4
+REL, ABS = 1e-3, 1e-4
+
+
+def _cuda(*ts):
+    return tuple(t.to(DEV) if t is not None else None for t in ts)
+
+
+def _match_fraction(ref, got):
+    same = (ref.cpu() == got.cpu()).flatten(1).all(1)
+    return float(same.float().mean())
+
+
+@pytest.mark.parametrize("name", ["small_a.pt", "small_b.pt"])
+def test_small_model_beam_search_cases(name):
+    """Golden cases of the tiny model: verb forcing gt / table, EOS freeze, b=1."""
+    from gpu_common import make_model, device_beam
+    fx = load_golden(name)
+    d, W = fx["dims_obj"], fx["weights"]
+    m = make_model(d, W, fx["verb_table"])
+    det, ds = fx["det"], fx["det_seqs"]
+    cases = [
+        ("bsv_gt_k3", (det, ds, fx["verbs_gt"]), True, True, slice(None)),
+        ("bsv_tab_k5", (det, ds, fx["verbs_tab"]), True, False, slice(None)),
+        ("bs_freeze_k4", (det, ds), False, False, slice(None)),
+        ("bsv_gt_b1", (det[:1], ds[:1], fx["verbs_gt"][:1]), True, True, slice(0, 1)),
+    ]
+    for cname, statics, use_verbs, gt, _ in cases:
+        c = fx["cases"][cname]
+        k, osz = c["beam"], c["out_size"]
+        (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(*statics), c["eos"], k, osz, use_verbs, gt)
+        v, o_outs, o_lps = verify_device_beam(W, d, statics, c["eos"], k, hist, use_verbs, gt, fx["verb_table"],
+                                              extra["step_out"], extra["step_gate"])
+        print(cname, v.summary())
+        assert not v.violations, v.violations[:5]
+        assert v.max_out_rel <= REL and v.max_gate_rel <= REL
+        # along the device's own trajectory the oracle reproduces the device's outputs exactly
+        ow, og = o_outs[0][:, :osz], o_outs[1][:, :osz]
+        assert torch.equal(w.cpu(), ow) and torch.equal(g.cpu(), og)
+        assert rel_close(lw.cpu(), o_lps[0][:, :osz], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, :osz], REL, ABS)
+        # and versus the reference's golden free run: identical unless a tie flipped a decision
+        gw = c["out"][0].reshape(w.shape)
+        frac = _match_fraction(gw, w)
+        print(cname, "captions identical to the reference golden run:", frac)
+        if v.in_band == 0:
+            assert frac == 1.0
+
+
+@pytest.mark.parametrize("name", ["small_a.pt", "small_b.pt"])
+def test_small_model_forward_teacher(name):
+    from gpu_common import make_model
+    fx = load_golden(name)
+    m = make_model(fx["dims_obj"], fx["weights"], fx["verb_table"])
+    det, caps, ctrl = _cuda(fx["det"], fx["captions"], fx["ctrl"])
+    out, gate = m((det,), (caps, ctrl))
+    torch.cuda.synchronize()
+    c = fx["cases"]["forward"]
+    assert out.shape == c["out"].shape and gate.shape == c["gate"].shape
+    print("forward max rel err out/gate:", max_rel_err(out.cpu(), c["out"]), max_rel_err(gate.cpu(), c["gate"]))
+    assert rel_close(out.cpu(), c["out"], REL, ABS)
+    assert rel_close(gate.cpu(), c["gate"], REL, ABS)
+
+
+def test_small_model_step_v_api():
+    """The reference-facing step_v surface with explicit state (golden: two feedback steps)."""
+    from gpu_common import make_model
+    fx = load_golden("small_a.pt")
+    d, c = fx["dims_obj"], fx["cases"]["step_v"]
+    m = make_model(d, fx["weights"], fx["verb_table"])
+    statics = _cuda(fx["det"], fx["det_seqs"], fx["verbs_gt"])
+    st = m.init_state(fx["det"].size(0), DEV)
+    (o0, g0), st = m.step_v(0, st, None, statics, None, mode="feedback", gt=True)
+    (o1, g1), st = m.step_v(1, st, [c["prev_word"].to(DEV), c["prev_gate"].to(DEV)], statics, None,
+                            mode="feedback", gt=True)
+    torch.cuda.synchronize()
+    for got, ref in ((o0, c["out0"]), (g0, c["gate0"]), (o1, c["out1"]), (g1, c["gate1"]),
+                     (st[0][0], c["h1"]), (st[0][1], c["c1"]), (st[1][0], c["h2"]), (st[1][1], c["c2"])):
+        assert rel_close(got.cpu(), ref, REL, ABS), max_rel_err(got.cpu(), ref)
+    assert torch.equal(st[2].cpu(), c["ptr"])
+    with pytest.raises(NameError):
+        m.step_v(0, m.init_state(6, DEV), None, statics, _cuda(fx["captions"], fx["ctrl"]), mode="teacher_forcing")
+    with pytest.raises(AssertionError):
+        m.step(0, m.init_state(6, DEV), None, statics, None, mode="sampling")
+
+
+def test_small_model_greedy():
+    from gpu_common import make_model
+    fx = load_golden("small_a.pt")
+    d, W = fx["dims_obj"], fx["weights"]
+    m = make_model(d, W, fx["verb_table"])
+    det, ds = fx["det"], fx["det_seqs"]
+    words, gates = m.test(*_cuda(det, ds))
+    torch.cuda.synchronize()
+    words, gates = words.cpu(), gates.cpu()
+    # replay the device's picks through the oracle: each pick must be an arg-max up to the tie band
+    state = O.init_state(d, det.size(0))
+    prev = None
+    with torch.no_grad():
+        for t in range(d.seq_len):
+            (out, gate), state = O.decoder_step(W, d, t, state, prev, (det, ds), None, "feedback")
+            pw, pg = words[:, t], gates[:, t]
+            assert bool((out.gather(1, pw[:, None]).squeeze(1) >= out.max(1).values - 1e-4).all())
+            assert bool((gate.gather(1, pg[:, None]).squeeze(1) >= gate.max(1).values - 1e-4).all())
+            prev = (pw, pg)
+    g = fx["cases"]["greedy"]
+    print("greedy captions identical to golden:", _match_fraction(g["words"], words))
+
+
+def test_errors_and_no_cpu_fallback():
+    from gpu_common import make_model
+    from vsrdec import VsrError
+    fx = load_golden("small_a.pt")
+    m = make_model(fx["dims_obj"], fx["weights"], fx["verb_table"])
+    det, ds, verbs = fx["det"], fx["det_seqs"], fx["verbs_gt"]
+    with pytest.raises(VsrError):
+        m.beam_search_v((det, ds, verbs), [3, -1], 3)                 # CPU tensors
+    with pytest.raises(VsrError):
+        m.beam_search_v(_cuda(det, ds, verbs), [3, -1], 9)            # beam > VSR_MAX_BEAM
+    with pytest.raises(VsrError):
+        m.beam_search_v(_cuda(det, ds, verbs), [3, -1], 3, 4)         # out_size > beam
+    with pytest.raises(VsrError):
+        m.beam_search_v(_cuda(det, ds[:, :, :, :64].contiguous(), verbs), [3, -1], 3)   # feature width
+
+
+def test_expanded_detections_and_weight_reload():
+    """eval_coco.py:243 passes one image expanded (stride 0) over its captions; load_state_dict after
+    the first decode must be picked up (packed-weight coherence)."""
+    from gpu_common import make_model
+    fx = load_golden("small_a.pt")
+    d, W = fx["dims_obj"], fx["weights"]
+    m = make_model(d, W, fx["verb_table"])
+    det, ds, verbs = _cuda(fx["det"], fx["det_seqs"], fx["verbs_gt"])
+    det1 = det[2].unsqueeze(0).expand(det.size(0), det.size(1), det.size(2))
+    assert det1.stride(0) == 0
+    o_exp, lp_exp = m.beam_search_v((det1, ds, verbs), [3, -1], 3, 1, gt=True)
+    o_mat, lp_mat = m.beam_search_v((det1.contiguous(), ds, verbs), [3, -1], 3, 1, gt=True)
+    torch.cuda.synchronize()
+    assert torch.equal(o_exp[0], o_mat[0]) and torch.equal(o_exp[1], o_mat[1])
+    assert torch.allclose(lp_exp[0], lp_mat[0], atol=1e-5)
+    # new weights -> different captions; old weights back -> the original captions again
+    W2 = O.init_weights(d, seed=77)
+    m.load_state_dict(W2)
+    o2, _ = m.beam_search_v((det1, ds, verbs), [3, -1], 3, 1, gt=True)
+    m.load_state_dict(W)
+    o3, _ = m.beam_search_v((det1, ds, verbs), [3, -1], 3, 1, gt=True)
+    torch.cuda.synchronize()
+    assert not torch.equal(o2[0], o_exp[0])
+    assert torch.equal(o3[0], o_exp[0]) and torch.equal(o3[1], o_exp[1])
+
+
+def _full_model(seed=1234, sharpen=None):
+    from gpu_common import make_model
+    d = O.Dims()
+    W = O.init_weights(d, seed=seed)
+    if sharpen:
+        W["out_fc.weight"] = W["out_fc.weight"] * sharpen
+    return d, W, make_model(d, W)
+
+
+@pytest.mark.parametrize("sharpen", [None, 100.0])
+def test_full_size_config1(sharpen):
+    """BASELINE config 1: b=8, beam 3, D=20, L=10, R=20, V=10000, gt=True, verb at slot 2."""
+    from gpu_common import device_beam
+    fx = load_golden("full_cfg1.pt")
+    d, W, m = _full_model(fx["seed_w"], sharpen)
+    det, ds, verbs = O.synth_inputs(**fx["synth"])
+    (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(det, ds, verbs), [3, -1], 3, 1, True, True)
+    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 3, hist, True, True, None,
+                                          extra["step_out"], extra["step_gate"])
+    print("config1 sharpen=%s" % sharpen, v.summary())
+    assert not v.violations, v.violations[:5]
+    assert v.max_out_rel <= REL and v.max_gate_rel <= REL
+    assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
+    # free-running oracle (== the reference, bit-exact) for the exact-match statistic
+    with torch.no_grad():
+        ref_o, _ = O.beam_search(W, d, (det, ds, verbs), [3, -1], 3, 1, use_verbs=True, gt=True)
+    frac = _match_fraction(ref_o[0], w.squeeze(1))
+    print("config1 sharpen=%s captions token-identical to the oracle free run: %.3f" % (sharpen, frac))
+    if sharpen:
+        assert frac >= 0.75
+
+
+def test_full_size_config2_eval_shape():
+    """BASELINE config 2 (eval_coco.py --gt shape): b=100, beam 5, D=50 padded, V=10000 — the
+    device's whole trajectory must be a valid tie-aware top-k under the oracle at every step."""
+    from gpu_common import device_beam
+    d, W, m = _full_model(1234, 100.0)
+    det, ds, verbs = O.synth_inputs(100, 50, 10, 20, 2048, seed=1002, vocab_size=d.vocab_size,
+                                    n_det_range=(10, 50), verb_slots=(2,), verb_vocab_id=17)
+    (w, g), (lw, lg), hist, _ = device_beam(m, _cuda(det, ds, verbs), [3, -1], 5, 1, True, True, trace=False)
+    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 5, hist, True, True)
+    print("config2 sharp100", v.summary())
+    assert not v.violations, v.violations[:5]
+    assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
+    assert rel_close(lw.cpu(), o_lps[0][:, :1], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, :1], REL, ABS)

@@ -1,0 +1,470 @@
+// C-ABI entry points of libvsrdec (include/vsrdec.h): context life-cycle, workspace
+// management and the decode drivers (beam search, teacher-forced forward, greedy, single step).
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace vsr {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return VSR_ENOMEM;
+  }
+  c->owned.push_back(*p);
+  if (zero) VSR_CHECK_CUDA(cudaMemset(*p, 0, bytes));
+  return VSR_OK;
+}
+
+static void dev_free(Ctx* c, void* p) {
+  if (p == nullptr) return;
+  auto it = std::find(c->owned.begin(), c->owned.end(), p);
+  if (it != c->owned.end()) c->owned.erase(it);
+  cudaFree(p);
+}
+
+PhaseScope::PhaseScope(Ctx* c_, int id_, cudaStream_t st_) : c(c_), id(id_), st(st_) {
+  c->phases[id].launches++;
+  if (!c->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); c->phases[id].ev.push_back(e); }
+}
+PhaseScope::~PhaseScope() {
+  if (!c->profiling) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); c->phases[id].ev.push_back(e); }
+}
+
+static const char* kPhaseNames[PH_COUNT] = {
+    "prologue", "gemm_a_lstm1_gates", "lstm1_pointwise", "gemm_b_sentinel_h1proj", "gate_pointwise",
+    "gemm_c_att_ga", "attend_gate", "gemm_d_lstm2_gates", "lstm2_pointwise", "gemm_e_vocab",
+    "softmax_topk", "beam_select", "state_reorder", "backtrack"};
+
+static void reset_phases(Ctx* c) {
+  for (int i = 0; i < PH_COUNT; ++i) {
+    for (cudaEvent_t e : c->phases[i].ev) cudaEventDestroy(e);
+    c->phases[i].ev.clear();
+    c->phases[i].launches = 0;
+  }
+}
+
+#define ALLOC_F(ptr, count) VSR_TRY(dev_alloc(c, (void**)&(ptr), sizeof(float) * (size_t)(count)))
+
+int ensure_rows(Ctx* c, int rows) {
+  if (rows <= c->cap_rows) return VSR_OK;
+  const int cap = round_up(rows, MPAD);
+  float** bufs[] = {&c->h1, &c->c1, &c->h2, &c->c2, &c->h1n, &c->c1n, &c->h2n, &c->c2n, &c->xt, &c->pre1,
+                    &c->s_t, &c->g_t, &c->sent, &c->hb, &c->ga, &c->att, &c->pre2, &c->logits, &c->gate_lp,
+                    &c->row_max, &c->row_lsum};
+  for (float** p : bufs) { dev_free(c, *p); *p = nullptr; }
+  dev_free(c, c->ptr); dev_free(c, c->ptrn); dev_free(c, c->forced); dev_free(c, c->cand); dev_free(c, c->word_in);
+  c->cap_rows = 0;
+  const size_t n = cap;
+  ALLOC_F(c->h1, n * c->Hp); ALLOC_F(c->c1, n * c->Hp); ALLOC_F(c->h2, n * c->Hp); ALLOC_F(c->c2, n * c->Hp);
+  ALLOC_F(c->h1n, n * c->Hp); ALLOC_F(c->c1n, n * c->Hp); ALLOC_F(c->h2n, n * c->Hp); ALLOC_F(c->c2n, n * c->Hp);
+  ALLOC_F(c->xt, n * c->Ep);
+  ALLOC_F(c->pre1, n * c->NA);
+  ALLOC_F(c->s_t, n * c->Hp); ALLOC_F(c->g_t, n * c->Hp);
+  ALLOC_F(c->sent, n * c->NB1); ALLOC_F(c->hb, n * c->NB2); ALLOC_F(c->ga, n * c->NC);
+  ALLOC_F(c->att, n * c->Fp); ALLOC_F(c->pre2, n * c->ND); ALLOC_F(c->logits, n * c->NE);
+  ALLOC_F(c->gate_lp, n * 2); ALLOC_F(c->row_max, n); ALLOC_F(c->row_lsum, n);
+  VSR_TRY(dev_alloc(c, (void**)&c->ptr, sizeof(int32_t) * n));
+  VSR_TRY(dev_alloc(c, (void**)&c->ptrn, sizeof(int32_t) * n));
+  VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));
+  VSR_TRY(dev_alloc(c, (void**)&c->cand, sizeof(int32_t) * n * VSR_MAX_BEAM));
+  VSR_TRY(dev_alloc(c, (void**)&c->word_in, sizeof(int64_t) * n));
+  c->cap_rows = cap;
+  return VSR_OK;
+}
+
+int ensure_beam_ws(Ctx* c, int caps, int T) {
+  if (caps <= c->cap_caps && T <= c->cap_T) return VSR_OK;
+  caps = std::max(caps, c->cap_caps); T = std::max(T, c->cap_T);
+  float** fb[] = {&c->seq_lp, &c->seq_lp_n, &c->m0, &c->m1, &c->m0n, &c->m1n, &c->hist_score, &c->hist_lpw, &c->hist_lpg};
+  int32_t** ib[] = {&c->sel_beam, &c->sel_word, &c->sel_gate, &c->hist_parent, &c->hist_word, &c->hist_gate};
+  for (float** p : fb) { dev_free(c, *p); *p = nullptr; }
+  for (int32_t** p : ib) { dev_free(c, *p); *p = nullptr; }
+  c->cap_caps = 0; c->cap_T = 0;
+  const size_t s = (size_t)caps * VSR_MAX_BEAM, hs = s * T;
+  ALLOC_F(c->seq_lp, s); ALLOC_F(c->seq_lp_n, s); ALLOC_F(c->m0, s); ALLOC_F(c->m1, s); ALLOC_F(c->m0n, s); ALLOC_F(c->m1n, s);
+  ALLOC_F(c->hist_score, hs); ALLOC_F(c->hist_lpw, hs); ALLOC_F(c->hist_lpg, hs);
+  VSR_TRY(dev_alloc(c, (void**)&c->sel_beam, sizeof(int32_t) * s));
+  VSR_TRY(dev_alloc(c, (void**)&c->sel_word, sizeof(int32_t) * s));
+  VSR_TRY(dev_alloc(c, (void**)&c->sel_gate, sizeof(int32_t) * s));
+  VSR_TRY(dev_alloc(c, (void**)&c->hist_parent, sizeof(int32_t) * hs));
+  VSR_TRY(dev_alloc(c, (void**)&c->hist_word, sizeof(int32_t) * hs));
+  VSR_TRY(dev_alloc(c, (void**)&c->hist_gate, sizeof(int32_t) * hs));
+  c->cap_caps = caps; c->cap_T = T;
+  return VSR_OK;
+}
+
+static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
+  VSR_REQUIRE(d != nullptr && w != nullptr && out != nullptr, VSR_EINVAL, "vsr_create: null argument");
+  VSR_REQUIRE(d->vocab_size > 0 && d->rnn_size > 0 && d->att_size > 0 && d->input_encoding_size > 0 &&
+                  d->det_feat_size > 0 && d->seq_len > 0,
+              VSR_EINVAL, "vsr_create: non-positive dimension");
+  VSR_REQUIRE(d->det_feat_size % 4 == 0, VSR_EINVAL,
+              "vsr_create: det_feat_size=%d must be a multiple of 4 (128-bit feature loads)", d->det_feat_size);
+  VSR_REQUIRE(d->bos_idx >= 0 && d->bos_idx < d->vocab_size, VSR_EINVAL, "vsr_create: bos_idx out of range");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  VSR_REQUIRE(e == cudaSuccess && ndev > 0, VSR_ECUDA,
+              "vsr_create: no CUDA device available (%s); libvsrdec has no CPU fallback",
+              cudaGetErrorString(e));
+  Ctx* c = new Ctx();
+  c->d = *d;
+  VSR_CHECK_CUDA(cudaGetDevice(&c->device));
+  c->V = d->vocab_size; c->E = d->input_encoding_size; c->H = d->rnn_size; c->F = d->det_feat_size; c->A = d->att_size;
+  c->Hp = round_up(c->H, KPAD); c->Ep = round_up(c->E, KPAD); c->Fp = round_up(c->F, KPAD); c->Ap = round_up(c->A, KPAD);
+  c->NA = round_up(6 * c->H, NPAD);
+  c->oB1_sa = c->Fp;
+  c->NB1 = round_up(c->oB1_sa + c->A, NPAD);
+  c->oB2_ha = c->Hp;
+  c->oB2_p2 = c->oB2_ha + c->Ap;
+  c->NB2 = round_up(c->oB2_p2 + 4 * c->H, NPAD);
+  c->NC = round_up(c->A, NPAD);
+  c->ND = round_up(4 * c->H, NPAD);
+  c->NE = round_up(c->V, NPAD);
+  c->NVA = round_up(c->A, NPAD);
+  c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Ep + c->Hp;
+  c->KD = c->Fp + c->Hp;
+  for (int i = 0; i < PH_COUNT; ++i) c->phases[i].name = kPhaseNames[i];
+  *out = c;   // from here on vsr_destroy can clean up a half-built context
+  ALLOC_F(c->WA, (size_t)c->NA * c->KA); ALLOC_F(c->WU, (size_t)c->NA * c->Fp); ALLOC_F(c->bU, c->NA);
+  ALLOC_F(c->WB1, (size_t)c->NB1 * c->Hp); ALLOC_F(c->bB1, c->NB1);
+  ALLOC_F(c->WB2, (size_t)c->NB2 * c->Hp);
+  ALLOC_F(c->WC, (size_t)c->NC * c->Hp);
+  ALLOC_F(c->WD, (size_t)c->ND * c->KD); ALLOC_F(c->bD, c->ND);
+  if (d->img_second_lstm) ALLOC_F(c->WU2, (size_t)c->ND * c->Fp);
+  ALLOC_F(c->WE, (size_t)c->NE * c->Hp); ALLOC_F(c->bE, c->NE);
+  ALLOC_F(c->Wva, (size_t)c->NVA * c->Fp);
+  ALLOC_F(c->v_a, c->Ap); ALLOC_F(c->v_s, c->Ap); ALLOC_F(c->v_g, c->Ap);
+  ALLOC_F(c->embed, (size_t)c->V * c->Ep);
+  VSR_TRY(pack_weights(c, w, 0));
+  VSR_CHECK_CUDA(cudaStreamSynchronize(0));
+  return VSR_OK;
+}
+
+static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, const float* det_seqs, int b,
+                         int L, int R, const void* verbs, int verbs_dtype, cudaStream_t st) {
+  VSR_REQUIRE(det != nullptr && det_seqs != nullptr, VSR_EINVAL, "vsr_prologue: null input");
+  VSR_REQUIRE(b > 0 && D > 0 && L > 0 && R > 0, VSR_EINVAL, "vsr_prologue: bad shape b=%d D=%d L=%d R=%d", b, D, L, R);
+  VSR_REQUIRE(R <= 64, VSR_EINVAL, "vsr_prologue: R=%d regions per slot > 64 unsupported", R);
+  VSR_REQUIRE(det_stride == 0 || det_stride >= (int64_t)D * c->F, VSR_EINVAL, "vsr_prologue: bad det_batch_stride");
+  VSR_REQUIRE(verbs == nullptr || (verbs_dtype >= 0 && verbs_dtype <= 2), VSR_EINVAL, "vsr_prologue: bad verbs dtype");
+  VSR_REQUIRE(((uintptr_t)det % 16) == 0 && ((uintptr_t)det_seqs % 16) == 0 && (det_stride % 4) == 0, VSR_EINVAL,
+              "vsr_prologue: feature tensors must be 16-byte aligned");
+  c->have_prologue = false;
+  c->b = b; c->D = D; c->L = L; c->R = R;
+  c->n_img = det_stride == 0 ? 1 : b;
+  c->det_seqs = det_seqs; c->verbs = verbs; c->verbs_dtype = verbs_dtype;
+  const size_t n_img_pad = round_up(c->n_img, MPAD);
+  if (n_img_pad > c->cap_img) {
+    dev_free(c, c->img); dev_free(c, c->U); dev_free(c, c->U2);
+    c->img = c->U = c->U2 = nullptr; c->cap_img = 0;
+    ALLOC_F(c->img, n_img_pad * c->Fp); ALLOC_F(c->U, n_img_pad * c->NA);
+    if (c->d.img_second_lstm) ALLOC_F(c->U2, n_img_pad * c->ND);
+    c->cap_img = n_img_pad;
+  }
+  const size_t prow = (size_t)b * L * R;
+  if (prow > c->cap_P) {
+    dev_free(c, c->P); dev_free(c, c->seq_valid);
+    c->P = nullptr; c->seq_valid = nullptr; c->cap_P = 0;
+    ALLOC_F(c->P, round_up((int)prow, MPAD) * (size_t)c->NVA);
+    VSR_TRY(dev_alloc(c, (void**)&c->seq_valid, round_up((int)prow, MPAD)));
+    c->cap_P = prow;
+  }
+  const size_t dvr = (size_t)c->n_img * D;
+  if (dvr > c->cap_detv) {
+    dev_free(c, c->det_valid); c->det_valid = nullptr; c->cap_detv = 0;
+    VSR_TRY(dev_alloc(c, (void**)&c->det_valid, dvr));
+    c->cap_detv = dvr;
+  }
+  VSR_TRY(ensure_rows(c, b));
+  VSR_TRY(run_prologue(c, det, det_stride, st));
+  c->have_prologue = true;
+  return VSR_OK;
+}
+
+// dst[n][0:w] = src[n][0:w] with different leading dims
+__global__ void k_copy2d(float* dst, int ld_dst, const float* src, int ld_src, int w, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (i < w && n < rows) dst[(size_t)n * ld_dst + i] = src[(size_t)n * ld_src + i];
+}
+__global__ void k_slots_from_i64(int32_t* ptr, const int64_t* slot, int rows, int L) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  int64_t s = slot[n];
+  s = s < 0 ? 0 : (s > L - 1 ? L - 1 : s);
+  ptr[n] = (int32_t)s;
+}
+__global__ void k_fill_i32(int32_t* p, int v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+static int copy2d(Ctx* c, float* dst, int ld_dst, const float* src, int ld_src, int w, int rows, cudaStream_t st) {
+  dim3 grid((w + 255) / 256, rows);
+  k_copy2d<<<grid, 256, 0, st>>>(dst, ld_dst, src, ld_src, w, rows);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, const float* c2,
+                     const int64_t* slot, const int64_t* word, int use_verbs, int gt, float* h1o, float* c1o,
+                     float* h2o, float* c2o, float* out_logp, float* gate_logp, cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_step: call vsr_prologue first");
+  VSR_REQUIRE(h1 && c1 && h2 && c2 && slot && word, VSR_EINVAL, "vsr_step: null state input");
+  VSR_REQUIRE(!use_verbs || c->verbs != nullptr, VSR_EINVAL, "vsr_step: use_verbs without a verbs tensor");
+  const int b = c->b, H = c->H;
+  VSR_TRY(copy2d(c, c->h1, c->Hp, h1, H, H, b, st));
+  VSR_TRY(copy2d(c, c->c1, c->Hp, c1, H, H, b, st));
+  VSR_TRY(copy2d(c, c->h2, c->Hp, h2, H, H, b, st));
+  VSR_TRY(copy2d(c, c->c2, c->Hp, c2, H, H, b, st));
+  k_slots_from_i64<<<(b + 127) / 128, 128, 0, st>>>(c->ptr, slot, b, c->L);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  VSR_TRY(launch_embed(c, word, b, st));
+  StepIO io{};
+  io.rows = b; io.cur_beam = 1; io.use_verbs = use_verbs != 0; io.gt = gt != 0;
+  io.out_logp = out_logp; io.out_stride = c->V; io.gate_out = gate_logp; io.gate_stride = 2; io.topk = 0;
+  VSR_TRY(run_step(c, io, st));
+  if (h1o) VSR_TRY(copy2d(c, h1o, H, c->h1n, c->Hp, H, b, st));
+  if (c1o) VSR_TRY(copy2d(c, c1o, H, c->c1n, c->Hp, H, b, st));
+  if (h2o) VSR_TRY(copy2d(c, h2o, H, c->h2n, c->Hp, H, b, st));
+  if (c2o) VSR_TRY(copy2d(c, c2o, H, c->c2n, c->Hp, H, b, st));
+  return VSR_OK;
+}
+
+static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int use_verbs, int gt,
+                            int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
+                            const VsrTrace* tr, cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_beam_search: call vsr_prologue first");
+  VSR_REQUIRE(k >= 1 && k <= VSR_MAX_BEAM, VSR_EINVAL, "vsr_beam_search: beam_size=%d not in [1,%d]", k, VSR_MAX_BEAM);
+  VSR_REQUIRE(out_size >= 1 && out_size <= k, VSR_EINVAL, "vsr_beam_search: out_size=%d not in [1,beam]", out_size);
+  VSR_REQUIRE(2 * c->V >= k, VSR_EINVAL, "vsr_beam_search: vocabulary smaller than the beam");
+  VSR_REQUIRE(eos && out_words && out_gates && lp_words && lp_gates, VSR_EINVAL, "vsr_beam_search: null argument");
+  VSR_REQUIRE(!use_verbs || c->verbs != nullptr, VSR_EINVAL, "vsr_beam_search: use_verbs without a verbs tensor");
+  const int b = c->b, T = c->d.seq_len;
+  VSR_TRY(ensure_rows(c, b * k));
+  VSR_TRY(ensure_beam_ws(c, b, T));
+  if (c->profiling) reset_phases(c);
+  c->hist_T = T; c->hist_b = b; c->hist_k = k;
+  VSR_TRY(launch_state_init(c, b, st));
+  const bool have_forced = tr && tr->forced_beam && tr->forced_word && tr->forced_gate;
+  for (int t = 0; t < T; ++t) {
+    const int cur = t == 0 ? 1 : k;
+    const int rows = b * cur;
+    StepIO io{};
+    io.rows = rows; io.cur_beam = cur; io.use_verbs = use_verbs != 0; io.gt = gt != 0; io.topk = k;
+    if (tr && tr->step_out) { io.out_logp = tr->step_out + (size_t)t * b * k * c->V; io.out_stride = c->V; }
+    if (tr && tr->step_gate) { io.gate_out = tr->step_gate + (size_t)t * b * k * 2; io.gate_stride = 2; }
+    VSR_TRY(run_step(c, io, st));
+    const size_t fo = (size_t)t * b * k;
+    VSR_TRY(launch_beam_select(c, t, b, cur, k, eos[0], eos[1], have_forced ? tr->forced_beam + fo : nullptr,
+                               have_forced ? tr->forced_word + fo : nullptr,
+                               have_forced ? tr->forced_gate + fo : nullptr, st));
+    if (t + 1 < T) VSR_TRY(launch_reorder(c, b, cur, k, st));
+  }
+  VSR_TRY(launch_backtrack(c, b, k, T, out_size, out_words, out_gates, lp_words, lp_gates, st));
+  return VSR_OK;
+}
+
+static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, float* gate, cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_forward_teacher: call vsr_prologue first");
+  VSR_REQUIRE(captions && out && gate, VSR_EINVAL, "vsr_forward_teacher: null argument");
+  VSR_REQUIRE(T >= 1 && T <= c->L, VSR_EINVAL, "vsr_forward_teacher: T=%d exceeds the prologue's slot count L=%d", T, c->L);
+  const int b = c->b;
+  VSR_TRY(ensure_rows(c, b));
+  if (c->profiling) reset_phases(c);
+  VSR_TRY(launch_state_init(c, b, st));
+  // the first input token is captions[:, 0], not bos (controllable_captioning.py:131-133)
+  for (int t = 0; t < T; ++t) {
+    if (t == 0) {
+      // xt <- embed[captions[:,0]], slot 0
+      VSR_CHECK_CUDA(cudaMemcpy2DAsync(c->word_in, sizeof(int64_t), captions, sizeof(int64_t) * T,
+                                       sizeof(int64_t), b, cudaMemcpyDeviceToDevice, st));
+      VSR_TRY(launch_embed(c, c->word_in, b, st));
+    }
+    StepIO io{};
+    io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 0;
+    io.out_logp = out + (size_t)t * c->V; io.out_stride = (int64_t)T * c->V;
+    io.gate_out = gate + (size_t)t * 2; io.gate_stride = (int64_t)T * 2;
+    VSR_TRY(run_step(c, io, st));
+    if (t + 1 < T) VSR_TRY(launch_commit_identity(c, b, captions + (t + 1), T, t + 1, st));
+  }
+  return VSR_OK;
+}
+
+static int greedy_impl(Ctx* c, int64_t* out_words, int64_t* out_gates, cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_greedy: call vsr_prologue first");
+  VSR_REQUIRE(out_words && out_gates, VSR_EINVAL, "vsr_greedy: null argument");
+  const int b = c->b, T = c->d.seq_len;
+  VSR_TRY(ensure_rows(c, b));
+  VSR_TRY(ensure_beam_ws(c, b, T));
+  if (c->profiling) reset_phases(c);
+  VSR_TRY(launch_state_init(c, b, st));
+  for (int t = 0; t < T; ++t) {
+    StepIO io{};
+    io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 1;
+    VSR_TRY(run_step(c, io, st));
+    VSR_TRY(launch_greedy_pick(c, b, t, T, out_words, out_gates, st));
+    if (t + 1 < T) VSR_TRY(launch_commit_identity(c, b, nullptr, 0, -1, st));
+  }
+  return VSR_OK;
+}
+
+}  // namespace vsr
+
+// ============================================================================ C ABI
+using vsr::Ctx;
+
+extern "C" {
+
+const char* vsr_last_error(void) { return vsr::g_err; }
+int32_t vsr_abi_version(void) { return VSR_ABI_VERSION; }
+
+int vsr_create(const VsrDims* dims, const float* const* weights, vsr_handle* out) {
+  if (out == nullptr) { vsr::set_error("vsr_create: null out"); return VSR_EINVAL; }
+  *out = nullptr;
+  Ctx* c = nullptr;
+  const int r = vsr::create_impl(dims, weights, &c);
+  if (r != VSR_OK) { if (c) vsr_destroy((vsr_handle)c); return r; }
+  *out = (vsr_handle)c;
+  return VSR_OK;
+}
+
+int vsr_load_weights(vsr_handle h, const float* const* weights, void* stream) {
+  if (!h || !weights) { vsr::set_error("vsr_load_weights: null argument"); return VSR_EINVAL; }
+  return vsr::pack_weights((Ctx*)h, weights, (cudaStream_t)stream);
+}
+
+void vsr_destroy(vsr_handle h) {
+  if (!h) return;
+  Ctx* c = (Ctx*)h;
+  cudaDeviceSynchronize();
+  vsr::reset_phases(c);
+  for (void* p : c->owned) cudaFree(p);
+  delete c;
+}
+
+int vsr_set_verb_table(vsr_handle h, const int64_t* keys, const int32_t* offsets, const int32_t* vocab_idx,
+                       int32_t n_keys) {
+  if (!h) { vsr::set_error("vsr_set_verb_table: null handle"); return VSR_EINVAL; }
+  Ctx* c = (Ctx*)h;
+  VSR_CHECK_CUDA(cudaDeviceSynchronize());
+  vsr::dev_free(c, c->vt_keys); vsr::dev_free(c, c->vt_off); vsr::dev_free(c, c->vt_idx);
+  c->vt_keys = nullptr; c->vt_off = nullptr; c->vt_idx = nullptr; c->vt_n = 0;
+  if (n_keys <= 0) return VSR_OK;
+  VSR_REQUIRE(keys && offsets && vocab_idx, VSR_EINVAL, "vsr_set_verb_table: null table");
+  for (int i = 1; i < n_keys; ++i)
+    VSR_REQUIRE(keys[i] > keys[i - 1], VSR_EINVAL, "vsr_set_verb_table: keys must be strictly increasing");
+  VSR_REQUIRE(offsets[0] == 0, VSR_EINVAL, "vsr_set_verb_table: offsets[0] must be 0");
+  for (int i = 0; i < n_keys; ++i)
+    VSR_REQUIRE(offsets[i + 1] >= offsets[i], VSR_EINVAL, "vsr_set_verb_table: offsets must be non-decreasing");
+  const int nnz = offsets[n_keys];
+  for (int i = 0; i < nnz; ++i)
+    VSR_REQUIRE(vocab_idx[i] >= 0 && vocab_idx[i] < c->V, VSR_EINVAL, "vsr_set_verb_table: vocab index %d out of range", vocab_idx[i]);
+  VSR_TRY(vsr::dev_alloc(c, (void**)&c->vt_keys, sizeof(int64_t) * n_keys, false));
+  VSR_TRY(vsr::dev_alloc(c, (void**)&c->vt_off, sizeof(int32_t) * (n_keys + 1), false));
+  VSR_TRY(vsr::dev_alloc(c, (void**)&c->vt_idx, sizeof(int32_t) * std::max(nnz, 1), false));
+  VSR_CHECK_CUDA(cudaMemcpy(c->vt_keys, keys, sizeof(int64_t) * n_keys, cudaMemcpyHostToDevice));
+  VSR_CHECK_CUDA(cudaMemcpy(c->vt_off, offsets, sizeof(int32_t) * (n_keys + 1), cudaMemcpyHostToDevice));
+  if (nnz > 0) VSR_CHECK_CUDA(cudaMemcpy(c->vt_idx, vocab_idx, sizeof(int32_t) * nnz, cudaMemcpyHostToDevice));
+  c->vt_n = n_keys;
+  return VSR_OK;
+}
+
+int vsr_prologue(vsr_handle h, const float* det, int64_t det_batch_stride, int32_t D, const float* det_seqs,
+                 int32_t b, int32_t L, int32_t R, const void* verbs, int32_t verbs_dtype, void* stream) {
+  if (!h) { vsr::set_error("vsr_prologue: null handle"); return VSR_EINVAL; }
+  return vsr::prologue_impl((Ctx*)h, det, det_batch_stride, D, det_seqs, b, L, R, verbs, verbs_dtype,
+                            (cudaStream_t)stream);
+}
+
+int vsr_step(vsr_handle h, const float* h1, const float* c1, const float* h2, const float* c2,
+             const int64_t* slot, const int64_t* word, int32_t use_verbs, int32_t gt, float* h1o, float* c1o,
+             float* h2o, float* c2o, float* out_logp, float* gate_logp, void* stream) {
+  if (!h) { vsr::set_error("vsr_step: null handle"); return VSR_EINVAL; }
+  return vsr::step_impl((Ctx*)h, h1, c1, h2, c2, slot, word, use_verbs, gt, h1o, c1o, h2o, c2o, out_logp,
+                        gate_logp, (cudaStream_t)stream);
+}
+
+int vsr_beam_search(vsr_handle h, int32_t beam_size, int32_t out_size, const int64_t* eos_idxs,
+                    int32_t use_verbs, int32_t gt, int64_t* out_words, int64_t* out_gates, float* lp_words,
+                    float* lp_gates, const VsrTrace* trace, void* stream) {
+  if (!h) { vsr::set_error("vsr_beam_search: null handle"); return VSR_EINVAL; }
+  return vsr::beam_search_impl((Ctx*)h, beam_size, out_size, eos_idxs, use_verbs, gt, out_words, out_gates,
+                               lp_words, lp_gates, trace, (cudaStream_t)stream);
+}
+
+int vsr_get_history(vsr_handle h, int32_t* parent, int32_t* word, int32_t* gate, float* score, void* stream) {
+  if (!h) { vsr::set_error("vsr_get_history: null handle"); return VSR_EINVAL; }
+  Ctx* c = (Ctx*)h;
+  VSR_REQUIRE(c->hist_T > 0, VSR_ESTATE, "vsr_get_history: no beam search has run on this handle");
+  const size_t n = (size_t)c->hist_T * c->hist_b * c->hist_k;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (parent) VSR_CHECK_CUDA(cudaMemcpyAsync(parent, c->hist_parent, n * 4, cudaMemcpyDeviceToDevice, st));
+  if (word) VSR_CHECK_CUDA(cudaMemcpyAsync(word, c->hist_word, n * 4, cudaMemcpyDeviceToDevice, st));
+  if (gate) VSR_CHECK_CUDA(cudaMemcpyAsync(gate, c->hist_gate, n * 4, cudaMemcpyDeviceToDevice, st));
+  if (score) VSR_CHECK_CUDA(cudaMemcpyAsync(score, c->hist_score, n * 4, cudaMemcpyDeviceToDevice, st));
+  return VSR_OK;
+}
+
+int vsr_forward_teacher(vsr_handle h, const int64_t* captions, int32_t T, float* out, float* gate, void* stream) {
+  if (!h) { vsr::set_error("vsr_forward_teacher: null handle"); return VSR_EINVAL; }
+  return vsr::forward_impl((Ctx*)h, captions, T, out, gate, (cudaStream_t)stream);
+}
+
+int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* stream) {
+  if (!h) { vsr::set_error("vsr_greedy: null handle"); return VSR_EINVAL; }
+  return vsr::greedy_impl((Ctx*)h, out_words, out_gates, (cudaStream_t)stream);
+}
+
+int64_t vsr_launch_count(vsr_handle h) { return h ? ((Ctx*)h)->launches : -1; }
+
+int vsr_set_profiling(vsr_handle h, int32_t enabled) {
+  if (!h) { vsr::set_error("vsr_set_profiling: null handle"); return VSR_EINVAL; }
+  Ctx* c = (Ctx*)h;
+  c->profiling = enabled != 0;
+  vsr::reset_phases(c);
+  return VSR_OK;
+}
+
+int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* launches, int32_t cap) {
+  if (!h) { vsr::set_error("vsr_get_phase_times: null handle"); return VSR_EINVAL; }
+  Ctx* c = (Ctx*)h;
+  VSR_CHECK_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (int i = 0; i < vsr::PH_COUNT && n < cap; ++i) {
+    float total = 0.f;
+    const auto& ev = c->phases[i].ev;
+    for (size_t j = 0; j + 1 < ev.size(); j += 2) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, ev[j], ev[j + 1]) == cudaSuccess) total += t;
+    }
+    if (names) names[n] = c->phases[i].name;
+    if (ms) ms[n] = total;
+    if (launches) launches[n] = c->phases[i].launches;
+    ++n;
+  }
+  return n;
+}
+
+}  // extern "C"

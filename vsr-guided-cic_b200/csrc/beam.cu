@@ -1,0 +1,332 @@
+// Beam expansion without host synchronisation: joint (word, gate) top-k per caption over
+// cur_beam x (k word candidates) x (2 gates), sticky EOS masks, back-pointer history, beam-state
+// reorder, and the final sort + back-track.
+// Reference: models/CaptioningModel.py:116-195 (beam_search), :197-294 (beam_search_v),
+// :78-114 (_select_beam).  Statics are never copied per beam: rows index
+// them by caption = row / beam.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace vsr {
+
+namespace {
+
+__device__ __forceinline__ bool before(float v1, int i1, float v2, int i2) {
+  return v1 > v2 || (v1 == v2 && i1 < i2);
+}
+
+// log-prob of vocabulary entry `word` in row `row` as returned by the step (post verb forcing)
+__device__ __forceinline__ float row_logp(const float* logits, int ld, const float* row_max,
+                                          const float* row_lsum, const int32_t* forced, int row, int word) {
+  const int f = forced[row];
+  if (f >= 0) return word == f ? 0.f : -1e6f;
+  return (logits[(size_t)row * ld + word] - row_max[row]) - row_lsum[row];
+}
+
+struct BeamArgs {
+  int t, b, cur, k, V;
+  int64_t eos0, eos1;
+  const float* logits; int ld;
+  const float* row_max; const float* row_lsum; const int32_t* forced; const int32_t* cand;
+  const float* gate_lp;
+  const float* seq_lp; float* seq_lp_n;
+  float *m0, *m1, *m0n, *m1n;
+  int32_t *sel_beam, *sel_word, *sel_gate;        // in: previous step's picks (t>0); out: this step's
+  int32_t *hist_parent, *hist_word, *hist_gate;    // [T][b][k] slices for step t
+  float *hist_score, *hist_lpw, *hist_lpg;
+  const int32_t *f_beam, *f_word, *f_gate;        // forced selections for step t or null
+};
+
+constexpr int MAXC = 2 * VSR_MAX_BEAM * VSR_MAX_BEAM;  // 128 candidates per caption
+
+// one warp per caption
+__global__ void __launch_bounds__(32) k_beam_select(const BeamArgs a) {
+  const int c = blockIdx.x, lane = threadIdx.x;
+  const int k = a.k, cur = a.cur;
+  __shared__ float s_seq[VSR_MAX_BEAM], s_m0[VSR_MAX_BEAM], s_m1[VSR_MAX_BEAM];
+  __shared__ int s_full[VSR_MAX_BEAM];
+  __shared__ int s_pb[VSR_MAX_BEAM], s_pw[VSR_MAX_BEAM], s_pg[VSR_MAX_BEAM];
+  __shared__ float s_ps[VSR_MAX_BEAM];
+
+  if (lane < cur) {
+    float m0 = 1.f, m1 = 1.f, seq = 0.f;
+    if (a.t > 0) {
+      // sticky masks: a head's mask drops to 0 once the slot's previous token was its EOS (:143-144)
+      seq = a.seq_lp[c * k + lane];
+      m0 = a.m0[c * k + lane] * ((int64_t)a.sel_word[c * k + lane] != a.eos0 ? 1.f : 0.f);
+      m1 = a.m1[c * k + lane] * ((int64_t)a.sel_gate[c * k + lane] != a.eos1 ? 1.f : 0.f);
+    }
+    s_seq[lane] = seq; s_m0[lane] = m0; s_m1[lane] = m1;
+    s_full[lane] = (a.t == 0) ? 1 : (fminf(fmaxf(m0 + m1, 0.f), 1.f) != 0.f);
+  }
+  __syncwarp();
+
+  if (a.f_beam == nullptr) {
+    // candidates: idx = (parent j, i-th word candidate, gate g); lane owns idx = lane + 32*q
+    float cs[MAXC / 32]; int cf[MAXC / 32]; bool used[MAXC / 32];
+    const int ncand = cur * k * 2;
+#pragma unroll
+    for (int q = 0; q < MAXC / 32; ++q) {
+      const int idx = lane + 32 * q;
+      cs[q] = -INFINITY; cf[q] = 0x7fffffff; used[q] = true;
+      if (idx < ncand) {
+        const int j = idx / (2 * k), i = (idx >> 1) % k, g = idx & 1;
+        const int row = c * cur + j;
+        int word; float sc;
+        if (s_full[j]) {
+          word = a.cand[row * VSR_MAX_BEAM + i];
+          const float wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+          sc = __fadd_rn(s_seq[j], __fadd_rn(wl, a.gate_lp[row * 2 + g]));   // seq + (word + gate), :139
+        } else {
+          // frozen beam: old score at word 0 (both gates), -999 elsewhere (:146-150)
+          word = i;
+          sc = (i == 0) ? s_seq[j] : -999.f;
+        }
+        cs[q] = sc; cf[q] = j * 2 * a.V + word * 2 + g; used[q] = false;
+      }
+    }
+    for (int sel = 0; sel < k; ++sel) {
+      float bv = -INFINITY; int bf = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < MAXC / 32; ++q)
+        if (!used[q] && before(cs[q], cf[q], bv, bf)) { bv = cs[q]; bf = cf[q]; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int of = __shfl_xor_sync(0xffffffffu, bf, o);
+        if (before(ov, of, bv, bf)) { bv = ov; bf = of; }
+      }
+#pragma unroll
+      for (int q = 0; q < MAXC / 32; ++q) if (cf[q] == bf) used[q] = true;
+      if (lane == 0) {
+        const int j = bf / (2 * a.V), rem = bf - j * 2 * a.V;
+        s_pb[sel] = j; s_pw[sel] = rem >> 1; s_pg[sel] = rem & 1; s_ps[sel] = bv;
+      }
+    }
+  } else if (lane < k) {
+    // trajectory replay: take the given selection, score it with this run's own numbers
+    const int j = a.f_beam[c * k + lane], word = a.f_word[c * k + lane], g = a.f_gate[c * k + lane];
+    const int row = c * cur + j;
+    float sc;
+    if (s_full[j]) {
+      const float wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+      sc = __fadd_rn(s_seq[j], __fadd_rn(wl, a.gate_lp[row * 2 + g]));
+    } else {
+      sc = (word == 0) ? s_seq[j] : -999.f;
+    }
+    s_pb[lane] = j; s_pw[lane] = word; s_pg[lane] = g; s_ps[lane] = sc;
+  }
+  __syncwarp();
+
+  if (lane < k) {
+    const int j = s_pb[lane], word = s_pw[lane], g = s_pg[lane];
+    const int row = c * cur + j;
+    const int o = c * k + lane;
+    // per-token log-probs of the pick, in slot order, masked by the parent's sticky masks (:145,175-177)
+    float lw = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+    float lg = a.gate_lp[row * 2 + g];
+    if (a.t > 0) { lw *= s_m0[j]; lg *= s_m1[j]; }
+    a.sel_beam[o] = j; a.sel_word[o] = word; a.sel_gate[o] = g;
+    a.seq_lp_n[o] = s_ps[lane];
+    a.m0n[o] = s_m0[j]; a.m1n[o] = s_m1[j];
+    a.hist_parent[o] = j; a.hist_word[o] = word; a.hist_gate[o] = g;
+    a.hist_score[o] = s_ps[lane]; a.hist_lpw[o] = lw; a.hist_lpg[o] = lg;
+  }
+}
+
+// ---------------------------------------------------------------- state advance / reorder
+struct AdvanceArgs {
+  int rows_new, cur, k;            // new row n' = c*k + i ; parent row = c*cur + parent[n'] (or n' if null)
+  const int32_t* parent;
+  const int32_t* word32;           // next input token per new row ...
+  const int64_t* word64; int64_t word64_stride;   // ... or int64 strided (teacher forcing)
+  const int32_t* gate32;           // slot shift per new row, or null
+  int fixed_slot;                  // >= 0: set the pointer to this slot (teacher forcing)
+  int L, Hp, Ep, V;
+  const float *h1n, *c1n, *h2n, *c2n;
+  float *h1, *c1, *h2, *c2, *xt;
+  const int32_t* ptr; int32_t* ptrn;
+  const float* embed;
+};
+
+__global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
+  const int n = blockIdx.x;
+  const int c = n / a.k;
+  const int p = a.parent != nullptr ? c * a.cur + a.parent[n] : n;
+  const size_t so = (size_t)p * a.Hp, dof = (size_t)n * a.Hp;
+  for (int i = threadIdx.x * 4; i < a.Hp; i += 256 * 4) {
+    *reinterpret_cast<float4*>(a.h1 + dof + i) = *reinterpret_cast<const float4*>(a.h1n + so + i);
+    *reinterpret_cast<float4*>(a.c1 + dof + i) = *reinterpret_cast<const float4*>(a.c1n + so + i);
+    *reinterpret_cast<float4*>(a.h2 + dof + i) = *reinterpret_cast<const float4*>(a.h2n + so + i);
+    *reinterpret_cast<float4*>(a.c2 + dof + i) = *reinterpret_cast<const float4*>(a.c2n + so + i);
+  }
+  int64_t w = a.word32 != nullptr ? (int64_t)a.word32[n] : a.word64[(size_t)n * a.word64_stride];
+  w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
+  const float* er = a.embed + (size_t)w * a.Ep;
+  for (int i = threadIdx.x * 4; i < a.Ep; i += 256 * 4)
+    *reinterpret_cast<float4*>(a.xt + (size_t)n * a.Ep + i) = *reinterpret_cast<const float4*>(er + i);
+  if (threadIdx.x == 0) {
+    int s;
+    if (a.fixed_slot >= 0) s = a.fixed_slot;
+    else {
+      s = a.ptr[p] + (a.gate32 != nullptr ? a.gate32[n] : 0);   // ctrl_det_idxs + prev gate, clamped
+      s = s < 0 ? 0 : (s > a.L - 1 ? a.L - 1 : s);             // (controllable_captioning.py:139-140)
+    }
+    a.ptrn[n] = s;
+  }
+}
+
+// zero state, slot 0, xt = embed[bos]   (init_state, controllable_captioning.py:109-115, :136)
+__global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, float* xt, int32_t* ptr,
+                             const float* embed, int bos, int Hp, int Ep) {
+  const int n = blockIdx.x;
+  for (int i = threadIdx.x; i < Hp; i += blockDim.x) {
+    h1[(size_t)n * Hp + i] = 0.f; c1[(size_t)n * Hp + i] = 0.f;
+    h2[(size_t)n * Hp + i] = 0.f; c2[(size_t)n * Hp + i] = 0.f;
+  }
+  for (int i = threadIdx.x; i < Ep; i += blockDim.x) xt[(size_t)n * Ep + i] = embed[(size_t)bos * Ep + i];
+  if (threadIdx.x == 0) ptr[n] = 0;
+}
+
+__global__ void k_embed(const int64_t* words, float* xt, const float* embed, int Ep, int V) {
+  const int n = blockIdx.x;
+  int64_t w = words[n];
+  w = w < 0 ? 0 : (w >= V ? V - 1 : w);
+  for (int i = threadIdx.x; i < Ep; i += blockDim.x) xt[(size_t)n * Ep + i] = embed[(size_t)w * Ep + i];
+}
+
+// greedy pick of both heads (CaptioningModel.test, CaptioningModel.py:47): first maximum wins
+__global__ void k_greedy_pick(const int32_t* cand, const float* gate_lp, int32_t* sel_word,
+                              int32_t* sel_gate, int64_t* out_words, int64_t* out_gates, int rows,
+                              int t, int T) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  const int w = cand[n * VSR_MAX_BEAM];
+  const int g = gate_lp[n * 2 + 1] > gate_lp[n * 2 + 0] ? 1 : 0;
+  sel_word[n] = w; sel_gate[n] = g;
+  out_words[(size_t)n * T + t] = w; out_gates[(size_t)n * T + t] = g;
+}
+
+// final ordering of the beams by accumulated score (stable, descending) and unroll of the
+// back-pointers (CaptioningModel.py:182-194 / 279-293).  One thread per caption.
+__global__ void k_backtrack(int b, int k, int T, int out_size, const float* seq_lp,
+                            const int32_t* hist_parent, const int32_t* hist_word,
+                            const int32_t* hist_gate, const float* hist_lpw, const float* hist_lpg,
+                            int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= b) return;
+  int order[VSR_MAX_BEAM];
+  for (int i = 0; i < k; ++i) order[i] = i;
+  for (int i = 1; i < k; ++i) {   // insertion sort, stable, descending
+    const int oi = order[i];
+    const float v = seq_lp[c * k + oi];
+    int j = i - 1;
+    while (j >= 0 && seq_lp[c * k + order[j]] < v) { order[j + 1] = order[j]; --j; }
+    order[j + 1] = oi;
+  }
+  for (int o = 0; o < out_size; ++o) {
+    const int final_slot = order[o];
+    int slot = final_slot;
+    const size_t ob = ((size_t)c * out_size + o) * T;
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t hi = ((size_t)t * b + c) * k;
+      out_words[ob + t] = hist_word[hi + slot];
+      out_gates[ob + t] = hist_gate[hi + slot];
+      // log-probs are NOT back-tracked: slot order at step t, permuted by the final sort only
+      lp_words[ob + t] = hist_lpw[hi + final_slot];
+      lp_gates[ob + t] = hist_lpg[hi + final_slot];
+      slot = hist_parent[hi + slot];
+    }
+  }
+}
+
+}  // namespace
+
+int launch_state_init(Ctx* c, int rows, cudaStream_t st) {
+  k_state_init<<<rows, 256, 0, st>>>(c->h1, c->c1, c->h2, c->c2, c->xt, c->ptr, c->embed, c->d.bos_idx,
+                                     c->Hp, c->Ep);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
+  k_embed<<<rows, 256, 0, st>>>(words, c->xt, c->embed, c->Ep, c->V);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+int launch_beam_select(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1,
+                       const int32_t* f_beam, const int32_t* f_word, const int32_t* f_gate,
+                       cudaStream_t st) {
+  PhaseScope ps(c, PH_BEAM, st);
+  BeamArgs a{};
+  a.t = t; a.b = b; a.cur = cur; a.k = k; a.V = c->V; a.eos0 = eos0; a.eos1 = eos1;
+  a.logits = c->logits; a.ld = c->NE; a.row_max = c->row_max; a.row_lsum = c->row_lsum;
+  a.forced = c->forced; a.cand = c->cand; a.gate_lp = c->gate_lp;
+  a.seq_lp = c->seq_lp; a.seq_lp_n = c->seq_lp_n;
+  a.m0 = c->m0; a.m1 = c->m1; a.m0n = c->m0n; a.m1n = c->m1n;
+  a.sel_beam = c->sel_beam; a.sel_word = c->sel_word; a.sel_gate = c->sel_gate;
+  const size_t off = (size_t)t * b * k;
+  a.hist_parent = c->hist_parent + off; a.hist_word = c->hist_word + off; a.hist_gate = c->hist_gate + off;
+  a.hist_score = c->hist_score + off; a.hist_lpw = c->hist_lpw + off; a.hist_lpg = c->hist_lpg + off;
+  a.f_beam = f_beam; a.f_word = f_word; a.f_gate = f_gate;
+  k_beam_select<<<b, 32, 0, st>>>(a);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  std::swap(c->seq_lp, c->seq_lp_n);
+  std::swap(c->m0, c->m0n);
+  std::swap(c->m1, c->m1n);
+  return VSR_OK;
+}
+
+static int launch_advance(Ctx* c, AdvanceArgs& a, cudaStream_t st) {
+  a.L = c->L; a.Hp = c->Hp; a.Ep = c->Ep; a.V = c->V;
+  a.h1n = c->h1n; a.c1n = c->c1n; a.h2n = c->h2n; a.c2n = c->c2n;
+  a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2; a.xt = c->xt;
+  a.ptr = c->ptr; a.ptrn = c->ptrn; a.embed = c->embed;
+  k_advance<<<a.rows_new, 256, 0, st>>>(a);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  std::swap(c->ptr, c->ptrn);
+  return VSR_OK;
+}
+
+int launch_reorder(Ctx* c, int b, int cur, int k, cudaStream_t st) {
+  PhaseScope ps(c, PH_REORDER, st);
+  AdvanceArgs a{};
+  a.rows_new = b * k; a.cur = cur; a.k = k;
+  a.parent = c->sel_beam; a.word32 = c->sel_word; a.gate32 = c->sel_gate; a.fixed_slot = -1;
+  return launch_advance(c, a, st);
+}
+
+int launch_commit_identity(Ctx* c, int rows, const int64_t* next_words, int64_t word_stride,
+                           int next_slot, cudaStream_t st) {
+  PhaseScope ps(c, PH_REORDER, st);
+  AdvanceArgs a{};
+  a.rows_new = rows; a.cur = 1; a.k = 1;
+  a.parent = nullptr;
+  if (next_words != nullptr) { a.word64 = next_words; a.word64_stride = word_stride; a.gate32 = nullptr; }
+  else { a.word32 = c->sel_word; a.gate32 = c->sel_gate; }
+  a.fixed_slot = next_slot;
+  return launch_advance(c, a, st);
+}
+
+int launch_greedy_pick(Ctx* c, int rows, int t, int T, int64_t* out_words, int64_t* out_gates,
+                       cudaStream_t st) {
+  PhaseScope ps(c, PH_BEAM, st);
+  k_greedy_pick<<<(rows + 127) / 128, 128, 0, st>>>(c->cand, c->gate_lp, c->sel_word, c->sel_gate,
+                                                    out_words, out_gates, rows, t, T);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+int launch_backtrack(Ctx* c, int b, int k, int T, int out_size, int64_t* out_words,
+                     int64_t* out_gates, float* lp_words, float* lp_gates, cudaStream_t st) {
+  PhaseScope ps(c, PH_FINAL, st);
+  k_backtrack<<<(b + 63) / 64, 64, 0, st>>>(b, k, T, out_size, c->seq_lp, c->hist_parent, c->hist_word,
+                                            c->hist_gate, c->hist_lpw, c->hist_lpg, out_words, out_gates,
+                                            lp_words, lp_gates);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+}  // namespace vsr

@@ -1,0 +1,192 @@
+// Shared declarations of libvsrdec: context, packed-weight layout, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/vsrdec.h"
+
+namespace vsr {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+#define VSR_CHECK_CUDA(expr)                                                                 \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      vsr::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,                   \
+                     cudaGetErrorString(_e));                                                \
+      return VSR_ECUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+#define VSR_REQUIRE(cond, code, ...)                                                         \
+  do {                                                                                       \
+    if (!(cond)) {                                                                           \
+      vsr::set_error(__VA_ARGS__);                                                           \
+      return (code);                                                                         \
+    }                                                                                        \
+  } while (0)
+#define VSR_TRY(expr)                                                                        \
+  do {                                                                                       \
+    int _r = (expr);                                                                         \
+    if (_r != VSR_OK) return _r;                                                             \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// K (reduction) dims are padded to KPAD floats (one 128-byte swizzle row of fp32), output-feature
+// dims to NPAD rows, activation row counts to MPAD rows; pads are zero so they never contribute.
+constexpr int KPAD = 32;
+constexpr int NPAD = 128;
+constexpr int MPAD = 128;
+
+// ---------------------------------------------------------------- GEMM (C = sum_seg A_seg * W_seg^T + ...)
+struct GemmSeg {
+  const float* a;   // [M][lda] activations, K contiguous
+  int lda;
+  int k;            // padded K of this segment in the weight layout (multiple of KPAD)
+  int k_valid;      // readable columns of a (multiple of 4, <= k); the rest reads as zero
+};
+struct GemmArgs {
+  GemmSeg seg[3];
+  int nseg;
+  const float* w;   // [N][ldw] packed weights, K contiguous, segments back to back
+  int ldw;
+  const float* bias;    // [N] or null
+  const float* rowadd;  // [(row / row_div) * rowadd_mul][ld_rowadd] added per row, or null
+  int ld_rowadd, row_div, rowadd_mul;
+  const float* cadd;    // [M][ld_cadd] added element-wise, or null
+  int ld_cadd;
+  float* c;             // [M][ldc]
+  int ldc;
+  int M, N;             // N multiple of NPAD
+  const uint8_t* row_skip;  // optional [M]: a 64-row tile whose flags are all 0 is skipped
+};
+int launch_gemm(const GemmArgs& g, cudaStream_t st);
+
+// ---------------------------------------------------------------- context
+struct Phase {
+  const char* name;
+  std::vector<cudaEvent_t> ev;  // start/stop pairs recorded during the last decode
+  int launches = 0;
+};
+
+enum PhaseId {
+  PH_PROLOGUE = 0, PH_GEMM_A, PH_LSTM1, PH_GEMM_B, PH_GT, PH_GEMM_C, PH_ATTEND, PH_GEMM_D, PH_LSTM2,
+  PH_GEMM_E, PH_SOFTMAX_TOPK, PH_BEAM, PH_REORDER, PH_FINAL, PH_COUNT
+};
+
+struct Ctx {
+  VsrDims d;
+  int device;
+  // model dims and padded dims
+  int V, E, H, F, A;
+  int Hp, Ep, Fp, Ap;          // K-padded
+  int NA, NB1, NB2, NC, ND, NE;  // padded output widths of the stacked GEMMs
+  int KA;                      // [h2 (Hp, if h2_first) | xt (Ep) | h1 (Hp)]
+  int KD;                      // [att (Fp) | h2 (Hp)]
+  // column offsets of the stacked output blocks (KPAD-aligned so float4 epilogues stay aligned)
+  int oB1_sa;                  // sent:  sentinel at 0 (F) | sa at oB1_sa (A)
+  int oB2_ha, oB2_p2;          // hb:    hg at 0 (H) | ha at oB2_ha (A) | pre2_h1 at oB2_p2 (4H)
+  // packed weights
+  float *WA, *WU, *bU;         // [NA][KA], [NA][Fp], [NA]   rows: i,f,g,o (4H) | s (H) | g (H)
+  float *WB1, *bB1;            // [NB1][Hp]: s_fc (F) | att_sa (A)
+  float *WB2;                  // [NB2][Hp]: W1_hg (H) | att_ha (A) | lstm2.W_ih[:, :H] (4H)
+  float *WC;                   // [NC][Hp]: att_ga
+  float *WD, *bD;              // [ND][KD]: lstm2.W_ih[:, H:H+F] | lstm2.W_hh ; b_ih2 + b_hh2
+  float *WU2;                  // [ND][Fp]: lstm2.W_ih[:, H+F:H+2F] (img_second_lstm) or null
+  float *WE, *bE;              // [NE][Hp]: out_fc
+  float *Wva;                  // [Ap128][Fp]: att_va
+  float *v_a, *v_s, *v_g;      // [Ap]
+  float *embed;                // [V][Ep]
+  int NVA;                     // padded rows of Wva
+  // verb table (device CSR)
+  int64_t* vt_keys = nullptr; int32_t* vt_off = nullptr; int32_t* vt_idx = nullptr; int vt_n = 0;
+  // prologue products (per batch)
+  bool have_prologue = false;
+  int b = 0, D = 0, L = 0, R = 0, n_img = 0;
+  const float* det_seqs = nullptr;
+  const void* verbs = nullptr; int verbs_dtype = 0;
+  float* img = nullptr;        // [n_img_alloc][Fp]
+  float* U = nullptr;          // [n_img_alloc][NA]
+  float* U2 = nullptr;         // [n_img_alloc][ND]
+  float* P = nullptr;          // [b*L*R (alloc)][NVA] att_va projections
+  uint8_t* seq_valid = nullptr;  // [b*L*R]
+  uint8_t* det_valid = nullptr;  // [n_img*D]
+  size_t cap_img = 0, cap_P = 0, cap_detv = 0;
+  // per-row workspace (rows = captions * beam), capacity cap_rows (multiple of MPAD)
+  int cap_rows = 0;
+  float *h1, *c1, *h2, *c2;          // current state [rows][Hp]
+  float *h1n, *c1n, *h2n, *c2n;      // state produced by the step
+  float *xt;                         // [rows][Ep]
+  int32_t *ptr, *ptrn;               // slot pointer per row
+  float *pre1;                       // [rows][NA]
+  float *s_t, *g_t;                  // [rows][Hp]
+  float *sent;                       // [rows][NB1] sentinel (F) | sa (A)
+  float *hb;                         // [rows][NB2] hg (H) | ha (A) | pre2_h1 (4H)
+  float *ga;                         // [rows][NC]
+  float *att;                        // [rows][Fp]
+  float *pre2;                       // [rows][ND]
+  float *logits;                     // [rows][NE]
+  float *gate_lp;                    // [rows][2]
+  float *row_max, *row_lsum;         // [rows]
+  int32_t *forced;                   // [rows] forced vocab idx or -1
+  int32_t *cand;                     // [rows][VSR_MAX_BEAM]
+  // beam workspace
+  int cap_caps = 0, cap_T = 0;
+  float *seq_lp, *seq_lp_n;          // [caps][beam]
+  float *m0, *m1, *m0n, *m1n;        // sticky EOS masks [caps][beam]
+  int32_t *sel_beam, *sel_word, *sel_gate;  // [caps][beam] selections of the current step
+  int32_t *hist_parent, *hist_word, *hist_gate;  // [T][caps][beam]
+  float *hist_score, *hist_lpw, *hist_lpg;       // [T][caps][beam]
+  int hist_T = 0, hist_b = 0, hist_k = 0;
+  int64_t* word_in = nullptr;        // [rows] scratch (teacher forcing / step)
+  // bookkeeping
+  int64_t launches = 0;
+  bool profiling = false;
+  Phase phases[PH_COUNT];
+  std::vector<void*> owned;          // every cudaMalloc'd pointer (freed in destroy)
+};
+
+int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero = true);
+
+struct PhaseScope {  // records start/stop events around a phase when profiling is on
+  Ctx* c; int id; cudaStream_t st;
+  PhaseScope(Ctx* c_, int id_, cudaStream_t st_);
+  ~PhaseScope();
+};
+
+// ---------------------------------------------------------------- kernels (defined in *.cu)
+int pack_weights(Ctx* c, const float* const* w, cudaStream_t st);
+int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st);
+int ensure_rows(Ctx* c, int rows);
+int ensure_beam_ws(Ctx* c, int caps, int T);
+
+struct StepIO {
+  int rows;          // rows processed this step
+  int cur_beam;      // rows per caption
+  bool use_verbs, gt;
+  float* out_logp;   // optional full log-prob rows
+  int64_t out_stride;
+  float* gate_out;   // optional (rows,2) post-forcing gate log-probs
+  int64_t gate_stride;
+  int topk;          // number of word candidates to extract per row (0 = none)
+};
+int run_step(Ctx* c, const StepIO& io, cudaStream_t st);
+
+int launch_state_init(Ctx* c, int rows, cudaStream_t st);
+int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st);
+int launch_beam_select(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1,
+                       const int32_t* f_beam, const int32_t* f_word, const int32_t* f_gate,
+                       cudaStream_t st);
+int launch_reorder(Ctx* c, int b, int cur, int k, cudaStream_t st);
+int launch_backtrack(Ctx* c, int b, int k, int T, int out_size, int64_t* out_words,
+                     int64_t* out_gates, float* lp_words, float* lp_gates, cudaStream_t st);
+int launch_commit_identity(Ctx* c, int rows, const int64_t* next_words, int64_t word_stride,
+                           int next_slot, cudaStream_t st);
+int launch_greedy_pick(Ctx* c, int rows, int t, int T, int64_t* out_words, int64_t* out_gates,
+                       cudaStream_t st);
+
+}  // namespace vsr

@@ -1,0 +1,210 @@
+// Weight packing and the once-per-batch prologue (time-invariant terms of step()/step_v()).
+//
+// Hoisted out of the per-step path:
+//   img[b]   = sum_d det[b,d,:] / #{d : sum_f det[b,d,f] != 0}   controllable_captioning.py:126-128, 203-205
+//   valid    = (sum_f x != 0) for every slot row                  :159, :240
+//   P[b,l,r] = att_va.weight . det_seqs[b,l,r,:]                   :161, :242
+//   U[b]     = S1[:, img cols] . img[b] + stacked biases           :151-152, :181 (img part of input_1)
+//   U2[b]    = lstm_cell_2.weight_ih[:, img cols] . img[b]         :174 (img_second_lstm only)
+#include "common.cuh"
+
+namespace vsr {
+
+namespace {
+
+// dst[r0+r][c0+c] = src[r][sc0+c]
+__global__ void k_pack_block(float* __restrict__ dst, int ld_dst, int r0, int c0,
+                             const float* __restrict__ src, int ld_src, int sc0, int rows, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c < cols && r < rows) dst[(size_t)(r0 + r) * ld_dst + c0 + c] = src[(size_t)r * ld_src + sc0 + c];
+}
+
+// dst[o0+i] = a[i] (+ b[i])
+__global__ void k_pack_bias(float* __restrict__ dst, int o0, const float* __restrict__ a,
+                            const float* __restrict__ b, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[o0 + i] = a[i] + (b != nullptr ? b[i] : 0.f);
+}
+
+// one warp per row: flag[row] = (sum_f x[row][f] != 0).  Row r of image/caption g lives at
+// base + g*group_stride + (r % rows_per_group)*F.
+__global__ void k_row_valid(const float* __restrict__ x, int64_t group_stride, int rows_per_group,
+                            int total_rows, int F, uint8_t* __restrict__ flag) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const float* p = x + (size_t)(row / rows_per_group) * group_stride + (size_t)(row % rows_per_group) * F;
+  float s = 0.f;
+  for (int f = lane * 4; f < F; f += 128) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + f));
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) flag[row] = (s != 0.f) ? 1 : 0;
+}
+
+// img[g][f] = sum_d det[g][d][f] / count(valid rows of g); one thread per float4 column.
+__global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D, int F,
+                       const uint8_t* __restrict__ valid, float* __restrict__ img, int ld_img) {
+  const int g = blockIdx.y;
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (f >= F) return;
+  const float* p = det + (size_t)g * img_stride + f;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int d = 0; d < D; ++d) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)d * F));
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    cnt += valid[g * D + d];
+  }
+  const float n = (float)cnt;
+  *reinterpret_cast<float4*>(img + (size_t)g * ld_img + f) = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
+}
+
+}  // namespace
+
+static int pack_block(Ctx* c, float* dst, int ld_dst, int r0, int c0, const float* src, int ld_src,
+                      int sc0, int rows, int cols, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return VSR_OK;
+  dim3 grid((cols + 255) / 256, rows);
+  k_pack_block<<<grid, 256, 0, st>>>(dst, ld_dst, r0, c0, src, ld_src, sc0, rows, cols);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  c->launches++;
+  return VSR_OK;
+}
+static int pack_bias(Ctx* c, float* dst, int o0, const float* a, const float* b, int n, cudaStream_t st) {
+  k_pack_bias<<<(n + 255) / 256, 256, 0, st>>>(dst, o0, a, b, n);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  c->launches++;
+  return VSR_OK;
+}
+
+// Build the stacked, K-padded weight blocks S1..S7 of SURVEY.md Appendix A from the 28
+// state_dict tensors (order documented in include/vsrdec.h).
+int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
+  const int H = c->H, E = c->E, F = c->F, A = c->A, V = c->V;
+  const int Hp = c->Hp, Ep = c->Ep;
+  const bool h2f = c->d.h2_first_lstm != 0, img2 = c->d.img_second_lstm != 0;
+  const int in1 = (h2f ? H : 0) + F + E;
+  const int in2 = H + F + (img2 ? F : 0);
+  const int c_img = h2f ? H : 0;        // column of the img block inside input_1
+  const int c_xt = c_img + F;           // column of the xt block
+  // column offsets inside WA's K axis
+  const int ka_h2 = 0, ka_xt = h2f ? Hp : 0, ka_h1 = ka_xt + Ep;
+
+  // all packed buffers were zero-filled at allocation; re-zero for repacks
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WA, 0, sizeof(float) * (size_t)c->NA * c->KA, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WU, 0, sizeof(float) * (size_t)c->NA * c->Fp, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->bU, 0, sizeof(float) * (size_t)c->NA, st));
+
+  // ---- S1 / S2 -> WA, WU, bU.  Row blocks: lstm1 gates i,f,g,o (4H) | W1_is (H) | W1_ig (H)
+  struct Blk { const float* wi; const float* wh; const float* bi; const float* bh; int rows; int r0; bool h_on_old; };
+  const Blk blks[3] = {
+      {w[10], w[11], w[12], w[13], 4 * H, 0, true},      // lstm_cell_1: W_ih, W_hh act on (input_1, h1_old)
+      {w[1], w[3], w[2], w[4], H, 4 * H, true},          // W1_is(input_1) + W1_hs(h1_old)      (:151)
+      {w[22], nullptr, w[23], w[25], H, 5 * H, false}};  // W1_ig(input_1); W1_hg acts on h1' (:181) -> WB2
+  for (const Blk& k : blks) {
+    if (h2f) VSR_TRY(pack_block(c, c->WA, c->KA, k.r0, ka_h2, k.wi, in1, 0, k.rows, H, st));
+    VSR_TRY(pack_block(c, c->WA, c->KA, k.r0, ka_xt, k.wi, in1, c_xt, k.rows, E, st));
+    if (k.h_on_old) VSR_TRY(pack_block(c, c->WA, c->KA, k.r0, ka_h1, k.wh, H, 0, k.rows, H, st));
+    VSR_TRY(pack_block(c, c->WU, c->Fp, k.r0, 0, k.wi, in1, c_img, k.rows, F, st));
+    VSR_TRY(pack_bias(c, c->bU, k.r0, k.bi, k.bh, k.rows, st));
+  }
+  // ---- S3 -> WB1: s_fc (F rows) | att_sa (A rows)
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WB1, 0, sizeof(float) * (size_t)c->NB1 * Hp, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->bB1, 0, sizeof(float) * (size_t)c->NB1, st));
+  VSR_TRY(pack_block(c, c->WB1, Hp, 0, 0, w[20], H, 0, F, H, st));
+  VSR_TRY(pack_block(c, c->WB1, Hp, c->oB1_sa, 0, w[8], H, 0, A, H, st));
+  VSR_TRY(pack_bias(c, c->bB1, 0, w[21], nullptr, F, st));
+  // ---- S4 -> WB2: W1_hg (H) | att_ha (A) | lstm2.W_ih[:, 0:H] (4H)
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WB2, 0, sizeof(float) * (size_t)c->NB2 * Hp, st));
+  VSR_TRY(pack_block(c, c->WB2, Hp, 0, 0, w[24], H, 0, H, H, st));
+  VSR_TRY(pack_block(c, c->WB2, Hp, c->oB2_ha, 0, w[6], H, 0, A, H, st));
+  VSR_TRY(pack_block(c, c->WB2, Hp, c->oB2_p2, 0, w[14], in2, 0, 4 * H, H, st));
+  // ---- S5 -> WC: att_ga
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WC, 0, sizeof(float) * (size_t)c->NC * Hp, st));
+  VSR_TRY(pack_block(c, c->WC, Hp, 0, 0, w[26], H, 0, A, H, st));
+  // ---- S6 -> WD: lstm2.W_ih[:, H:H+F] | lstm2.W_hh ; bias b_ih2 + b_hh2
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WD, 0, sizeof(float) * (size_t)c->ND * c->KD, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->bD, 0, sizeof(float) * (size_t)c->ND, st));
+  VSR_TRY(pack_block(c, c->WD, c->KD, 0, 0, w[14], in2, H, 4 * H, F, st));
+  VSR_TRY(pack_block(c, c->WD, c->KD, 0, c->Fp, w[15], H, 0, 4 * H, H, st));
+  VSR_TRY(pack_bias(c, c->bD, 0, w[16], w[17], 4 * H, st));
+  if (img2) {
+    VSR_CHECK_CUDA(cudaMemsetAsync(c->WU2, 0, sizeof(float) * (size_t)c->ND * c->Fp, st));
+    VSR_TRY(pack_block(c, c->WU2, c->Fp, 0, 0, w[14], in2, H + F, 4 * H, F, st));
+  }
+  // ---- S7 -> WE: out_fc
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WE, 0, sizeof(float) * (size_t)c->NE * Hp, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->bE, 0, sizeof(float) * (size_t)c->NE, st));
+  VSR_TRY(pack_block(c, c->WE, Hp, 0, 0, w[18], H, 0, V, H, st));
+  VSR_TRY(pack_bias(c, c->bE, 0, w[19], nullptr, V, st));
+  // ---- att_va, attention vectors, embedding
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->Wva, 0, sizeof(float) * (size_t)c->NVA * c->Fp, st));
+  VSR_TRY(pack_block(c, c->Wva, c->Fp, 0, 0, w[5], F, 0, A, F, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->v_a, 0, sizeof(float) * c->Ap, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->v_s, 0, sizeof(float) * c->Ap, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->v_g, 0, sizeof(float) * c->Ap, st));
+  VSR_TRY(pack_bias(c, c->v_a, 0, w[7], nullptr, A, st));
+  VSR_TRY(pack_bias(c, c->v_s, 0, w[9], nullptr, A, st));
+  VSR_TRY(pack_bias(c, c->v_g, 0, w[27], nullptr, A, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->embed, 0, sizeof(float) * (size_t)V * Ep, st));
+  VSR_TRY(pack_block(c, c->embed, Ep, 0, 0, w[0], E, 0, V, E, st));
+  return VSR_OK;
+}
+
+int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) {
+  PhaseScope ps(c, PH_PROLOGUE, st);
+  const int F = c->F, D = c->D, b = c->b, L = c->L, R = c->R;
+  const int n_img = c->n_img;
+  // validity of detection rows and slot rows
+  {
+    const int rows = n_img * D;
+    k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    const int srows = b * L * R;
+    k_row_valid<<<(int)(((size_t)srows * 32 + 255) / 256), 256, 0, st>>>(c->det_seqs, (int64_t)L * R * F, L * R,
+                                                                          srows, F, c->seq_valid);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    c->launches += 2;
+  }
+  // image descriptor
+  {
+    dim3 grid((F / 4 + 127) / 128, n_img);
+    k_pool<<<grid, 128, 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    c->launches++;
+  }
+  // U = WU . img + biases ; U2 likewise
+  {
+    GemmArgs g{};
+    g.nseg = 1; g.seg[0] = {c->img, c->Fp, c->Fp, c->Fp};
+    g.w = c->WU; g.ldw = c->Fp; g.bias = c->bU;
+    g.c = c->U; g.ldc = c->NA; g.M = n_img; g.N = c->NA;
+    VSR_TRY(launch_gemm(g, st));
+    c->launches++;
+    if (c->d.img_second_lstm) {
+      GemmArgs g2{};
+      g2.nseg = 1; g2.seg[0] = {c->img, c->Fp, c->Fp, c->Fp};
+      g2.w = c->WU2; g2.ldw = c->Fp;
+      g2.c = c->U2; g2.ldc = c->ND; g2.M = n_img; g2.N = c->ND;
+      VSR_TRY(launch_gemm(g2, st));
+      c->launches++;
+    }
+  }
+  // P = att_va . det_seqs rows (tiles of padding rows are skipped)
+  {
+    GemmArgs g{};
+    g.nseg = 1; g.seg[0] = {c->det_seqs, F, c->Fp, F};
+    g.w = c->Wva; g.ldw = c->Fp;
+    g.c = c->P; g.ldc = c->NVA; g.M = b * L * R; g.N = c->NVA;
+    g.row_skip = c->seq_valid;
+    VSR_TRY(launch_gemm(g, st));
+    c->launches++;
+  }
+  return VSR_OK;
+}
+
+}  // namespace vsr

@@ -1,0 +1,4 @@
+"""Host-side binding of libvsrdec.so (C ABI: include/vsrdec.h) for the role-shift decoder path."""
+from ._lib import load_library, library_path, VsrError, EXPORTED_SYMBOLS  # noqa: F401
+from .engine import DecoderEngine, PARAM_NAMES  # noqa: F401
+from .sharding import shard_range, decode_sharded  # noqa: F401
