@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — captions/sec of the role-shift decoder's beam search on synthetic COCO-Entities-shaped
+batches (BASELINE.json metric), on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE full beam-search decode of one batch: the once-per-batch prologue, the 20 decoder
+steps (beam 5) and the final back-track, through the reference-facing call
+`ControllableCaptioningModel.beam_search_v` of the drop-in `models` package (-> ctypes -> libvsrdec).
+Workload = BASELINE config 2 (eval_coco.py --gt shape): 100 captions x beam 5, <=50 detections
+x 2048-d, 10 slots x 20 regions, V = 10000, random-init weights.  Multi-GPU = weak scaling:
+every rank decodes its own 100-caption batch, then the finished captions are all-gathered.
+
+`--impl reference` times the CPU port of the reference's algorithm (oracle/vsr_oracle.py, torch CPU
+ops, all host threads) on a bounded sample of the same workload; the reference itself is Python
+and is not present on the GPU box.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "vsr-guided-cic_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(name="coco_entities_eval_gt(config2)", b=100, beam=5, D=50, L=10, R=20, F=2048, V=10000,
+                T=20, eos=[3, -1], gt=True)
+METRIC = "captions/sec beam-search decode (COCO-Entities shape)"
+CPU_SAMPLE_B = 10   # captions per CPU-port step (bounded sample of the 100-caption batch)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_tflops=p["bf16_tflops"],
+                    bf16_tflops_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+def make_inputs(rank: int):
+    from tools.synth import synth_inputs
+    w = WORKLOAD
+    return synth_inputs(w["b"], w["D"], w["L"], w["R"], w["F"], seed=1002 + rank, vocab_size=w["V"],
+                        n_det_range=(10, 50), verb_slots=(2,), verb_vocab_id=17)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if t0 - 0.05 <= ts <= t1 + 0.15 and len(r) >= 8] or \
+               [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in rows for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        f = lambda x: float(x) if x.replace(".", "", 1).isdigit() else None
+        sm = [f(r[1]) for r in rows if f(r[1]) is not None]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": f(rows[0][2]),
+                "power_w_max": max([f(r[3]) or 0.0 for r in rows]), "samples": len(rows), "reasons": reasons}
+
+
+# ------------------------------------------------------------------------------------------- CPU port
+def run_cpu_port(steps, warmup, sample_b):
+    """Times the oracle (CPU restatement of the reference's algorithm) on `sample_b` captions of the
+    workload per step.  Returns (captions_per_s, ms_per_step, cores)."""
+    from oracle import vsr_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = WORKLOAD
+    d = O.Dims(seq_len=w["T"], vocab_size=w["V"])
+    W = O.init_weights(d, seed=1234)
+    det, ds, verbs = make_inputs(0)
+    statics = (det[:sample_b], ds[:sample_b], verbs[:sample_b])
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.beam_search(W, d, statics, w["eos"], w["beam"], 1, use_verbs=True, gt=w["gt"])
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return sample_b * len(times) / total, 1e3 * total / len(times), cores
+
+
+def main_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = args.steps, args.warmup
+    cps, ms, cores = run_cpu_port(steps, warmup, CPU_SAMPLE_B)
+    sample = (f"{CPU_SAMPLE_B} of the {WORKLOAD['b']} captions of the workload per step, beam {WORKLOAD['beam']}, "
+              f"{WORKLOAD['T']} decoder steps; torch CPU ops, {cores} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "captions/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD["name"], "captions_per_step": CPU_SAMPLE_B, "beam": WORKLOAD["beam"],
+                       "vocab": WORKLOAD["V"], "decoder_steps": WORKLOAD["T"]},
+            "cpu_baseline": {"value": cps, "unit": "captions/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": cps, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def gemm_flops_per_row_step(dims):
+    """Algorithmic FLOPs (2*K*N_out) of the per-step dense contractions in the hoisted formulation
+    (SURVEY.md §8d): A = [h2|xt]->6H + h1->5H, B = s_t->(F+A) + h1'->(H+A+4H), C = g_t->A,
+    D = [att|h2]->4H, E = h2'->V."""
+    H, E, F, A, V = dims["H"], dims["E"], dims["F"], dims["A"], dims["V"]
+    return {"gemm_a_lstm1_gates": 2 * ((H + E) * 6 * H + H * 5 * H),
+            "gemm_b_sentinel_h1proj": 2 * (H * (F + A) + H * (H + A + 4 * H)),
+            "gemm_c_att_ga": 2 * H * A,
+            "gemm_d_lstm2_gates": 2 * (F + H) * 4 * H,
+            "gemm_e_vocab": 2 * H * V}
+
+
+def main_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from models import ControllableCaptioningModel
+    w = WORKLOAD
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    torch.manual_seed(1234)                       # the eval scripts' seed (eval_coco.py:22)
+    model = ControllableCaptioningModel(w["T"], w["V"], 2, verb_tables=({}, {})).to(dev).eval()
+    det, ds, verbs = make_inputs(rank)
+    host = [t.pin_memory() for t in (det, ds, verbs)]
+    dev_in = tuple(t.to(dev) for t in host)
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host)
+
+    def gather(words):
+        if world == 1:
+            return words
+        bufs = [torch.empty_like(words) for _ in range(world)]
+        dist.all_gather(bufs, words)
+        return torch.cat(bufs, 0)
+
+    def decode(statics):
+        (words, gates), (lpw, lpg) = model.beam_search_v(statics, w["eos"], w["beam"], 1, gt=w["gt"])
+        return gather(words), gates, lpw
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time via CUDA events, max over ranks."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        barrier()
+        t0 = time.time()
+        ev[0].record()
+        for i in range(steps):
+            fn()
+            ev[i + 1].record()
+        barrier()
+        t1 = time.time()
+        total = ev[0].elapsed_time(ev[-1])
+        per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        if world > 1:
+            tt = torch.tensor([total], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total = float(tt)
+        return total, per, t0, t1
+
+    for _ in range(args.warmup):
+        decode(dev_in)
+    eng = model._eng
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    l0 = eng.launch_count()
+    total_ms, per_ms, t0, t1 = timed(lambda: decode(dev_in), args.steps)
+    launches = eng.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * w["b"] * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host (pinned) inputs -> H2D -> decode through the public API -> D2H of the captions
+    result = {}
+
+    def e2e_step():
+        statics = tuple(t.to(dev, non_blocking=True) for t in host)
+        words, gates, lpw = decode(statics)
+        result["words"] = words.cpu()            # device->host read of the step's result (syncs)
+        result["gates"] = gates.cpu()
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t_e0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t_e0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt)
+    e2e_value = world * w["b"] * args.steps / e2e_s
+    d2h_bytes = int(result["words"].numel() * 8 + result["gates"].numel() * 8)
+
+    # ---- per-kernel times: the same K steps repeated with the library's CUDA-event phase profiler
+    # (events on the launching stream around every phase of every decoder step)
+    phase_acc, prof_ms = {}, None
+    if rank == 0:
+        eng.set_profiling(True)
+        prof_total = 0.0
+        n_prof = min(args.steps, 5)
+        for _ in range(n_prof):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            model.beam_search_v(dev_in, w["eos"], w["beam"], 1, gt=w["gt"])
+            e1.record()
+            torch.cuda.synchronize(dev)
+            prof_total += e0.elapsed_time(e1)
+            for name, ms, calls in eng.phase_times():
+                a = phase_acc.setdefault(name, [0.0, 0])
+                a[0] += ms
+                a[1] += calls
+        eng.set_profiling(False)
+        prof_ms = prof_total / n_prof
+        # slot pointer trajectory of the last decode -> exact bytes the attention kernel had to read
+        parent, word, gate, score = [x.cpu() for x in eng.history()]
+    barrier()
+
+    if rank == 0:
+        T, b, k = parent.shape
+        dims = dict(H=1000, E=1000, F=w["F"], A=512, V=w["V"])
+        rows_total = b * 1 + b * k * (T - 1)                     # row-steps per decode
+        fl = gemm_flops_per_row_step(dims)
+        gemm_names = list(fl.keys())
+        gemm_ms = sum(phase_acc[n][0] for n in gemm_names) / n_prof
+        gemm_flops = sum(fl.values()) * rows_total
+        gemm_calls = sum(phase_acc[n][1] for n in gemm_names) / n_prof
+        achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        gemm_kind = eng_gemm_kind()
+        # TF32 tensor peak = half the measured bf16 figure (B200_PROFILING.md); fp32 FFMA kernels are
+        # reported against the same tensor denominator since that is the roofline the path must reach
+        peak_tf = peaks["bf16_tflops_sustained"] / 2.0
+        roofline = {"kernel": gemm_kind["kernel"], "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": gemm_kind.get("traffic"),
+                    "peak_source": f"{peaks['source']} bf16_tflops_sustained/2 (tf32-rate denominator)",
+                    "flops_per_decode": gemm_flops, "ms_per_decode": gemm_ms, "launches_per_decode": gemm_calls,
+                    "share_of_step": gemm_ms / prof_ms, "passes": gemm_kind["passes"],
+                    "timing": f"CUDA events around every GEMM phase, {n_prof} profiled repeats of the timed step"}
+        # attention kernel against the HBM roofline
+        ptr = torch.zeros((b, 1), dtype=torch.long)
+        nvalid = (ds.sum(-1) != 0).sum(-1)                       # (b, L) valid regions per slot
+        att_bytes = 0
+        for t in range(T):
+            cur = ptr.size(1)
+            nv = torch.gather(nvalid, 1, ptr)                    # (b, cur)
+            att_bytes += int((nv * (dims["F"] + dims["A"]) * 4).sum()) + b * cur * ((dims["F"] + 3 * dims["A"] + dims["H"]) * 4 + (dims["F"] + 2) * 4)
+            ptr = torch.clamp(torch.gather(ptr, 1, parent[t].long()) + gate[t].long(), 0, w["L"] - 1)
+        att_ms = phase_acc["attend_gate"][0] / n_prof
+        att_gbs = att_bytes / (att_ms * 1e-3) / 1e9
+        roofline_att = {"kernel": "k_attend (slot attention + shift gate)", "bound": "hbm", "achieved": att_gbs,
+                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": att_gbs / peaks["hbm_gbs"], "traffic": None,
+                        "bytes_per_decode": att_bytes, "ms_per_decode": att_ms,
+                        "note": "beams of one caption mostly share a slot tile, so L2 serves the repeats"}
+        cpu_cps, cpu_ms, cores = run_cpu_port(1, 1, CPU_SAMPLE_B) if world == 1 and not args.no_cpu_baseline else (None, None, None)
+        line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": w["name"], "captions_per_gpu": w["b"], "beam": w["beam"], "vocab": w["V"],
+                           "decoder_steps": w["T"], "detections": w["D"], "slots": w["L"], "regions_per_slot": w["R"],
+                           "parallelism": f"caption-sharded x{world} (weights replicated, one all_gather of captions)",
+                           "l2": "per-step working set (inputs 0.21 GB + weights 0.29 GB) exceeds the 126 MB L2; no flush"},
+                "p50_step_latency_ms": statistics.median(per_ms) / w["T"],
+                "p50_decode_ms": statistics.median(per_ms),
+                "gpu_launches": int(launches) * world,
+                "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e2e_s / args.steps},
+                "roofline": roofline, "roofline_attend": roofline_att,
+                "phases_ms_per_decode": {n: v[0] / n_prof for n, v in phase_acc.items()},
+                "profiled_ms_per_step": prof_ms,
+                "clocks": clocks}
+        if cpu_cps is not None:
+            line["cpu_baseline"] = {"value": cpu_cps, "unit": "captions/s", "cores": cores, "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_B} of the {w['b']} captions, 1 warm-up + 1 timed decode "
+                                              f"of oracle/vsr_oracle.py (torch CPU ops, {cores} threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def eng_gemm_kind():
+    """Which GEMM implementation the library was built with (for the roofline annotation)."""
+    return {"kernel": "k_gemm_simt (fp32 FFMA, all five per-step GEMM phases)", "passes": 1, "traffic": None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        main_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the decoder path has no CPU fallback "
+                         "(use --impl reference for the CPU port)")
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    main_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

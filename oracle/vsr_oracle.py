@@ -437,56 +437,8 @@ def new_trace() -> BeamTrace:
 
 
 # --------------------------------------------------------------------------- synthetic inputs
-
-def synth_inputs(b: int, D: int, L: int, R: int, Fd: int, seed: int, vocab_size: int,
-                 n_det_range: Tuple[int, int] = None, real_slots: Tuple[int, int] = (4, 8),
-                 verb_slots: Sequence[int] = (2,), verb_vocab_id: Optional[int] = 17,
-                 verb_id_range: Optional[Tuple[int, int]] = None, one_region_slots: bool = False):
-    """Synthetic COCO/Flickr30k-Entities-shaped decoder inputs (SURVEY.md §8d recipe).
-
-    Features are relu(randn) (non-negative like Faster-RCNN pool5 features, so an all-zero
-    row is exactly a padding row); each slot has ``n_valid ~ U{1..R}`` non-zero rows; verb
-    slots hold one row = mean of the image's valid detections (data/field.py:460,517);
-    slots after the last real one repeat it and carry verb -1 (eval_coco.py:231-237).
-    Returns det (b,D,F) f32, det_seqs (b,L,R,F) f32, verbs (b,L) f64.
-    """
-    g = torch.Generator().manual_seed(seed)
-    det = torch.relu(torch.randn((b, D, Fd), generator=g))
-    if n_det_range is not None:
-        n_det = torch.randint(n_det_range[0], n_det_range[1] + 1, (b,), generator=g)
-        for i in range(b):
-            det[i, int(n_det[i]):] = 0
-    det_seqs = torch.zeros((b, L, R, Fd))
-    verbs = -torch.ones((b, L), dtype=torch.float64)
-    n_real = torch.randint(real_slots[0], min(real_slots[1], L) + 1, (b,), generator=g)
-    for i in range(b):
-        nr = int(n_real[i])
-        valid_rows = det[i][det[i].sum(-1) != 0]
-        for l in range(nr):
-            if l in verb_slots:
-                det_seqs[i, l, 0] = valid_rows.mean(0)
-                if verb_id_range is not None:
-                    verbs[i, l] = float(torch.randint(verb_id_range[0], verb_id_range[1], (1,), generator=g))
-                else:
-                    verbs[i, l] = float(verb_vocab_id if verb_vocab_id is not None else 0)
-            else:
-                nv = 1 if one_region_slots else int(torch.randint(1, R + 1, (1,), generator=g))
-                pick = torch.randint(0, valid_rows.size(0), (nv,), generator=g)
-                det_seqs[i, l, :nv] = valid_rows[pick]
-        det_seqs[i, nr:] = det_seqs[i, nr - 1]
-    return det, det_seqs, verbs
-
-
-def synth_verb_table(n_verbs: int, vocab_size: int, seed: int) -> Dict[str, List[int]]:
-    """Synthetic verb -> vocabulary-forms table in the JSON shape the reference loads
-    (controllable_captioning.py:25-34): {str(verb_id): [vocab idx, ...]}; some verbs have an
-    empty list and some ids are absent to exercise the fallback (:291-292)."""
-    g = torch.Generator().manual_seed(seed)
-    table = {}
-    for v in range(n_verbs):
-        r = int(torch.randint(0, 10, (1,), generator=g))
-        if r == 0:
-            continue            # missing key
-        n = 0 if r == 1 else int(torch.randint(1, 7, (1,), generator=g))
-        table[str(v)] = [int(x) for x in torch.randint(0, vocab_size, (n,), generator=g)]
-    return table
+# (shared with bench.py's product leg, which may not import oracle/: they live in tools/synth.py)
+import os as _os
+import sys as _sys
+_sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
+from tools.synth import synth_inputs, synth_verb_table  # noqa: E402,F401

@@ -1,0 +1,151 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/vsrdec.h declares,
+the drop-in class surface matches the reference's, host logic (sharding, error paths)."""
+import inspect
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "vsrdec.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vsr_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    import vsrdec
+    declared = _header_functions()
+    assert len(declared) >= 14
+    assert sorted(vsrdec.EXPORTED_SYMBOLS) == declared          # binding table == header
+    lib = vsrdec.load_library()                                  # binds each one (AttributeError if missing)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.vsr_abi_version() == 1
+    out = subprocess.run(["nm", "-D", "--defined-only", vsrdec.library_path()], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (vsr_[a-z_0-9]+)", out))
+    assert set(declared) <= exported
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device (or with CPU tensors) the product path must fail loudly."""
+    import vsrdec
+    from models import ControllableCaptioningModel
+    m = ControllableCaptioningModel(20, 157, 2, 96, 36, 50, 20, verb_tables=({}, {}))
+    statics = (torch.zeros(2, 3, 96), torch.zeros(2, 4, 5, 96), -torch.ones(2, 4))
+    with pytest.raises(vsrdec.VsrError):
+        m.beam_search_v(statics, [3, -1], 3)
+    with pytest.raises(vsrdec.VsrError):
+        m((statics[0],), (torch.zeros(2, 4, dtype=torch.long), torch.zeros(2, 4, 5, 96)))
+    if not torch.cuda.is_available():
+        lib = vsrdec.load_library()
+        import ctypes
+        from vsrdec._lib import VsrDims
+        h = ctypes.c_void_p()
+        d = VsrDims(20, 157, 2, 96, 36, 50, 20, 1, 0)
+        arr = (ctypes.c_void_p * 28)()
+        assert lib.vsr_create(ctypes.byref(d), arr, ctypes.byref(h)) < 0
+        assert b"no CPU fallback" in lib.vsr_last_error() or b"CUDA" in lib.vsr_last_error()
+
+
+def test_class_surface_matches_reference_signatures():
+    from models import ControllableCaptioningModel, _CaptioningModel
+    sig = inspect.signature(ControllableCaptioningModel.__init__)
+    names = [p for p in sig.parameters][:11]
+    assert names == ["self", "seq_len", "vocab_size", "bos_idx", "det_feat_size", "input_encoding_size",
+                     "rnn_size", "att_size", "h2_first_lstm", "img_second_lstm", "dataset"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["det_feat_size"], d["input_encoding_size"], d["rnn_size"], d["att_size"]) == (2048, 1000, 1000, 512)
+    assert d["h2_first_lstm"] is True and d["img_second_lstm"] is False and d["dataset"] == "coco"
+    for meth in ("init_state", "step", "step_v", "forward", "test", "sample_rl", "beam_search", "beam_search_v",
+                 "_select_beam", "_select_beam_i", "init_weights"):
+        assert hasattr(ControllableCaptioningModel, meth)
+    assert inspect.signature(_CaptioningModel.beam_search_v).parameters["gt"].default is False
+    assert inspect.signature(ControllableCaptioningModel.step).parameters["mode"].default == "teacher_forcing"
+    # state_dict layout == the oracle's restatement of the reference's (28 tensors, same order/shapes)
+    from oracle import vsr_oracle as O
+    for flags in ((True, False), (False, True)):
+        dims = O.Dims(20, 157, 2, 96, 36, 50, 20, *flags)
+        m = ControllableCaptioningModel(20, 157, 2, 96, 36, 50, 20, flags[0], flags[1], verb_tables=({}, {}))
+        assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == list(O.param_shapes(dims).items())
+    # missing verb tables raise like the reference (files are CWD-relative)
+    with pytest.raises(FileNotFoundError):
+        ControllableCaptioningModel(20, 157, 2, 96, 36, 50, 20)
+
+
+def test_init_weights_stream_matches_oracle():
+    """Same seed -> same random-init weights as the reference's constructor (via the oracle's restatement)."""
+    from models import ControllableCaptioningModel
+    from oracle import vsr_oracle as O
+    dims = O.Dims(20, 157, 2, 96, 36, 50, 20)
+    torch.manual_seed(5)
+    m = ControllableCaptioningModel(20, 157, 2, 96, 36, 50, 20, verb_tables=({}, {}))
+    W = O.init_weights(dims, seed=5)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, W[k]), k
+
+
+def test_select_beam_matches_gather_semantics():
+    from models import ControllableCaptioningModel
+    m = ControllableCaptioningModel(20, 157, 2, 96, 36, 50, 20, verb_tables=({}, {}))
+    b, cur, k = 3, 4, 4
+    x = torch.arange(b * cur * 5, dtype=torch.float32).view(b * cur, 5)
+    sel = torch.tensor([[3, 0, 0, 1], [2, 2, 1, 0], [0, 1, 2, 3]])
+    out = m._select_beam_i(x, sel, cur, k, b)
+    ref = torch.gather(x.view(b, cur, 5), 1, sel.view(b, k, 1).expand(b, k, 5)).view(b * k, 5)
+    assert torch.equal(out, ref)
+    nested = m._select_beam([(x, x), x], sel, cur, k, b)
+    assert torch.equal(nested[0][1], ref) and torch.equal(nested[1], ref)
+    y = x.view(b, cur, 5)
+    assert torch.equal(m._select_beam_i(y, sel, cur, k, b, reduced=False), ref.view(b, k, 5))
+
+
+def test_shard_range_partitions():
+    from vsrdec import shard_range
+    for n in (1, 7, 100, 101):
+        for world in (1, 2, 3, 8):
+            blocks = [shard_range(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [h - l for l, h in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "vsr-guided-cic_b200"))
+from vsrdec import decode_sharded, shard_range
+from oracle import vsr_oracle as O
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+d = O.Dims(seq_len=6, vocab_size=61, bos_idx=2, det_feat_size=32, input_encoding_size=12, rnn_size=14, att_size=8)
+W = O.init_weights(d, seed=3)
+det, ds, verbs = O.synth_inputs(5, 6, 4, 5, 32, seed=11, vocab_size=61, real_slots=(2, 4), verb_slots=(1,), verb_vocab_id=7)
+def decode(lo, hi):      # test-only stand-in for the device decode: the oracle on this rank's block
+    with torch.no_grad():
+        o, lp = O.beam_search(W, d, (det[lo:hi], ds[lo:hi], verbs[lo:hi]), [3, -1], 3, 1, use_verbs=True, gt=True)
+    return o[0], o[1], lp[0]
+words, gates, lpw = decode_sharded(decode, 5, rank, 2)
+fw, fg, fl = decode(0, 5)
+assert torch.equal(words, fw) and torch.equal(gates, fg) and torch.equal(lpw, fl), "sharded != unsharded"
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_sharded_decode_world2_gloo(tmp_path):
+    """N>1 host path on CPU: 2 ranks over gloo, caption blocks decoded independently and all-gathered
+    must equal the unsharded decode bit-for-bit (rows are independent units)."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

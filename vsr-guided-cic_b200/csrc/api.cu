@@ -171,6 +171,7 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
   VSR_REQUIRE(((uintptr_t)det % 16) == 0 && ((uintptr_t)det_seqs % 16) == 0 && (det_stride % 4) == 0, VSR_EINVAL,
               "vsr_prologue: feature tensors must be 16-byte aligned");
   c->have_prologue = false;
+  if (c->profiling) reset_phases(c);   // a decode job starts here
   c->b = b; c->D = D; c->L = L; c->R = R;
   c->n_img = det_stride == 0 ? 1 : b;
   c->det_seqs = det_seqs; c->verbs = verbs; c->verbs_dtype = verbs_dtype;
@@ -264,7 +265,6 @@ static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int
   const int b = c->b, T = c->d.seq_len;
   VSR_TRY(ensure_rows(c, b * k));
   VSR_TRY(ensure_beam_ws(c, b, T));
-  if (c->profiling) reset_phases(c);
   c->hist_T = T; c->hist_b = b; c->hist_k = k;
   VSR_TRY(launch_state_init(c, b, st));
   const bool have_forced = tr && tr->forced_beam && tr->forced_word && tr->forced_gate;
@@ -292,7 +292,6 @@ static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, floa
   VSR_REQUIRE(T >= 1 && T <= c->L, VSR_EINVAL, "vsr_forward_teacher: T=%d exceeds the prologue's slot count L=%d", T, c->L);
   const int b = c->b;
   VSR_TRY(ensure_rows(c, b));
-  if (c->profiling) reset_phases(c);
   VSR_TRY(launch_state_init(c, b, st));
   // the first input token is captions[:, 0], not bos (controllable_captioning.py:131-133)
   for (int t = 0; t < T; ++t) {
@@ -318,7 +317,6 @@ static int greedy_impl(Ctx* c, int64_t* out_words, int64_t* out_gates, cudaStrea
   const int b = c->b, T = c->d.seq_len;
   VSR_TRY(ensure_rows(c, b));
   VSR_TRY(ensure_beam_ws(c, b, T));
-  if (c->profiling) reset_phases(c);
   VSR_TRY(launch_state_init(c, b, st));
   for (int t = 0; t < T; ++t) {
     StepIO io{};
