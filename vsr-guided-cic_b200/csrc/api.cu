@@ -1,6 +1,7 @@
 // C-ABI entry points of libvsrdec (include/vsrdec.h): context life-cycle, workspace
 // management and the decode drivers (beam search, teacher-forced forward, greedy, single step).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -66,6 +67,19 @@ static void reset_phases(Ctx* c) {
 
 #define ALLOC_F(ptr, count) VSR_TRY(dev_alloc(c, (void**)&(ptr), sizeof(float) * (size_t)(count)))
 
+// (re)allocate a bf16 hi/lo twin of a [rows][ld] fp32 matrix and build its TMA tensor maps
+static int alloc_pair(Ctx* c, Bf16Pair* b, int rows, int ld, int box_rows) {
+  dev_free(c, b->hi); dev_free(c, b->lo);
+  b->hi = b->lo = nullptr;
+  if (!c->use_tc) return VSR_OK;
+  VSR_TRY(dev_alloc(c, &b->hi, (size_t)rows * ld * 2));
+  VSR_TRY(dev_alloc(c, &b->lo, (size_t)rows * ld * 2));
+  b->rows = rows; b->ld = ld; b->box_rows = box_rows;
+  VSR_TRY(make_tmap_bf16(b->map_hi, b->hi, rows, ld, ld, box_rows));
+  VSR_TRY(make_tmap_bf16(b->map_lo, b->lo, rows, ld, ld, box_rows));
+  return VSR_OK;
+}
+
 int ensure_rows(Ctx* c, int rows) {
   if (rows <= c->cap_rows) return VSR_OK;
   const int cap = round_up(rows, MPAD);
@@ -89,6 +103,10 @@ int ensure_rows(Ctx* c, int rows) {
   VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->cand, sizeof(int32_t) * n * VSR_MAX_BEAM));
   VSR_TRY(dev_alloc(c, (void**)&c->word_in, sizeof(int64_t) * n));
+  VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD));
+  VSR_TRY(alloc_pair(c, &c->xt_b, cap, c->Ep, MPAD)); VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD));
+  VSR_TRY(alloc_pair(c, &c->h1n_b, cap, c->Hp, MPAD)); VSR_TRY(alloc_pair(c, &c->g_t_b, cap, c->Hp, MPAD));
+  VSR_TRY(alloc_pair(c, &c->att_b, cap, c->Fp, MPAD)); VSR_TRY(alloc_pair(c, &c->h2n_b, cap, c->Hp, MPAD));
   c->cap_rows = cap;
   return VSR_OK;
 }
@@ -156,6 +174,14 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   ALLOC_F(c->Wva, (size_t)c->NVA * c->Fp);
   ALLOC_F(c->v_a, c->Ap); ALLOC_F(c->v_s, c->Ap); ALLOC_F(c->v_g, c->Ap);
   ALLOC_F(c->embed, (size_t)c->V * c->Ep);
+  {
+    const char* mode = getenv("VSRDEC_GEMM");   // "simt": fp32 FFMA twin for A/B verification of the tcgen05 path
+    c->use_tc = !(mode != nullptr && strcmp(mode, "simt") == 0);
+  }
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, NPAD)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, NPAD));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, NPAD)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, NPAD));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, NPAD)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, NPAD));
+  VSR_TRY(alloc_pair(c, &c->embed_b, c->V, c->Ep, 8));
   VSR_TRY(pack_weights(c, w, 0));
   VSR_CHECK_CUDA(cudaStreamSynchronize(0));
   return VSR_OK;
@@ -242,6 +268,11 @@ static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, 
   k_slots_from_i64<<<(b + 127) / 128, 128, 0, st>>>(c->ptr, slot, b, c->L);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   VSR_TRY(launch_embed(c, word, b, st));
+  if (c->use_tc) {
+    VSR_TRY(launch_split_bf16(c->h1, c->h1_b.hi, c->h1_b.lo, (size_t)b * c->Hp, st));
+    VSR_TRY(launch_split_bf16(c->h2, c->h2_b.hi, c->h2_b.lo, (size_t)b * c->Hp, st));
+    c->launches += 2;
+  }
   StepIO io{};
   io.rows = b; io.cur_beam = 1; io.use_verbs = use_verbs != 0; io.gt = gt != 0;
   io.out_logp = out_logp; io.out_stride = c->V; io.gate_out = gate_logp; io.gate_stride = 2; io.topk = 0;

@@ -4,6 +4,7 @@
 // Reference: models/CaptioningModel.py:116-195 (beam_search), :197-294 (beam_search_v),
 // :78-114 (_select_beam).  Statics are never copied per beam: rows index
 // them by caption = row / beam.
+#include <cuda_bf16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -148,6 +149,9 @@ struct AdvanceArgs {
   float *h1, *c1, *h2, *c2, *xt;
   const int32_t* ptr; int32_t* ptrn;
   const float* embed;
+  // bf16 hi/lo twins (null on the fp32 path): 16-byte vectors of 8 bf16
+  const uint4 *h1n_hi, *h1n_lo, *h2n_hi, *h2n_lo, *emb_hi, *emb_lo;
+  uint4 *h1_hi, *h1_lo, *h2_hi, *h2_lo, *xt_hi, *xt_lo;
 };
 
 __global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
@@ -166,6 +170,17 @@ __global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
   const float* er = a.embed + (size_t)w * a.Ep;
   for (int i = threadIdx.x * 4; i < a.Ep; i += 256 * 4)
     *reinterpret_cast<float4*>(a.xt + (size_t)n * a.Ep + i) = *reinterpret_cast<const float4*>(er + i);
+  if (a.h1_hi != nullptr) {
+    const size_t sv = (size_t)p * (a.Hp / 8), dv = (size_t)n * (a.Hp / 8);
+    for (int i = threadIdx.x; i < a.Hp / 8; i += 256) {
+      a.h1_hi[dv + i] = a.h1n_hi[sv + i]; a.h1_lo[dv + i] = a.h1n_lo[sv + i];
+      a.h2_hi[dv + i] = a.h2n_hi[sv + i]; a.h2_lo[dv + i] = a.h2n_lo[sv + i];
+    }
+    const size_t ev = (size_t)w * (a.Ep / 8), xv = (size_t)n * (a.Ep / 8);
+    for (int i = threadIdx.x; i < a.Ep / 8; i += 256) {
+      a.xt_hi[xv + i] = a.emb_hi[ev + i]; a.xt_lo[xv + i] = a.emb_lo[ev + i];
+    }
+  }
   if (threadIdx.x == 0) {
     int s;
     if (a.fixed_slot >= 0) s = a.fixed_slot;
@@ -178,22 +193,43 @@ __global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
 }
 
 // zero state, slot 0, xt = embed[bos]   (init_state, controllable_captioning.py:109-115, :136)
+struct PairPtr { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+
 __global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, float* xt, int32_t* ptr,
-                             const float* embed, int bos, int Hp, int Ep) {
+                             const float* embed, int bos, int Hp, int Ep, PairPtr h1b, PairPtr h2b,
+                             PairPtr xtb, PairPtr embb) {
   const int n = blockIdx.x;
+  const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
   for (int i = threadIdx.x; i < Hp; i += blockDim.x) {
     h1[(size_t)n * Hp + i] = 0.f; c1[(size_t)n * Hp + i] = 0.f;
     h2[(size_t)n * Hp + i] = 0.f; c2[(size_t)n * Hp + i] = 0.f;
+    if (h1b.hi != nullptr) {
+      h1b.hi[(size_t)n * Hp + i] = z; h1b.lo[(size_t)n * Hp + i] = z;
+      h2b.hi[(size_t)n * Hp + i] = z; h2b.lo[(size_t)n * Hp + i] = z;
+    }
   }
-  for (int i = threadIdx.x; i < Ep; i += blockDim.x) xt[(size_t)n * Ep + i] = embed[(size_t)bos * Ep + i];
+  for (int i = threadIdx.x; i < Ep; i += blockDim.x) {
+    xt[(size_t)n * Ep + i] = embed[(size_t)bos * Ep + i];
+    if (xtb.hi != nullptr) {
+      xtb.hi[(size_t)n * Ep + i] = embb.hi[(size_t)bos * Ep + i];
+      xtb.lo[(size_t)n * Ep + i] = embb.lo[(size_t)bos * Ep + i];
+    }
+  }
   if (threadIdx.x == 0) ptr[n] = 0;
 }
 
-__global__ void k_embed(const int64_t* words, float* xt, const float* embed, int Ep, int V) {
+__global__ void k_embed(const int64_t* words, float* xt, const float* embed, int Ep, int V, PairPtr xtb,
+                        PairPtr embb) {
   const int n = blockIdx.x;
   int64_t w = words[n];
   w = w < 0 ? 0 : (w >= V ? V - 1 : w);
-  for (int i = threadIdx.x; i < Ep; i += blockDim.x) xt[(size_t)n * Ep + i] = embed[(size_t)w * Ep + i];
+  for (int i = threadIdx.x; i < Ep; i += blockDim.x) {
+    xt[(size_t)n * Ep + i] = embed[(size_t)w * Ep + i];
+    if (xtb.hi != nullptr) {
+      xtb.hi[(size_t)n * Ep + i] = embb.hi[(size_t)w * Ep + i];
+      xtb.lo[(size_t)n * Ep + i] = embb.lo[(size_t)w * Ep + i];
+    }
+  }
 }
 
 // greedy pick of both heads (CaptioningModel.test, CaptioningModel.py:47): first maximum wins
@@ -243,15 +279,23 @@ __global__ void k_backtrack(int b, int k, int T, int out_size, const float* seq_
 
 }  // namespace
 
+static PairPtr pp(const Ctx* c, const Bf16Pair& b) {
+  PairPtr p;
+  p.hi = c->use_tc ? (__nv_bfloat16*)b.hi : nullptr;
+  p.lo = c->use_tc ? (__nv_bfloat16*)b.lo : nullptr;
+  return p;
+}
+
 int launch_state_init(Ctx* c, int rows, cudaStream_t st) {
   k_state_init<<<rows, 256, 0, st>>>(c->h1, c->c1, c->h2, c->c2, c->xt, c->ptr, c->embed, c->d.bos_idx,
-                                     c->Hp, c->Ep);
+                                     c->Hp, c->Ep, pp(c, c->h1_b), pp(c, c->h2_b), pp(c, c->xt_b),
+                                     pp(c, c->embed_b));
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   return VSR_OK;
 }
 
 int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
-  k_embed<<<rows, 256, 0, st>>>(words, c->xt, c->embed, c->Ep, c->V);
+  k_embed<<<rows, 256, 0, st>>>(words, c->xt, c->embed, c->Ep, c->V, pp(c, c->xt_b), pp(c, c->embed_b));
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   return VSR_OK;
 }
@@ -284,6 +328,14 @@ static int launch_advance(Ctx* c, AdvanceArgs& a, cudaStream_t st) {
   a.h1n = c->h1n; a.c1n = c->c1n; a.h2n = c->h2n; a.c2n = c->c2n;
   a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2; a.xt = c->xt;
   a.ptr = c->ptr; a.ptrn = c->ptrn; a.embed = c->embed;
+  if (c->use_tc) {
+    a.h1n_hi = (const uint4*)c->h1n_b.hi; a.h1n_lo = (const uint4*)c->h1n_b.lo;
+    a.h2n_hi = (const uint4*)c->h2n_b.hi; a.h2n_lo = (const uint4*)c->h2n_b.lo;
+    a.emb_hi = (const uint4*)c->embed_b.hi; a.emb_lo = (const uint4*)c->embed_b.lo;
+    a.h1_hi = (uint4*)c->h1_b.hi; a.h1_lo = (uint4*)c->h1_b.lo;
+    a.h2_hi = (uint4*)c->h2_b.hi; a.h2_lo = (uint4*)c->h2_b.lo;
+    a.xt_hi = (uint4*)c->xt_b.hi; a.xt_lo = (uint4*)c->xt_b.lo;
+  }
   k_advance<<<a.rows_new, 256, 0, st>>>(a);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   std::swap(c->ptr, c->ptrn);

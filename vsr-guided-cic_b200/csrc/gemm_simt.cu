@@ -102,7 +102,13 @@ __global__ void __launch_bounds__(THREADS) k_gemm_simt(const GemmArgs g) {
 
 }  // namespace
 
-int launch_gemm(const GemmArgs& g, cudaStream_t st) {
+int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st) {
+  bool tc = c->use_tc && g.wb != nullptr && g.wb->hi != nullptr;
+  for (int s = 0; s < g.nseg && tc; ++s) tc = g.seg[s].b != nullptr && g.seg[s].b->hi != nullptr;
+  return tc ? launch_gemm_tc(g, st) : launch_gemm_simt(g, st);
+}
+
+int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {
   VSR_REQUIRE(g.N % BN == 0 && g.M > 0 && g.nseg >= 1 && g.nseg <= 3, VSR_EINVAL,
               "launch_gemm: bad shape M=%d N=%d nseg=%d", g.M, g.N, g.nseg);
   for (int s = 0; s < g.nseg; ++s)

@@ -1,0 +1,332 @@
+// tcgen05 / TMEM / TMA GEMM for the per-step dense contractions (LSTM gates, sentinel / attention
+// projections, vocabulary projection):   C[M][N] = sum_seg A_seg[M][K_seg] * W[N][K]^T (+ epilogue).
+//
+// Precision: "bf16x3" error-compensated split.  Every fp32 operand x is carried as two bf16 arrays
+//   x_hi = bf16(x),  x_lo = bf16(x - x_hi)
+// and each product is issued as three tensor-core MMAs into the SAME fp32 TMEM accumulator:
+//   A_hi*W_hi + A_hi*W_lo + A_lo*W_hi        (dropped: A_lo*W_lo ~ 2^-16 relative)
+// which restores ~fp32 accuracy (token-identical to the reference where a single
+// bf16 / tf32 pass is not) at one third of the bf16 tensor rate.
+//
+// Structure (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0   : TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem tiles, mbarrier expect_tx
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN, K=16)
+//   warps 2-5: epilogue       tcgen05.ld TMEM -> registers -> (+bias, +per-caption row, +matrix) -> global
+// smem ring: kStages x {A_hi, A_lo (128 x 64 bf16), W_hi, W_lo (BN x 64 bf16)}, full/empty mbarriers;
+// the accumulator hand-off to the epilogue is a tcgen05.commit on a third mbarrier.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace vsr {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int TC_THREADS = 192;
+
+template <int BN> struct TcCfg {
+  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kABytes = BM * BK * 2;            // 16 KB
+  static constexpr int kWBytes = BN * BK * 2;            // 16 / 32 KB
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;   // + alignment slack
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart): UMMA smem descriptor
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);          // start address  [0,14)
+  d |= (uint64_t)1 << 16;                               // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset [32,46): 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, M=128, N=BN
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+  CUtensorMap a_hi[3], a_lo[3], w_hi, w_lo;
+  int nseg;
+  int kblocks[3];
+  const float* bias;
+  const float* rowadd; int ld_rowadd, row_div, rowadd_mul;
+  const float* cadd; int ld_cadd;
+  float* c; int ldc;
+  int M;
+  const uint8_t* row_skip;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcParams p) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+
+  if (p.row_skip != nullptr) {   // all-padding row tiles produce nothing (block-uniform)
+    int any = 0;
+    if (threadIdx.x < BM && m0 + (int)threadIdx.x < p.M) any = p.row_skip[m0 + threadIdx.x];
+    if (!__syncthreads_or(any)) return;
+  }
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024-B alignment
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); }
+    prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(&tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  int total_kb = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int seg = 0, kk = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        const int st = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t* base = smem + st * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+        tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * BK, m0);
+        tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * BK, n0);
+        tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * BK, n0);
+        tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * BK, m0);
+        if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<BN>();
+      for (int kb = 0; kb < total_kb; ++kb) {
+        const int st = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
+        const uint64_t ah = make_sw128_desc(base), al = make_sw128_desc(base + Cfg::kABytes);
+        const uint64_t wh = make_sw128_desc(base + 2 * Cfg::kABytes);
+        const uint64_t wl = make_sw128_desc(base + 2 * Cfg::kABytes + Cfg::kWBytes);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);     // advance inside the swizzle row
+          umma_bf16(tmem_base, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_bf16(tmem_base, ah + off, wl + off, idesc, 1u);
+          umma_bf16(tmem_base, al + off, wh + off, idesc, 1u);
+        }
+        umma_commit(&empty_bar[st]);          // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(&tmem_full_bar);            // accumulator complete -> epilogue
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool live = row < p.M;
+    const float* radd = (p.rowadd != nullptr && live)
+                            ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
+    const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
+    float* crow = p.c + (size_t)row * p.ldc;
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 32; ++ch) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
+      const int n = n0 + ch * 32;
+      if (live) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (p.bias != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (radd != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(radd + n + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (cadd != nullptr) {
+            const float4 b = *reinterpret_cast<const float4*>(cadd + n + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          *reinterpret_cast<float4*>(crow + n + j) = o;
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// x -> (bf16 hi, bf16 lo) with lo = bf16(x - hi)
+__global__ void k_split_bf16(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                             __nv_bfloat16* __restrict__ lo, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  hi[i] = h;
+  lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+}  // namespace
+
+// 2-D bf16 tensor map over a row-major [rows][ld] buffer: box = 64 (K) x box_rows, 128-byte swizzle
+int make_tmap_bf16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VSR_REQUIRE(enc != nullptr, VSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VSR_REQUIRE(r == CUDA_SUCCESS, VSR_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+  return VSR_OK;
+}
+
+int launch_split_bf16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st) {
+  if (n == 0) return VSR_OK;
+  k_split_bf16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, n);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  return VSR_OK;
+}
+
+int tc_gemm_init() {
+  static bool done = false;
+  if (done) return VSR_OK;
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes));
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+  done = true;
+  return VSR_OK;
+}
+
+int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
+  VSR_TRY(tc_gemm_init());
+  const int BN = g.wb->box_rows;
+  VSR_REQUIRE((BN == 128 || BN == 256) && g.N % BN == 0, VSR_EINVAL, "launch_gemm_tc: N=%d not a multiple of BN=%d", g.N, BN);
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.nseg = g.nseg;
+  for (int s = 0; s < g.nseg; ++s) {
+    VSR_REQUIRE(g.seg[s].b != nullptr && g.seg[s].k % BK == 0, VSR_EINVAL, "launch_gemm_tc: segment %d not tensor-core ready", s);
+    memcpy(&p.a_hi[s], g.seg[s].b->map_hi, sizeof(CUtensorMap));
+    memcpy(&p.a_lo[s], g.seg[s].b->map_lo, sizeof(CUtensorMap));
+    p.kblocks[s] = g.seg[s].k / BK;
+  }
+  memcpy(&p.w_hi, g.wb->map_hi, sizeof(CUtensorMap));
+  memcpy(&p.w_lo, g.wb->map_lo, sizeof(CUtensorMap));
+  p.bias = g.bias; p.rowadd = g.rowadd; p.ld_rowadd = g.ld_rowadd; p.row_div = g.row_div > 0 ? g.row_div : 1;
+  p.rowadd_mul = g.rowadd_mul; p.cadd = g.cadd; p.ld_cadd = g.ld_cadd; p.c = g.c; p.ldc = g.ldc; p.M = g.M;
+  p.row_skip = g.row_skip;
+  dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
+  if (BN == 256) k_gemm_tc<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(p);
+  else k_gemm_tc<128><<<grid, TC_THREADS, TcCfg<128>::kSmemBytes, st>>>(p);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  return VSR_OK;
+}
+
+}  // namespace vsr

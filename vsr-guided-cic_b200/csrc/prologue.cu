@@ -152,6 +152,17 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   VSR_TRY(pack_bias(c, c->v_g, 0, w[27], nullptr, A, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->embed, 0, sizeof(float) * (size_t)V * Ep, st));
   VSR_TRY(pack_block(c, c->embed, Ep, 0, 0, w[0], E, 0, V, E, st));
+  // bf16 hi/lo twins of the per-step weights and of the embedding table (tcgen05 operands)
+  struct Tw { const float* f; Bf16Pair* b; size_t n; };
+  const Tw tw[] = {{c->WA, &c->WA_b, (size_t)c->NA * c->KA}, {c->WB1, &c->WB1_b, (size_t)c->NB1 * Hp},
+                   {c->WB2, &c->WB2_b, (size_t)c->NB2 * Hp}, {c->WC, &c->WC_b, (size_t)c->NC * Hp},
+                   {c->WD, &c->WD_b, (size_t)c->ND * c->KD}, {c->WE, &c->WE_b, (size_t)c->NE * Hp},
+                   {c->embed, &c->embed_b, (size_t)V * Ep}};
+  for (const Tw& t : tw) {
+    if (t.b->hi == nullptr) continue;
+    VSR_TRY(launch_split_bf16(t.f, t.b->hi, t.b->lo, t.n, st));
+    c->launches++;
+  }
   return VSR_OK;
 }
 
@@ -183,14 +194,14 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     g.nseg = 1; g.seg[0] = {c->img, c->Fp, c->Fp, c->Fp};
     g.w = c->WU; g.ldw = c->Fp; g.bias = c->bU;
     g.c = c->U; g.ldc = c->NA; g.M = n_img; g.N = c->NA;
-    VSR_TRY(launch_gemm(g, st));
+    VSR_TRY(launch_gemm_simt(g, st));
     c->launches++;
     if (c->d.img_second_lstm) {
       GemmArgs g2{};
       g2.nseg = 1; g2.seg[0] = {c->img, c->Fp, c->Fp, c->Fp};
       g2.w = c->WU2; g2.ldw = c->Fp;
       g2.c = c->U2; g2.ldc = c->ND; g2.M = n_img; g2.N = c->ND;
-      VSR_TRY(launch_gemm(g2, st));
+      VSR_TRY(launch_gemm_simt(g2, st));
       c->launches++;
     }
   }
@@ -201,7 +212,7 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     g.w = c->Wva; g.ldw = c->Fp;
     g.c = c->P; g.ldc = c->NVA; g.M = b * L * R; g.N = c->NVA;
     g.row_skip = c->seq_valid;
-    VSR_TRY(launch_gemm(g, st));
+    VSR_TRY(launch_gemm_simt(g, st));
     c->launches++;
   }
   return VSR_OK;

@@ -1,0 +1,99 @@
+// Stand-alone check of the tcgen05 GEMM against the fp32 FFMA GEMM on random data (GPU box only):
+//   build/selftest_gemm      -> prints max |tc - simt| per shape and a timing, exit code 0 if all close
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+using namespace vsr;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA %s: %s\n", #x, cudaGetErrorString(e)); exit(2); } } while (0)
+#define VK(x) do { int r = (x); if (r != 0) { printf("VSR %s: %s\n", #x, vsr_last_error()); exit(3); } } while (0)
+
+static float* dev_rand(size_t n, float scale, unsigned seed) {
+  std::vector<float> h(n);
+  srand(seed);
+  for (size_t i = 0; i < n; ++i) h[i] = scale * ((rand() / (float)RAND_MAX) * 2.f - 1.f);
+  float* d; CK(cudaMalloc(&d, n * 4)); CK(cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+static void make_pair(Bf16Pair* b, const float* f, int rows, int ld, int box) {
+  CK(cudaMalloc(&b->hi, (size_t)rows * ld * 2)); CK(cudaMalloc(&b->lo, (size_t)rows * ld * 2));
+  b->rows = rows; b->ld = ld; b->box_rows = box;
+  VK(launch_split_bf16(f, b->hi, b->lo, (size_t)rows * ld, 0));
+  VK(make_tmap_bf16(b->map_hi, b->hi, rows, ld, ld, box));
+  VK(make_tmap_bf16(b->map_lo, b->lo, rows, ld, ld, box));
+}
+
+static int run_case(int M, int N, int nseg, const int* ks, bool extras, int BN) {
+  const int Mp = (M + 127) / 128 * 128;
+  int K = 0; for (int s = 0; s < nseg; ++s) K += ks[s];
+  float* W = dev_rand((size_t)N * K, 0.05f, 1);
+  Bf16Pair wb{}; make_pair(&wb, W, N, K, BN);
+  GemmArgs g{};
+  g.nseg = nseg;
+  Bf16Pair ab[3];
+  for (int s = 0; s < nseg; ++s) {
+    float* A = dev_rand((size_t)Mp * ks[s], 1.0f, 10 + s);
+    memset(&ab[s], 0, sizeof(Bf16Pair));
+    make_pair(&ab[s], A, Mp, ks[s], 128);
+    g.seg[s] = {A, ks[s], ks[s], ks[s], &ab[s]};
+  }
+  g.w = W; g.ldw = K; g.wb = &wb;
+  float *bias = nullptr, *radd = nullptr, *cadd = nullptr;
+  if (extras) {
+    bias = dev_rand(N, 1.f, 5); radd = dev_rand((size_t)(Mp / 5 + 1) * N, 1.f, 6); cadd = dev_rand((size_t)Mp * (N + 64), 1.f, 7);
+    g.bias = bias; g.rowadd = radd; g.ld_rowadd = N; g.row_div = 5; g.rowadd_mul = 1; g.cadd = cadd + 64; g.ld_cadd = N + 64;
+  }
+  float *C1, *C2;
+  CK(cudaMalloc(&C1, (size_t)Mp * N * 4)); CK(cudaMalloc(&C2, (size_t)Mp * N * 4));
+  CK(cudaMemset(C1, 0, (size_t)Mp * N * 4)); CK(cudaMemset(C2, 0, (size_t)Mp * N * 4));
+  g.M = M; g.N = N; g.ldc = N;
+  g.c = C1; VK(launch_gemm_simt(g, 0));
+  g.c = C2; VK(launch_gemm_tc(g, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> h1((size_t)M * N), h2((size_t)M * N);
+  CK(cudaMemcpy(h1.data(), C1, h1.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h2.data(), C2, h2.size() * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0;
+  for (size_t i = 0; i < h1.size(); ++i) { maxerr = fmax(maxerr, fabs((double)h1[i] - h2[i])); maxref = fmax(maxref, fabs((double)h1[i])); }
+  // timing of both
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms_tc = 0, ms_simt = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaEventRecord(e0); for (int i = 0; i < 10; ++i) { g.c = C2; VK(launch_gemm_tc(g, 0)); } cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+    cudaEventElapsedTime(&ms_tc, e0, e1);
+  }
+  cudaEventRecord(e0); for (int i = 0; i < 3; ++i) { g.c = C1; VK(launch_gemm_simt(g, 0)); } cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+  cudaEventElapsedTime(&ms_simt, e0, e1);
+  const double flops = 2.0 * M * N * K;
+  const bool ok = maxerr <= 2e-4 * fmax(1.0, maxref);
+  printf("M=%4d N=%5d K=%4d segs=%d extras=%d BN=%d : max|tc-simt|=%.3e (max|ref|=%.2f) %s | tc %.1f us (%.1f TF/s algorithmic) simt %.1f us\n",
+         M, N, K, nseg, (int)extras, BN, maxerr, maxref, ok ? "OK" : "MISMATCH", ms_tc * 100, flops / (ms_tc * 1e-4) / 1e12,
+         ms_simt * 1000 / 3);
+  fflush(stdout);
+  return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  int bad = 0;
+  const int k1[] = {64}, k2[] = {1024}, k3[] = {1024, 1024, 1024}, k4[] = {2048, 1024}, k5[] = {64, 64, 64};
+  const int bns[2] = {256, 128};
+  for (int bi = 0; bi < 2; ++bi) {
+    const int BN = bns[bi];
+    bad += run_case(128, 256, 1, k1, false, BN);
+    bad += run_case(100, 256, 3, k5, true, BN);
+    bad += run_case(500, 512, 1, k2, false, BN);
+    bad += run_case(500, 2560, 1, k2, true, BN);
+    bad += run_case(500, 6144, 3, k3, true, BN);
+    bad += run_case(500, 4096, 2, k4, true, BN);
+    bad += run_case(500, 10240, 1, k2, true, BN);
+    bad += run_case(100, 6144, 3, k3, true, BN);
+  }
+  printf("%s\n", bad ? "SELFTEST FAILED" : "SELFTEST PASSED");
+  return bad ? 1 : 0;
+}

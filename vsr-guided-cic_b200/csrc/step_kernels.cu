@@ -5,6 +5,8 @@
 #include <float.h>
 #include <math.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace vsr {
@@ -12,6 +14,15 @@ namespace vsr {
 namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// store x as fp32 and as the error-compensated bf16 pair the tcgen05 GEMMs consume
+struct PairOut { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+__device__ __forceinline__ void store_pair(const PairOut& o, size_t i, float v) {
+  if (o.hi == nullptr) return;
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  o.hi[i] = h;
+  o.lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -29,7 +40,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // c1' = sig(f) c1 + sig(i) tanh(g); h1' = sig(o) tanh(c1'); s_t = sig(s) tanh(c1')   (:151-154)
 __global__ void k_lstm1(const float* __restrict__ pre1, int ld_pre, const float* __restrict__ c1,
                         float* __restrict__ h1n, float* __restrict__ c1n, float* __restrict__ s_t,
-                        int ld, int H, int rows) {
+                        PairOut h1n_b, PairOut s_t_b, int ld, int H, int rows) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (u >= H || n >= rows) return;
@@ -39,23 +50,30 @@ __global__ void k_lstm1(const float* __restrict__ pre1, int ld_pre, const float*
   const float c = fg * c1[(size_t)n * ld + u] + ig * gg;
   const float tc = tanhf(c);
   c1n[(size_t)n * ld + u] = c;
-  h1n[(size_t)n * ld + u] = og * tc;
-  s_t[(size_t)n * ld + u] = sg * tc;
+  const float hv = og * tc, sv = sg * tc;
+  h1n[(size_t)n * ld + u] = hv;
+  s_t[(size_t)n * ld + u] = sv;
+  store_pair(h1n_b, (size_t)n * ld + u, hv);
+  store_pair(s_t_b, (size_t)n * ld + u, sv);
 }
 
 // g_t = sig(gq + hg) * tanh(c1')   (:181-182; hg = W1_hg . h1' comes from the h1' GEMM)
 __global__ void k_gt(const float* __restrict__ pre1, int ld_pre, const float* __restrict__ hb, int ld_hb,
-                     const float* __restrict__ c1n, float* __restrict__ g_t, int ld, int H, int rows) {
+                     const float* __restrict__ c1n, float* __restrict__ g_t, PairOut g_t_b, int ld, int H,
+                     int rows) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (u >= H || n >= rows) return;
   const float gq = pre1[(size_t)n * ld_pre + 5 * H + u] + hb[(size_t)n * ld_hb + u];
-  g_t[(size_t)n * ld + u] = sigmoidf_(gq) * tanhf(c1n[(size_t)n * ld + u]);
+  const float gv = sigmoidf_(gq) * tanhf(c1n[(size_t)n * ld + u]);
+  g_t[(size_t)n * ld + u] = gv;
+  store_pair(g_t_b, (size_t)n * ld + u, gv);
 }
 
 // LSTM cell 2: pre2 rows [i | f | g | o]   (:177 / :258)
 __global__ void k_lstm2(const float* __restrict__ pre2, int ld_pre, const float* __restrict__ c2,
-                        float* __restrict__ h2n, float* __restrict__ c2n, int ld, int H, int rows) {
+                        float* __restrict__ h2n, float* __restrict__ c2n, PairOut h2n_b, int ld, int H,
+                        int rows) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (u >= H || n >= rows) return;
@@ -64,7 +82,9 @@ __global__ void k_lstm2(const float* __restrict__ pre2, int ld_pre, const float*
               og = sigmoidf_(p[3 * H + u]);
   const float c = fg * c2[(size_t)n * ld + u] + ig * gg;
   c2n[(size_t)n * ld + u] = c;
-  h2n[(size_t)n * ld + u] = og * tanhf(c);
+  const float hv = og * tanhf(c);
+  h2n[(size_t)n * ld + u] = hv;
+  store_pair(h2n_b, (size_t)n * ld + u, hv);
 }
 
 // ---------------------------------------------------------------- slot attention + shift gate
@@ -88,6 +108,7 @@ struct AttendArgs {
   const float* ga; int ld_ga;
   const float *v_a, *v_s, *v_g;
   float* att; int ld_att;
+  PairOut att_b;
   float* gate_lp;          // [rows][2]
   int rows, cur_beam, L, R, F, A, H, ldP;
 };
@@ -209,6 +230,9 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
       acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
     }
     *reinterpret_cast<float4*>(out + f) = acc;
+    const size_t o = (size_t)n * a.ld_att + f;
+    store_pair(a.att_b, o, acc.x); store_pair(a.att_b, o + 1, acc.y);
+    store_pair(a.att_b, o + 2, acc.z); store_pair(a.att_b, o + 3, acc.w);
   }
 }
 
@@ -393,6 +417,13 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
 }  // namespace
 
 // ---------------------------------------------------------------- one decoder step (host side)
+static PairOut pair_out(const Ctx* c, const Bf16Pair& b) {
+  PairOut o;
+  o.hi = c->use_tc ? (__nv_bfloat16*)b.hi : nullptr;
+  o.lo = c->use_tc ? (__nv_bfloat16*)b.lo : nullptr;
+  return o;
+}
+
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   const int rows = io.rows, H = c->H;
   VSR_REQUIRE(rows > 0 && rows <= c->cap_rows, VSR_ESTATE, "run_step: rows=%d cap=%d", rows, c->cap_rows);
@@ -404,45 +435,47 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     PhaseScope ps(c, PH_GEMM_A, st);
     GemmArgs g{};
     int s = 0;
-    if (h2f) g.seg[s++] = {c->h2, c->Hp, c->Hp, c->Hp};
-    g.seg[s++] = {c->xt, c->Ep, c->Ep, c->Ep};
-    g.seg[s++] = {c->h1, c->Hp, c->Hp, c->Hp};
+    if (h2f) g.seg[s++] = {c->h2, c->Hp, c->Hp, c->Hp, &c->h2_b};
+    g.seg[s++] = {c->xt, c->Ep, c->Ep, c->Ep, &c->xt_b};
+    g.seg[s++] = {c->h1, c->Hp, c->Hp, c->Hp, &c->h1_b};
     g.nseg = s;
-    g.w = c->WA; g.ldw = c->KA;
+    g.w = c->WA; g.ldw = c->KA; g.wb = &c->WA_b;
     g.rowadd = c->U; g.ld_rowadd = c->NA; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
-    VSR_TRY(launch_gemm(g, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
   {
     PhaseScope ps(c, PH_LSTM1, st);
-    k_lstm1<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->c1, c->h1n, c->c1n, c->s_t, c->Hp, H, rows);
+    k_lstm1<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->c1, c->h1n, c->c1n, c->s_t, pair_out(c, c->h1n_b),
+                                     pair_out(c, c->s_t_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // B: [sentinel | sa] = WB1 . s_t + b ;  [hg | ha | pre2_h1] = WB2 . h1'
     PhaseScope ps(c, PH_GEMM_B, st);
     GemmArgs g{};
-    g.nseg = 1; g.seg[0] = {c->s_t, c->Hp, c->Hp, c->Hp};
-    g.w = c->WB1; g.ldw = c->Hp; g.bias = c->bB1;
+    g.nseg = 1; g.seg[0] = {c->s_t, c->Hp, c->Hp, c->Hp, &c->s_t_b};
+    g.w = c->WB1; g.ldw = c->Hp; g.bias = c->bB1; g.wb = &c->WB1_b;
     g.c = c->sent; g.ldc = c->NB1; g.M = rows; g.N = c->NB1;
-    VSR_TRY(launch_gemm(g, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
     GemmArgs g2{};
-    g2.nseg = 1; g2.seg[0] = {c->h1n, c->Hp, c->Hp, c->Hp};
-    g2.w = c->WB2; g2.ldw = c->Hp;
+    g2.nseg = 1; g2.seg[0] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
+    g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b;
     g2.c = c->hb; g2.ldc = c->NB2; g2.M = rows; g2.N = c->NB2;
-    VSR_TRY(launch_gemm(g2, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g2, st)); c->launches++;
   }
   {
     PhaseScope ps(c, PH_GT, st);
-    k_gt<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->hb, c->NB2, c->c1n, c->g_t, c->Hp, H, rows);
+    k_gt<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->hb, c->NB2, c->c1n, c->g_t, pair_out(c, c->g_t_b), c->Hp, H,
+                                  rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // C: ga = att_ga . g_t
     PhaseScope ps(c, PH_GEMM_C, st);
     GemmArgs g{};
-    g.nseg = 1; g.seg[0] = {c->g_t, c->Hp, c->Hp, c->Hp};
-    g.w = c->WC; g.ldw = c->Hp;
+    g.nseg = 1; g.seg[0] = {c->g_t, c->Hp, c->Hp, c->Hp, &c->g_t_b};
+    g.w = c->WC; g.ldw = c->Hp; g.wb = &c->WC_b;
     g.c = c->ga; g.ldc = c->NC; g.M = rows; g.N = c->NC;
-    VSR_TRY(launch_gemm(g, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
   {
     PhaseScope ps(c, PH_ATTEND, st);
@@ -451,7 +484,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.sent = c->sent; a.ld_sent = c->NB1; a.o_sa = c->oB1_sa;
     a.hb = c->hb; a.ld_hb = c->NB2; a.o_ha = c->oB2_ha; a.ga = c->ga; a.ld_ga = c->NC;
     a.v_a = c->v_a; a.v_s = c->v_s; a.v_g = c->v_g;
-    a.att = c->att; a.ld_att = c->Fp; a.gate_lp = c->gate_lp;
+    a.att = c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.gate_lp = c->gate_lp;
     a.rows = rows; a.cur_beam = io.cur_beam; a.L = c->L; a.R = c->R; a.F = c->F; a.A = c->A; a.H = H;
     a.ldP = c->NVA;
     const size_t smem = sizeof(float) * (size_t)(c->A + c->R + 1);
@@ -462,28 +495,28 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     PhaseScope ps(c, PH_GEMM_D, st);
     GemmArgs g{};
     g.nseg = 2;
-    g.seg[0] = {c->att, c->Fp, c->Fp, c->Fp};
-    g.seg[1] = {c->h2, c->Hp, c->Hp, c->Hp};
-    g.w = c->WD; g.ldw = c->KD; g.bias = c->bD;
+    g.seg[0] = {c->att, c->Fp, c->Fp, c->Fp, &c->att_b};
+    g.seg[1] = {c->h2, c->Hp, c->Hp, c->Hp, &c->h2_b};
+    g.w = c->WD; g.ldw = c->KD; g.bias = c->bD; g.wb = &c->WD_b;
     g.cadd = c->hb + c->oB2_p2; g.ld_cadd = c->NB2;
     if (c->d.img_second_lstm) {
       g.rowadd = c->U2; g.ld_rowadd = c->ND; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     }
     g.c = c->pre2; g.ldc = c->ND; g.M = rows; g.N = c->ND;
-    VSR_TRY(launch_gemm(g, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
   {
     PhaseScope ps(c, PH_LSTM2, st);
-    k_lstm2<<<pw_grid, 128, 0, st>>>(c->pre2, c->ND, c->c2, c->h2n, c->c2n, c->Hp, H, rows);
+    k_lstm2<<<pw_grid, 128, 0, st>>>(c->pre2, c->ND, c->c2, c->h2n, c->c2n, pair_out(c, c->h2n_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // E: logits = out_fc . h2' + b
     PhaseScope ps(c, PH_GEMM_E, st);
     GemmArgs g{};
-    g.nseg = 1; g.seg[0] = {c->h2n, c->Hp, c->Hp, c->Hp};
-    g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE;
+    g.nseg = 1; g.seg[0] = {c->h2n, c->Hp, c->Hp, c->Hp, &c->h2n_b};
+    g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE; g.wb = &c->WE_b;
     g.c = c->logits; g.ldc = c->NE; g.M = rows; g.N = c->NE;
-    VSR_TRY(launch_gemm(g, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
   {
     PhaseScope ps(c, PH_SOFTMAX_TOPK, st);
