@@ -156,6 +156,11 @@ int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* strea
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t vsr_launch_count(vsr_handle h);
 
+/* Which GEMM path this handle runs: "tcgen05-f16x3" (default: tcgen05.mma kind::f16 on fp16 hi/lo
+ * splits, three MMAs per product into one fp32 TMEM accumulator) or "simt-fp32" (FFMA verification
+ * twin, selected with VSRDEC_GEMM=simt at create time). */
+const char* vsr_gemm_kind(vsr_handle h);
+
 /* Per-phase device time of the last decode when enabled (CUDA events around each phase of each
  * step; adds event overhead, off by default).  names/ms are [host] arrays of capacity cap;
  * returns the number of phases written, or a negative error. */

@@ -44,7 +44,7 @@ def test_small_model_beam_search_cases(name):
                                               extra["step_out"], extra["step_gate"])
         print(cname, v.summary())
         assert not v.violations, v.violations[:5]
-        assert v.max_out_rel <= REL and v.max_gate_rel <= REL
+        assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0    # fraction of (1e-3*|x| + 1e-4)
         # along the device's own trajectory the oracle reproduces the device's outputs exactly
         ow, og = o_outs[0][:, :osz], o_outs[1][:, :osz]
         assert torch.equal(w.cpu(), ow) and torch.equal(g.cpu(), og)
@@ -180,7 +180,7 @@ def test_full_size_config1(sharpen):
                                           extra["step_out"], extra["step_gate"])
     print("config1 sharpen=%s" % sharpen, v.summary())
     assert not v.violations, v.violations[:5]
-    assert v.max_out_rel <= REL and v.max_gate_rel <= REL
+    assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0    # fraction of (1e-3*|x| + 1e-4)
     assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
     # free-running oracle (== the reference, bit-exact) for the exact-match statistic
     with torch.no_grad():

@@ -67,16 +67,16 @@ static void reset_phases(Ctx* c) {
 
 #define ALLOC_F(ptr, count) VSR_TRY(dev_alloc(c, (void**)&(ptr), sizeof(float) * (size_t)(count)))
 
-// (re)allocate a bf16 hi/lo twin of a [rows][ld] fp32 matrix and build its TMA tensor maps
-static int alloc_pair(Ctx* c, Bf16Pair* b, int rows, int ld, int box_rows) {
+// (re)allocate a fp16 hi/lo twin of a [rows][ld] fp32 matrix and build its TMA tensor maps
+int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows) {
   dev_free(c, b->hi); dev_free(c, b->lo);
   b->hi = b->lo = nullptr;
   if (!c->use_tc) return VSR_OK;
   VSR_TRY(dev_alloc(c, &b->hi, (size_t)rows * ld * 2));
   VSR_TRY(dev_alloc(c, &b->lo, (size_t)rows * ld * 2));
   b->rows = rows; b->ld = ld; b->box_rows = box_rows;
-  VSR_TRY(make_tmap_bf16(b->map_hi, b->hi, rows, ld, ld, box_rows));
-  VSR_TRY(make_tmap_bf16(b->map_lo, b->lo, rows, ld, ld, box_rows));
+  VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box_rows));
+  VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box_rows));
   return VSR_OK;
 }
 
@@ -178,10 +178,16 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
     const char* mode = getenv("VSRDEC_GEMM");   // "simt": fp32 FFMA twin for A/B verification of the tcgen05 path
     c->use_tc = !(mode != nullptr && strcmp(mode, "simt") == 0);
   }
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, NPAD)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, NPAD));
-  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, NPAD)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, NPAD));
-  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, NPAD)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, NPAD));
+  // UMMA N tile per GEMM (128 or 256): 128 measured faster on B200 for every per-step shape (more CTAs
+  // in flight, 3-stage ring); VSRDEC_BN=256 switches all of them for experiments
+  int bn = 128;
+  if (const char* e = getenv("VSRDEC_BN")) bn = atoi(e) == 256 ? 256 : 128;
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, bn)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, bn));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, bn)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn));
   VSR_TRY(alloc_pair(c, &c->embed_b, c->V, c->Ep, 8));
+  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, bn)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn));
+  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, bn));
   VSR_TRY(pack_weights(c, w, 0));
   VSR_CHECK_CUDA(cudaStreamSynchronize(0));
   return VSR_OK;
@@ -207,6 +213,7 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     c->img = c->U = c->U2 = nullptr; c->cap_img = 0;
     ALLOC_F(c->img, n_img_pad * c->Fp); ALLOC_F(c->U, n_img_pad * c->NA);
     if (c->d.img_second_lstm) ALLOC_F(c->U2, n_img_pad * c->ND);
+    VSR_TRY(alloc_pair(c, &c->img_b, (int)n_img_pad, c->Fp, MPAD));
     c->cap_img = n_img_pad;
   }
   const size_t prow = (size_t)b * L * R;
@@ -215,6 +222,7 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     c->P = nullptr; c->seq_valid = nullptr; c->cap_P = 0;
     ALLOC_F(c->P, round_up((int)prow, MPAD) * (size_t)c->NVA);
     VSR_TRY(dev_alloc(c, (void**)&c->seq_valid, round_up((int)prow, MPAD)));
+    VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)prow, MPAD), c->Fp, MPAD));
     c->cap_P = prow;
   }
   const size_t dvr = (size_t)c->n_img * D;
@@ -269,8 +277,8 @@ static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, 
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   VSR_TRY(launch_embed(c, word, b, st));
   if (c->use_tc) {
-    VSR_TRY(launch_split_bf16(c->h1, c->h1_b.hi, c->h1_b.lo, (size_t)b * c->Hp, st));
-    VSR_TRY(launch_split_bf16(c->h2, c->h2_b.hi, c->h2_b.lo, (size_t)b * c->Hp, st));
+    VSR_TRY(launch_split_f16(c->h1, c->h1_b.hi, c->h1_b.lo, (size_t)b * c->Hp, st));
+    VSR_TRY(launch_split_f16(c->h2, c->h2_b.hi, c->h2_b.lo, (size_t)b * c->Hp, st));
     c->launches += 2;
   }
   StepIO io{};
@@ -467,6 +475,11 @@ int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* strea
 }
 
 int64_t vsr_launch_count(vsr_handle h) { return h ? ((Ctx*)h)->launches : -1; }
+
+const char* vsr_gemm_kind(vsr_handle h) {
+  if (!h) return "none";
+  return ((Ctx*)h)->use_tc ? "tcgen05-f16x3" : "simt-fp32";
+}
 
 int vsr_set_profiling(vsr_handle h, int32_t enabled) {
   if (!h) { vsr::set_error("vsr_set_profiling: null handle"); return VSR_EINVAL; }

@@ -4,7 +4,7 @@
 // Reference: models/CaptioningModel.py:116-195 (beam_search), :197-294 (beam_search_v),
 // :78-114 (_select_beam).  Statics are never copied per beam: rows index
 // them by caption = row / beam.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -149,7 +149,7 @@ struct AdvanceArgs {
   float *h1, *c1, *h2, *c2, *xt;
   const int32_t* ptr; int32_t* ptrn;
   const float* embed;
-  // bf16 hi/lo twins (null on the fp32 path): 16-byte vectors of 8 bf16
+  // fp16 hi/lo twins (null on the fp32 path): 16-byte vectors of 8 fp16
   const uint4 *h1n_hi, *h1n_lo, *h2n_hi, *h2n_lo, *emb_hi, *emb_lo;
   uint4 *h1_hi, *h1_lo, *h2_hi, *h2_lo, *xt_hi, *xt_lo;
 };
@@ -193,13 +193,13 @@ __global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
 }
 
 // zero state, slot 0, xt = embed[bos]   (init_state, controllable_captioning.py:109-115, :136)
-struct PairPtr { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+struct PairPtr { __half* hi; __half* lo; };
 
 __global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, float* xt, int32_t* ptr,
                              const float* embed, int bos, int Hp, int Ep, PairPtr h1b, PairPtr h2b,
                              PairPtr xtb, PairPtr embb) {
   const int n = blockIdx.x;
-  const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+  const __half z = __float2half_rn(0.f);
   for (int i = threadIdx.x; i < Hp; i += blockDim.x) {
     h1[(size_t)n * Hp + i] = 0.f; c1[(size_t)n * Hp + i] = 0.f;
     h2[(size_t)n * Hp + i] = 0.f; c2[(size_t)n * Hp + i] = 0.f;
@@ -279,10 +279,10 @@ __global__ void k_backtrack(int b, int k, int T, int out_size, const float* seq_
 
 }  // namespace
 
-static PairPtr pp(const Ctx* c, const Bf16Pair& b) {
+static PairPtr pp(const Ctx* c, const F16Pair& b) {
   PairPtr p;
-  p.hi = c->use_tc ? (__nv_bfloat16*)b.hi : nullptr;
-  p.lo = c->use_tc ? (__nv_bfloat16*)b.lo : nullptr;
+  p.hi = c->use_tc ? (__half*)b.hi : nullptr;
+  p.lo = c->use_tc ? (__half*)b.lo : nullptr;
   return p;
 }
 

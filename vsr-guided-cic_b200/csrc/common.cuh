@@ -38,14 +38,14 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 // K (reduction) dims are padded to KPAD floats (one 128-byte swizzle row of fp32), output-feature
 // dims to NPAD rows, activation row counts to MPAD rows; pads are zero so they never contribute.
-constexpr int KPAD = 64;    // 64 bf16 = one 128-byte swizzle row of the tensor-core operand tiles
+constexpr int KPAD = 64;    // 64 fp16 = one 128-byte swizzle row of the tensor-core operand tiles
 constexpr int NPAD = 256;   // widest UMMA N tile
 constexpr int MPAD = 128;   // UMMA M tile
 
-// An fp32 matrix carried as an error-compensated bf16 pair (x = hi + lo + O(2^-17 x)) with the TMA
+// An fp32 matrix carried as an error-compensated fp16 pair (x = hi + lo + O(2^-22 x)) with the TMA
 // tensor maps (64 x box_rows boxes, 128-byte swizzle) the tcgen05 GEMM loads it through.
-struct Bf16Pair {
-  void* hi = nullptr;   // __nv_bfloat16 [rows][ld]
+struct F16Pair {
+  void* hi = nullptr;   // __half [rows][ld]
   void* lo = nullptr;
   int rows = 0, ld = 0, box_rows = 0;
   alignas(64) unsigned char map_hi[128];
@@ -58,7 +58,7 @@ struct GemmSeg {
   int lda;
   int k;            // padded K of this segment in the weight layout (multiple of KPAD)
   int k_valid;      // readable columns of a (multiple of 4, <= k); the rest reads as zero
-  const Bf16Pair* b = nullptr;   // bf16 hi/lo twin of a (tensor-core path), or null
+  const F16Pair* b = nullptr;   // fp16 hi/lo twin of a (tensor-core path), or null
 };
 struct GemmArgs {
   GemmSeg seg[3];
@@ -74,14 +74,14 @@ struct GemmArgs {
   int ldc;
   int M, N;             // N multiple of NPAD
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
-  const Bf16Pair* wb = nullptr;  // bf16 hi/lo twin of w (tensor-core path), or null
+  const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
 };
 struct Ctx;
-int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st);   // tcgen05 when every operand has a bf16 twin
+int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st);   // tcgen05 when every operand has an fp16 twin
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
-int make_tmap_bf16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows);
-int launch_split_bf16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
+int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows);
+int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
 // ---------------------------------------------------------------- context
 struct Phase {
@@ -119,10 +119,12 @@ struct Ctx {
   float *v_a, *v_s, *v_g;      // [Ap]
   float *embed;                // [V][Ep]
   int NVA;                     // padded rows of Wva
-  // bf16 hi/lo twins for the tcgen05 GEMMs
+  // fp16 hi/lo twins for the tcgen05 GEMMs
   bool use_tc = true;
-  Bf16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b, embed_b;
-  Bf16Pair h1_b, h2_b, xt_b, s_t_b, h1n_b, g_t_b, att_b, h2n_b;
+  F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b, embed_b;
+  F16Pair WU_b, WU2_b, Wva_b;   // prologue weights
+  F16Pair ds_b, img_b;          // prologue activations: slot rows [b*L*R][Fp], image descriptors [n_img][Fp]
+  F16Pair h1_b, h2_b, xt_b, s_t_b, h1n_b, g_t_b, att_b, h2n_b;
   // verb table (device CSR)
   int64_t* vt_keys = nullptr; int32_t* vt_off = nullptr; int32_t* vt_idx = nullptr; int vt_n = 0;
   // prologue products (per batch)

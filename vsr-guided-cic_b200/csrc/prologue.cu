@@ -6,11 +6,27 @@
 //   P[b,l,r] = att_va.weight . det_seqs[b,l,r,:]                   :161, :242
 //   U[b]     = S1[:, img cols] . img[b] + stacked biases           :151-152, :181 (img part of input_1)
 //   U2[b]    = lstm_cell_2.weight_ih[:, img cols] . img[b]         :174 (img_second_lstm only)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace vsr {
 
 namespace {
+
+struct PairOut { __half* hi; __half* lo; int ld; };
+__device__ __forceinline__ void store_pair4(const PairOut& o, size_t i, const float4& v) {
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  __half h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float xv = fminf(fmaxf(x[j], -65504.f), 65504.f);   // fp16 range (saturate, never inf)
+    h[j] = __float2half_rn(xv);
+    l[j] = __float2half_rn(xv - __half2float(h[j]));
+  }
+  *reinterpret_cast<uint2*>(o.hi + i) = *reinterpret_cast<const uint2*>(h);
+  *reinterpret_cast<uint2*>(o.lo + i) = *reinterpret_cast<const uint2*>(l);
+}
 
 // dst[r0+r][c0+c] = src[r][sc0+c]
 __global__ void k_pack_block(float* __restrict__ dst, int ld_dst, int r0, int c0,
@@ -29,8 +45,9 @@ __global__ void k_pack_bias(float* __restrict__ dst, int o0, const float* __rest
 
 // one warp per row: flag[row] = (sum_f x[row][f] != 0).  Row r of image/caption g lives at
 // base + g*group_stride + (r % rows_per_group)*F.
+// Optionally also writes the row's fp16 hi/lo split (operand of the tcgen05 att_va projection).
 __global__ void k_row_valid(const float* __restrict__ x, int64_t group_stride, int rows_per_group,
-                            int total_rows, int F, uint8_t* __restrict__ flag) {
+                            int total_rows, int F, uint8_t* __restrict__ flag, PairOut split) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= total_rows) return;
@@ -39,6 +56,7 @@ __global__ void k_row_valid(const float* __restrict__ x, int64_t group_stride, i
   for (int f = lane * 4; f < F; f += 128) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p + f));
     s += (v.x + v.y) + (v.z + v.w);
+    if (split.hi != nullptr) store_pair4(split, (size_t)row * split.ld + f, v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -47,7 +65,7 @@ __global__ void k_row_valid(const float* __restrict__ x, int64_t group_stride, i
 
 // img[g][f] = sum_d det[g][d][f] / count(valid rows of g); one thread per float4 column.
 __global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D, int F,
-                       const uint8_t* __restrict__ valid, float* __restrict__ img, int ld_img) {
+                       const uint8_t* __restrict__ valid, float* __restrict__ img, int ld_img, PairOut split) {
   const int g = blockIdx.y;
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (f >= F) return;
@@ -60,7 +78,9 @@ __global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D,
     cnt += valid[g * D + d];
   }
   const float n = (float)cnt;
-  *reinterpret_cast<float4*>(img + (size_t)g * ld_img + f) = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
+  const float4 o = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
+  *reinterpret_cast<float4*>(img + (size_t)g * ld_img + f) = o;
+  if (split.hi != nullptr) store_pair4(split, (size_t)g * split.ld + f, o);
 }
 
 }  // namespace
@@ -152,15 +172,17 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   VSR_TRY(pack_bias(c, c->v_g, 0, w[27], nullptr, A, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->embed, 0, sizeof(float) * (size_t)V * Ep, st));
   VSR_TRY(pack_block(c, c->embed, Ep, 0, 0, w[0], E, 0, V, E, st));
-  // bf16 hi/lo twins of the per-step weights and of the embedding table (tcgen05 operands)
-  struct Tw { const float* f; Bf16Pair* b; size_t n; };
-  const Tw tw[] = {{c->WA, &c->WA_b, (size_t)c->NA * c->KA}, {c->WB1, &c->WB1_b, (size_t)c->NB1 * Hp},
+  // fp16 hi/lo twins of the per-step weights and of the embedding table (tcgen05 operands)
+  struct Tw { const float* f; F16Pair* b; size_t n; };
+  const Tw tw[] = {{c->WU, &c->WU_b, (size_t)c->NA * c->Fp}, {c->WU2, &c->WU2_b, (size_t)c->ND * c->Fp},
+                   {c->Wva, &c->Wva_b, (size_t)c->NVA * c->Fp},
+                   {c->WA, &c->WA_b, (size_t)c->NA * c->KA}, {c->WB1, &c->WB1_b, (size_t)c->NB1 * Hp},
                    {c->WB2, &c->WB2_b, (size_t)c->NB2 * Hp}, {c->WC, &c->WC_b, (size_t)c->NC * Hp},
                    {c->WD, &c->WD_b, (size_t)c->ND * c->KD}, {c->WE, &c->WE_b, (size_t)c->NE * Hp},
                    {c->embed, &c->embed_b, (size_t)V * Ep}};
   for (const Tw& t : tw) {
-    if (t.b->hi == nullptr) continue;
-    VSR_TRY(launch_split_bf16(t.f, t.b->hi, t.b->lo, t.n, st));
+    if (t.b->hi == nullptr || t.f == nullptr) continue;
+    VSR_TRY(launch_split_f16(t.f, t.b->hi, t.b->lo, t.n, st));
     c->launches++;
   }
   return VSR_OK;
@@ -173,46 +195,49 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
   // validity of detection rows and slot rows
   {
     const int rows = n_img * D;
-    k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid);
+    const PairOut none{nullptr, nullptr, 0};
+    k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, none);
     VSR_CHECK_CUDA(cudaGetLastError());
     const int srows = b * L * R;
+    const PairOut dsp{c->use_tc ? (__half*)c->ds_b.hi : nullptr, (__half*)c->ds_b.lo, c->Fp};
     k_row_valid<<<(int)(((size_t)srows * 32 + 255) / 256), 256, 0, st>>>(c->det_seqs, (int64_t)L * R * F, L * R,
-                                                                          srows, F, c->seq_valid);
+                                                                          srows, F, c->seq_valid, dsp);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches += 2;
   }
   // image descriptor
   {
     dim3 grid((F / 4 + 127) / 128, n_img);
-    k_pool<<<grid, 128, 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp);
+    const PairOut ip{c->use_tc ? (__half*)c->img_b.hi : nullptr, (__half*)c->img_b.lo, c->Fp};
+    k_pool<<<grid, 128, 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches++;
   }
   // U = WU . img + biases ; U2 likewise
   {
     GemmArgs g{};
-    g.nseg = 1; g.seg[0] = {c->img, c->Fp, c->Fp, c->Fp};
-    g.w = c->WU; g.ldw = c->Fp; g.bias = c->bU;
+    g.nseg = 1; g.seg[0] = {c->img, c->Fp, c->Fp, c->Fp, &c->img_b};
+    g.w = c->WU; g.ldw = c->Fp; g.bias = c->bU; g.wb = &c->WU_b;
     g.c = c->U; g.ldc = c->NA; g.M = n_img; g.N = c->NA;
-    VSR_TRY(launch_gemm_simt(g, st));
+    VSR_TRY(launch_gemm(c, g, st));
     c->launches++;
     if (c->d.img_second_lstm) {
       GemmArgs g2{};
-      g2.nseg = 1; g2.seg[0] = {c->img, c->Fp, c->Fp, c->Fp};
-      g2.w = c->WU2; g2.ldw = c->Fp;
+      g2.nseg = 1; g2.seg[0] = {c->img, c->Fp, c->Fp, c->Fp, &c->img_b};
+      g2.w = c->WU2; g2.ldw = c->Fp; g2.wb = &c->WU2_b;
       g2.c = c->U2; g2.ldc = c->ND; g2.M = n_img; g2.N = c->ND;
-      VSR_TRY(launch_gemm_simt(g2, st));
+      VSR_TRY(launch_gemm(c, g2, st));
       c->launches++;
     }
   }
   // P = att_va . det_seqs rows (tiles of padding rows are skipped)
   {
     GemmArgs g{};
-    g.nseg = 1; g.seg[0] = {c->det_seqs, F, c->Fp, F};
-    g.w = c->Wva; g.ldw = c->Fp;
+    g.nseg = 1; g.seg[0] = {c->det_seqs, F, c->Fp, F, &c->ds_b};
+    g.w = c->Wva; g.ldw = c->Fp; g.wb = &c->Wva_b;
     g.c = c->P; g.ldc = c->NVA; g.M = b * L * R; g.N = c->NVA;
     g.row_skip = c->seq_valid;
-    VSR_TRY(launch_gemm_simt(g, st));
+    VSR_TRY(launch_gemm(c, g, st));
     c->launches++;
   }
   return VSR_OK;

@@ -21,25 +21,25 @@ static float* dev_rand(size_t n, float scale, unsigned seed) {
   float* d; CK(cudaMalloc(&d, n * 4)); CK(cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice));
   return d;
 }
-static void make_pair(Bf16Pair* b, const float* f, int rows, int ld, int box) {
+static void make_pair(F16Pair* b, const float* f, int rows, int ld, int box) {
   CK(cudaMalloc(&b->hi, (size_t)rows * ld * 2)); CK(cudaMalloc(&b->lo, (size_t)rows * ld * 2));
   b->rows = rows; b->ld = ld; b->box_rows = box;
-  VK(launch_split_bf16(f, b->hi, b->lo, (size_t)rows * ld, 0));
-  VK(make_tmap_bf16(b->map_hi, b->hi, rows, ld, ld, box));
-  VK(make_tmap_bf16(b->map_lo, b->lo, rows, ld, ld, box));
+  VK(launch_split_f16(f, b->hi, b->lo, (size_t)rows * ld, 0));
+  VK(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box));
+  VK(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box));
 }
 
 static int run_case(int M, int N, int nseg, const int* ks, bool extras, int BN) {
   const int Mp = (M + 127) / 128 * 128;
   int K = 0; for (int s = 0; s < nseg; ++s) K += ks[s];
   float* W = dev_rand((size_t)N * K, 0.05f, 1);
-  Bf16Pair wb{}; make_pair(&wb, W, N, K, BN);
+  F16Pair wb{}; make_pair(&wb, W, N, K, BN);
   GemmArgs g{};
   g.nseg = nseg;
-  Bf16Pair ab[3];
+  F16Pair ab[3];
   for (int s = 0; s < nseg; ++s) {
     float* A = dev_rand((size_t)Mp * ks[s], 1.0f, 10 + s);
-    memset(&ab[s], 0, sizeof(Bf16Pair));
+    memset(&ab[s], 0, sizeof(F16Pair));
     make_pair(&ab[s], A, Mp, ks[s], 128);
     g.seg[s] = {A, ks[s], ks[s], ks[s], &ab[s]};
   }

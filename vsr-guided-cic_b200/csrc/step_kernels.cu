@@ -5,7 +5,7 @@
 #include <float.h>
 #include <math.h>
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -15,13 +15,14 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// store x as fp32 and as the error-compensated bf16 pair the tcgen05 GEMMs consume
-struct PairOut { __nv_bfloat16* hi; __nv_bfloat16* lo; };
+// store x as fp32 and as the error-compensated fp16 pair the tcgen05 GEMMs consume
+struct PairOut { __half* hi; __half* lo; };
 __device__ __forceinline__ void store_pair(const PairOut& o, size_t i, float v) {
   if (o.hi == nullptr) return;
-  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  v = fminf(fmaxf(v, -65504.f), 65504.f);   // fp16 range (saturate, never inf)
+  const __half h = __float2half_rn(v);
   o.hi[i] = h;
-  o.lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+  o.lo[i] = __float2half_rn(v - __half2float(h));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -417,10 +418,10 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
 }  // namespace
 
 // ---------------------------------------------------------------- one decoder step (host side)
-static PairOut pair_out(const Ctx* c, const Bf16Pair& b) {
+static PairOut pair_out(const Ctx* c, const F16Pair& b) {
   PairOut o;
-  o.hi = c->use_tc ? (__nv_bfloat16*)b.hi : nullptr;
-  o.lo = c->use_tc ? (__nv_bfloat16*)b.lo : nullptr;
+  o.hi = c->use_tc ? (__half*)b.hi : nullptr;
+  o.lo = c->use_tc ? (__half*)b.lo : nullptr;
   return o;
 }
 

@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = {
     "vsr_forward_teacher": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "vsr_greedy": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "vsr_launch_count": (c_i64, [c_vp]),
+    "vsr_gemm_kind": (ctypes.c_char_p, [c_vp]),
     "vsr_set_profiling": (ctypes.c_int, [c_vp, c_i32]),
     "vsr_get_phase_times": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_f),
                                            ctypes.POINTER(c_i32), c_i32]),

@@ -225,6 +225,9 @@ class DecoderEngine:
     def launch_count(self) -> int:
         return int(self.lib.vsr_launch_count(self.handle))
 
+    def gemm_kind(self) -> str:
+        return self.lib.vsr_gemm_kind(self.handle).decode()
+
     def set_profiling(self, on: bool):
         _lib.check(self.lib, self.lib.vsr_set_profiling(self.handle, int(on)))
 
