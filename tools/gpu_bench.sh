@@ -9,7 +9,7 @@ echo "bench rc=$?"; cat gpurun_out/bench_$R.json; tail -5 gpurun_out/bench_$R.er
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 900 --csv \
     --log-file gpurun_out/launches_$R.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_$R.log 2>&1
 echo "ncu launches rc=$?"
-for K in k_gemm_simt k_attend k_softmax_topk; do
+for K in k_gemm_tc k_attend k_softmax_topk; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 25 -c 3 -f \
       -o gpurun_out/prof_${K}_$R python tools/perf_probe.py > gpurun_out/ncu_${K}_$R.log 2>&1
   echo "ncu $K rc=$?"

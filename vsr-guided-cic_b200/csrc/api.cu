@@ -84,7 +84,7 @@ int ensure_rows(Ctx* c, int rows) {
   if (rows <= c->cap_rows) return VSR_OK;
   const int cap = round_up(rows, MPAD);
   float** bufs[] = {&c->h1, &c->c1, &c->h2, &c->c2, &c->h1n, &c->c1n, &c->h2n, &c->c2n, &c->xt, &c->pre1,
-                    &c->s_t, &c->g_t, &c->sent, &c->hb, &c->ga, &c->att, &c->pre2, &c->logits, &c->gate_lp,
+                    &c->s_t, &c->g_t, &c->gq, &c->sent, &c->hb, &c->ga, &c->att, &c->pre2, &c->logits, &c->gate_lp,
                     &c->row_max, &c->row_lsum};
   for (float** p : bufs) { dev_free(c, *p); *p = nullptr; }
   dev_free(c, c->ptr); dev_free(c, c->ptrn); dev_free(c, c->forced); dev_free(c, c->cand); dev_free(c, c->word_in);
@@ -94,7 +94,7 @@ int ensure_rows(Ctx* c, int rows) {
   ALLOC_F(c->h1n, n * c->Hp); ALLOC_F(c->c1n, n * c->Hp); ALLOC_F(c->h2n, n * c->Hp); ALLOC_F(c->c2n, n * c->Hp);
   ALLOC_F(c->xt, n * c->Ep);
   ALLOC_F(c->pre1, n * c->NA);
-  ALLOC_F(c->s_t, n * c->Hp); ALLOC_F(c->g_t, n * c->Hp);
+  ALLOC_F(c->s_t, n * c->Hp); ALLOC_F(c->g_t, n * c->Hp); ALLOC_F(c->gq, n * c->Hp);
   ALLOC_F(c->sent, n * c->NB1); ALLOC_F(c->hb, n * c->NB2); ALLOC_F(c->ga, n * c->NC);
   ALLOC_F(c->att, n * c->Fp); ALLOC_F(c->pre2, n * c->ND); ALLOC_F(c->logits, n * c->NE);
   ALLOC_F(c->gate_lp, n * 2); ALLOC_F(c->row_max, n); ALLOC_F(c->row_lsum, n);
@@ -150,14 +150,14 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   VSR_CHECK_CUDA(cudaGetDevice(&c->device));
   c->V = d->vocab_size; c->E = d->input_encoding_size; c->H = d->rnn_size; c->F = d->det_feat_size; c->A = d->att_size;
   c->Hp = round_up(c->H, KPAD); c->Ep = round_up(c->E, KPAD); c->Fp = round_up(c->F, KPAD); c->Ap = round_up(c->A, KPAD);
-  c->NA = round_up(6 * c->H, NPAD);
+  c->NA = 6 * c->Hp;                       // gate-interleaved: 6 gates x Hp units (multiple of 192 and 128)
   c->oB1_sa = c->Fp;
   c->NB1 = round_up(c->oB1_sa + c->A, NPAD);
-  c->oB2_ha = c->Hp;
+  c->oB2_ha = round_up(c->Hp, 128);        // hg block padded to whole 128-column tiles (fused g_t epilogue)
   c->oB2_p2 = c->oB2_ha + c->Ap;
-  c->NB2 = round_up(c->oB2_p2 + 4 * c->H, NPAD);
+  c->NB2 = round_up(c->oB2_p2 + 4 * c->Hp, NPAD);
   c->NC = round_up(c->A, NPAD);
-  c->ND = round_up(4 * c->H, NPAD);
+  c->ND = 4 * c->Hp;                       // gate-interleaved: 4 gates x Hp units (multiple of 256)
   c->NE = round_up(c->V, NPAD);
   c->NVA = round_up(c->A, NPAD);
   c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Ep + c->Hp;
@@ -182,12 +182,13 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // in flight, 3-stage ring); VSRDEC_BN=256 switches all of them for experiments
   int bn = 128;
   if (const char* e = getenv("VSRDEC_BN")) bn = atoi(e) == 256 ? 256 : 128;
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, bn)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn));
+  // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn));
   VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, bn));
-  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, bn)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn));
   VSR_TRY(alloc_pair(c, &c->embed_b, c->V, c->Ep, 8));
-  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, bn)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn));
-  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, bn));
+  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn));
+  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128));
   VSR_TRY(pack_weights(c, w, 0));
   VSR_CHECK_CUDA(cudaStreamSynchronize(0));
   return VSR_OK;

@@ -60,6 +60,27 @@ struct GemmSeg {
   int k_valid;      // readable columns of a (multiple of 4, <= k); the rest reads as zero
   const F16Pair* b = nullptr;   // fp16 hi/lo twin of a (tensor-core path), or null
 };
+// Column of (gate g, hidden unit u) in a gate-interleaved LSTM pre-activation row with NG gates:
+// 32-unit chunks, each laid out as 4 sub-blocks of [gate][8 units], so that one 128 x (NG*32) tensor-core
+// tile holds every gate of its 32 units and the cell math can run in the GEMM epilogue.
+__host__ __device__ inline int cell_col(int g, int u, int ng) {
+  return (u >> 5) * (ng * 32) + ((u >> 3) & 3) * (ng * 8) + g * 8 + (u & 7);
+}
+
+// Optional epilogue fusion of the tensor-core GEMM (ignored by the FFMA twin, whose callers run the
+// stand-alone pointwise kernels instead).
+struct FusedCell {
+  int mode = 0;                 // 0 = plain, 1 = LSTM cell 1 (+ sentinel gate, 6 gates), 2 = LSTM cell 2 (4 gates)
+  const float* c_old = nullptr; float* c_new = nullptr; float* h_new = nullptr;
+  void *h_hi = nullptr, *h_lo = nullptr;
+  float* s_new = nullptr; void *s_hi = nullptr, *s_lo = nullptr;   // mode 1: s_t = sig(s) * tanh(c1')
+  float* gq = nullptr;                                              // mode 1: shift-gate pre-activation (input_1 part)
+  int ld_state = 0;
+  // plain mode only: on output columns [0, gt_cols) write g_t = sig(gq + acc) * tanh(c1') instead of acc
+  int gt_cols = 0; const float* gt_gq = nullptr; const float* gt_c1n = nullptr;
+  float* g_t = nullptr; void *g_hi = nullptr, *g_lo = nullptr;
+};
+
 struct GemmArgs {
   GemmSeg seg[3];
   int nseg;
@@ -75,11 +96,14 @@ struct GemmArgs {
   int M, N;             // N multiple of NPAD
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
   const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
+  FusedCell cell;               // epilogue fusion (tensor-core path only)
 };
 struct Ctx;
-int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st);   // tcgen05 when every operand has an fp16 twin
+// tcgen05 when every operand has an fp16 twin, else FFMA; g2 = optional independent problem sharing the launch
+int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st, const GemmArgs* g2 = nullptr);
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t st);
+int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st);
+bool gemm_uses_tc(const Ctx* c, const GemmArgs& g);
 int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows);
 int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
@@ -147,6 +171,7 @@ struct Ctx {
   int32_t *ptr, *ptrn;               // slot pointer per row
   float *pre1;                       // [rows][NA]
   float *s_t, *g_t;                  // [rows][Hp]
+  float *gq;                         // [rows][Hp] shift-gate pre-activation, input_1 part (W1_ig . input_1 + biases)
   float *sent;                       // [rows][NB1] sentinel (F) | sa (A)
   float *hb;                         // [rows][NB2] hg (H) | ha (A) | pre2_h1 (4H)
   float *ga;                         // [rows][NC]

@@ -102,10 +102,17 @@ __global__ void __launch_bounds__(THREADS) k_gemm_simt(const GemmArgs g) {
 
 }  // namespace
 
-int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st) {
+bool gemm_uses_tc(const Ctx* c, const GemmArgs& g) {
   bool tc = c->use_tc && g.wb != nullptr && g.wb->hi != nullptr;
   for (int s = 0; s < g.nseg && tc; ++s) tc = g.seg[s].b != nullptr && g.seg[s].b->hi != nullptr;
-  return tc ? launch_gemm_tc(g, st) : launch_gemm_simt(g, st);
+  return tc;
+}
+
+int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st, const GemmArgs* g2) {
+  if (gemm_uses_tc(c, g) && (g2 == nullptr || gemm_uses_tc(c, *g2))) return launch_gemm_tc(g, g2, st);
+  VSR_TRY(launch_gemm_simt(g, st));
+  if (g2 != nullptr) VSR_TRY(launch_gemm_simt(*g2, st));
+  return VSR_OK;
 }
 
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st) {

@@ -32,7 +32,8 @@ constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;
 
 template <int BN> struct TcCfg {
-  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kStages = (BN == 128) ? 3 : 2;
+  static constexpr int kTmemCols = (BN == 128) ? 128 : 256;   // power of two >= BN
   static constexpr int kABytes = BM * BK * 2;            // 16 KB
   static constexpr int kWBytes = BN * BK * 2;            // 16 / 32 KB
   static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
@@ -107,20 +108,69 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct TcParams {
+// tcgen05.ld of 8 consecutive fp32 columns of this warp's 32 TMEM lanes (no wait)
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// 8 consecutive fp32 values -> fp32 store + fp16 hi/lo stores (16-byte vectors)
+__device__ __forceinline__ void store8(float* f32, __half* hi, __half* lo, size_t off, const float (&v)[8]) {
+  if (f32 != nullptr) {
+    *reinterpret_cast<float4*>(f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(f32 + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (hi != nullptr) {
+    __align__(16) __half h[8];
+    __align__(16) __half l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float x = fminf(fmaxf(v[j], -65504.f), 65504.f);
+      h[j] = __float2half_rn(x);
+      l[j] = __float2half_rn(x - __half2float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+enum { EPI_PLAIN = 0, EPI_LSTM1 = 1, EPI_LSTM2 = 2 };
+
+// One GEMM problem.  Up to two independent problems (same tile shape) share a launch.
+struct TcProblem {
   CUtensorMap a_hi[3], a_lo[3], w_hi, w_lo;
   int nseg;
   int kblocks[3];
+  int n_tiles, m_tiles, M;
+  const uint8_t* row_skip;
+  // plain epilogue: C = acc + bias[n] + rowadd[(row/row_div)*rowadd_mul][n] + cadd[row][n]
   const float* bias;
   const float* rowadd; int ld_rowadd, row_div, rowadd_mul;
   const float* cadd; int ld_cadd;
   float* c; int ldc;
-  int M;
-  const uint8_t* row_skip;
+  // fused LSTM-cell epilogues (gate-interleaved output columns, see cell_col() in common.cuh)
+  int mode;
+  const float* c_old; float* c_new; float* h_new; __half* h_hi; __half* h_lo;
+  float* s_new; __half* s_hi; __half* s_lo; float* gq;
+  int ld_state;
+  // fused g_t = sig(gq + acc) * tanh(c1') on the tiles with n0 < gt_cols (plain epilogue elsewhere)
+  int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; __half* g_hi; __half* g_lo;
+};
+struct TcParams {
+  TcProblem pr[2];
+  int nprob;
 };
 
 template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcParams params) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
@@ -129,7 +179,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   __shared__ uint32_t tmem_base_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  // tile of this CTA: problems back to back; consecutive CTAs walk the M tiles of one W tile (L2 reuse)
+  int t = blockIdx.x;
+  const int tiles0 = params.pr[0].n_tiles * params.pr[0].m_tiles;
+  const int pi = (params.nprob > 1 && t >= tiles0) ? 1 : 0;
+  t -= pi * tiles0;
+  const TcProblem& p = params.pr[pi];
+  const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+  const int m0 = m_tile * BM, n0 = n_tile * BN;
 
   if (p.row_skip != nullptr) {   // all-padding row tiles produce nothing (block-uniform)
     int any = 0;
@@ -150,7 +207,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -208,16 +265,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
     const int row = m0 + q * 32 + lane;
     const bool live = row < p.M;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float* radd = (p.rowadd != nullptr && live)
                             ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
     const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
-    float* crow = p.c + (size_t)row * p.ldc;
+
+    if (p.mode == EPI_PLAIN) {
+      float* crow = p.c + (size_t)row * p.ldc;
+      const bool gt_tile = n0 < p.gt_cols;
 #pragma unroll 1
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), r);
-      const int n = n0 + ch * 32;
-      if (live) {
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tlane + (uint32_t)(ch * 32), r);
+        const int n = n0 + ch * 32;
+        if (!live) continue;
+        if (gt_tile) {
+          // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n + j >= p.ld_state) break;       // hg block is padded up to a whole tile
+            float gq[8], cc[8], o[8];
+            load8(p.gt_gq + (size_t)row * p.ld_state + n + j, gq);
+            load8(p.gt_c1n + (size_t)row * p.ld_state + n + j, cc);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u] = sigmoidf_(gq[u] + __uint_as_float(r[j + u])) * tanhf(cc[u]);
+            store8(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n + j, o);
+          }
+          continue;
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -237,13 +312,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
           *reinterpret_cast<float4*>(crow + n + j) = o;
         }
       }
+    } else {
+      // Fused LSTM cell.  The tile's BN = NG*32 columns hold NG gates x 32 units as 4 sub-blocks of
+      // [gate][8 units] (cell_col()).  LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq),
+      // LSTM2: NG = 4.  pre = acc + bias + rowadd + cadd ; then the cell math of nn.LSTMCell.
+      constexpr int NG = BN / 32;
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {
+        uint32_t r[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) tmem_ld8_nowait(tlane + (uint32_t)(sub * NG * 8 + g * 8), r[g]);
+        tmem_ld_wait();
+        if (!live) continue;
+        const int ncol = n0 + sub * NG * 8;                 // first output column of this sub-block
+        const int unit0 = n_tile * 32 + sub * 8;            // first hidden unit of this sub-block
+        float pre[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float add[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pre[g][u] = __uint_as_float(r[g][u]);
+          if (p.bias != nullptr) { load8(p.bias + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+          if (radd != nullptr) { load8(radd + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+          if (cadd != nullptr) { load8(cadd + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+        }
+        const size_t so = (size_t)row * p.ld_state + unit0;
+        float cold[8], cn[8], hn[8];
+        load8(p.c_old + so, cold);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoidf_(pre[0][u]), fg = sigmoidf_(pre[1][u]), gg = tanhf(pre[2][u]),
+                      og = sigmoidf_(pre[3][u]);
+          cn[u] = fg * cold[u] + ig * gg;
+          hn[u] = og * tanhf(cn[u]);
+        }
+        store8(p.c_new, nullptr, nullptr, so, cn);
+        store8(p.h_new, p.h_hi, p.h_lo, so, hn);
+        if constexpr (NG == 6) {
+          float sv[8], gq[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { sv[u] = sigmoidf_(pre[4][u]) * tanhf(cn[u]); gq[u] = pre[5][u]; }
+          store8(p.s_new, p.s_hi, p.s_lo, so, sv);
+          store8(p.gq, nullptr, nullptr, so, gq);
+        }
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -302,32 +427,59 @@ int tc_gemm_init() {
   static bool done = false;
   if (done) return VSR_OK;
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes));
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<192>::kSmemBytes));
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
   done = true;
   return VSR_OK;
 }
 
-int launch_gemm_tc(const GemmArgs& g, cudaStream_t st) {
-  VSR_TRY(tc_gemm_init());
-  const int BN = g.wb->box_rows;
-  VSR_REQUIRE((BN == 128 || BN == 256) && g.N % BN == 0, VSR_EINVAL, "launch_gemm_tc: N=%d not a multiple of BN=%d", g.N, BN);
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  p.nseg = g.nseg;
+static int fill_problem(TcProblem* p, const GemmArgs& g, int BN) {
+  VSR_REQUIRE(g.N % BN == 0 && g.M > 0, VSR_EINVAL, "launch_gemm_tc: N=%d not a multiple of BN=%d", g.N, BN);
+  p->nseg = g.nseg;
   for (int s = 0; s < g.nseg; ++s) {
     VSR_REQUIRE(g.seg[s].b != nullptr && g.seg[s].k % BK == 0, VSR_EINVAL, "launch_gemm_tc: segment %d not tensor-core ready", s);
-    memcpy(&p.a_hi[s], g.seg[s].b->map_hi, sizeof(CUtensorMap));
-    memcpy(&p.a_lo[s], g.seg[s].b->map_lo, sizeof(CUtensorMap));
-    p.kblocks[s] = g.seg[s].k / BK;
+    memcpy(&p->a_hi[s], g.seg[s].b->map_hi, sizeof(CUtensorMap));
+    memcpy(&p->a_lo[s], g.seg[s].b->map_lo, sizeof(CUtensorMap));
+    p->kblocks[s] = g.seg[s].k / BK;
   }
-  memcpy(&p.w_hi, g.wb->map_hi, sizeof(CUtensorMap));
-  memcpy(&p.w_lo, g.wb->map_lo, sizeof(CUtensorMap));
-  p.bias = g.bias; p.rowadd = g.rowadd; p.ld_rowadd = g.ld_rowadd; p.row_div = g.row_div > 0 ? g.row_div : 1;
-  p.rowadd_mul = g.rowadd_mul; p.cadd = g.cadd; p.ld_cadd = g.ld_cadd; p.c = g.c; p.ldc = g.ldc; p.M = g.M;
-  p.row_skip = g.row_skip;
-  dim3 grid(g.N / BN, (g.M + BM - 1) / BM);
-  if (BN == 256) k_gemm_tc<256><<<grid, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(p);
-  else k_gemm_tc<128><<<grid, TC_THREADS, TcCfg<128>::kSmemBytes, st>>>(p);
+  memcpy(&p->w_hi, g.wb->map_hi, sizeof(CUtensorMap));
+  memcpy(&p->w_lo, g.wb->map_lo, sizeof(CUtensorMap));
+  p->n_tiles = g.N / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
+  p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
+  p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
+  const FusedCell& f = g.cell;
+  p->mode = f.mode;
+  if (f.mode != 0) {
+    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && BN == 128), VSR_EINVAL,
+                "launch_gemm_tc: fused cell mode %d needs BN=%d", f.mode, f.mode == EPI_LSTM1 ? 192 : 128);
+    p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_hi = (__half*)f.h_hi; p->h_lo = (__half*)f.h_lo;
+    p->s_new = f.s_new; p->s_hi = (__half*)f.s_hi; p->s_lo = (__half*)f.s_lo; p->gq = f.gq;
+  }
+  p->ld_state = f.ld_state;
+  p->gt_cols = f.gt_cols; p->gt_gq = f.gt_gq; p->gt_c1n = f.gt_c1n; p->g_t = f.g_t;
+  p->g_hi = (__half*)f.g_hi; p->g_lo = (__half*)f.g_lo;
+  return VSR_OK;
+}
+
+// g2 (optional) is an independent problem with the same N tile that shares the launch
+int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
+  VSR_TRY(tc_gemm_init());
+  const int BN = g.wb->box_rows;
+  VSR_REQUIRE(BN == 128 || BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc: unsupported N tile %d", BN);
+  VSR_REQUIRE(g2 == nullptr || g2->wb->box_rows == BN, VSR_EINVAL, "launch_gemm_tc: grouped problems need one tile shape");
+  TcParams p;            // ~2.7 KB; passed by value at launch
+  memset(&p, 0, sizeof(p));
+  VSR_TRY(fill_problem(&p.pr[0], g, BN));
+  p.nprob = 1;
+  int tiles = p.pr[0].n_tiles * p.pr[0].m_tiles;
+  if (g2 != nullptr) {
+    VSR_TRY(fill_problem(&p.pr[1], *g2, BN));
+    p.nprob = 2;
+    tiles += p.pr[1].n_tiles * p.pr[1].m_tiles;
+  }
+  if (BN == 256) k_gemm_tc<256><<<tiles, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(p);
+  else if (BN == 192) k_gemm_tc<192><<<tiles, TC_THREADS, TcCfg<192>::kSmemBytes, st>>>(p);
+  else k_gemm_tc<128><<<tiles, TC_THREADS, TcCfg<128>::kSmemBytes, st>>>(p);
   VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }

@@ -36,6 +36,21 @@ __global__ void k_pack_block(float* __restrict__ dst, int ld_dst, int r0, int c0
   if (c < cols && r < rows) dst[(size_t)(r0 + r) * ld_dst + c0 + c] = src[(size_t)r * ld_src + sc0 + c];
 }
 
+// gate-interleaved variants: source row/element r (a hidden unit) goes to row/element cell_col(gate, r, ng)
+__global__ void k_pack_block_perm(float* __restrict__ dst, int ld_dst, int r0, int c0,
+                                  const float* __restrict__ src, int ld_src, int sc0, int rows, int cols,
+                                  int gate, int ng) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c < cols && r < rows)
+    dst[(size_t)(r0 + cell_col(gate, r, ng)) * ld_dst + c0 + c] = src[(size_t)r * ld_src + sc0 + c];
+}
+__global__ void k_pack_bias_perm(float* __restrict__ dst, const float* __restrict__ a,
+                                 const float* __restrict__ b, int n, int gate, int ng) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[cell_col(gate, i, ng)] = a[i] + (b != nullptr ? b[i] : 0.f);
+}
+
 // dst[o0+i] = a[i] (+ b[i])
 __global__ void k_pack_bias(float* __restrict__ dst, int o0, const float* __restrict__ a,
                             const float* __restrict__ b, int n) {
@@ -101,6 +116,22 @@ static int pack_bias(Ctx* c, float* dst, int o0, const float* a, const float* b,
   return VSR_OK;
 }
 
+static int pack_perm(Ctx* c, float* dst, int ld_dst, int r0, int c0, const float* src, int ld_src, int sc0,
+                     int units, int cols, int gate, int ng, cudaStream_t st) {
+  if (units == 0 || cols == 0) return VSR_OK;
+  dim3 grid((cols + 255) / 256, units);
+  k_pack_block_perm<<<grid, 256, 0, st>>>(dst, ld_dst, r0, c0, src, ld_src, sc0, units, cols, gate, ng);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  c->launches++;
+  return VSR_OK;
+}
+static int pack_bias_perm(Ctx* c, float* dst, const float* a, const float* b, int n, int gate, int ng, cudaStream_t st) {
+  k_pack_bias_perm<<<(n + 255) / 256, 256, 0, st>>>(dst, a, b, n, gate, ng);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  c->launches++;
+  return VSR_OK;
+}
+
 // Build the stacked, K-padded weight blocks S1..S7 of SURVEY.md Appendix A from the 28
 // state_dict tensors (order documented in include/vsrdec.h).
 int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
@@ -119,18 +150,21 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WU, 0, sizeof(float) * (size_t)c->NA * c->Fp, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->bU, 0, sizeof(float) * (size_t)c->NA, st));
 
-  // ---- S1 / S2 -> WA, WU, bU.  Row blocks: lstm1 gates i,f,g,o (4H) | W1_is (H) | W1_ig (H)
-  struct Blk { const float* wi; const float* wh; const float* bi; const float* bh; int rows; int r0; bool h_on_old; };
-  const Blk blks[3] = {
-      {w[10], w[11], w[12], w[13], 4 * H, 0, true},      // lstm_cell_1: W_ih, W_hh act on (input_1, h1_old)
-      {w[1], w[3], w[2], w[4], H, 4 * H, true},          // W1_is(input_1) + W1_hs(h1_old)      (:151)
-      {w[22], nullptr, w[23], w[25], H, 5 * H, false}};  // W1_ig(input_1); W1_hg acts on h1' (:181) -> WB2
-  for (const Blk& k : blks) {
-    if (h2f) VSR_TRY(pack_block(c, c->WA, c->KA, k.r0, ka_h2, k.wi, in1, 0, k.rows, H, st));
-    VSR_TRY(pack_block(c, c->WA, c->KA, k.r0, ka_xt, k.wi, in1, c_xt, k.rows, E, st));
-    if (k.h_on_old) VSR_TRY(pack_block(c, c->WA, c->KA, k.r0, ka_h1, k.wh, H, 0, k.rows, H, st));
-    VSR_TRY(pack_block(c, c->WU, c->Fp, k.r0, 0, k.wi, in1, c_img, k.rows, F, st));
-    VSR_TRY(pack_bias(c, c->bU, k.r0, k.bi, k.bh, k.rows, st));
+  // ---- S1 / S2 -> WA, WU, bU.  Six "gates" per hidden unit, rows gate-interleaved (cell_col(g, u, 6)):
+  //      0..3 = lstm_cell_1 i,f,g,o | 4 = sentinel gate (W1_is + W1_hs) | 5 = shift gate, input_1 part (W1_ig)
+  struct Gate { const float* wi; const float* wh; const float* bi; const float* bh; };
+  Gate gates[6];
+  for (int g = 0; g < 4; ++g)       // lstm_cell_1: W_ih / W_hh act on (input_1, h1_old)
+    gates[g] = {w[10] + (size_t)g * H * in1, w[11] + (size_t)g * H * H, w[12] + g * H, w[13] + g * H};
+  gates[4] = {w[1], w[3], w[2], w[4]};           // W1_is(input_1) + W1_hs(h1_old)            (:151)
+  gates[5] = {w[22], nullptr, w[23], w[25]};     // W1_ig(input_1); W1_hg acts on h1' (:181) -> WB2
+  for (int g = 0; g < 6; ++g) {
+    const Gate& k = gates[g];
+    if (h2f) VSR_TRY(pack_perm(c, c->WA, c->KA, 0, ka_h2, k.wi, in1, 0, H, H, g, 6, st));
+    VSR_TRY(pack_perm(c, c->WA, c->KA, 0, ka_xt, k.wi, in1, c_xt, H, E, g, 6, st));
+    if (k.wh != nullptr) VSR_TRY(pack_perm(c, c->WA, c->KA, 0, ka_h1, k.wh, H, 0, H, H, g, 6, st));
+    VSR_TRY(pack_perm(c, c->WU, c->Fp, 0, 0, k.wi, in1, c_img, H, F, g, 6, st));
+    VSR_TRY(pack_bias_perm(c, c->bU, k.bi, k.bh, H, g, 6, st));
   }
   // ---- S3 -> WB1: s_fc (F rows) | att_sa (A rows)
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WB1, 0, sizeof(float) * (size_t)c->NB1 * Hp, st));
@@ -142,19 +176,21 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WB2, 0, sizeof(float) * (size_t)c->NB2 * Hp, st));
   VSR_TRY(pack_block(c, c->WB2, Hp, 0, 0, w[24], H, 0, H, H, st));
   VSR_TRY(pack_block(c, c->WB2, Hp, c->oB2_ha, 0, w[6], H, 0, A, H, st));
-  VSR_TRY(pack_block(c, c->WB2, Hp, c->oB2_p2, 0, w[14], in2, 0, 4 * H, H, st));
+  for (int g = 0; g < 4; ++g)   // lstm2 gates, interleaved like GEMM-D's output (cell_col(g, u, 4))
+    VSR_TRY(pack_perm(c, c->WB2, Hp, c->oB2_p2, 0, w[14] + (size_t)g * H * in2, in2, 0, H, H, g, 4, st));
   // ---- S5 -> WC: att_ga
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WC, 0, sizeof(float) * (size_t)c->NC * Hp, st));
   VSR_TRY(pack_block(c, c->WC, Hp, 0, 0, w[26], H, 0, A, H, st));
   // ---- S6 -> WD: lstm2.W_ih[:, H:H+F] | lstm2.W_hh ; bias b_ih2 + b_hh2
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WD, 0, sizeof(float) * (size_t)c->ND * c->KD, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->bD, 0, sizeof(float) * (size_t)c->ND, st));
-  VSR_TRY(pack_block(c, c->WD, c->KD, 0, 0, w[14], in2, H, 4 * H, F, st));
-  VSR_TRY(pack_block(c, c->WD, c->KD, 0, c->Fp, w[15], H, 0, 4 * H, H, st));
-  VSR_TRY(pack_bias(c, c->bD, 0, w[16], w[17], 4 * H, st));
-  if (img2) {
-    VSR_CHECK_CUDA(cudaMemsetAsync(c->WU2, 0, sizeof(float) * (size_t)c->ND * c->Fp, st));
-    VSR_TRY(pack_block(c, c->WU2, c->Fp, 0, 0, w[14], in2, H + F, 4 * H, F, st));
+  if (img2) VSR_CHECK_CUDA(cudaMemsetAsync(c->WU2, 0, sizeof(float) * (size_t)c->ND * c->Fp, st));
+  for (int g = 0; g < 4; ++g) {
+    const float* wi = w[14] + (size_t)g * H * in2;
+    VSR_TRY(pack_perm(c, c->WD, c->KD, 0, 0, wi, in2, H, H, F, g, 4, st));
+    VSR_TRY(pack_perm(c, c->WD, c->KD, 0, c->Fp, w[15] + (size_t)g * H * H, H, 0, H, H, g, 4, st));
+    VSR_TRY(pack_bias_perm(c, c->bD, w[16] + g * H, w[17] + g * H, H, g, 4, st));
+    if (img2) VSR_TRY(pack_perm(c, c->WU2, c->Fp, 0, 0, wi, in2, H + F, H, F, g, 4, st));
   }
   // ---- S7 -> WE: out_fc
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WE, 0, sizeof(float) * (size_t)c->NE * Hp, st));

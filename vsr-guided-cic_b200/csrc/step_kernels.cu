@@ -37,17 +37,20 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------- LSTM cell 1 + sentinel gate
-// pre1 rows: [i | f | g | o | s | gq] each H wide (gq is consumed later by k_gt).
+// (FFMA-twin path; the tensor-core path runs this math in the GEMM-A epilogue.)
+// pre1 columns are gate-interleaved: gate g of unit u at cell_col(g, u, 6); gates i,f,g,o,s,gq.
 // c1' = sig(f) c1 + sig(i) tanh(g); h1' = sig(o) tanh(c1'); s_t = sig(s) tanh(c1')   (:151-154)
 __global__ void k_lstm1(const float* __restrict__ pre1, int ld_pre, const float* __restrict__ c1,
                         float* __restrict__ h1n, float* __restrict__ c1n, float* __restrict__ s_t,
-                        PairOut h1n_b, PairOut s_t_b, int ld, int H, int rows) {
+                        float* __restrict__ gq, PairOut h1n_b, PairOut s_t_b, int ld, int H, int rows) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (u >= H || n >= rows) return;
   const float* p = pre1 + (size_t)n * ld_pre;
-  const float ig = sigmoidf_(p[u]), fg = sigmoidf_(p[H + u]), gg = tanhf(p[2 * H + u]),
-              og = sigmoidf_(p[3 * H + u]), sg = sigmoidf_(p[4 * H + u]);
+  const float ig = sigmoidf_(p[cell_col(0, u, 6)]), fg = sigmoidf_(p[cell_col(1, u, 6)]),
+              gg = tanhf(p[cell_col(2, u, 6)]), og = sigmoidf_(p[cell_col(3, u, 6)]),
+              sg = sigmoidf_(p[cell_col(4, u, 6)]);
+  gq[(size_t)n * ld + u] = p[cell_col(5, u, 6)];
   const float c = fg * c1[(size_t)n * ld + u] + ig * gg;
   const float tc = tanhf(c);
   c1n[(size_t)n * ld + u] = c;
@@ -59,19 +62,19 @@ __global__ void k_lstm1(const float* __restrict__ pre1, int ld_pre, const float*
 }
 
 // g_t = sig(gq + hg) * tanh(c1')   (:181-182; hg = W1_hg . h1' comes from the h1' GEMM)
-__global__ void k_gt(const float* __restrict__ pre1, int ld_pre, const float* __restrict__ hb, int ld_hb,
+__global__ void k_gt(const float* __restrict__ gq_in, const float* __restrict__ hb, int ld_hb,
                      const float* __restrict__ c1n, float* __restrict__ g_t, PairOut g_t_b, int ld, int H,
                      int rows) {
   const int u = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y;
   if (u >= H || n >= rows) return;
-  const float gq = pre1[(size_t)n * ld_pre + 5 * H + u] + hb[(size_t)n * ld_hb + u];
+  const float gq = gq_in[(size_t)n * ld + u] + hb[(size_t)n * ld_hb + u];
   const float gv = sigmoidf_(gq) * tanhf(c1n[(size_t)n * ld + u]);
   g_t[(size_t)n * ld + u] = gv;
   store_pair(g_t_b, (size_t)n * ld + u, gv);
 }
 
-// LSTM cell 2: pre2 rows [i | f | g | o]   (:177 / :258)
+// LSTM cell 2 (FFMA-twin path): pre2 columns gate-interleaved, cell_col(g, u, 4)   (:177 / :258)
 __global__ void k_lstm2(const float* __restrict__ pre2, int ld_pre, const float* __restrict__ c2,
                         float* __restrict__ h2n, float* __restrict__ c2n, PairOut h2n_b, int ld, int H,
                         int rows) {
@@ -79,8 +82,8 @@ __global__ void k_lstm2(const float* __restrict__ pre2, int ld_pre, const float*
   const int n = blockIdx.y;
   if (u >= H || n >= rows) return;
   const float* p = pre2 + (size_t)n * ld_pre;
-  const float ig = sigmoidf_(p[u]), fg = sigmoidf_(p[H + u]), gg = tanhf(p[2 * H + u]),
-              og = sigmoidf_(p[3 * H + u]);
+  const float ig = sigmoidf_(p[cell_col(0, u, 4)]), fg = sigmoidf_(p[cell_col(1, u, 4)]),
+              gg = tanhf(p[cell_col(2, u, 4)]), og = sigmoidf_(p[cell_col(3, u, 4)]);
   const float c = fg * c2[(size_t)n * ld + u] + ig * gg;
   c2n[(size_t)n * ld + u] = c;
   const float hv = og * tanhf(c);
@@ -431,6 +434,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   VSR_REQUIRE(c->R <= ATT_MAX_R, VSR_EINVAL, "max_detections per slot R=%d > %d", c->R, ATT_MAX_R);
   const bool h2f = c->d.h2_first_lstm != 0;
   const dim3 pw_grid((H + 127) / 128, rows);
+  bool fused = false;   // tensor-core path: cell / gate pointwise math runs inside the GEMM epilogues
 
   {  // A: pre1 = [h2 | xt | h1_old] . WA^T + U[img]
     PhaseScope ps(c, PH_GEMM_A, st);
@@ -443,11 +447,18 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.w = c->WA; g.ldw = c->KA; g.wb = &c->WA_b;
     g.rowadd = c->U; g.ld_rowadd = c->NA; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
+    fused = gemm_uses_tc(c, g);
+    if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
+      g.cell.mode = 1; g.cell.c_old = c->c1; g.cell.c_new = c->c1n; g.cell.h_new = c->h1n;
+      g.cell.h_hi = c->h1n_b.hi; g.cell.h_lo = c->h1n_b.lo;
+      g.cell.s_new = c->s_t; g.cell.s_hi = c->s_t_b.hi; g.cell.s_lo = c->s_t_b.lo;
+      g.cell.gq = c->gq; g.cell.ld_state = c->Hp;
+    }
     VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
-  {
+  if (!fused) {
     PhaseScope ps(c, PH_LSTM1, st);
-    k_lstm1<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->c1, c->h1n, c->c1n, c->s_t, pair_out(c, c->h1n_b),
+    k_lstm1<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->c1, c->h1n, c->c1n, c->s_t, c->gq, pair_out(c, c->h1n_b),
                                      pair_out(c, c->s_t_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
@@ -457,17 +468,19 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.nseg = 1; g.seg[0] = {c->s_t, c->Hp, c->Hp, c->Hp, &c->s_t_b};
     g.w = c->WB1; g.ldw = c->Hp; g.bias = c->bB1; g.wb = &c->WB1_b;
     g.c = c->sent; g.ldc = c->NB1; g.M = rows; g.N = c->NB1;
-    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
     GemmArgs g2{};
     g2.nseg = 1; g2.seg[0] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
     g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b;
     g2.c = c->hb; g2.ldc = c->NB2; g2.M = rows; g2.N = c->NB2;
-    VSR_TRY(launch_gemm(c, g2, st)); c->launches++;
+    if (fused) {   // g_t = sig(gq + W1_hg.h1') * tanh(c1') on the hg column block of the h1' projection
+      g2.cell.gt_cols = c->oB2_ha; g2.cell.gt_gq = c->gq; g2.cell.gt_c1n = c->c1n; g2.cell.g_t = c->g_t;
+      g2.cell.g_hi = c->g_t_b.hi; g2.cell.g_lo = c->g_t_b.lo; g2.cell.ld_state = c->Hp;
+    }
+    VSR_TRY(launch_gemm(c, g, st, &g2)); c->launches += fused ? 1 : 2;   // one grouped launch on tensor cores
   }
-  {
+  if (!fused) {
     PhaseScope ps(c, PH_GT, st);
-    k_gt<<<pw_grid, 128, 0, st>>>(c->pre1, c->NA, c->hb, c->NB2, c->c1n, c->g_t, pair_out(c, c->g_t_b), c->Hp, H,
-                                  rows);
+    k_gt<<<pw_grid, 128, 0, st>>>(c->gq, c->hb, c->NB2, c->c1n, c->g_t, pair_out(c, c->g_t_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // C: ga = att_ga . g_t
@@ -504,9 +517,13 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
       g.rowadd = c->U2; g.ld_rowadd = c->ND; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     }
     g.c = c->pre2; g.ldc = c->ND; g.M = rows; g.N = c->ND;
+    if (fused) {   // LSTM cell 2 in the epilogue
+      g.cell.mode = 2; g.cell.c_old = c->c2; g.cell.c_new = c->c2n; g.cell.h_new = c->h2n;
+      g.cell.h_hi = c->h2n_b.hi; g.cell.h_lo = c->h2n_b.lo; g.cell.ld_state = c->Hp;
+    }
     VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
-  {
+  if (!fused) {
     PhaseScope ps(c, PH_LSTM2, st);
     k_lstm2<<<pw_grid, 128, 0, st>>>(c->pre2, c->ND, c->c2, c->h2n, c->c2n, pair_out(c, c->h2n_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
