@@ -85,7 +85,7 @@ int ensure_rows(Ctx* c, int rows) {
   const int cap = round_up(rows, MPAD);
   float** bufs[] = {&c->h1, &c->c1, &c->h2, &c->c2, &c->h1n, &c->c1n, &c->h2n, &c->c2n, &c->xt, &c->pre1,
                     &c->s_t, &c->g_t, &c->gq, &c->sent, &c->hb, &c->ga, &c->att, &c->pre2, &c->logits, &c->gate_lp,
-                    &c->row_max, &c->row_lsum};
+                    &c->row_max, &c->row_lsum, &c->shift};
   for (float** p : bufs) { dev_free(c, *p); *p = nullptr; }
   dev_free(c, c->ptr); dev_free(c, c->ptrn); dev_free(c, c->forced); dev_free(c, c->cand); dev_free(c, c->word_in);
   c->cap_rows = 0;
@@ -97,7 +97,7 @@ int ensure_rows(Ctx* c, int rows) {
   ALLOC_F(c->s_t, n * c->Hp); ALLOC_F(c->g_t, n * c->Hp); ALLOC_F(c->gq, n * c->Hp);
   ALLOC_F(c->sent, n * c->NB1); ALLOC_F(c->hb, n * c->NB2); ALLOC_F(c->ga, n * c->NC);
   ALLOC_F(c->att, n * c->Fp); ALLOC_F(c->pre2, n * c->ND); ALLOC_F(c->logits, n * c->NE);
-  ALLOC_F(c->gate_lp, n * 2); ALLOC_F(c->row_max, n); ALLOC_F(c->row_lsum, n);
+  ALLOC_F(c->gate_lp, n * 2); ALLOC_F(c->row_max, n); ALLOC_F(c->row_lsum, n); ALLOC_F(c->shift, n);
   VSR_TRY(dev_alloc(c, (void**)&c->ptr, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->ptrn, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));
@@ -115,7 +115,8 @@ int ensure_beam_ws(Ctx* c, int caps, int T) {
   if (caps <= c->cap_caps && T <= c->cap_T) return VSR_OK;
   caps = std::max(caps, c->cap_caps); T = std::max(T, c->cap_T);
   float** fb[] = {&c->seq_lp, &c->seq_lp_n, &c->m0, &c->m1, &c->m0n, &c->m1n, &c->hist_score, &c->hist_lpw, &c->hist_lpg};
-  int32_t** ib[] = {&c->sel_beam, &c->sel_word, &c->sel_gate, &c->hist_parent, &c->hist_word, &c->hist_gate};
+  int32_t** ib[] = {&c->sel_beam, &c->sel_word, &c->sel_gate, &c->sel_beam_n, &c->sel_word_n, &c->sel_gate_n,
+                    &c->hist_parent, &c->hist_word, &c->hist_gate};
   for (float** p : fb) { dev_free(c, *p); *p = nullptr; }
   for (int32_t** p : ib) { dev_free(c, *p); *p = nullptr; }
   c->cap_caps = 0; c->cap_T = 0;
@@ -125,6 +126,9 @@ int ensure_beam_ws(Ctx* c, int caps, int T) {
   VSR_TRY(dev_alloc(c, (void**)&c->sel_beam, sizeof(int32_t) * s));
   VSR_TRY(dev_alloc(c, (void**)&c->sel_word, sizeof(int32_t) * s));
   VSR_TRY(dev_alloc(c, (void**)&c->sel_gate, sizeof(int32_t) * s));
+  VSR_TRY(dev_alloc(c, (void**)&c->sel_beam_n, sizeof(int32_t) * s));
+  VSR_TRY(dev_alloc(c, (void**)&c->sel_word_n, sizeof(int32_t) * s));
+  VSR_TRY(dev_alloc(c, (void**)&c->sel_gate_n, sizeof(int32_t) * s));
   VSR_TRY(dev_alloc(c, (void**)&c->hist_parent, sizeof(int32_t) * hs));
   VSR_TRY(dev_alloc(c, (void**)&c->hist_word, sizeof(int32_t) * hs));
   VSR_TRY(dev_alloc(c, (void**)&c->hist_gate, sizeof(int32_t) * hs));
@@ -137,9 +141,12 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   VSR_REQUIRE(d->vocab_size > 0 && d->rnn_size > 0 && d->att_size > 0 && d->input_encoding_size > 0 &&
                   d->det_feat_size > 0 && d->seq_len > 0,
               VSR_EINVAL, "vsr_create: non-positive dimension");
-  VSR_REQUIRE(d->det_feat_size % 4 == 0, VSR_EINVAL,
-              "vsr_create: det_feat_size=%d must be a multiple of 4 (128-bit feature loads)", d->det_feat_size);
+  VSR_REQUIRE(d->det_feat_size % 4 == 0 && d->att_size % 4 == 0, VSR_EINVAL,
+              "vsr_create: det_feat_size=%d and att_size=%d must be multiples of 4 (128-bit loads)",
+              d->det_feat_size, d->att_size);
   VSR_REQUIRE(d->bos_idx >= 0 && d->bos_idx < d->vocab_size, VSR_EINVAL, "vsr_create: bos_idx out of range");
+  VSR_REQUIRE(d->vocab_size <= 1024 * 48, VSR_EINVAL,
+              "vsr_create: vocab_size=%d > 49152 unsupported (register-resident softmax/top-k row)", d->vocab_size);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   VSR_REQUIRE(e == cudaSuccess && ndev > 0, VSR_ECUDA,
@@ -184,7 +191,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   if (const char* e = getenv("VSRDEC_BN")) bn = atoi(e) == 256 ? 256 : 128;
   // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128
   VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn));
-  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, bn));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128));
   VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn));
   VSR_TRY(alloc_pair(c, &c->embed_b, c->V, c->Ep, 8));
   VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn));
@@ -317,10 +324,9 @@ static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int
     if (tr && tr->step_gate) { io.gate_out = tr->step_gate + (size_t)t * b * k * 2; io.gate_stride = 2; }
     VSR_TRY(run_step(c, io, st));
     const size_t fo = (size_t)t * b * k;
-    VSR_TRY(launch_beam_select(c, t, b, cur, k, eos[0], eos[1], have_forced ? tr->forced_beam + fo : nullptr,
-                               have_forced ? tr->forced_word + fo : nullptr,
-                               have_forced ? tr->forced_gate + fo : nullptr, st));
-    if (t + 1 < T) VSR_TRY(launch_reorder(c, b, cur, k, st));
+    VSR_TRY(launch_beam_step(c, t, b, cur, k, eos[0], eos[1], have_forced ? tr->forced_beam + fo : nullptr,
+                             have_forced ? tr->forced_word + fo : nullptr,
+                             have_forced ? tr->forced_gate + fo : nullptr, t + 1 < T, st));
   }
   VSR_TRY(launch_backtrack(c, b, k, T, out_size, out_words, out_gates, lp_words, lp_gates, st));
   return VSR_OK;

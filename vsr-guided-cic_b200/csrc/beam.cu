@@ -33,7 +33,8 @@ struct BeamArgs {
   const float* gate_lp;
   const float* seq_lp; float* seq_lp_n;
   float *m0, *m1, *m0n, *m1n;
-  int32_t *sel_beam, *sel_word, *sel_gate;        // in: previous step's picks (t>0); out: this step's
+  const int32_t *prev_word, *prev_gate;            // previous step's picks per current slot (t > 0)
+  int32_t *sel_beam, *sel_word, *sel_gate;        // this step's picks (double-buffered against prev_*)
   int32_t *hist_parent, *hist_word, *hist_gate;    // [T][b][k] slices for step t
   float *hist_score, *hist_lpw, *hist_lpg;
   const int32_t *f_beam, *f_word, *f_gate;        // forced selections for step t or null
@@ -41,22 +42,24 @@ struct BeamArgs {
 
 constexpr int MAXC = 2 * VSR_MAX_BEAM * VSR_MAX_BEAM;  // 128 candidates per caption
 
-// one warp per caption
-__global__ void __launch_bounds__(32) k_beam_select(const BeamArgs a) {
-  const int c = blockIdx.x, lane = threadIdx.x;
+struct BeamSmem {
+  float seq[VSR_MAX_BEAM], m0[VSR_MAX_BEAM], m1[VSR_MAX_BEAM], ps[VSR_MAX_BEAM];
+  int full[VSR_MAX_BEAM], pb[VSR_MAX_BEAM], pw[VSR_MAX_BEAM], pg[VSR_MAX_BEAM];
+};
+
+// selection for caption c by one warp; leaves the picks (parent, word, gate) in sh.pb / pw / pg
+__device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh, int c, int lane, bool write) {
   const int k = a.k, cur = a.cur;
-  __shared__ float s_seq[VSR_MAX_BEAM], s_m0[VSR_MAX_BEAM], s_m1[VSR_MAX_BEAM];
-  __shared__ int s_full[VSR_MAX_BEAM];
-  __shared__ int s_pb[VSR_MAX_BEAM], s_pw[VSR_MAX_BEAM], s_pg[VSR_MAX_BEAM];
-  __shared__ float s_ps[VSR_MAX_BEAM];
+  float* s_seq = sh.seq; float* s_m0 = sh.m0; float* s_m1 = sh.m1; float* s_ps = sh.ps;
+  int* s_full = sh.full; int* s_pb = sh.pb; int* s_pw = sh.pw; int* s_pg = sh.pg;
 
   if (lane < cur) {
     float m0 = 1.f, m1 = 1.f, seq = 0.f;
     if (a.t > 0) {
       // sticky masks: a head's mask drops to 0 once the slot's previous token was its EOS (:143-144)
       seq = a.seq_lp[c * k + lane];
-      m0 = a.m0[c * k + lane] * ((int64_t)a.sel_word[c * k + lane] != a.eos0 ? 1.f : 0.f);
-      m1 = a.m1[c * k + lane] * ((int64_t)a.sel_gate[c * k + lane] != a.eos1 ? 1.f : 0.f);
+      m0 = a.m0[c * k + lane] * ((int64_t)a.prev_word[c * k + lane] != a.eos0 ? 1.f : 0.f);
+      m1 = a.m1[c * k + lane] * ((int64_t)a.prev_gate[c * k + lane] != a.eos1 ? 1.f : 0.f);
     }
     s_seq[lane] = seq; s_m0[lane] = m0; s_m1[lane] = m1;
     s_full[lane] = (a.t == 0) ? 1 : (fminf(fmaxf(m0 + m1, 0.f), 1.f) != 0.f);
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(32) k_beam_select(const BeamArgs a) {
   }
   __syncwarp();
 
-  if (lane < k) {
+  if (lane < k && write) {
     const int j = s_pb[lane], word = s_pw[lane], g = s_pg[lane];
     const int row = c * cur + j;
     const int o = c * k + lane;
@@ -154,30 +157,27 @@ struct AdvanceArgs {
   uint4 *h1_hi, *h1_lo, *h2_hi, *h2_lo, *xt_hi, *xt_lo;
 };
 
-__global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
-  const int n = blockIdx.x;
-  const int c = n / a.k;
-  const int p = a.parent != nullptr ? c * a.cur + a.parent[n] : n;
+// copy the state of parent row p into new row n, embed the next input word, update the slot pointer
+__device__ __forceinline__ void advance_row(const AdvanceArgs& a, int n, int p, int64_t w, int gate_shift) {
   const size_t so = (size_t)p * a.Hp, dof = (size_t)n * a.Hp;
-  for (int i = threadIdx.x * 4; i < a.Hp; i += 256 * 4) {
+  for (int i = threadIdx.x * 4; i < a.Hp; i += blockDim.x * 4) {
     *reinterpret_cast<float4*>(a.h1 + dof + i) = *reinterpret_cast<const float4*>(a.h1n + so + i);
     *reinterpret_cast<float4*>(a.c1 + dof + i) = *reinterpret_cast<const float4*>(a.c1n + so + i);
     *reinterpret_cast<float4*>(a.h2 + dof + i) = *reinterpret_cast<const float4*>(a.h2n + so + i);
     *reinterpret_cast<float4*>(a.c2 + dof + i) = *reinterpret_cast<const float4*>(a.c2n + so + i);
   }
-  int64_t w = a.word32 != nullptr ? (int64_t)a.word32[n] : a.word64[(size_t)n * a.word64_stride];
   w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
   const float* er = a.embed + (size_t)w * a.Ep;
-  for (int i = threadIdx.x * 4; i < a.Ep; i += 256 * 4)
+  for (int i = threadIdx.x * 4; i < a.Ep; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(a.xt + (size_t)n * a.Ep + i) = *reinterpret_cast<const float4*>(er + i);
   if (a.h1_hi != nullptr) {
     const size_t sv = (size_t)p * (a.Hp / 8), dv = (size_t)n * (a.Hp / 8);
-    for (int i = threadIdx.x; i < a.Hp / 8; i += 256) {
+    for (int i = threadIdx.x; i < a.Hp / 8; i += blockDim.x) {
       a.h1_hi[dv + i] = a.h1n_hi[sv + i]; a.h1_lo[dv + i] = a.h1n_lo[sv + i];
       a.h2_hi[dv + i] = a.h2n_hi[sv + i]; a.h2_lo[dv + i] = a.h2n_lo[sv + i];
     }
     const size_t ev = (size_t)w * (a.Ep / 8), xv = (size_t)n * (a.Ep / 8);
-    for (int i = threadIdx.x; i < a.Ep / 8; i += 256) {
+    for (int i = threadIdx.x; i < a.Ep / 8; i += blockDim.x) {
       a.xt_hi[xv + i] = a.emb_hi[ev + i]; a.xt_lo[xv + i] = a.emb_lo[ev + i];
     }
   }
@@ -185,11 +185,31 @@ __global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
     int s;
     if (a.fixed_slot >= 0) s = a.fixed_slot;
     else {
-      s = a.ptr[p] + (a.gate32 != nullptr ? a.gate32[n] : 0);   // ctrl_det_idxs + prev gate, clamped
+      s = a.ptr[p] + gate_shift;                               // ctrl_det_idxs + prev gate, clamped
       s = s < 0 ? 0 : (s > a.L - 1 ? a.L - 1 : s);             // (controllable_captioning.py:139-140)
     }
     a.ptrn[n] = s;
   }
+}
+
+__global__ void __launch_bounds__(256) k_advance(const AdvanceArgs a) {
+  const int n = blockIdx.x;
+  const int c = n / a.k;
+  const int p = a.parent != nullptr ? c * a.cur + a.parent[n] : n;
+  const int64_t w = a.word32 != nullptr ? (int64_t)a.word32[n] : a.word64[(size_t)n * a.word64_stride];
+  advance_row(a, n, p, w, a.gate32 != nullptr ? a.gate32[n] : 0);
+}
+
+// beam selection fused with the reorder of the beam states.  Grid (captions, k): every CTA of a caption
+// repeats the (cheap, deterministic) selection with its warp 0 — only CTA y = 0 records it — and then
+// moves ONE new beam row, so the copy keeps captions x k CTAs of parallelism without a second launch.
+__global__ void __launch_bounds__(256) k_beam_step(const BeamArgs b, const AdvanceArgs a, int do_advance) {
+  __shared__ BeamSmem sh;
+  const int c = blockIdx.x, i = blockIdx.y;
+  if (threadIdx.x < 32) beam_select_warp(b, sh, c, threadIdx.x, i == 0);
+  __syncthreads();
+  if (!do_advance) return;
+  advance_row(a, c * b.k + i, c * b.cur + sh.pb[i], (int64_t)sh.pw[i], sh.pg[i]);
 }
 
 // zero state, slot 0, xt = embed[bos]   (init_state, controllable_captioning.py:109-115, :136)
@@ -300,30 +320,7 @@ int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
   return VSR_OK;
 }
 
-int launch_beam_select(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1,
-                       const int32_t* f_beam, const int32_t* f_word, const int32_t* f_gate,
-                       cudaStream_t st) {
-  PhaseScope ps(c, PH_BEAM, st);
-  BeamArgs a{};
-  a.t = t; a.b = b; a.cur = cur; a.k = k; a.V = c->V; a.eos0 = eos0; a.eos1 = eos1;
-  a.logits = c->logits; a.ld = c->NE; a.row_max = c->row_max; a.row_lsum = c->row_lsum;
-  a.forced = c->forced; a.cand = c->cand; a.gate_lp = c->gate_lp;
-  a.seq_lp = c->seq_lp; a.seq_lp_n = c->seq_lp_n;
-  a.m0 = c->m0; a.m1 = c->m1; a.m0n = c->m0n; a.m1n = c->m1n;
-  a.sel_beam = c->sel_beam; a.sel_word = c->sel_word; a.sel_gate = c->sel_gate;
-  const size_t off = (size_t)t * b * k;
-  a.hist_parent = c->hist_parent + off; a.hist_word = c->hist_word + off; a.hist_gate = c->hist_gate + off;
-  a.hist_score = c->hist_score + off; a.hist_lpw = c->hist_lpw + off; a.hist_lpg = c->hist_lpg + off;
-  a.f_beam = f_beam; a.f_word = f_word; a.f_gate = f_gate;
-  k_beam_select<<<b, 32, 0, st>>>(a);
-  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
-  std::swap(c->seq_lp, c->seq_lp_n);
-  std::swap(c->m0, c->m0n);
-  std::swap(c->m1, c->m1n);
-  return VSR_OK;
-}
-
-static int launch_advance(Ctx* c, AdvanceArgs& a, cudaStream_t st) {
+static void fill_advance(Ctx* c, AdvanceArgs& a) {
   a.L = c->L; a.Hp = c->Hp; a.Ep = c->Ep; a.V = c->V;
   a.h1n = c->h1n; a.c1n = c->c1n; a.h2n = c->h2n; a.c2n = c->c2n;
   a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2; a.xt = c->xt;
@@ -336,18 +333,45 @@ static int launch_advance(Ctx* c, AdvanceArgs& a, cudaStream_t st) {
     a.h2_hi = (uint4*)c->h2_b.hi; a.h2_lo = (uint4*)c->h2_b.lo;
     a.xt_hi = (uint4*)c->xt_b.hi; a.xt_lo = (uint4*)c->xt_b.lo;
   }
+}
+
+// beam selection of step t and (unless it is the last step) the state reorder for step t+1, one launch
+int launch_beam_step(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1, const int32_t* f_beam,
+                     const int32_t* f_word, const int32_t* f_gate, bool advance, cudaStream_t st) {
+  PhaseScope ps(c, PH_BEAM, st);
+  BeamArgs a{};
+  a.t = t; a.b = b; a.cur = cur; a.k = k; a.V = c->V; a.eos0 = eos0; a.eos1 = eos1;
+  a.logits = c->logits; a.ld = c->NE; a.row_max = c->row_max; a.row_lsum = c->row_lsum;
+  a.forced = c->forced; a.cand = c->cand; a.gate_lp = c->gate_lp;
+  a.seq_lp = c->seq_lp; a.seq_lp_n = c->seq_lp_n;
+  a.m0 = c->m0; a.m1 = c->m1; a.m0n = c->m0n; a.m1n = c->m1n;
+  a.prev_word = c->sel_word; a.prev_gate = c->sel_gate;
+  a.sel_beam = c->sel_beam_n; a.sel_word = c->sel_word_n; a.sel_gate = c->sel_gate_n;
+  const size_t off = (size_t)t * b * k;
+  a.hist_parent = c->hist_parent + off; a.hist_word = c->hist_word + off; a.hist_gate = c->hist_gate + off;
+  a.hist_score = c->hist_score + off; a.hist_lpw = c->hist_lpw + off; a.hist_lpg = c->hist_lpg + off;
+  a.f_beam = f_beam; a.f_word = f_word; a.f_gate = f_gate;
+  AdvanceArgs ad{};
+  ad.rows_new = b * k; ad.cur = cur; ad.k = k; ad.fixed_slot = -1;
+  fill_advance(c, ad);
+  k_beam_step<<<dim3(b, advance ? k : 1), 256, 0, st>>>(a, ad, advance ? 1 : 0);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  std::swap(c->sel_beam, c->sel_beam_n);
+  std::swap(c->sel_word, c->sel_word_n);
+  std::swap(c->sel_gate, c->sel_gate_n);
+  std::swap(c->seq_lp, c->seq_lp_n);
+  std::swap(c->m0, c->m0n);
+  std::swap(c->m1, c->m1n);
+  if (advance) std::swap(c->ptr, c->ptrn);
+  return VSR_OK;
+}
+
+static int launch_advance(Ctx* c, AdvanceArgs& a, cudaStream_t st) {
+  fill_advance(c, a);
   k_advance<<<a.rows_new, 256, 0, st>>>(a);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   std::swap(c->ptr, c->ptrn);
   return VSR_OK;
-}
-
-int launch_reorder(Ctx* c, int b, int cur, int k, cudaStream_t st) {
-  PhaseScope ps(c, PH_REORDER, st);
-  AdvanceArgs a{};
-  a.rows_new = b * k; a.cur = cur; a.k = k;
-  a.parent = c->sel_beam; a.word32 = c->sel_word; a.gate32 = c->sel_gate; a.fixed_slot = -1;
-  return launch_advance(c, a, st);
 }
 
 int launch_commit_identity(Ctx* c, int rows, const int64_t* next_words, int64_t word_stride,

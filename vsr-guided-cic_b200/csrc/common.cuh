@@ -179,6 +179,7 @@ struct Ctx {
   float *pre2;                       // [rows][ND]
   float *logits;                     // [rows][NE]
   float *gate_lp;                    // [rows][2]
+  float *shift;                      // [rows] raw shift-gate logit
   float *row_max, *row_lsum;         // [rows]
   int32_t *forced;                   // [rows] forced vocab idx or -1
   int32_t *cand;                     // [rows][VSR_MAX_BEAM]
@@ -187,6 +188,7 @@ struct Ctx {
   float *seq_lp, *seq_lp_n;          // [caps][beam]
   float *m0, *m1, *m0n, *m1n;        // sticky EOS masks [caps][beam]
   int32_t *sel_beam, *sel_word, *sel_gate;  // [caps][beam] selections of the current step
+  int32_t *sel_beam_n, *sel_word_n, *sel_gate_n;
   int32_t *hist_parent, *hist_word, *hist_gate;  // [T][caps][beam]
   float *hist_score, *hist_lpw, *hist_lpg;       // [T][caps][beam]
   int hist_T = 0, hist_b = 0, hist_k = 0;
@@ -226,10 +228,9 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st);
 
 int launch_state_init(Ctx* c, int rows, cudaStream_t st);
 int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st);
-int launch_beam_select(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1,
-                       const int32_t* f_beam, const int32_t* f_word, const int32_t* f_gate,
-                       cudaStream_t st);
-int launch_reorder(Ctx* c, int b, int cur, int k, cudaStream_t st);
+int launch_beam_step(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1,
+                     const int32_t* f_beam, const int32_t* f_word, const int32_t* f_gate, bool advance,
+                     cudaStream_t st);
 int launch_backtrack(Ctx* c, int b, int k, int T, int out_size, int64_t* out_words,
                      int64_t* out_gates, float* lp_words, float* lp_gates, cudaStream_t st);
 int launch_commit_identity(Ctx* c, int rows, const int64_t* next_words, int64_t word_stride,

@@ -109,11 +109,10 @@ struct AttendArgs {
   const int32_t* ptr;      // [rows]
   const float* sent; int ld_sent; int o_sa;   // sentinel (F) at 0 | sa (A) at o_sa
   const float* hb; int ld_hb; int o_ha;       // hg (H) at 0 | ha (A) at o_ha | ...
-  const float* ga; int ld_ga;
-  const float *v_a, *v_s, *v_g;
+  const float *v_a, *v_s;
   float* att; int ld_att;
   PairOut att_b;
-  float* gate_lp;          // [rows][2]
+  float* shift;            // [rows] sum of the valid region scores = the "shift" gate logit (:187)
   int rows, cur_beam, L, R, F, A, H, ldP;
 };
 
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   float* ha = sm;                       // [A]
   float* e = ha + a.A;                  // [R+1] scores, later alpha; index 0 = sentinel
   __shared__ float red[ATT_THREADS / 32];
-  __shared__ float s_stay, s_sent_sum, s_pad;
+  __shared__ float s_pad;
   __shared__ uint8_t s_valid[ATT_MAX_R];
   __shared__ int s_rows[ATT_MAX_R];     // compacted valid region rows and their weights
   __shared__ float s_w[ATT_MAX_R];
@@ -130,7 +129,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
 
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarp = ATT_THREADS / 32;
+  constexpr int nwarp = ATT_THREADS / 32;
   const int cap = n / a.cur_beam;
   const int slot = a.ptr[n];
   const size_t tile_row0 = ((size_t)cap * a.L + slot) * a.R;
@@ -138,7 +137,6 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   const float* Pt = a.P + tile_row0 * a.ldP;
   const float* sent = a.sent + (size_t)n * a.ld_sent;   // sentinel feature row
   const float* sa = sent + a.o_sa;
-  const float* gav = a.ga + (size_t)n * a.ld_ga;
 
   for (int i = tid; i < a.A; i += ATT_THREADS) ha[i] = a.hb[(size_t)n * a.ld_hb + a.o_ha + i];
   if (tid < a.R) s_valid[tid] = a.seq_valid[tile_row0 + tid];
@@ -151,97 +149,150 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   ssum = warp_sum(ssum);
   if (lane == 0) red[warp] = ssum;
   __syncthreads();
-  if (tid == 0) {
-    float s = 0.f;
-    for (int w = 0; w < nwarp; ++w) s += red[w];
-    s_sent_sum = s;
+
+  // pull the valid region rows towards L2 while the scores are being computed
+  {
+    const int lines_per_row = (a.F * 4 + 127) / 128;
+    for (int idx = tid; idx < a.R * lines_per_row; idx += ATT_THREADS) {
+      const int r = idx / lines_per_row;
+      if (s_valid[r]) {
+        const float* pf = tile + (size_t)r * a.F + (size_t)(idx - r * lines_per_row) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+      }
+    }
   }
 
-  // scores: job 0 = sentinel, 1 = stay-gate logit, 2 = padding-row score, 3.. = valid regions
-  for (int job = warp; job < a.R + 3; job += nwarp) {
+  // scores: job 0 = sentinel, 1 = padding-row score, 2.. = valid regions; one warp per job
+  for (int job = warp; job < a.R + 2; job += nwarp) {
     const float* add = nullptr;
     const float* vec = a.v_a;
-    bool run = true;
     if (job == 0) { add = sa; vec = a.v_s; }
-    else if (job == 1) { add = gav; vec = a.v_g; }
-    else if (job == 2) { add = nullptr; }
-    else { const int r = job - 3; run = s_valid[r] != 0; add = Pt + (size_t)r * a.ldP; }
-    if (!run) continue;
+    else if (job >= 2) {
+      const int r = job - 2;
+      if (!s_valid[r]) continue;
+      add = Pt + (size_t)r * a.ldP;
+    }
     float acc = 0.f;
-    for (int i = lane; i < a.A; i += 32) acc += vec[i] * tanhf((add != nullptr ? add[i] : 0.f) + ha[i]);
+    for (int i0 = 0; i0 < a.A; i0 += 512) {     // 4 x float4 per lane in flight, then the tanh math
+      float4 pv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * 128 + lane * 4;
+        pv[q] = (add != nullptr && i < a.A) ? __ldg(reinterpret_cast<const float4*>(add + i))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * 128 + lane * 4;
+        if (i < a.A) {
+          const float4 hv = *reinterpret_cast<const float4*>(ha + i);
+          const float4 vv = __ldg(reinterpret_cast<const float4*>(vec + i));
+          acc += vv.x * tanhf(pv[q].x + hv.x) + vv.y * tanhf(pv[q].y + hv.y) +
+                 vv.z * tanhf(pv[q].z + hv.z) + vv.w * tanhf(pv[q].w + hv.w);
+        }
+      }
+    }
     acc = warp_sum(acc);
     if (lane == 0) {
       if (job == 0) e[0] = acc;
-      else if (job == 1) s_stay = acc;
-      else if (job == 2) s_pad = acc;       // score shared by all padding rows
-      else e[job - 2] = acc;
+      else if (job == 1) s_pad = acc;       // score shared by all padding rows
+      else e[job - 1] = acc;
     }
-  }
-  __syncthreads();
-  if (tid == 0) {
-    const float e_pad = s_pad;
-    float m = e[0];
-    float shift = 0.f;
-    for (int r = 0; r < a.R; ++r) {
-      if (!s_valid[r]) e[r + 1] = e_pad; else shift += e[r + 1];
-      m = fmaxf(m, e[r + 1]);
-    }
-    float S = 0.f;
-    for (int r = 0; r <= a.R; ++r) { e[r] = expf(e[r] - m); S += e[r]; }
-    float T = 0.f;
-    for (int r = 0; r <= a.R; ++r) {
-      const bool valid = (r == 0) ? (s_sent_sum != 0.f) : (s_valid[r - 1] != 0);
-      e[r] = valid ? e[r] / S : 0.f;
-      T += e[r];
-    }
-    int nv = 0;
-    for (int r = 0; r <= a.R; ++r) {
-      e[r] = e[r] / T;
-      if (r > 0 && s_valid[r - 1]) { s_rows[nv] = r - 1; s_w[nv] = e[r]; ++nv; }
-    }
-    s_nv = nv;
-    // shift-gate head
-    const float stay = s_stay;
-    const float gm = fmaxf(stay, shift);
-    const float ls = logf(expf(stay - gm) + expf(shift - gm));
-    a.gate_lp[(size_t)n * 2 + 0] = (stay - gm) - ls;
-    a.gate_lp[(size_t)n * 2 + 1] = (shift - gm) - ls;
   }
   __syncthreads();
 
-  // weighted sum over sentinel + valid regions
+  if (warp == 0) {
+    float sent_sum = 0.f;
+    for (int w = 0; w < nwarp; ++w) sent_sum += red[w];
+    if (a.R + 1 <= 32) {
+      // masked softmax over [sentinel, regions] with one lane per entry (:167-169)
+      const bool in = lane <= a.R;
+      const bool valid = in && (lane == 0 ? (sent_sum != 0.f) : (s_valid[lane - 1] != 0));
+      const bool region = in && lane >= 1 && valid;
+      float ev = -INFINITY;
+      if (in) ev = (lane == 0 || valid) ? e[lane] : s_pad;
+      const float m = warp_max(ev);
+      float w = in ? expf(ev - m) : 0.f;
+      const float S = warp_sum(w);
+      w = valid ? w / S : 0.f;
+      const float T = warp_sum(w);
+      w = w / T;
+      const float shift = warp_sum(region ? ev : 0.f);
+      const unsigned msk = __ballot_sync(0xffffffffu, region);
+      if (region) { const int pos = __popc(msk & ((1u << lane) - 1u)); s_rows[pos] = lane - 1; s_w[pos] = w; }
+      if (lane == 0) { e[0] = w; s_nv = __popc(msk); a.shift[n] = shift; }
+    } else if (lane == 0) {
+      const float e_pad = s_pad;
+      float m = e[0];
+      float shift = 0.f;
+      for (int r = 0; r < a.R; ++r) {
+        if (!s_valid[r]) e[r + 1] = e_pad; else shift += e[r + 1];
+        m = fmaxf(m, e[r + 1]);
+      }
+      float S = 0.f;
+      for (int r = 0; r <= a.R; ++r) { e[r] = expf(e[r] - m); S += e[r]; }
+      float T = 0.f;
+      for (int r = 0; r <= a.R; ++r) {
+        const bool valid = (r == 0) ? (sent_sum != 0.f) : (s_valid[r - 1] != 0);
+        e[r] = valid ? e[r] / S : 0.f;
+        T += e[r];
+      }
+      int nv = 0;
+      for (int r = 0; r <= a.R; ++r) {
+        e[r] = e[r] / T;
+        if (r > 0 && s_valid[r - 1]) { s_rows[nv] = r - 1; s_w[nv] = e[r]; ++nv; }
+      }
+      s_nv = nv;
+      a.shift[n] = shift;    // the gate head is finished in k_softmax_topk (needs the att_ga projection)
+    }
+  }
+  __syncthreads();
+
+  // weighted sum over sentinel + valid regions: each thread owns two float4 columns, 4 rows x 2 columns
+  // (8 independent 128-bit loads) in flight
   float* out = a.att + (size_t)n * a.ld_att;
   const float a_s = e[0];
   const int nv = s_nv;
-  for (int f = tid * 4; f < a.F; f += ATT_THREADS * 4) {
-    const float4 sv = *reinterpret_cast<const float4*>(sent + f);
-    float4 acc = make_float4(a_s * sv.x, a_s * sv.y, a_s * sv.z, a_s * sv.w);
-    int i = 0;
-    for (; i + 4 <= nv; i += 4) {   // four independent 128-bit loads in flight per thread
-      float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        v[u] = __ldg(reinterpret_cast<const float4*>(tile + (size_t)s_rows[i + u] * a.F + f));
+  for (int f0 = tid * 4; f0 < a.F; f0 += ATT_THREADS * 8) {
+    const int f1 = f0 + ATT_THREADS * 4;
+    const bool two = f1 < a.F;
+    const float4 s0 = *reinterpret_cast<const float4*>(sent + f0);
+    const float4 s1 = two ? *reinterpret_cast<const float4*>(sent + f1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc0 = make_float4(a_s * s0.x, a_s * s0.y, a_s * s0.z, a_s * s0.w);
+    float4 acc1 = make_float4(a_s * s1.x, a_s * s1.y, a_s * s1.z, a_s * s1.w);
+    for (int i = 0; i < nv; i += 4) {
+      float4 v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float w = s_w[i + u];
-        acc.x += w * v[u].x; acc.y += w * v[u].y; acc.z += w * v[u].z; acc.w += w * v[u].w;
+        const int r = s_rows[min(i + u, nv - 1)];
+        const float* rp = tile + (size_t)r * a.F;
+        v0[u] = __ldg(reinterpret_cast<const float4*>(rp + f0));
+        v1[u] = two ? __ldg(reinterpret_cast<const float4*>(rp + f1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float w = (i + u < nv) ? s_w[i + u] : 0.f;
+        acc0.x += w * v0[u].x; acc0.y += w * v0[u].y; acc0.z += w * v0[u].z; acc0.w += w * v0[u].w;
+        acc1.x += w * v1[u].x; acc1.y += w * v1[u].y; acc1.z += w * v1[u].z; acc1.w += w * v1[u].w;
       }
     }
-    for (; i < nv; ++i) {
-      const float w = s_w[i];
-      const float4 v = __ldg(reinterpret_cast<const float4*>(tile + (size_t)s_rows[i] * a.F + f));
-      acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+    *reinterpret_cast<float4*>(out + f0) = acc0;
+    const size_t o0 = (size_t)n * a.ld_att + f0;
+    store_pair(a.att_b, o0, acc0.x); store_pair(a.att_b, o0 + 1, acc0.y);
+    store_pair(a.att_b, o0 + 2, acc0.z); store_pair(a.att_b, o0 + 3, acc0.w);
+    if (two) {
+      *reinterpret_cast<float4*>(out + f1) = acc1;
+      const size_t o1 = (size_t)n * a.ld_att + f1;
+      store_pair(a.att_b, o1, acc1.x); store_pair(a.att_b, o1 + 1, acc1.y);
+      store_pair(a.att_b, o1 + 2, acc1.z); store_pair(a.att_b, o1 + 3, acc1.w);
     }
-    *reinterpret_cast<float4*>(out + f) = acc;
-    const size_t o = (size_t)n * a.ld_att + f;
-    store_pair(a.att_b, o, acc.x); store_pair(a.att_b, o + 1, acc.y);
-    store_pair(a.att_b, o + 2, acc.z); store_pair(a.att_b, o + 3, acc.w);
   }
 }
 
-// ---------------------------------------------------------------- log-softmax + verb forcing + top-k
-constexpr int SM_THREADS = 256;
+// ---------------------------------------------------------------- log-softmax + gate head + verb forcing + top-k
+// One CTA per row; the row's logits are read ONCE into registers.  Also finishes the
+// shift-gate head (stay logit = att_g . tanh(ga + ha), controllable_captioning.py:184-188) so the
+// att_ga projection is off the attention kernel's critical path, and applies verb forcing (:271-295).
 
 __device__ __forceinline__ int64_t load_verb(const void* verbs, int dtype, size_t i) {
   if (dtype == VSR_DT_F64) return (int64_t) reinterpret_cast<const double*>(verbs)[i];
@@ -253,6 +304,14 @@ __device__ __forceinline__ int64_t load_verb(const void* verbs, int dtype, size_
 __device__ __forceinline__ bool before(float v1, int i1, float v2, int i2) {
   return v1 > v2 || (v1 == v2 && i1 < i2);
 }
+__device__ __forceinline__ void warp_argbest(float& bv, int& bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+}
 
 struct SoftmaxArgs {
   const float* logits; int ld;   // [rows][ld]
@@ -260,76 +319,114 @@ struct SoftmaxArgs {
   const int32_t* ptr;
   const void* verbs; int verbs_dtype; int use_verbs, gt;
   const int64_t* vt_keys; const int32_t* vt_off; const int32_t* vt_idx; int vt_n;
+  // gate head inputs
+  const float* ha; int ld_ha;     // [rows] att_ha . h1'   (A wide)
+  const float* ga; int ld_ga;     // [rows] att_ga . g_t
+  const float* v_g; int A;
+  const float* shift;             // [rows] sum of the valid region scores (from the attention kernel)
   float* row_max; float* row_lsum; int32_t* forced; int32_t* cand;  // cand [rows][VSR_MAX_BEAM]
-  float* gate_lp;                 // [rows][2], overwritten with [-1e3, 0] on verb rows
+  float* gate_lp;                 // [rows][2] post-forcing gate log-probs
   float* out_logp; int64_t out_stride;   // optional full rows
-  float* gate_out; int64_t gate_stride;  // optional copy of the post-forcing gate rows
+  float* gate_out; int64_t gate_stride;  // optional copy of the gate rows
 };
 
+// The row is staged ONCE in shared memory (each thread re-reads only the float4s it loaded itself, so no
+// barrier guards the staging); statistics use the exact two-pass formula
+// log_softmax = (x - max) - log(sum exp(x - max)); the top-k is k rounds of block arg-best over each
+// thread's best remaining element (the owner of a pick rescans its own elements for the next one).
+constexpr int SM_THREADS = 256;
 __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a) {
-  __shared__ float red_v[SM_THREADS / 32];
-  __shared__ int red_i[SM_THREADS / 32];
-  __shared__ float s_max, s_lsum;
-  __shared__ int s_forced, s_pick;
+  constexpr int THREADS = SM_THREADS;
+  constexpr int NW = THREADS / 32;
+  extern __shared__ float4 row4[];        // [ceil(V/4)]
+  __shared__ float red_v[2][NW];
+  __shared__ int red_i[2][NW];
+  __shared__ float red_s[NW];
+  __shared__ float s_stay;
+  __shared__ int s_forced;
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = SM_THREADS / 32;
   const float* x = a.logits + (size_t)n * a.ld;
   const int V = a.V;
+  const int n4 = (V + 3) >> 2;
 
-  // pass 1: running max and the thread-local top-K list (K = VSR_MAX_BEAM, registers)
-  float tv[VSR_MAX_BEAM]; int ti[VSR_MAX_BEAM];
-#pragma unroll
-  for (int j = 0; j < VSR_MAX_BEAM; ++j) { tv[j] = -INFINITY; ti[j] = 0x7fffffff; }
-  float mx = -INFINITY;
-  for (int v0 = tid * 4; v0 < V; v0 += SM_THREADS * 4) {
-    const float4 q = *reinterpret_cast<const float4*>(x + v0);
-    const float qs[4] = {q.x, q.y, q.z, q.w};
+  // stage + this thread's best element, tail of the last float4 masked to -inf
+  float cv = -INFINITY; int ci = 0x7fffffff;
+  for (int j0 = tid; j0 < n4; j0 += THREADS * 4) {
+    float4 q[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int v = v0 + u;
-      if (v < V) {
-        const float val = qs[u];
-        mx = fmaxf(mx, val);
-        if (before(val, v, tv[VSR_MAX_BEAM - 1], ti[VSR_MAX_BEAM - 1])) {
-          float cv = val; int ci = v;   // insertion into the sorted list
+      const int j = j0 + u * THREADS;
+      if (j < n4) q[u] = *reinterpret_cast<const float4*>(x + j * 4);
+    }
 #pragma unroll
-          for (int j = 0; j < VSR_MAX_BEAM; ++j) {
-            if (before(cv, ci, tv[j], ti[j])) {
-              const float t1 = tv[j]; const int t2 = ti[j];
-              tv[j] = cv; ti[j] = ci; cv = t1; ci = t2;
-            }
-          }
-        }
-      }
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * THREADS;
+      if (j >= n4) break;
+      const int v0 = j * 4;
+      if (v0 + 1 >= V) q[u].y = -INFINITY;
+      if (v0 + 2 >= V) q[u].z = -INFINITY;
+      if (v0 + 3 >= V) q[u].w = -INFINITY;
+      row4[j] = q[u];
+      const float e4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) if (before(e4[e], v0 + e, cv, ci)) { cv = e4[e]; ci = v0 + e; }
     }
   }
-  mx = warp_max(mx);
-  if (lane == 0) red_v[warp] = mx;
-  __syncthreads();
-  if (tid == 0) {
-    float m = red_v[0];
-    for (int w = 1; w < NW; ++w) m = fmaxf(m, red_v[w]);
-    s_max = m;
+  // stay-gate logit (last warp)
+  if (warp == NW - 1) {
+    const float* ha = a.ha + (size_t)n * a.ld_ha;
+    const float* ga = a.ga + (size_t)n * a.ld_ga;
+    float acc = 0.f;
+    for (int i = lane; i < a.A; i += 32) acc += a.v_g[i] * tanhf(ga[i] + ha[i]);
+    acc = warp_sum(acc);
+    if (lane == 0) s_stay = acc;
   }
-  __syncthreads();
-  mx = s_max;
-  // pass 2: sum exp(x - max)
+
+  // block arg-best of the per-thread candidates; round r uses smem buffer r&1 (one barrier per round)
+  auto block_best = [&](int r, float& bv, int& bi) {
+    bv = cv; bi = ci;
+    warp_argbest(bv, bi);
+    if (lane == 0) { red_v[r & 1][warp] = bv; red_i[r & 1][warp] = bi; }
+    __syncthreads();
+    bv = red_v[r & 1][0]; bi = red_i[r & 1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w)
+      if (before(red_v[r & 1][w], red_i[r & 1][w], bv, bi)) { bv = red_v[r & 1][w]; bi = red_i[r & 1][w]; }
+  };
+  // the owner of the selected element moves on to its next best (strictly after (pv,pi) in the order)
+  auto pop = [&](float pv, int pi) {
+    if (ci != pi) return;
+    cv = -INFINITY; ci = 0x7fffffff;
+    for (int j = tid; j < n4; j += THREADS) {
+      const float4 qq = row4[j];
+      const int v0 = j * 4;
+      const float e4[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (before(pv, pi, e4[u], v0 + u) && before(e4[u], v0 + u, cv, ci)) { cv = e4[u]; ci = v0 + u; }
+    }
+  };
+
+  float bv; int bi;
+  block_best(0, bv, bi);                 // round 0: the row maximum (and the first candidate)
+  const float mx = bv;
+  const int first = bi;
   float se = 0.f;
-  for (int v0 = tid * 4; v0 < V; v0 += SM_THREADS * 4) {
-    const float4 q = *reinterpret_cast<const float4*>(x + v0);
-    se += (v0 + 0 < V ? expf(q.x - mx) : 0.f) + (v0 + 1 < V ? expf(q.y - mx) : 0.f) +
-          (v0 + 2 < V ? expf(q.z - mx) : 0.f) + (v0 + 3 < V ? expf(q.w - mx) : 0.f);
+  for (int j = tid; j < n4; j += THREADS) {
+    const float4 qq = row4[j];
+    se += (expf(qq.x - mx) + expf(qq.y - mx)) + (expf(qq.z - mx) + expf(qq.w - mx));   // exp(-inf) = 0 on the tail
   }
   se = warp_sum(se);
+  if (lane == 0) red_s[warp] = se;
+  pop(bv, bi);
   __syncthreads();
-  if (lane == 0) red_v[warp] = se;
-  __syncthreads();
+  se = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) se += red_s[w];
+  const float lsum = logf(se);
+
   if (tid == 0) {
-    float s = 0.f;
-    for (int w = 0; w < NW; ++w) s += red_v[w];
-    const float lsum = logf(s);
-    s_lsum = lsum;
     // verb forcing (:271-295): which vocabulary index does the current slot force, if any
     int forced = -1;
     if (a.use_verbs && a.verbs != nullptr) {
@@ -349,8 +446,8 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
           }
           if (pos >= 0 && a.vt_off[pos + 1] > a.vt_off[pos]) {
             float best = -1e6f; int best_i = -1;    // strict '>' : first maximum wins (:284-289)
-            for (int q = a.vt_off[pos]; q < a.vt_off[pos + 1]; ++q) {
-              const int idx = a.vt_idx[q];
+            for (int qq = a.vt_off[pos]; qq < a.vt_off[pos + 1]; ++qq) {
+              const int idx = a.vt_idx[qq];
               const float lp = (x[idx] - mx) - lsum;
               if (lp > best) { best = lp; best_i = idx; }
             }
@@ -364,20 +461,35 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     a.row_max[n] = mx;
     a.row_lsum[n] = lsum;
     a.forced[n] = forced;
-    if (forced >= 0) { a.gate_lp[(size_t)n * 2] = -1e3f; a.gate_lp[(size_t)n * 2 + 1] = 0.f; }
+    // gate head: log_softmax([stay, shift]) (:187-188), or [-1e3, 0] on a verb slot (:295)
+    float g0, g1;
+    if (forced >= 0) { g0 = -1e3f; g1 = 0.f; }
+    else {
+      const float stay = s_stay, shift = a.shift[n];
+      const float gm = fmaxf(stay, shift);
+      const float ls = logf(expf(stay - gm) + expf(shift - gm));
+      g0 = (stay - gm) - ls; g1 = (shift - gm) - ls;
+    }
+    a.gate_lp[(size_t)n * 2] = g0; a.gate_lp[(size_t)n * 2 + 1] = g1;
     if (a.gate_out != nullptr) {
-      a.gate_out[(size_t)n * a.gate_stride + 0] = a.gate_lp[(size_t)n * 2 + 0];
-      a.gate_out[(size_t)n * a.gate_stride + 1] = a.gate_lp[(size_t)n * 2 + 1];
+      a.gate_out[(size_t)n * a.gate_stride + 0] = g0;
+      a.gate_out[(size_t)n * a.gate_stride + 1] = g1;
     }
   }
+  if (a.out_logp == nullptr && a.topk <= 0) return;
   __syncthreads();
-  const float lsum = s_lsum;
   const int forced = s_forced;
 
   if (a.out_logp != nullptr) {
     float* o = a.out_logp + (size_t)n * a.out_stride;
-    for (int v = tid; v < V; v += SM_THREADS)
-      o[v] = forced >= 0 ? (v == forced ? 0.f : -1e6f) : (x[v] - mx) - lsum;
+    for (int j = tid; j < n4; j += THREADS) {
+      const float4 qq = row4[j];
+      const int v0 = j * 4;
+      const float e4[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (v0 + u < V) o[v0 + u] = forced >= 0 ? (v0 + u == forced ? 0.f : -1e6f) : (e4[u] - mx) - lsum;
+    }
   }
   if (a.topk <= 0) return;
 
@@ -391,30 +503,11 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     }
     return;
   }
-  // merge the thread-local lists: topk rounds of block arg-best over list heads
-  int head = 0;
-  for (int j = 0; j < a.topk; ++j) {
-    float hv = -INFINITY; int hi = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < VSR_MAX_BEAM; ++q) if (q == head) { hv = tv[q]; hi = ti[q]; }
-    float bv = hv; int bi = hi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-    }
-    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
-    __syncthreads();
-    if (tid == 0) {
-      float fv = red_v[0]; int fi = red_i[0];
-      for (int w = 1; w < NW; ++w) if (before(red_v[w], red_i[w], fv, fi)) { fv = red_v[w]; fi = red_i[w]; }
-      s_pick = fi;
-      cd[j] = fi;
-    }
-    __syncthreads();
-    if (hi == s_pick && head < VSR_MAX_BEAM) ++head;   // the owner pops its head
-    __syncthreads();
+  if (tid == 0) cd[0] = first;
+  for (int j = 1; j < a.topk; ++j) {
+    block_best(j, bv, bi);
+    if (tid == 0) cd[j] = bi;
+    pop(bv, bi);
   }
 }
 
@@ -483,30 +576,27 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     k_gt<<<pw_grid, 128, 0, st>>>(c->gq, c->hb, c->NB2, c->c1n, c->g_t, pair_out(c, c->g_t_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
-  {  // C: ga = att_ga . g_t
-    PhaseScope ps(c, PH_GEMM_C, st);
-    GemmArgs g{};
-    g.nseg = 1; g.seg[0] = {c->g_t, c->Hp, c->Hp, c->Hp, &c->g_t_b};
-    g.w = c->WC; g.ldw = c->Hp; g.wb = &c->WC_b;
-    g.c = c->ga; g.ldc = c->NC; g.M = rows; g.N = c->NC;
-    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
-  }
   {
     PhaseScope ps(c, PH_ATTEND, st);
     AttendArgs a{};
     a.det_seqs = c->det_seqs; a.P = c->P; a.seq_valid = c->seq_valid; a.ptr = c->ptr;
     a.sent = c->sent; a.ld_sent = c->NB1; a.o_sa = c->oB1_sa;
-    a.hb = c->hb; a.ld_hb = c->NB2; a.o_ha = c->oB2_ha; a.ga = c->ga; a.ld_ga = c->NC;
-    a.v_a = c->v_a; a.v_s = c->v_s; a.v_g = c->v_g;
-    a.att = c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.gate_lp = c->gate_lp;
+    a.hb = c->hb; a.ld_hb = c->NB2; a.o_ha = c->oB2_ha;
+    a.v_a = c->v_a; a.v_s = c->v_s;
+    a.att = c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.shift = c->shift;
     a.rows = rows; a.cur_beam = io.cur_beam; a.L = c->L; a.R = c->R; a.F = c->F; a.A = c->A; a.H = H;
     a.ldP = c->NVA;
     const size_t smem = sizeof(float) * (size_t)(c->A + c->R + 1);
     k_attend<<<rows, ATT_THREADS, smem, st>>>(a);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
-  {  // D: pre2 = pre2_h1 + WD . [att | h2_old] + b (+ U2[img])
+  {  // D: pre2 = pre2_h1 + WD . [att | h2_old] + b (+ U2[img]);  C: ga = att_ga . g_t rides in the same launch
+     // (the stay-gate logit that needs ga is finished in k_softmax_topk, off the attention's critical path)
     PhaseScope ps(c, PH_GEMM_D, st);
+    GemmArgs gc{};
+    gc.nseg = 1; gc.seg[0] = {c->g_t, c->Hp, c->Hp, c->Hp, &c->g_t_b};
+    gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b;
+    gc.c = c->ga; gc.ldc = c->NC; gc.M = rows; gc.N = c->NC;
     GemmArgs g{};
     g.nseg = 2;
     g.seg[0] = {c->att, c->Fp, c->Fp, c->Fp, &c->att_b};
@@ -521,7 +611,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
       g.cell.mode = 2; g.cell.c_old = c->c2; g.cell.c_new = c->c2n; g.cell.h_new = c->h2n;
       g.cell.h_hi = c->h2n_b.hi; g.cell.h_lo = c->h2n_b.lo; g.cell.ld_state = c->Hp;
     }
-    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
+    VSR_TRY(launch_gemm(c, g, st, &gc)); c->launches += fused ? 1 : 2;
   }
   if (!fused) {
     PhaseScope ps(c, PH_LSTM2, st);
@@ -543,10 +633,18 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.topk = io.topk; a.ptr = c->ptr;
     a.verbs = c->verbs; a.verbs_dtype = c->verbs_dtype; a.use_verbs = io.use_verbs; a.gt = io.gt;
     a.vt_keys = c->vt_keys; a.vt_off = c->vt_off; a.vt_idx = c->vt_idx; a.vt_n = c->vt_n;
+    a.ha = c->hb + c->oB2_ha; a.ld_ha = c->NB2; a.ga = c->ga; a.ld_ga = c->NC; a.v_g = c->v_g; a.A = c->A;
+    a.shift = c->shift;
     a.row_max = c->row_max; a.row_lsum = c->row_lsum; a.forced = c->forced; a.cand = c->cand;
     a.gate_lp = c->gate_lp; a.out_logp = io.out_logp; a.out_stride = io.out_stride;
     a.gate_out = io.gate_out; a.gate_stride = io.gate_stride;
-    k_softmax_topk<<<rows, SM_THREADS, 0, st>>>(a);
+    const size_t smem = sizeof(float) * 4 * (size_t)((c->V + 3) / 4);
+    static bool attr_set = false;
+    if (!attr_set) {
+      VSR_CHECK_CUDA(cudaFuncSetAttribute(k_softmax_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    k_softmax_topk<<<rows, SM_THREADS, smem, st>>>(a);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   return VSR_OK;
