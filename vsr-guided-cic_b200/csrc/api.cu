@@ -83,16 +83,17 @@ int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows) {
 int ensure_rows(Ctx* c, int rows) {
   if (rows <= c->cap_rows) return VSR_OK;
   const int cap = round_up(rows, MPAD);
-  float** bufs[] = {&c->h1, &c->c1, &c->h2, &c->c2, &c->h1n, &c->c1n, &c->h2n, &c->c2n, &c->xt, &c->pre1,
+  float** bufs[] = {&c->h1, &c->c1, &c->h2, &c->c2, &c->h1n, &c->c1n, &c->h2n, &c->c2n, &c->pre1,
                     &c->s_t, &c->g_t, &c->gq, &c->sent, &c->hb, &c->ga, &c->att, &c->pre2, &c->logits, &c->gate_lp,
                     &c->row_max, &c->row_lsum, &c->shift};
   for (float** p : bufs) { dev_free(c, *p); *p = nullptr; }
+  dev_free(c, c->word_idx);
   dev_free(c, c->ptr); dev_free(c, c->ptrn); dev_free(c, c->forced); dev_free(c, c->cand); dev_free(c, c->word_in);
   c->cap_rows = 0;
   const size_t n = cap;
   ALLOC_F(c->h1, n * c->Hp); ALLOC_F(c->c1, n * c->Hp); ALLOC_F(c->h2, n * c->Hp); ALLOC_F(c->c2, n * c->Hp);
   ALLOC_F(c->h1n, n * c->Hp); ALLOC_F(c->c1n, n * c->Hp); ALLOC_F(c->h2n, n * c->Hp); ALLOC_F(c->c2n, n * c->Hp);
-  ALLOC_F(c->xt, n * c->Ep);
+  VSR_TRY(dev_alloc(c, (void**)&c->word_idx, sizeof(int32_t) * n));
   ALLOC_F(c->pre1, n * c->NA);
   ALLOC_F(c->s_t, n * c->Hp); ALLOC_F(c->g_t, n * c->Hp); ALLOC_F(c->gq, n * c->Hp);
   ALLOC_F(c->sent, n * c->NB1); ALLOC_F(c->hb, n * c->NB2); ALLOC_F(c->ga, n * c->NC);
@@ -104,7 +105,7 @@ int ensure_rows(Ctx* c, int rows) {
   VSR_TRY(dev_alloc(c, (void**)&c->cand, sizeof(int32_t) * n * VSR_MAX_BEAM));
   VSR_TRY(dev_alloc(c, (void**)&c->word_in, sizeof(int64_t) * n));
   VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD));
-  VSR_TRY(alloc_pair(c, &c->xt_b, cap, c->Ep, MPAD)); VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD));
+  VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD));
   VSR_TRY(alloc_pair(c, &c->h1n_b, cap, c->Hp, MPAD)); VSR_TRY(alloc_pair(c, &c->g_t_b, cap, c->Hp, MPAD));
   VSR_TRY(alloc_pair(c, &c->att_b, cap, c->Fp, MPAD)); VSR_TRY(alloc_pair(c, &c->h2n_b, cap, c->Hp, MPAD));
   c->cap_rows = cap;
@@ -167,7 +168,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   c->ND = 4 * c->Hp;                       // gate-interleaved: 4 gates x Hp units (multiple of 256)
   c->NE = round_up(c->V, NPAD);
   c->NVA = round_up(c->A, NPAD);
-  c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Ep + c->Hp;
+  c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Hp;
   c->KD = c->Fp + c->Hp;
   for (int i = 0; i < PH_COUNT; ++i) c->phases[i].name = kPhaseNames[i];
   *out = c;   // from here on vsr_destroy can clean up a half-built context
@@ -181,6 +182,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   ALLOC_F(c->Wva, (size_t)c->NVA * c->Fp);
   ALLOC_F(c->v_a, c->Ap); ALLOC_F(c->v_s, c->Ap); ALLOC_F(c->v_g, c->Ap);
   ALLOC_F(c->embed, (size_t)c->V * c->Ep);
+  ALLOC_F(c->WAx, (size_t)c->NA * c->Ep); ALLOC_F(c->X, (size_t)c->V * c->NA);
   {
     const char* mode = getenv("VSRDEC_GEMM");   // "simt": fp32 FFMA twin for A/B verification of the tcgen05 path
     c->use_tc = !(mode != nullptr && strcmp(mode, "simt") == 0);
@@ -193,7 +195,6 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn));
   VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128));
   VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn));
-  VSR_TRY(alloc_pair(c, &c->embed_b, c->V, c->Ep, 8));
   VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn));
   if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128));
   VSR_TRY(pack_weights(c, w, 0));
@@ -283,7 +284,7 @@ static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, 
   VSR_TRY(copy2d(c, c->c2, c->Hp, c2, H, H, b, st));
   k_slots_from_i64<<<(b + 127) / 128, 128, 0, st>>>(c->ptr, slot, b, c->L);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
-  VSR_TRY(launch_embed(c, word, b, st));
+  VSR_TRY(launch_words(c, word, b, st));
   if (c->use_tc) {
     VSR_TRY(launch_split_f16(c->h1, c->h1_b.hi, c->h1_b.lo, (size_t)b * c->Hp, st));
     VSR_TRY(launch_split_f16(c->h2, c->h2_b.hi, c->h2_b.lo, (size_t)b * c->Hp, st));
@@ -345,7 +346,7 @@ static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, floa
       // xt <- embed[captions[:,0]], slot 0
       VSR_CHECK_CUDA(cudaMemcpy2DAsync(c->word_in, sizeof(int64_t), captions, sizeof(int64_t) * T,
                                        sizeof(int64_t), b, cudaMemcpyDeviceToDevice, st));
-      VSR_TRY(launch_embed(c, c->word_in, b, st));
+      VSR_TRY(launch_words(c, c->word_in, b, st));
     }
     StepIO io{};
     io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 0;

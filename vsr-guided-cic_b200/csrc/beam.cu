@@ -149,15 +149,15 @@ struct AdvanceArgs {
   int fixed_slot;                  // >= 0: set the pointer to this slot (teacher forcing)
   int L, Hp, Ep, V;
   const float *h1n, *c1n, *h2n, *c2n;
-  float *h1, *c1, *h2, *c2, *xt;
+  float *h1, *c1, *h2, *c2;
   const int32_t* ptr; int32_t* ptrn;
-  const float* embed;
+  int32_t* word_idx;
   // fp16 hi/lo twins (null on the fp32 path): 16-byte vectors of 8 fp16
-  const uint4 *h1n_hi, *h1n_lo, *h2n_hi, *h2n_lo, *emb_hi, *emb_lo;
-  uint4 *h1_hi, *h1_lo, *h2_hi, *h2_lo, *xt_hi, *xt_lo;
+  const uint4 *h1n_hi, *h1n_lo, *h2n_hi, *h2n_lo;
+  uint4 *h1_hi, *h1_lo, *h2_hi, *h2_lo;
 };
 
-// copy the state of parent row p into new row n, embed the next input word, update the slot pointer
+// copy the state of parent row p into new row n, record the next input word, update the slot pointer
 __device__ __forceinline__ void advance_row(const AdvanceArgs& a, int n, int p, int64_t w, int gate_shift) {
   const size_t so = (size_t)p * a.Hp, dof = (size_t)n * a.Hp;
   for (int i = threadIdx.x * 4; i < a.Hp; i += blockDim.x * 4) {
@@ -167,21 +167,15 @@ __device__ __forceinline__ void advance_row(const AdvanceArgs& a, int n, int p, 
     *reinterpret_cast<float4*>(a.c2 + dof + i) = *reinterpret_cast<const float4*>(a.c2n + so + i);
   }
   w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
-  const float* er = a.embed + (size_t)w * a.Ep;
-  for (int i = threadIdx.x * 4; i < a.Ep; i += blockDim.x * 4)
-    *reinterpret_cast<float4*>(a.xt + (size_t)n * a.Ep + i) = *reinterpret_cast<const float4*>(er + i);
   if (a.h1_hi != nullptr) {
     const size_t sv = (size_t)p * (a.Hp / 8), dv = (size_t)n * (a.Hp / 8);
     for (int i = threadIdx.x; i < a.Hp / 8; i += blockDim.x) {
       a.h1_hi[dv + i] = a.h1n_hi[sv + i]; a.h1_lo[dv + i] = a.h1n_lo[sv + i];
       a.h2_hi[dv + i] = a.h2n_hi[sv + i]; a.h2_lo[dv + i] = a.h2n_lo[sv + i];
     }
-    const size_t ev = (size_t)w * (a.Ep / 8), xv = (size_t)n * (a.Ep / 8);
-    for (int i = threadIdx.x; i < a.Ep / 8; i += blockDim.x) {
-      a.xt_hi[xv + i] = a.emb_hi[ev + i]; a.xt_lo[xv + i] = a.emb_lo[ev + i];
-    }
   }
   if (threadIdx.x == 0) {
+    a.word_idx[n] = (int32_t)w;
     int s;
     if (a.fixed_slot >= 0) s = a.fixed_slot;
     else {
@@ -212,12 +206,11 @@ __global__ void __launch_bounds__(256) k_beam_step(const BeamArgs b, const Advan
   advance_row(a, c * b.k + i, c * b.cur + sh.pb[i], (int64_t)sh.pw[i], sh.pg[i]);
 }
 
-// zero state, slot 0, xt = embed[bos]   (init_state, controllable_captioning.py:109-115, :136)
+// zero state, slot 0, input word = bos   (init_state, controllable_captioning.py:109-115, :136)
 struct PairPtr { __half* hi; __half* lo; };
 
-__global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, float* xt, int32_t* ptr,
-                             const float* embed, int bos, int Hp, int Ep, PairPtr h1b, PairPtr h2b,
-                             PairPtr xtb, PairPtr embb) {
+__global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, int32_t* word_idx, int32_t* ptr,
+                             int bos, int Hp, PairPtr h1b, PairPtr h2b) {
   const int n = blockIdx.x;
   const __half z = __float2half_rn(0.f);
   for (int i = threadIdx.x; i < Hp; i += blockDim.x) {
@@ -228,28 +221,15 @@ __global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, float* 
       h2b.hi[(size_t)n * Hp + i] = z; h2b.lo[(size_t)n * Hp + i] = z;
     }
   }
-  for (int i = threadIdx.x; i < Ep; i += blockDim.x) {
-    xt[(size_t)n * Ep + i] = embed[(size_t)bos * Ep + i];
-    if (xtb.hi != nullptr) {
-      xtb.hi[(size_t)n * Ep + i] = embb.hi[(size_t)bos * Ep + i];
-      xtb.lo[(size_t)n * Ep + i] = embb.lo[(size_t)bos * Ep + i];
-    }
-  }
-  if (threadIdx.x == 0) ptr[n] = 0;
+  if (threadIdx.x == 0) { ptr[n] = 0; word_idx[n] = bos; }
 }
 
-__global__ void k_embed(const int64_t* words, float* xt, const float* embed, int Ep, int V, PairPtr xtb,
-                        PairPtr embb) {
-  const int n = blockIdx.x;
+__global__ void k_words_from_i64(const int64_t* words, int32_t* word_idx, int rows, int V) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
   int64_t w = words[n];
   w = w < 0 ? 0 : (w >= V ? V - 1 : w);
-  for (int i = threadIdx.x; i < Ep; i += blockDim.x) {
-    xt[(size_t)n * Ep + i] = embed[(size_t)w * Ep + i];
-    if (xtb.hi != nullptr) {
-      xtb.hi[(size_t)n * Ep + i] = embb.hi[(size_t)w * Ep + i];
-      xtb.lo[(size_t)n * Ep + i] = embb.lo[(size_t)w * Ep + i];
-    }
-  }
+  word_idx[n] = (int32_t)w;
 }
 
 // greedy pick of both heads (CaptioningModel.test, CaptioningModel.py:47): first maximum wins
@@ -307,15 +287,14 @@ static PairPtr pp(const Ctx* c, const F16Pair& b) {
 }
 
 int launch_state_init(Ctx* c, int rows, cudaStream_t st) {
-  k_state_init<<<rows, 256, 0, st>>>(c->h1, c->c1, c->h2, c->c2, c->xt, c->ptr, c->embed, c->d.bos_idx,
-                                     c->Hp, c->Ep, pp(c, c->h1_b), pp(c, c->h2_b), pp(c, c->xt_b),
-                                     pp(c, c->embed_b));
+  k_state_init<<<rows, 256, 0, st>>>(c->h1, c->c1, c->h2, c->c2, c->word_idx, c->ptr, c->d.bos_idx, c->Hp,
+                                     pp(c, c->h1_b), pp(c, c->h2_b));
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   return VSR_OK;
 }
 
-int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
-  k_embed<<<rows, 256, 0, st>>>(words, c->xt, c->embed, c->Ep, c->V, pp(c, c->xt_b), pp(c, c->embed_b));
+int launch_words(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
+  k_words_from_i64<<<(rows + 127) / 128, 128, 0, st>>>(words, c->word_idx, rows, c->V);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   return VSR_OK;
 }
@@ -323,15 +302,13 @@ int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
 static void fill_advance(Ctx* c, AdvanceArgs& a) {
   a.L = c->L; a.Hp = c->Hp; a.Ep = c->Ep; a.V = c->V;
   a.h1n = c->h1n; a.c1n = c->c1n; a.h2n = c->h2n; a.c2n = c->c2n;
-  a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2; a.xt = c->xt;
-  a.ptr = c->ptr; a.ptrn = c->ptrn; a.embed = c->embed;
+  a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2;
+  a.ptr = c->ptr; a.ptrn = c->ptrn; a.word_idx = c->word_idx;
   if (c->use_tc) {
     a.h1n_hi = (const uint4*)c->h1n_b.hi; a.h1n_lo = (const uint4*)c->h1n_b.lo;
     a.h2n_hi = (const uint4*)c->h2n_b.hi; a.h2n_lo = (const uint4*)c->h2n_b.lo;
-    a.emb_hi = (const uint4*)c->embed_b.hi; a.emb_lo = (const uint4*)c->embed_b.lo;
     a.h1_hi = (uint4*)c->h1_b.hi; a.h1_lo = (uint4*)c->h1_b.lo;
     a.h2_hi = (uint4*)c->h2_b.hi; a.h2_lo = (uint4*)c->h2_b.lo;
-    a.xt_hi = (uint4*)c->xt_b.hi; a.xt_lo = (uint4*)c->xt_b.lo;
   }
 }
 

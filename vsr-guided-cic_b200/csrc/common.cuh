@@ -94,6 +94,9 @@ struct GemmArgs {
   float* c;             // [M][ldc]
   int ldc;
   int M, N;             // N multiple of NPAD
+  const float* gather = nullptr;      // optional [*][ld_gather]: adds gather[gather_idx[row]][n] (embedding-side
+  int ld_gather = 0;                  //   projections precomputed per vocabulary entry)
+  const int32_t* gather_idx = nullptr;
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
   const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
   FusedCell cell;               // epilogue fusion (tensor-core path only)
@@ -126,7 +129,7 @@ struct Ctx {
   int V, E, H, F, A;
   int Hp, Ep, Fp, Ap;          // K-padded
   int NA, NB1, NB2, NC, ND, NE;  // padded output widths of the stacked GEMMs
-  int KA;                      // [h2 (Hp, if h2_first) | xt (Ep) | h1 (Hp)]
+  int KA;                      // [h2 (Hp, if h2_first) | h1 (Hp)]  (the xt part is a per-word table, see X)
   int KD;                      // [att (Fp) | h2 (Hp)]
   // column offsets of the stacked output blocks (KPAD-aligned so float4 epilogues stay aligned)
   int oB1_sa;                  // sent:  sentinel at 0 (F) | sa at oB1_sa (A)
@@ -142,13 +145,15 @@ struct Ctx {
   float *Wva;                  // [Ap128][Fp]: att_va
   float *v_a, *v_s, *v_g;      // [Ap]
   float *embed;                // [V][Ep]
+  float *WAx;                  // [NA][Ep]  xt columns of the stacked lstm1 / s-gate / g-gate input weights
+  float *X;                    // [V][NA]   X[v] = WAx . embed[v]: the xt contribution per vocabulary entry
   int NVA;                     // padded rows of Wva
   // fp16 hi/lo twins for the tcgen05 GEMMs
   bool use_tc = true;
-  F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b, embed_b;
+  F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b;
   F16Pair WU_b, WU2_b, Wva_b;   // prologue weights
   F16Pair ds_b, img_b;          // prologue activations: slot rows [b*L*R][Fp], image descriptors [n_img][Fp]
-  F16Pair h1_b, h2_b, xt_b, s_t_b, h1n_b, g_t_b, att_b, h2n_b;
+  F16Pair h1_b, h2_b, s_t_b, h1n_b, g_t_b, att_b, h2n_b;
   // verb table (device CSR)
   int64_t* vt_keys = nullptr; int32_t* vt_off = nullptr; int32_t* vt_idx = nullptr; int vt_n = 0;
   // prologue products (per batch)
@@ -167,7 +172,7 @@ struct Ctx {
   int cap_rows = 0;
   float *h1, *c1, *h2, *c2;          // current state [rows][Hp]
   float *h1n, *c1n, *h2n, *c2n;      // state produced by the step
-  float *xt;                         // [rows][Ep]
+  int32_t *word_idx;                 // [rows] input token of the step (bos / previous pick / teacher token)
   int32_t *ptr, *ptrn;               // slot pointer per row
   float *pre1;                       // [rows][NA]
   float *s_t, *g_t;                  // [rows][Hp]
@@ -227,7 +232,7 @@ struct StepIO {
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st);
 
 int launch_state_init(Ctx* c, int rows, cudaStream_t st);
-int launch_embed(Ctx* c, const int64_t* words, int rows, cudaStream_t st);
+int launch_words(Ctx* c, const int64_t* words, int rows, cudaStream_t st);
 int launch_beam_step(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t eos1,
                      const int32_t* f_beam, const int32_t* f_word, const int32_t* f_gate, bool advance,
                      cudaStream_t st);

@@ -96,6 +96,10 @@ __global__ void __launch_bounds__(THREADS) k_gemm_simt(const GemmArgs g) {
       const float4 r = *reinterpret_cast<const float4*>(g.cadd + (size_t)row * g.ld_cadd + n);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
+    if (g.gather != nullptr) {
+      const float4 r = *reinterpret_cast<const float4*>(g.gather + (size_t)g.gather_idx[row] * g.ld_gather + n);
+      o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+    }
     *reinterpret_cast<float4*>(g.c + (size_t)row * g.ldc + n) = o;
   }
 }

@@ -155,6 +155,7 @@ struct TcProblem {
   const float* bias;
   const float* rowadd; int ld_rowadd, row_div, rowadd_mul;
   const float* cadd; int ld_cadd;
+  const float* gather; int ld_gather; const int32_t* gather_idx;   // + gather[gather_idx[row]][n]
   float* c; int ldc;
   // fused LSTM-cell epilogues (gate-interleaved output columns, see cell_col() in common.cuh)
   int mode;
@@ -269,6 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     const float* radd = (p.rowadd != nullptr && live)
                             ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
     const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
+    const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
 
     if (p.mode == EPI_PLAIN) {
       float* crow = p.c + (size_t)row * p.ldc;
@@ -309,6 +311,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
             const float4 b = *reinterpret_cast<const float4*>(cadd + n + j);
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
+          if (gath != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(gath + n + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
           *reinterpret_cast<float4*>(crow + n + j) = o;
         }
       }
@@ -339,6 +345,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
 #pragma unroll
             for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
           if (cadd != nullptr) { load8(cadd + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+          if (gath != nullptr) { load8(gath + ncol + g * 8, add);
 #pragma unroll
             for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
         }
@@ -447,6 +456,7 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN) {
   p->n_tiles = g.N / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
   p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
   p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
+  p->gather = g.gather; p->ld_gather = g.ld_gather; p->gather_idx = g.gather_idx;
   const FusedCell& f = g.cell;
   p->mode = f.mode;
   if (f.mode != 0) {

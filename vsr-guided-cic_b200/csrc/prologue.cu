@@ -143,10 +143,11 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   const int c_img = h2f ? H : 0;        // column of the img block inside input_1
   const int c_xt = c_img + F;           // column of the xt block
   // column offsets inside WA's K axis
-  const int ka_h2 = 0, ka_xt = h2f ? Hp : 0, ka_h1 = ka_xt + Ep;
+  const int ka_h2 = 0, ka_h1 = h2f ? Hp : 0;
 
   // all packed buffers were zero-filled at allocation; re-zero for repacks
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WA, 0, sizeof(float) * (size_t)c->NA * c->KA, st));
+  VSR_CHECK_CUDA(cudaMemsetAsync(c->WAx, 0, sizeof(float) * (size_t)c->NA * Ep, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WU, 0, sizeof(float) * (size_t)c->NA * c->Fp, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->bU, 0, sizeof(float) * (size_t)c->NA, st));
 
@@ -161,7 +162,7 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   for (int g = 0; g < 6; ++g) {
     const Gate& k = gates[g];
     if (h2f) VSR_TRY(pack_perm(c, c->WA, c->KA, 0, ka_h2, k.wi, in1, 0, H, H, g, 6, st));
-    VSR_TRY(pack_perm(c, c->WA, c->KA, 0, ka_xt, k.wi, in1, c_xt, H, E, g, 6, st));
+    VSR_TRY(pack_perm(c, c->WAx, Ep, 0, 0, k.wi, in1, c_xt, H, E, g, 6, st));
     if (k.wh != nullptr) VSR_TRY(pack_perm(c, c->WA, c->KA, 0, ka_h1, k.wh, H, 0, H, H, g, 6, st));
     VSR_TRY(pack_perm(c, c->WU, c->Fp, 0, 0, k.wi, in1, c_img, H, F, g, 6, st));
     VSR_TRY(pack_bias_perm(c, c->bU, k.bi, k.bh, H, g, 6, st));
@@ -208,14 +209,22 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   VSR_TRY(pack_bias(c, c->v_g, 0, w[27], nullptr, A, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->embed, 0, sizeof(float) * (size_t)V * Ep, st));
   VSR_TRY(pack_block(c, c->embed, Ep, 0, 0, w[0], E, 0, V, E, st));
+  {  // X[v] = WAx . embed[v]  (exact fp32 FFMA, once per weight load): the xt third of input_1 never enters
+     // the per-step GEMM; step t adds row X[word] in the GEMM-A epilogue instead
+    GemmArgs g{};
+    g.nseg = 1; g.seg[0] = {c->embed, Ep, Ep, Ep};
+    g.w = c->WAx; g.ldw = Ep;
+    g.c = c->X; g.ldc = c->NA; g.M = V; g.N = c->NA;
+    VSR_TRY(launch_gemm_simt(g, st));
+    c->launches++;
+  }
   // fp16 hi/lo twins of the per-step weights and of the embedding table (tcgen05 operands)
   struct Tw { const float* f; F16Pair* b; size_t n; };
   const Tw tw[] = {{c->WU, &c->WU_b, (size_t)c->NA * c->Fp}, {c->WU2, &c->WU2_b, (size_t)c->ND * c->Fp},
                    {c->Wva, &c->Wva_b, (size_t)c->NVA * c->Fp},
                    {c->WA, &c->WA_b, (size_t)c->NA * c->KA}, {c->WB1, &c->WB1_b, (size_t)c->NB1 * Hp},
                    {c->WB2, &c->WB2_b, (size_t)c->NB2 * Hp}, {c->WC, &c->WC_b, (size_t)c->NC * Hp},
-                   {c->WD, &c->WD_b, (size_t)c->ND * c->KD}, {c->WE, &c->WE_b, (size_t)c->NE * Hp},
-                   {c->embed, &c->embed_b, (size_t)V * Ep}};
+                   {c->WD, &c->WD_b, (size_t)c->ND * c->KD}, {c->WE, &c->WE_b, (size_t)c->NE * Hp}};
   for (const Tw& t : tw) {
     if (t.b->hi == nullptr || t.f == nullptr) continue;
     VSR_TRY(launch_split_f16(t.f, t.b->hi, t.b->lo, t.n, st));

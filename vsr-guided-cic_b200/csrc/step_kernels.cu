@@ -529,15 +529,15 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   const dim3 pw_grid((H + 127) / 128, rows);
   bool fused = false;   // tensor-core path: cell / gate pointwise math runs inside the GEMM epilogues
 
-  {  // A: pre1 = [h2 | xt | h1_old] . WA^T + U[img]
+  {  // A: pre1 = [h2 | h1_old] . WA^T + U[img] + X[word]
     PhaseScope ps(c, PH_GEMM_A, st);
     GemmArgs g{};
     int s = 0;
     if (h2f) g.seg[s++] = {c->h2, c->Hp, c->Hp, c->Hp, &c->h2_b};
-    g.seg[s++] = {c->xt, c->Ep, c->Ep, c->Ep, &c->xt_b};
     g.seg[s++] = {c->h1, c->Hp, c->Hp, c->Hp, &c->h1_b};
     g.nseg = s;
     g.w = c->WA; g.ldw = c->KA; g.wb = &c->WA_b;
+    g.gather = c->X; g.ld_gather = c->NA; g.gather_idx = c->word_idx;
     g.rowadd = c->U; g.ld_rowadd = c->NA; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
     fused = gemm_uses_tc(c, g);
