@@ -204,3 +204,139 @@ def test_full_size_config2_eval_shape():
     assert not v.violations, v.violations[:5]
     assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
     assert rel_close(lw.cpu(), o_lps[0][:, :1], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, :1], REL, ABS)
+
+
+# ----------------------------------------------------------------------------- remaining BASELINE configs
+def test_full_size_config3_det_regions_verb_table():
+    """BASELINE config 3 shape (eval_coco.py --det): D=100 detections, gt=False with a CSR verb table
+    (~2662 verbs x 1-6 vocabulary forms), beam 5.  32 captions keep the CPU oracle replay short."""
+    from gpu_common import make_model, device_beam
+    d = O.Dims()
+    W = O.init_weights(d, seed=1234)
+    W["out_fc.weight"] = W["out_fc.weight"] * 100.0
+    table = O.synth_verb_table(2662, d.vocab_size, seed=11)
+    m = make_model(d, W, table)
+    det, ds, verbs = O.synth_inputs(32, 100, 10, 20, 2048, seed=1003, vocab_size=d.vocab_size, n_det_range=(10, 100),
+                                    verb_slots=(1, 3), verb_id_range=(0, 2700))
+    (w, g), (lw, lg), hist, _ = device_beam(m, _cuda(det, ds, verbs), [3, -1], 5, 1, True, False, trace=False)
+    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 5, hist, True, False, table)
+    print("config3 (det, verb table)", v.summary())
+    assert not v.violations, v.violations[:5]
+    assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
+    assert rel_close(lw.cpu(), o_lps[0][:, :1], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, :1], REL, ABS)
+
+
+def test_full_size_config4_flickr_shape():
+    """BASELINE config 4 (eval_flickr.py shape): Flickr vocabulary (V=7000 is not a multiple of the tile
+    sizes), slots with a single valid region (data/field.py:1190,1356), dataset='flickr' tables."""
+    from gpu_common import make_model, device_beam
+    d = O.Dims(vocab_size=7000)
+    W = O.init_weights(d, seed=4242)
+    W["out_fc.weight"] = W["out_fc.weight"] * 100.0
+    m = make_model(d, W)
+    det, ds, verbs = O.synth_inputs(32, 100, 10, 20, 2048, seed=1004, vocab_size=d.vocab_size, n_det_range=(10, 100),
+                                    verb_slots=(2,), verb_vocab_id=23, one_region_slots=True)
+    (w, g), (lw, lg), hist, _ = device_beam(m, _cuda(det, ds, verbs), [3, -1], 5, 1, True, True, trace=False)
+    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 5, hist, True, True)
+    print("config4 (flickr shape)", v.summary())
+    assert not v.violations, v.violations[:5]
+    assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
+
+
+def test_full_size_config5_teacher_forced_forward():
+    """BASELINE config 5 (train.py XE shape): B=100, T=20, D=100, ctrl_det_seqs (100,20,20,2048); every
+    per-step log-prob of both heads against the oracle."""
+    from gpu_common import make_model
+    d = O.Dims()
+    W = O.init_weights(d, seed=1234)
+    m = make_model(d, W)
+    det, ds, _ = O.synth_inputs(100, 100, 10, 20, 2048, seed=1005, vocab_size=d.vocab_size, n_det_range=(10, 100))
+    g = torch.Generator().manual_seed(7)
+    caps = torch.randint(0, d.vocab_size, (100, 20), generator=g)
+    ctrl = torch.stack([ds[:, min(t // 2, 9)] for t in range(20)], 1).contiguous()
+    out, gate = m((det.to(DEV),), (caps.to(DEV), ctrl.to(DEV)))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ro, rg = O.forward_teacher(W, d, (det,), (caps, ctrl))
+    from common import tol_ratio
+    print("config5 forward: tolerance fraction out/gate:", tol_ratio(out.cpu(), ro), tol_ratio(gate.cpu(), rg))
+    assert out.shape == ro.shape == (100, 20, d.vocab_size) and gate.shape == rg.shape
+    assert rel_close(out.cpu(), ro, REL, ABS) and rel_close(gate.cpu(), rg, REL, ABS)
+
+
+# ----------------------------------------------------------------------------- size-independent properties
+def _config2_inputs(b=100, seed=1002):
+    return O.synth_inputs(b, 50, 10, 20, 2048, seed=seed, vocab_size=10000, n_det_range=(10, 50), verb_slots=(2,),
+                          verb_vocab_id=17)
+
+
+def test_properties_at_full_size():
+    """At BASELINE config-2 size, without the oracle: (1) determinism, (2) captions are independent units
+    (a batch decodes to exactly what its halves decode to: the basis of the multi-GPU sharding),
+    (3) beams come out sorted by score and every history entry is in range, (4) a forced trajectory
+    replays to the same scores."""
+    from gpu_common import device_beam
+    d, W, m = _full_model(1234, 100.0)
+    det, ds, verbs = _cuda(*_config2_inputs())
+    (w1, g1), (lw1, lg1), hist1, _ = device_beam(m, (det, ds, verbs), [3, -1], 5, 5, True, True, trace=False)
+    (w2, g2), (lw2, lg2), hist2, _ = device_beam(m, (det, ds, verbs), [3, -1], 5, 5, True, True, trace=False)
+    assert torch.equal(w1, w2) and torch.equal(g1, g2) and torch.equal(lw1, lw2) and torch.equal(hist1[3], hist2[3])
+    parts = [device_beam(m, (det[s], ds[s], verbs[s]), [3, -1], 5, 5, True, True, trace=False)
+             for s in (slice(0, 37), slice(37, 100))]
+    assert torch.equal(torch.cat([p[0][0] for p in parts]), w1)
+    assert torch.equal(torch.cat([p[0][1] for p in parts]), g1)
+    assert torch.equal(torch.cat([p[1][0] for p in parts]), lw1)
+    parent, word, gate, score = hist1
+    assert bool((score[:, :, :-1] >= score[:, :, 1:]).all())            # each step emits beams best-first
+    assert int(parent.min()) >= 0 and int(parent[1:].max()) < 5 and int(parent[0].max()) == 0
+    assert int(word.min()) >= 0 and int(word.max()) < d.vocab_size and set(gate.unique().tolist()) <= {0, 1}
+    eng = m._engine_for((det, ds, verbs))
+    _, _, _ = eng.beam_search(5, 5, [3, -1], use_verbs=True, gt=True, forced=(parent, word, gate))
+    _, _, _, score_f = eng.history()
+    torch.cuda.synchronize()
+    assert torch.equal(score_f, score)
+
+
+def test_edge_cases_ragged_and_empty_slots():
+    """Slots with NO valid region (attention collapses onto the sentinel), a single detection, b = 1,
+    every region valid; checked against the oracle on the tiny model."""
+    from gpu_common import make_model, device_beam
+    fx = load_golden("small_a.pt")
+    d, W = fx["dims_obj"], fx["weights"]
+    m = make_model(d, W, fx["verb_table"])
+    det, ds, verbs = fx["det"].clone(), fx["det_seqs"].clone(), fx["verbs_gt"].clone()
+    ds[0, 1] = 0                      # an empty slot in the middle of caption 0
+    ds[1, :, 5:] = 0                  # ragged: at most 5 regions everywhere in caption 1
+    det[2, 1:] = 0                    # a single valid detection
+    ds[3] = torch.relu(torch.randn(ds[3].shape, generator=torch.Generator().manual_seed(3))) + 0.1   # all valid
+    for sl in (slice(None), slice(0, 1)):
+        statics = (det[sl], ds[sl], verbs[sl])
+        (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(*statics), [3, -1], 3, 2, True, True)
+        v, o_outs, o_lps = verify_device_beam(W, d, statics, [3, -1], 3, hist, True, True, fx["verb_table"],
+                                              extra["step_out"], extra["step_gate"])
+        print("edge cases", v.summary())
+        assert not v.violations, v.violations[:5]
+        assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0
+        assert torch.equal(w.cpu(), o_outs[0][:, :2]) and torch.equal(g.cpu(), o_outs[1][:, :2])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_sharded_decode_matches_single_gpu():
+    """Caption-sharded decode on 2 devices (one engine each, weights replicated) == 1-device decode."""
+    from gpu_common import make_model
+    from vsrdec import shard_range
+    d = O.Dims()
+    W = O.init_weights(d, seed=1234)
+    det, ds, verbs = _config2_inputs(b=40)
+    outs = []
+    for r in range(2):
+        dev = f"cuda:{r}"
+        m = make_model(d, W, device=dev)
+        lo, hi = shard_range(40, r, 2)
+        o, lp = m.beam_search_v(tuple(t[lo:hi].to(dev) for t in (det, ds, verbs)), [3, -1], 5, 1, gt=True)
+        outs.append((o[0].cpu(), o[1].cpu(), lp[0].cpu()))
+    m0 = make_model(d, W, device="cuda:0")
+    o, lp = m0.beam_search_v(_cuda(det, ds, verbs), [3, -1], 5, 1, gt=True)
+    assert torch.equal(torch.cat([x[0] for x in outs]), o[0].cpu())
+    assert torch.equal(torch.cat([x[1] for x in outs]), o[1].cpu())
+    assert torch.equal(torch.cat([x[2] for x in outs]), lp[0].cpu())

@@ -33,6 +33,13 @@ def main(b=100, k=5, D=50, L=10, R=20, V=10000, iters=5):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     print(f"decode b={b} k={k}: {ms:.3f} ms -> {b / ms * 1e3:.1f} captions/s")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    m.beam_search_v(statics, [3, -1], k, 1, gt=True)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"host enqueue time of one decode: {1e3 * (t1 - t0):.3f} ms (then {1e3 * (t2 - t1):.3f} ms until the GPU drains)")
     m._eng.set_profiling(True)
     m.beam_search_v(statics, [3, -1], k, 1, gt=True)
     tot = 0.0
