@@ -68,7 +68,7 @@ static void reset_phases(Ctx* c) {
 #define ALLOC_F(ptr, count) VSR_TRY(dev_alloc(c, (void**)&(ptr), sizeof(float) * (size_t)(count)))
 
 // (re)allocate a fp16 hi/lo twin of a [rows][ld] fp32 matrix and build its TMA tensor maps
-int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows) {
+int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int half_rows = 0) {
   dev_free(c, b->hi); dev_free(c, b->lo);
   b->hi = b->lo = nullptr;
   if (!c->use_tc) return VSR_OK;
@@ -77,6 +77,12 @@ int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows) {
   b->rows = rows; b->ld = ld; b->box_rows = box_rows;
   VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box_rows));
   VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box_rows));
+  b->half_rows = 0;
+  if (half_rows > 0 && c->use_pair && rows % (2 * half_rows) == 0) {
+    VSR_TRY(make_tmap_f16(b->half_hi, b->hi, rows, ld, ld, half_rows));
+    VSR_TRY(make_tmap_f16(b->half_lo, b->lo, rows, ld, ld, half_rows));
+    b->half_rows = half_rows;
+  }
   return VSR_OK;
 }
 
@@ -161,7 +167,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   c->NA = 6 * c->Hp;                       // gate-interleaved: 6 gates x Hp units (multiple of 192 and 128)
   c->oB1_sa = c->Fp;
   c->NB1 = round_up(c->oB1_sa + c->A, NPAD);
-  c->oB2_ha = round_up(c->Hp, 128);        // hg block padded to whole 128-column tiles (fused g_t epilogue)
+  c->oB2_ha = round_up(c->Hp, 256);        // hg block padded to whole N tiles (fused g_t epilogue)
   c->oB2_p2 = c->oB2_ha + c->Ap;
   c->NB2 = round_up(c->oB2_p2 + 4 * c->Hp, NPAD);
   c->NC = round_up(c->A, NPAD);
@@ -191,12 +197,14 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // in flight, 3-stage ring); VSRDEC_BN=256 switches all of them for experiments
   int bn = 128;
   if (const char* e = getenv("VSRDEC_BN")) bn = atoi(e) == 256 ? 256 : 128;
-  // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn));
-  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128));
-  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn));
-  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn));
-  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128));
+  // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128.
+  // CTA-pair kernel (default; VSRDEC_2CTA=0 disables): 256 x 192 tiles for A, 256 x 256 elsewhere.
+  if (const char* e = getenv("VSRDEC_2CTA")) c->use_pair = atoi(e) != 0;
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 96)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, 128));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, 128)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, 128));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, 128));
+  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn, 128));
+  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128, 128));
   VSR_TRY(pack_weights(c, w, 0));
   VSR_CHECK_CUDA(cudaStreamSynchronize(0));
   return VSR_OK;

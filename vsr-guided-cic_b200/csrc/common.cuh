@@ -48,8 +48,11 @@ struct F16Pair {
   void* hi = nullptr;   // __half [rows][ld]
   void* lo = nullptr;
   int rows = 0, ld = 0, box_rows = 0;
+  int half_rows = 0;    // > 0 (weights only): CTA-pair GEMM, each CTA loads half_rows of a 2*half_rows-wide W tile
   alignas(64) unsigned char map_hi[128];
   alignas(64) unsigned char map_lo[128];
+  alignas(64) unsigned char half_hi[128];
+  alignas(64) unsigned char half_lo[128];
 };
 
 // ---------------------------------------------------------------- GEMM (C = sum_seg A_seg * W_seg^T + ...)
@@ -150,6 +153,7 @@ struct Ctx {
   int NVA;                     // padded rows of Wva
   // fp16 hi/lo twins for the tcgen05 GEMMs
   bool use_tc = true;
+  bool use_pair = false;         // CTA-pair (cta_group::2) GEMM tiles: correct but measured slower (VSRDEC_2CTA=1)
   F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b;
   F16Pair WU_b, WU2_b, Wva_b;   // prologue weights
   F16Pair ds_b, img_b;          // prologue activations: slot rows [b*L*R][Fp], image descriptors [n_img][Fp]

@@ -18,6 +18,8 @@
 // smem ring: kStages x {A_hi, A_lo (128 x 64 fp16), W_hi, W_lo (BN x 64 fp16)}, full/empty mbarriers;
 // the accumulator hand-off to the epilogue is a tcgen05.commit on a third mbarrier.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -32,7 +34,10 @@ constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;
 
 template <int BN> struct TcCfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 2;
+#ifndef TC_STAGES128
+#define TC_STAGES128 3
+#endif
+  static constexpr int kStages = (BN == 128) ? TC_STAGES128 : 2;
   static constexpr int kTmemCols = (BN == 128) ? 128 : 256;   // power of two >= BN
   static constexpr int kABytes = BM * BK * 2;            // 16 KB
   static constexpr int kWBytes = BN * BK * 2;            // 16 / 32 KB
@@ -168,7 +173,138 @@ struct TcProblem {
 struct TcParams {
   TcProblem pr[2];
   int nprob;
+  int dbg_passes;   // debugging only: 1 = issue only the hi*hi MMA (results wrong, timing experiment)
 };
+
+// Fused LSTM cell epilogue.  Every 32-unit chunk of the tile is NG*32 columns laid out as 4 sub-blocks of
+// [gate][8 units] (cell_col()).  LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq), LSTM2: NG = 4.
+// pre = acc + bias + rowadd + cadd + gather ; then the cell math of nn.LSTMCell.
+template <int BN, int NG>
+__device__ __forceinline__ void cell_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0, int n_tile,
+                                              const float* radd, const float* cadd, const float* gath) {
+  constexpr int CH = BN / (NG * 32);
+#pragma unroll 1
+  for (int chunk = 0; chunk < CH; ++chunk) {
+    const int cbase = chunk * NG * 32;               // first tile column of this chunk
+    const int ubase = (n_tile * CH + chunk) * 32;     // first hidden unit of this chunk
+#pragma unroll 1
+      for (int sub = 0; sub < 4; ++sub) {
+        uint32_t r[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) tmem_ld8_nowait(tlane + (uint32_t)(cbase + sub * NG * 8 + g * 8), r[g]);
+        tmem_ld_wait();
+        if (!live) continue;
+        const int ncol = n0 + cbase + sub * NG * 8;                 // first output column of this sub-block
+        const int unit0 = ubase + sub * 8;            // first hidden unit of this sub-block
+        float pre[NG][8];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+          float add[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pre[g][u] = __uint_as_float(r[g][u]);
+          if (p.bias != nullptr) { load8(p.bias + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+          if (radd != nullptr) { load8(radd + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+          if (cadd != nullptr) { load8(cadd + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+          if (gath != nullptr) { load8(gath + ncol + g * 8, add);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
+        }
+        const size_t so = (size_t)row * p.ld_state + unit0;
+        float cold[8], cn[8], hn[8];
+        load8(p.c_old + so, cold);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float ig = sigmoidf_(pre[0][u]), fg = sigmoidf_(pre[1][u]), gg = tanhf(pre[2][u]),
+                      og = sigmoidf_(pre[3][u]);
+          cn[u] = fg * cold[u] + ig * gg;
+          hn[u] = og * tanhf(cn[u]);
+        }
+        store8(p.c_new, nullptr, nullptr, so, cn);
+        store8(p.h_new, p.h_hi, p.h_lo, so, hn);
+        if constexpr (NG == 6) {
+          float sv[8], gq[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) { sv[u] = sigmoidf_(pre[4][u]) * tanhf(cn[u]); gq[u] = pre[5][u]; }
+          store8(p.s_new, p.s_hi, p.s_lo, so, sv);
+          store8(p.gq, nullptr, nullptr, so, gq);
+        }
+      }
+  }
+}
+
+template <int BN>
+__device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int n_tile,
+                                            int warp, int lane) {
+    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    const bool live = row < p.M;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float* radd = (p.rowadd != nullptr && live)
+                            ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
+    const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
+    const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
+
+    if (p.mode == EPI_PLAIN) {
+      float* crow = p.c + (size_t)row * p.ldc;
+      const bool gt_tile = n0 < p.gt_cols;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        uint32_t r[32];
+        tmem_ld32(tlane + (uint32_t)(ch * 32), r);
+        const int n = n0 + ch * 32;
+        if (!live) continue;
+        if (gt_tile) {
+          // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            if (n + j >= p.ld_state) break;       // hg block is padded up to a whole tile
+            float gq[8], cc[8], o[8];
+            load8(p.gt_gq + (size_t)row * p.ld_state + n + j, gq);
+            load8(p.gt_c1n + (size_t)row * p.ld_state + n + j, cc);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[u] = sigmoidf_(gq[u] + __uint_as_float(r[j + u])) * tanhf(cc[u]);
+            store8(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n + j, o);
+          }
+          continue;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                 __uint_as_float(r[j + 3]));
+          if (p.bias != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (radd != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(radd + n + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (cadd != nullptr) {
+            const float4 b = *reinterpret_cast<const float4*>(cadd + n + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (gath != nullptr) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(gath + n + j));
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          *reinterpret_cast<float4*>(crow + n + j) = o;
+        }
+      }
+    } else {
+      // Fused LSTM cell.  The tile's BN = NG*32 columns hold NG gates x 32 units as 4 sub-blocks of
+      // [gate][8 units] (cell_col()).  LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq),
+      // LSTM2: NG = 4.  pre = acc + bias + rowadd + cadd ; then the cell math of nn.LSTMCell.
+      // (a tile may hold several such 32-unit chunks: BN = chunks * NG * 32)
+      if constexpr (BN % 192 == 0) { if (p.mode == EPI_LSTM1) cell_epilogue<BN, 6>(p, tlane, row, live, n0, n_tile, radd, cadd, gath); }
+      if constexpr (BN % 128 == 0) { if (p.mode == EPI_LSTM2) cell_epilogue<BN, 4>(p, tlane, row, live, n0, n_tile, radd, cadd, gath); }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcParams params) {
@@ -263,121 +399,183 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   } else {
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool live = row < p.M;
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float* radd = (p.rowadd != nullptr && live)
-                            ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
-    const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
-    const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
-
-    if (p.mode == EPI_PLAIN) {
-      float* crow = p.c + (size_t)row * p.ldc;
-      const bool gt_tile = n0 < p.gt_cols;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tlane + (uint32_t)(ch * 32), r);
-        const int n = n0 + ch * 32;
-        if (!live) continue;
-        if (gt_tile) {
-          // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j >= p.ld_state) break;       // hg block is padded up to a whole tile
-            float gq[8], cc[8], o[8];
-            load8(p.gt_gq + (size_t)row * p.ld_state + n + j, gq);
-            load8(p.gt_c1n + (size_t)row * p.ld_state + n + j, cc);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) o[u] = sigmoidf_(gq[u] + __uint_as_float(r[j + u])) * tanhf(cc[u]);
-            store8(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n + j, o);
-          }
-          continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3]));
-          if (p.bias != nullptr) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (radd != nullptr) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(radd + n + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (cadd != nullptr) {
-            const float4 b = *reinterpret_cast<const float4*>(cadd + n + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (gath != nullptr) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(gath + n + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          *reinterpret_cast<float4*>(crow + n + j) = o;
-        }
-      }
-    } else {
-      // Fused LSTM cell.  The tile's BN = NG*32 columns hold NG gates x 32 units as 4 sub-blocks of
-      // [gate][8 units] (cell_col()).  LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq),
-      // LSTM2: NG = 4.  pre = acc + bias + rowadd + cadd ; then the cell math of nn.LSTMCell.
-      constexpr int NG = BN / 32;
-#pragma unroll 1
-      for (int sub = 0; sub < 4; ++sub) {
-        uint32_t r[NG][8];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) tmem_ld8_nowait(tlane + (uint32_t)(sub * NG * 8 + g * 8), r[g]);
-        tmem_ld_wait();
-        if (!live) continue;
-        const int ncol = n0 + sub * NG * 8;                 // first output column of this sub-block
-        const int unit0 = n_tile * 32 + sub * 8;            // first hidden unit of this sub-block
-        float pre[NG][8];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          float add[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) pre[g][u] = __uint_as_float(r[g][u]);
-          if (p.bias != nullptr) { load8(p.bias + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-          if (radd != nullptr) { load8(radd + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-          if (cadd != nullptr) { load8(cadd + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-          if (gath != nullptr) { load8(gath + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-        }
-        const size_t so = (size_t)row * p.ld_state + unit0;
-        float cold[8], cn[8], hn[8];
-        load8(p.c_old + so, cold);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float ig = sigmoidf_(pre[0][u]), fg = sigmoidf_(pre[1][u]), gg = tanhf(pre[2][u]),
-                      og = sigmoidf_(pre[3][u]);
-          cn[u] = fg * cold[u] + ig * gg;
-          hn[u] = og * tanhf(cn[u]);
-        }
-        store8(p.c_new, nullptr, nullptr, so, cn);
-        store8(p.h_new, p.h_hi, p.h_lo, so, hn);
-        if constexpr (NG == 6) {
-          float sv[8], gq[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { sv[u] = sigmoidf_(pre[4][u]) * tanhf(cn[u]); gq[u] = pre[5][u]; }
-          store8(p.s_new, p.s_hi, p.s_lo, so, sv);
-          store8(p.gq, nullptr, nullptr, so, gq);
-        }
-      }
-    }
+    tc_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
+// Two CTAs of a cluster (one TPC) compute a 256 x BN tile: each CTA stages its own 128 rows of A and HALF
+// of the W tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both
+// halves, and each CTA ends up with its 128 x BN accumulator half in its own TMEM.  Operand bytes pulled
+// from L2 per output drop by ~2x versus the 128 x 128 single-CTA tile, which is what bounds these skinny
+// three-pass GEMMs (measured: the single-CTA kernel saturates the L2->SM fabric, not the tensor pipe).
+template <int BN> struct Tc2Cfg {
+  static constexpr int kStages = 3;
+  static constexpr int kABytes = BM * BK * 2;                 // 16 KB   (this CTA's 128 rows)
+  static constexpr int kWBytes = (BN / 2) * BK * 2;           // 12/16 KB (this CTA's half of the W tile)
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kTmemCols = 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (count 1) on the same mbarrier of CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// commit: arrive on the same mbarrier in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc_pair() {   // M = 256
+  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+k_gemm_tc2(const __grid_constant__ TcParams params) {
+  using Cfg = Tc2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];     // used in the leader CTA only
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();         // 0 = leader (issues the MMAs), 1 = peer
+  // pair tile of this cluster: problems back to back; consecutive clusters walk the M pairs of one W tile
+  int t = blockIdx.x >> 1;
+  const int m_pairs0 = (params.pr[0].m_tiles + 1) >> 1;
+  const int tiles0 = params.pr[0].n_tiles * m_pairs0;
+  const int pi = (params.nprob > 1 && t >= tiles0) ? 1 : 0;
+  t -= pi * tiles0;
+  const TcProblem& p = params.pr[pi];
+  const int m_pairs = (p.m_tiles + 1) >> 1;
+  const int m_pair = t % m_pairs, n_tile = t / m_pairs;
+  const int m0 = (m_pair * 2 + (int)rank) * BM, n0 = n_tile * BN;
+
+  if (p.row_skip != nullptr) {   // pair-uniform: skip only when all 256 rows of the pair are padding
+    int any = 0;
+    for (int r = threadIdx.x; r < 2 * BM; r += TC_THREADS) {
+      const int row = m_pair * 2 * BM + r;
+      if (row < p.M) any |= p.row_skip[row];
+    }
+    if (!__syncthreads_or(any)) return;
+  }
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); }
+    prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+      mbar_init(&tmem_full_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();            // barriers of both CTAs initialised, TMEM allocated in both
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  int total_kb = 0;
+  for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int seg = 0, kk = 0;
+      const int wrow = n0 + (int)rank * (BN / 2);     // this CTA's half of the W tile
+      for (int kb = 0; kb < total_kb; ++kb) {
+        const int st = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&empty_bar[st], ph ^ 1);
+        uint8_t* base = smem + st * Cfg::kStageBytes;
+        if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
+        tma_load_2d_pair(&p.a_hi[seg], &full_bar[st], base, kk * BK, m0);
+        tma_load_2d_pair(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * BK, wrow);
+        tma_load_2d_pair(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * BK, wrow);
+        tma_load_2d_pair(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * BK, m0);
+        if (rank != 0) mbar_arrive_cluster(&full_bar[st], 0);
+        if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = make_idesc_pair<BN>();
+      for (int kb = 0; kb < total_kb; ++kb) {
+        const int st = kb % Cfg::kStages;
+        const uint32_t ph = (kb / Cfg::kStages) & 1;
+        mbar_wait(&full_bar[st], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
+        const uint64_t ah = make_sw128_desc(base), al = make_sw128_desc(base + Cfg::kABytes);
+        const uint64_t wh = make_sw128_desc(base + 2 * Cfg::kABytes);
+        const uint64_t wl = make_sw128_desc(base + 2 * Cfg::kABytes + Cfg::kWBytes);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
+          umma_f16_pair(tmem_base, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (params.dbg_passes != 1) {
+            umma_f16_pair(tmem_base, ah + off, wl + off, idesc, 1u);
+            umma_f16_pair(tmem_base, al + off, wh + off, idesc, 1u);
+          }
+        }
+        umma_commit_pair(&empty_bar[st]);     // frees this stage in BOTH CTAs
+      }
+      umma_commit_pair(&tmem_full_bar);       // accumulators complete in both CTAs -> epilogues
+    }
+    __syncwarp();
+  } else {
+    mbar_wait(&tmem_full_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    tc_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  }
+  // neither CTA may release TMEM / exit while the pair's MMAs or the other epilogue are still running
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
   }
 }
 
@@ -438,11 +636,13 @@ int tc_gemm_init() {
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes));
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<192>::kSmemBytes));
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<256>::kSmemBytes));
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<192>::kSmemBytes));
   done = true;
   return VSR_OK;
 }
 
-static int fill_problem(TcProblem* p, const GemmArgs& g, int BN) {
+static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = false) {
   VSR_REQUIRE(g.N % BN == 0 && g.M > 0, VSR_EINVAL, "launch_gemm_tc: N=%d not a multiple of BN=%d", g.N, BN);
   p->nseg = g.nseg;
   for (int s = 0; s < g.nseg; ++s) {
@@ -451,8 +651,8 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN) {
     memcpy(&p->a_lo[s], g.seg[s].b->map_lo, sizeof(CUtensorMap));
     p->kblocks[s] = g.seg[s].k / BK;
   }
-  memcpy(&p->w_hi, g.wb->map_hi, sizeof(CUtensorMap));
-  memcpy(&p->w_lo, g.wb->map_lo, sizeof(CUtensorMap));
+  memcpy(&p->w_hi, pair ? g.wb->half_hi : g.wb->map_hi, sizeof(CUtensorMap));
+  memcpy(&p->w_lo, pair ? g.wb->half_lo : g.wb->map_lo, sizeof(CUtensorMap));
   p->n_tiles = g.N / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
   p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
   p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
@@ -460,8 +660,8 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN) {
   const FusedCell& f = g.cell;
   p->mode = f.mode;
   if (f.mode != 0) {
-    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && BN == 128), VSR_EINVAL,
-                "launch_gemm_tc: fused cell mode %d needs BN=%d", f.mode, f.mode == EPI_LSTM1 ? 192 : 128);
+    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN % 192 == 0) || (f.mode == EPI_LSTM2 && BN % 128 == 0), VSR_EINVAL,
+                "launch_gemm_tc: fused cell mode %d does not fit N tile %d", f.mode, BN);
     p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_hi = (__half*)f.h_hi; p->h_lo = (__half*)f.h_lo;
     p->s_new = f.s_new; p->s_hi = (__half*)f.s_hi; p->s_lo = (__half*)f.s_lo; p->gq = f.gq;
   }
@@ -472,8 +672,31 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN) {
 }
 
 // g2 (optional) is an independent problem with the same N tile that shares the launch
+// CTA-pair launch: 256 x BN2 tiles, BN2 = 2 * (rows of the weight's half-tile tensor map)
+static int launch_gemm_tc_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
+  const int BN = 2 * g.wb->half_rows;
+  VSR_REQUIRE(BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc_pair: unsupported N tile %d", BN);
+  VSR_REQUIRE(g2 == nullptr || 2 * g2->wb->half_rows == BN, VSR_EINVAL, "launch_gemm_tc_pair: grouped problems need one tile shape");
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  VSR_TRY(fill_problem(&p.pr[0], g, BN, true));
+  p.nprob = 1;
+  if (const char* e = getenv("VSRDEC_DBG_PASSES")) p.dbg_passes = atoi(e);
+  int pairs = p.pr[0].n_tiles * ((p.pr[0].m_tiles + 1) / 2);
+  if (g2 != nullptr) {
+    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, true));
+    p.nprob = 2;
+    pairs += p.pr[1].n_tiles * ((p.pr[1].m_tiles + 1) / 2);
+  }
+  if (BN == 256) k_gemm_tc2<256><<<2 * pairs, TC_THREADS, Tc2Cfg<256>::kSmemBytes, st>>>(p);
+  else k_gemm_tc2<192><<<2 * pairs, TC_THREADS, Tc2Cfg<192>::kSmemBytes, st>>>(p);
+  VSR_CHECK_CUDA(cudaGetLastError());
+  return VSR_OK;
+}
+
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   VSR_TRY(tc_gemm_init());
+  if (g.wb->half_rows > 0 && (g2 == nullptr || g2->wb->half_rows > 0)) return launch_gemm_tc_pair(g, g2, st);
   const int BN = g.wb->box_rows;
   VSR_REQUIRE(BN == 128 || BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc: unsupported N tile %d", BN);
   VSR_REQUIRE(g2 == nullptr || g2->wb->box_rows == BN, VSR_EINVAL, "launch_gemm_tc: grouped problems need one tile shape");
