@@ -354,8 +354,10 @@ def main_ours(args, rank, world, local_rank):
 def eng_gemm_kind(kind):
     """Roofline annotation of the GEMM path the handle runs (vsr_gemm_kind)."""
     if kind.startswith("tcgen05"):
+        # dram__bytes_read+write of the largest single launch (GEMM-A, grid 128) from the committed
+        # `ncu --set full` capture profiles/r01e_gemm_step_ncu_summary.md
         return {"kernel": "k_gemm_tc (tcgen05.mma kind::f16, f16x3 hi/lo split, TMA + TMEM; all per-step GEMM phases)",
-                "passes": 3, "traffic": None}
+                "passes": 3, "traffic": 63.7e6}
     return {"kernel": "k_gemm_simt (fp32 FFMA, all five per-step GEMM phases)", "passes": 1, "traffic": None}
 
 
