@@ -68,7 +68,15 @@ static void reset_phases(Ctx* c) {
 #define ALLOC_F(ptr, count) VSR_TRY(dev_alloc(c, (void**)&(ptr), sizeof(float) * (size_t)(count)))
 
 // (re)allocate a fp16 hi/lo twin of a [rows][ld] fp32 matrix and build its TMA tensor maps
-int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int half_rows = 0) {
+// padded row count of a weight whose GEMM may run with N tile `bn` or `alt_bn`
+static int pad_rows(int n_valid, int bn, int alt_bn) {
+  int r = round_up(n_valid, bn);
+  if (alt_bn > 0) r = std::max(r, round_up(n_valid, alt_bn));
+  return round_up(r, 128);
+}
+
+int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int half_rows = 0, int n_valid = 0,
+               int alt_bn = 0, int alt_kb = 64) {
   dev_free(c, b->hi); dev_free(c, b->lo);
   b->hi = b->lo = nullptr;
   if (!c->use_tc) return VSR_OK;
@@ -77,6 +85,16 @@ int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int half_rows
   b->rows = rows; b->ld = ld; b->box_rows = box_rows;
   VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box_rows));
   VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box_rows));
+  VSR_TRY(make_tmap_f16(b->map32_hi, b->hi, rows, ld, ld, box_rows, 32));
+  VSR_TRY(make_tmap_f16(b->map32_lo, b->lo, rows, ld, ld, box_rows, 32));
+  b->kb = c->gemm_kb;
+  b->n_valid = n_valid > 0 ? n_valid : rows;
+  b->alt_bn = 0;
+  if (alt_bn > 0 && c->use_alt_tiles) {
+    VSR_TRY(make_tmap_f16(b->alt_hi, b->hi, rows, ld, ld, alt_bn, alt_kb));
+    VSR_TRY(make_tmap_f16(b->alt_lo, b->lo, rows, ld, ld, alt_bn, alt_kb));
+    b->alt_bn = alt_bn; b->alt_kb = alt_kb;
+  }
   b->half_rows = 0;
   if (half_rows > 0 && c->use_pair && rows % (2 * half_rows) == 0) {
     VSR_TRY(make_tmap_f16(b->half_hi, b->hi, rows, ld, ld, half_rows));
@@ -165,14 +183,20 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   c->V = d->vocab_size; c->E = d->input_encoding_size; c->H = d->rnn_size; c->F = d->det_feat_size; c->A = d->att_size;
   c->Hp = round_up(c->H, KPAD); c->Ep = round_up(c->E, KPAD); c->Fp = round_up(c->F, KPAD); c->Ap = round_up(c->A, KPAD);
   c->NA = 6 * c->Hp;                       // gate-interleaved: 6 gates x Hp units (multiple of 192 and 128)
+  // N tiles: 128 by default; the vocabulary projection also gets an alternative tile (144) that the launcher
+  // picks when it covers the problem in fewer waves of 148 CTAs (V = 10000 at 500 rows: 280 tiles = 2 waves
+  // instead of 316 = 3).  Tiles wider than 192 measured slow on B200 (operand delivery per SM drops), so the
+  // h1'/s_t projections stay at 128.
   c->oB1_sa = c->Fp;
-  c->NB1 = round_up(c->oB1_sa + c->A, NPAD);
-  c->oB2_ha = round_up(c->Hp, 256);        // hg block padded to whole N tiles (fused g_t epilogue)
+  c->NB1v = c->oB1_sa + c->A;
+  c->NB1 = pad_rows(c->NB1v, 128, 0);
+  c->oB2_ha = c->Hp;
   c->oB2_p2 = c->oB2_ha + c->Ap;
-  c->NB2 = round_up(c->oB2_p2 + 4 * c->Hp, NPAD);
+  c->NB2v = c->oB2_p2 + 4 * c->Hp;
+  c->NB2 = pad_rows(c->NB2v, 128, 0);
   c->NC = round_up(c->A, NPAD);
   c->ND = 4 * c->Hp;                       // gate-interleaved: 4 gates x Hp units (multiple of 256)
-  c->NE = round_up(c->V, NPAD);
+  c->NE = pad_rows(c->V, 128, 144);
   c->NVA = round_up(c->A, NPAD);
   c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Hp;
   c->KD = c->Fp + c->Hp;
@@ -200,9 +224,14 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128.
   // CTA-pair kernel (default; VSRDEC_2CTA=0 disables): 256 x 192 tiles for A, 256 x 256 elsewhere.
   if (const char* e = getenv("VSRDEC_2CTA")) c->use_pair = atoi(e) != 0;
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 96)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, 128));
-  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, 128)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, 128));
-  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, 128));
+  if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
+  if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 96)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, 128, c->NB1v));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, 128, c->NB2v)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, 128));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, 128, c->V, 144, 64));
+  // GEMM-A's 192-wide tile only fits 2 ring stages with 64-element k-blocks; 32-element blocks give 5
+  c->WA_b.kb = 32;
+  if (const char* e = getenv("VSRDEC_KB_A")) c->WA_b.kb = atoi(e) == 32 ? 32 : 64;
   VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn, 128));
   if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128, 128));
   VSR_TRY(pack_weights(c, w, 0));

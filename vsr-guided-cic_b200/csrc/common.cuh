@@ -49,10 +49,18 @@ struct F16Pair {
   void* lo = nullptr;
   int rows = 0, ld = 0, box_rows = 0;
   int half_rows = 0;    // > 0 (weights only): CTA-pair GEMM, each CTA loads half_rows of a 2*half_rows-wide W tile
+  int kb = 64;          // (weights only) k-block of the GEMMs that use this weight: 64 (128B swizzle) or 32 (64B)
   alignas(64) unsigned char map_hi[128];
   alignas(64) unsigned char map_lo[128];
   alignas(64) unsigned char half_hi[128];
   alignas(64) unsigned char half_lo[128];
+  alignas(64) unsigned char map32_hi[128];   // 32-element k-blocks, 64-byte swizzle
+  alignas(64) unsigned char map32_lo[128];
+  // (weights only) alternative N tile, chosen per launch when it needs fewer waves over the 148 SMs
+  int n_valid = 0;      // real number of output rows (<= rows)
+  int alt_bn = 0, alt_kb = 64;
+  alignas(64) unsigned char alt_hi[128];
+  alignas(64) unsigned char alt_lo[128];
 };
 
 // ---------------------------------------------------------------- GEMM (C = sum_seg A_seg * W_seg^T + ...)
@@ -110,7 +118,7 @@ int launch_gemm(Ctx* c, const GemmArgs& g, cudaStream_t st, const GemmArgs* g2 =
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st);
 bool gemm_uses_tc(const Ctx* c, const GemmArgs& g);
-int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows);
+int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows, int kb = 64);
 int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
 
 // ---------------------------------------------------------------- context
@@ -132,6 +140,7 @@ struct Ctx {
   int V, E, H, F, A;
   int Hp, Ep, Fp, Ap;          // K-padded
   int NA, NB1, NB2, NC, ND, NE;  // padded output widths of the stacked GEMMs
+  int NB1v, NB2v;                // their un-padded widths
   int KA;                      // [h2 (Hp, if h2_first) | h1 (Hp)]  (the xt part is a per-word table, see X)
   int KD;                      // [att (Fp) | h2 (Hp)]
   // column offsets of the stacked output blocks (KPAD-aligned so float4 epilogues stay aligned)
@@ -153,6 +162,8 @@ struct Ctx {
   int NVA;                     // padded rows of Wva
   // fp16 hi/lo twins for the tcgen05 GEMMs
   bool use_tc = true;
+  bool use_alt_tiles = true;     // per-launch choice between the default and the alternative N tile (VSRDEC_ALT_TILES=0)
+  int gemm_kb = 64;              // k-block of the tensor-core GEMMs (VSRDEC_KB=32: 64-byte swizzle, deeper ring)
   bool use_pair = false;         // CTA-pair (cta_group::2) GEMM tiles: correct but measured slower (VSRDEC_2CTA=1)
   F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b;
   F16Pair WU_b, WU2_b, Wva_b;   // prologue weights

@@ -33,14 +33,15 @@ constexpr int BK = 64;                 // fp16 elements per k-block = one 128-by
 constexpr int UMMA_K = 16;
 constexpr int TC_THREADS = 192;
 
-template <int BN> struct TcCfg {
-#ifndef TC_STAGES128
-#define TC_STAGES128 3
-#endif
-  static constexpr int kStages = (BN == 128) ? TC_STAGES128 : 2;
-  static constexpr int kTmemCols = (BN == 128) ? 128 : 256;   // power of two >= BN
-  static constexpr int kABytes = BM * BK * 2;            // 16 KB
-  static constexpr int kWBytes = BN * BK * 2;            // 16 / 32 KB
+// KB = fp16 elements per k-block: 64 (one 128-byte swizzle row) or 32 (64-byte swizzle).  The smaller
+// block halves the stage size, i.e. doubles the ring depth that fits in 227 KB of shared memory — these
+// GEMMs are bound by operand-delivery latency (measured: 2 -> 3 stages = +17..26 % on the K = 3072 shapes).
+template <int BN, int KB> struct TcCfg {
+  static constexpr int kStageB = 2 * BM * KB * 2 + 2 * BN * KB * 2;
+  static constexpr int kStages = (220 * 1024) / kStageB > 8 ? 8 : (220 * 1024) / kStageB;
+  static constexpr int kTmemCols = (BN <= 128) ? 128 : 256;   // power of two >= BN
+  static constexpr int kABytes = BM * KB * 2;            // 16 / 8 KB
+  static constexpr int kWBytes = BN * KB * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024;   // + alignment slack
 };
@@ -73,6 +74,18 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// K-major operand tile with 64-byte swizzle (rows of 64 B, 8-row groups 512 B apart)
+__device__ __forceinline__ uint64_t make_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;                      // stride byte offset: 8 rows x 64 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;                               // layout type: SWIZZLE_64B
+  return d;
+}
+template <int KB> __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr);
+
 // K-major, 128-byte-swizzled operand tile (rows of 128 B, 8-row groups 1024 B apart): UMMA smem descriptor
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -83,6 +96,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
   return d;
 }
+
+template <> __device__ __forceinline__ uint64_t make_kmajor_desc<64>(uint32_t a) { return make_sw128_desc(a); }
+template <> __device__ __forceinline__ uint64_t make_kmajor_desc<32>(uint32_t a) { return make_sw64_desc(a); }
 
 // instruction descriptor, kind::f16: D=f32 (bit 4), A=B=f16 (format 0), both K-major, M=128, N=BN
 template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
@@ -100,24 +116,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 // tcgen05.ld of 8 consecutive fp32 columns of this warp's 32 TMEM lanes (no wait)
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -169,6 +181,7 @@ struct TcProblem {
   int ld_state;
   // fused g_t = sig(gq + acc) * tanh(c1') on the tiles with n0 < gt_cols (plain epilogue elsewhere)
   int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; __half* g_hi; __half* g_lo;
+  int dbg_nostore;   // debugging only: skip the plain epilogue's global stores (timing experiment)
 };
 struct TcParams {
   TcProblem pr[2];
@@ -252,18 +265,16 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
 
     if (p.mode == EPI_PLAIN) {
       float* crow = p.c + (size_t)row * p.ldc;
-      const bool gt_tile = n0 < p.gt_cols;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        uint32_t r[32];
-        tmem_ld32(tlane + (uint32_t)(ch * 32), r);
-        const int n = n0 + ch * 32;
+      for (int ch = 0; ch < BN / 16; ++ch) {       // 16 accumulator columns per TMEM load: any BN % 16 == 0
+        uint32_t r[16];
+        tmem_ld16(tlane + (uint32_t)(ch * 16), r);
+        const int n = n0 + ch * 16;
         if (!live) continue;
-        if (gt_tile) {
+        if (n < p.gt_cols) {
           // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (n + j >= p.ld_state) break;       // hg block is padded up to a whole tile
+          for (int j = 0; j < 16; j += 8) {
             float gq[8], cc[8], o[8];
             load8(p.gt_gq + (size_t)row * p.ld_state + n + j, gq);
             load8(p.gt_c1n + (size_t)row * p.ld_state + n + j, cc);
@@ -274,7 +285,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
           continue;
         }
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < 16; j += 4) {
           float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                  __uint_as_float(r[j + 3]));
           if (p.bias != nullptr) {
@@ -293,7 +304,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
             const float4 b = __ldg(reinterpret_cast<const float4*>(gath + n + j));
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          *reinterpret_cast<float4*>(crow + n + j) = o;
+          if (!p.dbg_nostore) *reinterpret_cast<float4*>(crow + n + j) = o;
         }
       }
     } else {
@@ -306,9 +317,9 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
     }
 }
 
-template <int BN>
+template <int BN, int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcParams params) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, KB>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
   __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
@@ -364,10 +375,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* base = smem + st * Cfg::kStageBytes;
         mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
-        tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * BK, m0);
-        tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * BK, n0);
-        tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * BK, n0);
-        tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * BK, m0);
+        tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
+        tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
+        tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+        tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
         if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
       }
     }
@@ -381,11 +392,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         mbar_wait(&full_bar[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
-        const uint64_t ah = make_sw128_desc(base), al = make_sw128_desc(base + Cfg::kABytes);
-        const uint64_t wh = make_sw128_desc(base + 2 * Cfg::kABytes);
-        const uint64_t wl = make_sw128_desc(base + 2 * Cfg::kABytes + Cfg::kWBytes);
+        const uint64_t ah = make_kmajor_desc<KB>(base), al = make_kmajor_desc<KB>(base + Cfg::kABytes);
+        const uint64_t wh = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes);
+        const uint64_t wl = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
+        for (int k = 0; k < KB / UMMA_K; ++k) {
           const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);     // advance inside the swizzle row
           umma_f16(tmem_base, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_f16(tmem_base, ah + off, wl + off, idesc, 1u);
@@ -609,15 +620,15 @@ EncodeTiledFn get_encode() {
 }  // namespace
 
 // 2-D fp16 tensor map over a row-major [rows][ld] buffer: box = 64 (K) x box_rows, 128-byte swizzle
-int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows) {
+int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows, int kb) {
   EncodeTiledFn enc = get_encode();
   VSR_REQUIRE(enc != nullptr, VSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   const cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstr,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VSR_REQUIRE(r == CUDA_SUCCESS, VSR_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
   return VSR_OK;
@@ -633,30 +644,34 @@ int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t 
 int tc_gemm_init() {
   static bool done = false;
   if (done) return VSR_OK;
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::kSmemBytes));
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<192>::kSmemBytes));
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::kSmemBytes));
+#define TC_SET_SMEM(BN_, KB_) VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN_, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_, KB_>::kSmemBytes))
+  TC_SET_SMEM(256, 64); TC_SET_SMEM(192, 64); TC_SET_SMEM(128, 64);
+  TC_SET_SMEM(256, 32); TC_SET_SMEM(192, 32); TC_SET_SMEM(128, 32);
+  TC_SET_SMEM(144, 64); TC_SET_SMEM(240, 32);
+#undef TC_SET_SMEM
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<256>::kSmemBytes));
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<192>::kSmemBytes));
   done = true;
   return VSR_OK;
 }
 
-static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = false) {
-  VSR_REQUIRE(g.N % BN == 0 && g.M > 0, VSR_EINVAL, "launch_gemm_tc: N=%d not a multiple of BN=%d", g.N, BN);
+static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = false, int kb = 64) {
+  VSR_REQUIRE(g.M > 0 && g.N >= round_up(g.wb->n_valid, BN), VSR_EINVAL, "launch_gemm_tc: N=%d too small for N tile %d", g.N, BN);
   p->nseg = g.nseg;
   for (int s = 0; s < g.nseg; ++s) {
     VSR_REQUIRE(g.seg[s].b != nullptr && g.seg[s].k % BK == 0, VSR_EINVAL, "launch_gemm_tc: segment %d not tensor-core ready", s);
-    memcpy(&p->a_hi[s], g.seg[s].b->map_hi, sizeof(CUtensorMap));
-    memcpy(&p->a_lo[s], g.seg[s].b->map_lo, sizeof(CUtensorMap));
-    p->kblocks[s] = g.seg[s].k / BK;
+    memcpy(&p->a_hi[s], kb == 32 ? g.seg[s].b->map32_hi : g.seg[s].b->map_hi, sizeof(CUtensorMap));
+    memcpy(&p->a_lo[s], kb == 32 ? g.seg[s].b->map32_lo : g.seg[s].b->map_lo, sizeof(CUtensorMap));
+    p->kblocks[s] = g.seg[s].k / kb;
   }
-  memcpy(&p->w_hi, pair ? g.wb->half_hi : g.wb->map_hi, sizeof(CUtensorMap));
-  memcpy(&p->w_lo, pair ? g.wb->half_lo : g.wb->map_lo, sizeof(CUtensorMap));
-  p->n_tiles = g.N / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
+  const bool alt = !pair && BN == g.wb->alt_bn && BN != g.wb->box_rows;
+  memcpy(&p->w_hi, pair ? g.wb->half_hi : alt ? g.wb->alt_hi : (kb == 32 ? g.wb->map32_hi : g.wb->map_hi), sizeof(CUtensorMap));
+  memcpy(&p->w_lo, pair ? g.wb->half_lo : alt ? g.wb->alt_lo : (kb == 32 ? g.wb->map32_lo : g.wb->map_lo), sizeof(CUtensorMap));
+  p->n_tiles = (g.wb->n_valid + BN - 1) / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
   p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
   p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
   p->gather = g.gather; p->ld_gather = g.ld_gather; p->gather_idx = g.gather_idx;
+  if (const char* e = getenv("VSRDEC_DBG_NOSTORE")) p->dbg_nostore = atoi(e);
   const FusedCell& f = g.cell;
   p->mode = f.mode;
   if (f.mode != 0) {
@@ -697,22 +712,43 @@ static int launch_gemm_tc_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   VSR_TRY(tc_gemm_init());
   if (g.wb->half_rows > 0 && (g2 == nullptr || g2->wb->half_rows > 0)) return launch_gemm_tc_pair(g, g2, st);
-  const int BN = g.wb->box_rows;
+  int BN = g.wb->box_rows;
   VSR_REQUIRE(BN == 128 || BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc: unsupported N tile %d", BN);
   VSR_REQUIRE(g2 == nullptr || g2->wb->box_rows == BN, VSR_EINVAL, "launch_gemm_tc: grouped problems need one tile shape");
   TcParams p;            // ~2.7 KB; passed by value at launch
   memset(&p, 0, sizeof(p));
-  VSR_TRY(fill_problem(&p.pr[0], g, BN));
+  int kb = g.wb->kb;          // k-block (64 or 32 fp16) chosen per weight at pack time
+  VSR_REQUIRE(g2 == nullptr || g2->wb->kb == kb, VSR_EINVAL, "launch_gemm_tc: grouped problems need one k-block size");
+  // Tile choice: operand delivery bounds these GEMMs, so a tile costs ~ (BM + BN) and a launch costs
+  // waves(tiles / 148 SMs) * (BM + BN).  Take the alternative N tile when that is cheaper.
+  if (g.wb->alt_bn > 0 && g.cell.mode == 0 && (g2 == nullptr || (g2->wb->alt_bn == g.wb->alt_bn && g2->cell.mode == 0))) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const int mt = (g.M + BM - 1) / BM;
+    auto cost = [&](int bn) {
+      int tiles = mt * ((g.wb->n_valid + bn - 1) / bn);
+      if (g2 != nullptr) tiles += ((g2->M + BM - 1) / BM) * ((g2->wb->n_valid + bn - 1) / bn);
+      return ((tiles + sms - 1) / sms) * (BM + bn);
+    };
+    if (cost(g.wb->alt_bn) < cost(BN)) { BN = g.wb->alt_bn; kb = g.wb->alt_kb; }
+  }
+  VSR_TRY(fill_problem(&p.pr[0], g, BN, false, kb));
   p.nprob = 1;
   int tiles = p.pr[0].n_tiles * p.pr[0].m_tiles;
   if (g2 != nullptr) {
-    VSR_TRY(fill_problem(&p.pr[1], *g2, BN));
+    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, false, kb));
     p.nprob = 2;
     tiles += p.pr[1].n_tiles * p.pr[1].m_tiles;
   }
-  if (BN == 256) k_gemm_tc<256><<<tiles, TC_THREADS, TcCfg<256>::kSmemBytes, st>>>(p);
-  else if (BN == 192) k_gemm_tc<192><<<tiles, TC_THREADS, TcCfg<192>::kSmemBytes, st>>>(p);
-  else k_gemm_tc<128><<<tiles, TC_THREADS, TcCfg<128>::kSmemBytes, st>>>(p);
+#define TC_LAUNCH(BN_, KB_) k_gemm_tc<BN_, KB_><<<tiles, TC_THREADS, TcCfg<BN_, KB_>::kSmemBytes, st>>>(p)
+  if (BN == 144) TC_LAUNCH(144, 64);
+  else if (BN == 240) TC_LAUNCH(240, 32);
+  else if (kb == 32) {
+    if (BN == 256) TC_LAUNCH(256, 32); else if (BN == 192) TC_LAUNCH(192, 32); else TC_LAUNCH(128, 32);
+  } else {
+    if (BN == 256) TC_LAUNCH(256, 64); else if (BN == 192) TC_LAUNCH(192, 64); else TC_LAUNCH(128, 64);
+  }
+#undef TC_LAUNCH
   VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }

@@ -23,10 +23,13 @@ static float* dev_rand(size_t n, float scale, unsigned seed) {
 }
 static void make_pair(F16Pair* b, const float* f, int rows, int ld, int box, int half = 0) {
   CK(cudaMalloc(&b->hi, (size_t)rows * ld * 2)); CK(cudaMalloc(&b->lo, (size_t)rows * ld * 2));
-  b->rows = rows; b->ld = ld; b->box_rows = box;
+  b->rows = rows; b->ld = ld; b->box_rows = box; b->n_valid = rows;
   VK(launch_split_f16(f, b->hi, b->lo, (size_t)rows * ld, 0));
   VK(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box));
   VK(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box));
+  VK(make_tmap_f16(b->map32_hi, b->hi, rows, ld, ld, box, 32));
+  VK(make_tmap_f16(b->map32_lo, b->lo, rows, ld, ld, box, 32));
+  b->kb = getenv("VSRDEC_KB") && atoi(getenv("VSRDEC_KB")) == 32 ? 32 : 64;
   b->half_rows = 0;
   if (half > 0) {
     VK(make_tmap_f16(b->half_hi, b->hi, rows, ld, ld, half));
