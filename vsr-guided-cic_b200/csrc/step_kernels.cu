@@ -330,49 +330,109 @@ struct SoftmaxArgs {
   float* gate_out; int64_t gate_stride;  // optional copy of the gate rows
 };
 
-// The row is staged ONCE in shared memory (each thread re-reads only the float4s it loaded itself, so no
-// barrier guards the staging); statistics use the exact two-pass formula
-// log_softmax = (x - max) - log(sum exp(x - max)); the top-k is k rounds of block arg-best over each
-// thread's best remaining element (the owner of a pick rescans its own elements for the next one).
+// One pass over the row (each thread: its float4s in register batches): online (max, sum exp) per thread,
+// merged block-wide, plus the thread's two best elements.  Every warp then picks the top-k of its 64
+// candidates with redux.sync rounds (no shuffles trees, no barriers), and after the single block barrier
+// warp 0 merges the 8 x k survivors the same way.  That is exact unless one thread owns three of the
+// top-k, which the final pick reveals (a thread's SECOND candidate chosen); such rows (~1e-4 of them)
+// take the slow exact path: k rounds of block arg-best with the owner rescanning its elements.
+// Serial single-warp sections are kept to a few hundred cycles: they dominated earlier versions.
 constexpr int SM_THREADS = 256;
+
+__device__ __forceinline__ unsigned orderable(float v) {     // monotone float -> unsigned
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// warp arg-best in (value desc, index asc) order with two redux.sync; every lane gets the winner
+__device__ __forceinline__ void warp_argbest_redux(float v, int i, unsigned& kbest, int& ibest) {
+  const unsigned key = orderable(v);
+  kbest = __reduce_max_sync(0xffffffffu, key);
+  ibest = (int)__reduce_min_sync(0xffffffffu, key == kbest ? (unsigned)i : 0xffffffffu);
+}
+
 __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a) {
   constexpr int THREADS = SM_THREADS;
   constexpr int NW = THREADS / 32;
-  extern __shared__ float4 row4[];        // [ceil(V/4)]
+  __shared__ float red_m[NW], red_s[NW];
+  __shared__ float wl_v[NW][VSR_MAX_BEAM];      // per-warp top-k lists
+  __shared__ int wl_i[NW][VSR_MAX_BEAM];
+  __shared__ int wl_second[NW][VSR_MAX_BEAM];
   __shared__ float red_v[2][NW];
   __shared__ int red_i[2][NW];
-  __shared__ float red_s[NW];
   __shared__ float s_stay;
-  __shared__ int s_forced;
+  __shared__ int s_forced, s_slow;
+  __shared__ int s_pick[VSR_MAX_BEAM];
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = a.logits + (size_t)n * a.ld;
   const int V = a.V;
   const int n4 = (V + 3) >> 2;
+  const int topk = a.topk;
 
-  // stage + this thread's best element, tail of the last float4 masked to -inf
-  float cv = -INFINITY; int ci = 0x7fffffff;
-  for (int j0 = tid; j0 < n4; j0 += THREADS * 4) {
-    float4 q[4];
+  // thread 0 starts its dependent loads early (slot pointer -> verb id, shift logit)
+  int64_t verb = -1; float shift_logit = 0.f;
+  if (tid == 0) {
+    shift_logit = a.shift[n];
+    if (a.use_verbs && a.verbs != nullptr)
+      verb = load_verb(a.verbs, a.verbs_dtype, (size_t)(n / a.cur_beam) * a.L + a.ptr[n]);
+  }
+
+  float v1 = -INFINITY, v2 = -INFINITY; int i1 = 0x7fffffff, i2 = 0x7fffffff;   // this thread's two best
+  float m = -INFINITY, ssum = 0.f;
+  constexpr int PRE = 5;
+  for (int j0 = tid; j0 < n4; j0 += THREADS * PRE) {
+    float4 q[PRE];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < PRE; ++u) {
       const int j = j0 + u * THREADS;
-      if (j < n4) q[u] = *reinterpret_cast<const float4*>(x + j * 4);
+      q[u] = j < n4 ? *reinterpret_cast<const float4*>(x + j * 4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     }
+    float bm = -INFINITY;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int j = j0 + u * THREADS;
-      if (j >= n4) break;
-      const int v0 = j * 4;
-      if (v0 + 1 >= V) q[u].y = -INFINITY;
-      if (v0 + 2 >= V) q[u].z = -INFINITY;
-      if (v0 + 3 >= V) q[u].w = -INFINITY;
-      row4[j] = q[u];
+    for (int u = 0; u < PRE; ++u) {
+      const int v0 = (j0 + u * THREADS) * 4;
+      if (v0 + 3 >= V) {                        // only the row's last float4 (or an out-of-range one) needs masking
+        if (v0 + 1 >= V) q[u].y = -INFINITY;
+        if (v0 + 2 >= V) q[u].z = -INFINITY;
+        q[u].w = -INFINITY;
+        if (v0 >= V) q[u].x = -INFINITY;
+      }
       const float e4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) if (before(e4[e], v0 + e, cv, ci)) { cv = e4[e]; ci = v0 + e; }
+      for (int e = 0; e < 4; ++e) {
+        const float val = e4[e];
+        bm = fmaxf(bm, val);
+        if (val > v2) {                         // strict: equal values keep the earlier (smaller) index
+          if (val > v1) { v2 = v1; i2 = i1; v1 = val; i1 = v0 + e; } else { v2 = val; i2 = v0 + e; }
+        }
+      }
+    }
+    if (bm > m) { ssum *= expf(m - bm); m = bm; }
+    if (m > -INFINITY) {
+#pragma unroll
+      for (int u = 0; u < PRE; ++u)
+        ssum += (expf(q[u].x - m) + expf(q[u].y - m)) + (expf(q[u].z - m) + expf(q[u].w - m));   // exp(-inf) = 0
     }
   }
+  {
+    const float wm = warp_max(m);
+    const float ws = warp_sum(m > -INFINITY ? ssum * expf(m - wm) : 0.f);
+    if (lane == 0) { red_m[warp] = wm; red_s[warp] = ws; }
+  }
+  // warp-level top-k of the warp's 64 candidates
+  {
+    int head = 0;
+    for (int j = 0; j < topk; ++j) {
+      const float hv = head == 0 ? v1 : (head == 1 ? v2 : -INFINITY);
+      const int hi = head == 0 ? i1 : (head == 1 ? i2 : 0x7fffffff);
+      unsigned kb; int ib;
+      warp_argbest_redux(hv, hi, kb, ib);
+      const bool mine = hi == ib && ib != 0x7fffffff;
+      if (mine) { wl_v[warp][j] = hv; wl_i[warp][j] = hi; wl_second[warp][j] = head; ++head; }
+      if (ib == 0x7fffffff && lane == 0) { wl_v[warp][j] = -INFINITY; wl_i[warp][j] = 0x7fffffff; wl_second[warp][j] = 0; }
+    }
+  }
+  if (tid == 0) s_slow = 0;
   // stay-gate logit (last warp)
   if (warp == NW - 1) {
     const float* ha = a.ha + (size_t)n * a.ld_ha;
@@ -382,80 +442,67 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     acc = warp_sum(acc);
     if (lane == 0) s_stay = acc;
   }
-
-  // block arg-best of the per-thread candidates; round r uses smem buffer r&1 (one barrier per round)
-  auto block_best = [&](int r, float& bv, int& bi) {
-    bv = cv; bi = ci;
-    warp_argbest(bv, bi);
-    if (lane == 0) { red_v[r & 1][warp] = bv; red_i[r & 1][warp] = bi; }
-    __syncthreads();
-    bv = red_v[r & 1][0]; bi = red_i[r & 1][0];
-#pragma unroll
-    for (int w = 1; w < NW; ++w)
-      if (before(red_v[r & 1][w], red_i[r & 1][w], bv, bi)) { bv = red_v[r & 1][w]; bi = red_i[r & 1][w]; }
-  };
-  // the owner of the selected element moves on to its next best (strictly after (pv,pi) in the order)
-  auto pop = [&](float pv, int pi) {
-    if (ci != pi) return;
-    cv = -INFINITY; ci = 0x7fffffff;
-    for (int j = tid; j < n4; j += THREADS) {
-      const float4 qq = row4[j];
-      const int v0 = j * 4;
-      const float e4[4] = {qq.x, qq.y, qq.z, qq.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (before(pv, pi, e4[u], v0 + u) && before(e4[u], v0 + u, cv, ci)) { cv = e4[u]; ci = v0 + u; }
-    }
-  };
-
-  float bv; int bi;
-  block_best(0, bv, bi);                 // round 0: the row maximum (and the first candidate)
-  const float mx = bv;
-  const int first = bi;
-  float se = 0.f;
-  for (int j = tid; j < n4; j += THREADS) {
-    const float4 qq = row4[j];
-    se += (expf(qq.x - mx) + expf(qq.y - mx)) + (expf(qq.z - mx) + expf(qq.w - mx));   // exp(-inf) = 0 on the tail
-  }
-  se = warp_sum(se);
-  if (lane == 0) red_s[warp] = se;
-  pop(bv, bi);
   __syncthreads();
-  se = 0.f;
+
+  float mx = red_m[0];
 #pragma unroll
-  for (int w = 0; w < NW; ++w) se += red_s[w];
+  for (int w = 1; w < NW; ++w) mx = fmaxf(mx, red_m[w]);
+  float se = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) se += red_s[w] * expf(red_m[w] - mx);
   const float lsum = logf(se);
+
+  if (warp == 0) {
+    // merge the NW per-warp lists (NW * topk <= 64 entries: two per lane)
+    float cvv[2] = {-INFINITY, -INFINITY}; int cii[2] = {0x7fffffff, 0x7fffffff}; int csec[2] = {0, 0};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = lane + 32 * q;
+      if (e < NW * topk) { cvv[q] = wl_v[e / topk][e % topk]; cii[q] = wl_i[e / topk][e % topk]; csec[q] = wl_second[e / topk][e % topk]; }
+    }
+    int slow = 0;
+    for (int j = 0; j < topk; ++j) {
+      const bool first = before(cvv[0], cii[0], cvv[1], cii[1]);
+      const float hv = first ? cvv[0] : cvv[1];
+      const int hi = first ? cii[0] : cii[1];
+      unsigned kb; int ib;
+      warp_argbest_redux(hv, hi, kb, ib);
+      if (hi == ib && ib != 0x7fffffff) {
+        slow |= first ? csec[0] : csec[1];
+        if (first) { cvv[0] = -INFINITY; cii[0] = 0x7fffffff; } else { cvv[1] = -INFINITY; cii[1] = 0x7fffffff; }
+      }
+      if (lane == 0) s_pick[j] = ib;
+    }
+    slow = __any_sync(0xffffffffu, slow != 0);
+    if (lane == 0) s_slow = slow;
+  }
 
   if (tid == 0) {
     // verb forcing (:271-295): which vocabulary index does the current slot force, if any
     int forced = -1;
-    if (a.use_verbs && a.verbs != nullptr) {
-      const int cap = n / a.cur_beam;
-      const int64_t verb = load_verb(a.verbs, a.verbs_dtype, (size_t)cap * a.L + a.ptr[n]);
-      if (verb != -1) {
-        if (a.gt) {
-          forced = (int)verb;
-        } else {
-          forced = 0;   // key missing or empty list -> vocabulary index 0 (:291-292)
-          int lo = 0, hi = a.vt_n - 1, pos = -1;
-          while (lo <= hi) {
-            const int mid = (lo + hi) >> 1;
-            const int64_t k = a.vt_keys[mid];
-            if (k == verb) { pos = mid; break; }
-            if (k < verb) lo = mid + 1; else hi = mid - 1;
-          }
-          if (pos >= 0 && a.vt_off[pos + 1] > a.vt_off[pos]) {
-            float best = -1e6f; int best_i = -1;    // strict '>' : first maximum wins (:284-289)
-            for (int qq = a.vt_off[pos]; qq < a.vt_off[pos + 1]; ++qq) {
-              const int idx = a.vt_idx[qq];
-              const float lp = (x[idx] - mx) - lsum;
-              if (lp > best) { best = lp; best_i = idx; }
-            }
-            forced = best_i < 0 ? V - 1 : best_i;   // python index -1 == last vocabulary entry
-          }
+    if (verb != -1) {
+      if (a.gt) {
+        forced = (int)verb;
+      } else {
+        forced = 0;   // key missing or empty list -> vocabulary index 0 (:291-292)
+        int lo = 0, hi = a.vt_n - 1, pos = -1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          const int64_t k = a.vt_keys[mid];
+          if (k == verb) { pos = mid; break; }
+          if (k < verb) lo = mid + 1; else hi = mid - 1;
         }
-        forced = min(max(forced, 0), V - 1);
+        if (pos >= 0 && a.vt_off[pos + 1] > a.vt_off[pos]) {
+          float best = -1e6f; int best_i = -1;    // strict '>' : first maximum wins (:284-289)
+          for (int qq = a.vt_off[pos]; qq < a.vt_off[pos + 1]; ++qq) {
+            const int idx = a.vt_idx[qq];
+            const float lp = (x[idx] - mx) - lsum;
+            if (lp > best) { best = lp; best_i = idx; }
+          }
+          forced = best_i < 0 ? V - 1 : best_i;   // python index -1 == last vocabulary entry
+        }
       }
+      forced = min(max(forced, 0), V - 1);
     }
     s_forced = forced;
     a.row_max[n] = mx;
@@ -465,10 +512,10 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     float g0, g1;
     if (forced >= 0) { g0 = -1e3f; g1 = 0.f; }
     else {
-      const float stay = s_stay, shift = a.shift[n];
-      const float gm = fmaxf(stay, shift);
-      const float ls = logf(expf(stay - gm) + expf(shift - gm));
-      g0 = (stay - gm) - ls; g1 = (shift - gm) - ls;
+      const float stay = s_stay;
+      const float gm = fmaxf(stay, shift_logit);
+      const float ls = logf(expf(stay - gm) + expf(shift_logit - gm));
+      g0 = (stay - gm) - ls; g1 = (shift_logit - gm) - ls;
     }
     a.gate_lp[(size_t)n * 2] = g0; a.gate_lp[(size_t)n * 2 + 1] = g1;
     if (a.gate_out != nullptr) {
@@ -476,22 +523,16 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
       a.gate_out[(size_t)n * a.gate_stride + 1] = g1;
     }
   }
-  if (a.out_logp == nullptr && a.topk <= 0) return;
+  if (a.out_logp == nullptr && topk <= 0) return;
   __syncthreads();
   const int forced = s_forced;
 
   if (a.out_logp != nullptr) {
     float* o = a.out_logp + (size_t)n * a.out_stride;
-    for (int j = tid; j < n4; j += THREADS) {
-      const float4 qq = row4[j];
-      const int v0 = j * 4;
-      const float e4[4] = {qq.x, qq.y, qq.z, qq.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (v0 + u < V) o[v0 + u] = forced >= 0 ? (v0 + u == forced ? 0.f : -1e6f) : (e4[u] - mx) - lsum;
-    }
+    for (int v = tid; v < V; v += THREADS)
+      o[v] = forced >= 0 ? (v == forced ? 0.f : -1e6f) : (x[v] - mx) - lsum;
   }
-  if (a.topk <= 0) return;
+  if (topk <= 0) return;
 
   int32_t* cd = a.cand + (size_t)n * VSR_MAX_BEAM;
   if (forced >= 0) {
@@ -499,15 +540,37 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     if (tid == 0) {
       cd[0] = forced;
       int v = 0;
-      for (int j = 1; j < a.topk; ++j) { if (v == forced) ++v; cd[j] = min(v, V - 1); ++v; }
+      for (int j = 1; j < topk; ++j) { if (v == forced) ++v; cd[j] = min(v, V - 1); ++v; }
     }
     return;
   }
-  if (tid == 0) cd[0] = first;
-  for (int j = 1; j < a.topk; ++j) {
-    block_best(j, bv, bi);
+  if (!s_slow) {
+    if (tid < topk) cd[tid] = s_pick[tid];
+    return;
+  }
+  // ---- slow exact path (block-uniform): k rounds of block arg-best, owners rescan from global memory
+  float cv = v1; int ci = i1;
+  for (int j = 0; j < topk; ++j) {
+    float bv = cv; int bi = ci;
+    warp_argbest(bv, bi);
+    if (lane == 0) { red_v[j & 1][warp] = bv; red_i[j & 1][warp] = bi; }
+    __syncthreads();
+    bv = red_v[j & 1][0]; bi = red_i[j & 1][0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w)
+      if (before(red_v[j & 1][w], red_i[j & 1][w], bv, bi)) { bv = red_v[j & 1][w]; bi = red_i[j & 1][w]; }
     if (tid == 0) cd[j] = bi;
-    pop(bv, bi);
+    if (ci == bi) {   // owner: next best strictly after (bv, bi) among its own elements
+      cv = -INFINITY; ci = 0x7fffffff;
+      for (int jj = tid; jj < n4; jj += THREADS) {
+        const float4 qq = *reinterpret_cast<const float4*>(x + jj * 4);
+        const int v0 = jj * 4;
+        const float e4[4] = {qq.x, qq.y, qq.z, qq.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (v0 + u < V && before(bv, bi, e4[u], v0 + u) && before(e4[u], v0 + u, cv, ci)) { cv = e4[u]; ci = v0 + u; }
+      }
+    }
   }
 }
 
@@ -638,13 +701,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.row_max = c->row_max; a.row_lsum = c->row_lsum; a.forced = c->forced; a.cand = c->cand;
     a.gate_lp = c->gate_lp; a.out_logp = io.out_logp; a.out_stride = io.out_stride;
     a.gate_out = io.gate_out; a.gate_stride = io.gate_stride;
-    const size_t smem = sizeof(float) * 4 * (size_t)((c->V + 3) / 4);
-    static bool attr_set = false;
-    if (!attr_set) {
-      VSR_CHECK_CUDA(cudaFuncSetAttribute(k_softmax_topk, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
-    k_softmax_topk<<<rows, SM_THREADS, smem, st>>>(a);
+    k_softmax_topk<<<rows, SM_THREADS, 0, st>>>(a);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   return VSR_OK;
