@@ -95,11 +95,14 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
 #pragma unroll
       for (int q = 0; q < MAXC / 32; ++q)
         if (!used[q] && before(cs[q], cf[q], bv, bf)) { bv = cs[q]; bf = cf[q]; }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int of = __shfl_xor_sync(0xffffffffu, bf, o);
-        if (before(ov, of, bv, bf)) { bv = ov; bf = of; }
+      {   // warp arg-best in (score desc, flat index asc) order: two redux.sync + one broadcast
+        const unsigned u = __float_as_uint(bv);
+        const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        const unsigned kbest = __reduce_max_sync(0xffffffffu, key);
+        const int fbest = (int)__reduce_min_sync(0xffffffffu, key == kbest ? (unsigned)bf : 0xffffffffu);
+        const unsigned owner = __ballot_sync(0xffffffffu, key == kbest && bf == fbest);
+        bv = __shfl_sync(0xffffffffu, bv, __ffs(owner) - 1);
+        bf = fbest;
       }
 #pragma unroll
       for (int q = 0; q < MAXC / 32; ++q) if (cf[q] == bf) used[q] = true;

@@ -36,6 +36,15 @@ void set_error(const char* fmt, ...);
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
+#ifdef __CUDACC__
+// Gate non-linearities on the SFU (ex2.approx + fast reciprocal): absolute error ~1e-7, i.e. fp32 rounding
+// level, at ~1/4 of the instructions of expf/tanhf.  tanh via 1 - 2/(e^{2x}+1) saturates cleanly (e^{2x} = inf
+// -> 1, = 0 -> -1); its relative error grows for |x| << 1 but the ABSOLUTE error stays ~1e-7, which is what
+// the attention scores / LSTM cells need (checked by the parity tests against the fp32 oracle).
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
+#endif
+
 // K (reduction) dims are padded to KPAD floats (one 128-byte swizzle row of fp32), output-feature
 // dims to NPAD rows, activation row counts to MPAD rows; pads are zero so they never contribute.
 constexpr int KPAD = 64;    // 64 fp16 = one 128-byte swizzle row of the tensor-core operand tiles

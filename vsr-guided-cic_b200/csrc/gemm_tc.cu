@@ -133,7 +133,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // 8 consecutive fp32 values -> fp32 store + fp16 hi/lo stores (16-byte vectors)
 __device__ __forceinline__ void store8(float* f32, __half* hi, __half* lo, size_t off, const float (&v)[8]) {
@@ -233,17 +232,17 @@ __device__ __forceinline__ void cell_epilogue(const TcProblem& p, uint32_t tlane
         load8(p.c_old + so, cold);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const float ig = sigmoidf_(pre[0][u]), fg = sigmoidf_(pre[1][u]), gg = tanhf(pre[2][u]),
-                      og = sigmoidf_(pre[3][u]);
+          const float ig = fast_sigmoid(pre[0][u]), fg = fast_sigmoid(pre[1][u]), gg = fast_tanh(pre[2][u]),
+                      og = fast_sigmoid(pre[3][u]);
           cn[u] = fg * cold[u] + ig * gg;
-          hn[u] = og * tanhf(cn[u]);
+          hn[u] = og * fast_tanh(cn[u]);
         }
         store8(p.c_new, nullptr, nullptr, so, cn);
         store8(p.h_new, p.h_hi, p.h_lo, so, hn);
         if constexpr (NG == 6) {
           float sv[8], gq[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) { sv[u] = sigmoidf_(pre[4][u]) * tanhf(cn[u]); gq[u] = pre[5][u]; }
+          for (int u = 0; u < 8; ++u) { sv[u] = fast_sigmoid(pre[4][u]) * fast_tanh(cn[u]); gq[u] = pre[5][u]; }
           store8(p.s_new, p.s_hi, p.s_lo, so, sv);
           store8(p.gq, nullptr, nullptr, so, gq);
         }
@@ -279,7 +278,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
             load8(p.gt_gq + (size_t)row * p.ld_state + n + j, gq);
             load8(p.gt_c1n + (size_t)row * p.ld_state + n + j, cc);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) o[u] = sigmoidf_(gq[u] + __uint_as_float(r[j + u])) * tanhf(cc[u]);
+            for (int u = 0; u < 8; ++u) o[u] = fast_sigmoid(gq[u] + __uint_as_float(r[j + u])) * fast_tanh(cc[u]);
             store8(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n + j, o);
           }
           continue;

@@ -187,8 +187,8 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
         if (i < a.A) {
           const float4 hv = *reinterpret_cast<const float4*>(ha + i);
           const float4 vv = __ldg(reinterpret_cast<const float4*>(vec + i));
-          acc += vv.x * tanhf(pv[q].x + hv.x) + vv.y * tanhf(pv[q].y + hv.y) +
-                 vv.z * tanhf(pv[q].z + hv.z) + vv.w * tanhf(pv[q].w + hv.w);
+          acc += vv.x * fast_tanh(pv[q].x + hv.x) + vv.y * fast_tanh(pv[q].y + hv.y) +
+                 vv.z * fast_tanh(pv[q].z + hv.z) + vv.w * fast_tanh(pv[q].w + hv.w);
         }
       }
     }
@@ -407,11 +407,11 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
         }
       }
     }
-    if (bm > m) { ssum *= expf(m - bm); m = bm; }
+    if (bm > m) { ssum *= __expf(m - bm); m = bm; }
     if (m > -INFINITY) {
 #pragma unroll
       for (int u = 0; u < PRE; ++u)
-        ssum += (expf(q[u].x - m) + expf(q[u].y - m)) + (expf(q[u].z - m) + expf(q[u].w - m));   // exp(-inf) = 0
+        ssum += (__expf(q[u].x - m) + __expf(q[u].y - m)) + (__expf(q[u].z - m) + __expf(q[u].w - m));   // exp(-inf) = 0
     }
   }
   {
@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     const float* ha = a.ha + (size_t)n * a.ld_ha;
     const float* ga = a.ga + (size_t)n * a.ld_ga;
     float acc = 0.f;
-    for (int i = lane; i < a.A; i += 32) acc += a.v_g[i] * tanhf(ga[i] + ha[i]);
+    for (int i = lane; i < a.A; i += 32) acc += a.v_g[i] * fast_tanh(ga[i] + ha[i]);
     acc = warp_sum(acc);
     if (lane == 0) s_stay = acc;
   }
