@@ -264,10 +264,11 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
   }
   const size_t prow = (size_t)b * L * R;
   if (prow > c->cap_P) {
-    dev_free(c, c->P); dev_free(c, c->seq_valid);
-    c->P = nullptr; c->seq_valid = nullptr; c->cap_P = 0;
+    dev_free(c, c->P); dev_free(c, c->seq_valid); dev_free(c, c->slot_mask);
+    c->P = nullptr; c->seq_valid = nullptr; c->slot_mask = nullptr; c->cap_P = 0;
     ALLOC_F(c->P, round_up((int)prow, MPAD) * (size_t)c->NVA);
     VSR_TRY(dev_alloc(c, (void**)&c->seq_valid, round_up((int)prow, MPAD)));
+    VSR_TRY(dev_alloc(c, (void**)&c->slot_mask, sizeof(unsigned long long) * ((size_t)b * L + 1)));
     VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)prow, MPAD), c->Fp, MPAD));
     c->cap_P = prow;
   }

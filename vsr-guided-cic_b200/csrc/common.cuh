@@ -190,6 +190,7 @@ struct Ctx {
   float* U2 = nullptr;         // [n_img_alloc][ND]
   float* P = nullptr;          // [b*L*R (alloc)][NVA] att_va projections
   uint8_t* seq_valid = nullptr;  // [b*L*R]
+  unsigned long long* slot_mask = nullptr;  // [b*L] bit r set = region r of the slot is a real (non-padding) row
   uint8_t* det_valid = nullptr;  // [n_img*D]
   size_t cap_img = 0, cap_P = 0, cap_detv = 0;
   // per-row workspace (rows = captions * beam), capacity cap_rows (multiple of MPAD)

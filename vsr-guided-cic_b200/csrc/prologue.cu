@@ -78,6 +78,15 @@ __global__ void k_row_valid(const float* __restrict__ x, int64_t group_stride, i
   if (lane == 0) flag[row] = (s != 0.f) ? 1 : 0;
 }
 
+// one 64-bit validity mask per slot tile (R <= 64 regions)
+__global__ void k_slot_masks(const uint8_t* __restrict__ valid, int R, int n_slots, unsigned long long* __restrict__ mask) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  unsigned long long m = 0;
+  for (int r = 0; r < R; ++r) if (valid[(size_t)s * R + r]) m |= 1ull << r;
+  mask[s] = m;
+}
+
 // img[g][f] = sum_d det[g][d][f] / count(valid rows of g); one thread per float4 column.
 __global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D, int F,
                        const uint8_t* __restrict__ valid, float* __restrict__ img, int ld_img, PairOut split) {
@@ -248,7 +257,9 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     k_row_valid<<<(int)(((size_t)srows * 32 + 255) / 256), 256, 0, st>>>(c->det_seqs, (int64_t)L * R * F, L * R,
                                                                           srows, F, c->seq_valid, dsp);
     VSR_CHECK_CUDA(cudaGetLastError());
-    c->launches += 2;
+    k_slot_masks<<<(b * L + 127) / 128, 128, 0, st>>>(c->seq_valid, R, b * L, c->slot_mask);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    c->launches += 3;
   }
   // image descriptor
   {

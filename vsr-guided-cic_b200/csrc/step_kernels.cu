@@ -105,7 +105,7 @@ constexpr int ATT_MAX_R = 64;
 struct AttendArgs {
   const float* det_seqs;   // (b, L, R, F)
   const float* P;          // [b*L*R][ldP]
-  const uint8_t* seq_valid;  // [b*L*R]
+  const unsigned long long* slot_mask;  // [b*L] validity bits of each slot tile
   const int32_t* ptr;      // [rows]
   const float* sent; int ld_sent; int o_sa;   // sentinel (F) at 0 | sa (A) at o_sa
   const float* hb; int ld_hb; int o_ha;       // hg (H) at 0 | ha (A) at o_ha | ...
@@ -117,12 +117,12 @@ struct AttendArgs {
 };
 
 __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* ha = sm;                       // [A]
-  float* e = ha + a.A;                  // [R+1] scores, later alpha; index 0 = sentinel
+  float* Ps = ha + a.A;                 // [R][A] att_va projections of the slot's valid regions (cp.async)
+  float* e = Ps + (size_t)a.R * a.A;    // [R+1] scores, later alpha; index 0 = sentinel
   __shared__ float red[ATT_THREADS / 32];
   __shared__ float s_pad;
-  __shared__ uint8_t s_valid[ATT_MAX_R];
   __shared__ int s_rows[ATT_MAX_R];     // compacted valid region rows and their weights
   __shared__ float s_w[ATT_MAX_R];
   __shared__ int s_nv;
@@ -130,37 +130,77 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int nwarp = ATT_THREADS / 32;
+#ifdef VSR_DBG_CLK
+  long long tk[8]; int nt = 0;
+#define TICK() do { if (lane == 0) tk[nt++] = clock64(); } while (0)
+#else
+#define TICK() do {} while (0)
+#endif
+  TICK();
   const int cap = n / a.cur_beam;
-  const int slot = a.ptr[n];
+  const float* sent = a.sent + (size_t)n * a.ld_sent;   // sentinel feature row
+  const float* sa = sent + a.o_sa;
+  // loads that depend only on the row index go first so that they overlap the ptr -> mask chain
+  float4 sent_v[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int f = tid * 4 + u * ATT_THREADS * 4;
+    sent_v[u] = f < a.F ? *reinterpret_cast<const float4*>(sent + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float ha_v[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int i = tid + u * ATT_THREADS;
+    ha_v[u] = i < a.A ? a.hb[(size_t)n * a.ld_hb + a.o_ha + i] : 0.f;
+  }
+  // all L slot masks of the caption are fetched alongside the slot pointer; the right one is picked by shuffle
+  unsigned long long vmask;
+  int slot;
+  if (a.L <= 32) {
+    const unsigned long long ml = lane < a.L ? a.slot_mask[(size_t)cap * a.L + lane] : 0ull;
+    slot = a.ptr[n];
+    vmask = __shfl_sync(0xffffffffu, ml, slot);
+  } else {
+    slot = a.ptr[n];
+    vmask = a.slot_mask[(size_t)cap * a.L + slot];
+  }
   const size_t tile_row0 = ((size_t)cap * a.L + slot) * a.R;
   const float* tile = a.det_seqs + tile_row0 * a.F;
   const float* Pt = a.P + tile_row0 * a.ldP;
-  const float* sent = a.sent + (size_t)n * a.ld_sent;   // sentinel feature row
-  const float* sa = sent + a.o_sa;
 
-  for (int i = tid; i < a.A; i += ATT_THREADS) ha[i] = a.hb[(size_t)n * a.ld_hb + a.o_ha + i];
-  if (tid < a.R) s_valid[tid] = a.seq_valid[tile_row0 + tid];
+  // stage the valid regions' projections with cp.async (16-byte chunks, no registers held) and pull the
+  // valid feature rows towards L2 while the scores are computed; one warp per region row, no divisions
+  for (int r = warp; r < a.R; r += nwarp) {
+    if (!((vmask >> r) & 1ull)) continue;
+    const float* prow = Pt + (size_t)r * a.ldP;
+    float* pdst = Ps + (size_t)r * a.A;
+    for (int ch = lane * 4; ch < a.A; ch += 128) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(pdst + ch);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(prow + ch) : "memory");
+    }
+    const float* frow = tile + (size_t)r * a.F;
+    for (int f = lane * 32; f < a.F; f += 32 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(frow + f));
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int i = tid + u * ATT_THREADS;
+    if (i < a.A) ha[i] = ha_v[u];
+  }
+  for (int i = tid + 2 * ATT_THREADS; i < a.A; i += ATT_THREADS) ha[i] = a.hb[(size_t)n * a.ld_hb + a.o_ha + i];
   // sum of the sentinel row (its mask is computed like any region row, :159)
-  float ssum = 0.f;
-  for (int f = tid * 4; f < a.F; f += ATT_THREADS * 4) {
+  float ssum = ((sent_v[0].x + sent_v[0].y) + (sent_v[0].z + sent_v[0].w)) + ((sent_v[1].x + sent_v[1].y) + (sent_v[1].z + sent_v[1].w));
+  for (int f = tid * 4 + 2 * ATT_THREADS * 4; f < a.F; f += ATT_THREADS * 4) {
     const float4 v = *reinterpret_cast<const float4*>(sent + f);
     ssum += (v.x + v.y) + (v.z + v.w);
   }
   ssum = warp_sum(ssum);
   if (lane == 0) red[warp] = ssum;
+  TICK();
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-
-  // pull the valid region rows towards L2 while the scores are being computed
-  {
-    const int lines_per_row = (a.F * 4 + 127) / 128;
-    for (int idx = tid; idx < a.R * lines_per_row; idx += ATT_THREADS) {
-      const int r = idx / lines_per_row;
-      if (s_valid[r]) {
-        const float* pf = tile + (size_t)r * a.F + (size_t)(idx - r * lines_per_row) * 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-      }
-    }
-  }
+  if (lane == 0) e[0] += 0.f;   // (consumer of the barrier for the debug clock)
+  TICK();
 
   // scores: job 0 = sentinel, 1 = padding-row score, 2.. = valid regions; one warp per job
   for (int job = warp; job < a.R + 2; job += nwarp) {
@@ -169,8 +209,8 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
     if (job == 0) { add = sa; vec = a.v_s; }
     else if (job >= 2) {
       const int r = job - 2;
-      if (!s_valid[r]) continue;
-      add = Pt + (size_t)r * a.ldP;
+      if (!((vmask >> r) & 1ull)) continue;
+      add = Ps + (size_t)r * a.A;
     }
     float acc = 0.f;
     for (int i0 = 0; i0 < a.A; i0 += 512) {     // 4 x float4 per lane in flight, then the tanh math
@@ -178,7 +218,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int i = i0 + q * 128 + lane * 4;
-        pv[q] = (add != nullptr && i < a.A) ? __ldg(reinterpret_cast<const float4*>(add + i))
+        pv[q] = (add != nullptr && i < a.A) ? *reinterpret_cast<const float4*>(add + i)
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
@@ -199,6 +239,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
       else e[job - 1] = acc;
     }
   }
+  TICK();
   __syncthreads();
 
   if (warp == 0) {
@@ -207,7 +248,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
     if (a.R + 1 <= 32) {
       // masked softmax over [sentinel, regions] with one lane per entry (:167-169)
       const bool in = lane <= a.R;
-      const bool valid = in && (lane == 0 ? (sent_sum != 0.f) : (s_valid[lane - 1] != 0));
+      const bool valid = in && (lane == 0 ? (sent_sum != 0.f) : (((vmask >> (lane - 1)) & 1ull) != 0));
       const bool region = in && lane >= 1 && valid;
       float ev = -INFINITY;
       if (in) ev = (lane == 0 || valid) ? e[lane] : s_pad;
@@ -226,21 +267,21 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
       float m = e[0];
       float shift = 0.f;
       for (int r = 0; r < a.R; ++r) {
-        if (!s_valid[r]) e[r + 1] = e_pad; else shift += e[r + 1];
+        if (!((vmask >> r) & 1ull)) e[r + 1] = e_pad; else shift += e[r + 1];
         m = fmaxf(m, e[r + 1]);
       }
       float S = 0.f;
       for (int r = 0; r <= a.R; ++r) { e[r] = expf(e[r] - m); S += e[r]; }
       float T = 0.f;
       for (int r = 0; r <= a.R; ++r) {
-        const bool valid = (r == 0) ? (sent_sum != 0.f) : (s_valid[r - 1] != 0);
+        const bool valid = (r == 0) ? (sent_sum != 0.f) : (((vmask >> (r - 1)) & 1ull) != 0);
         e[r] = valid ? e[r] / S : 0.f;
         T += e[r];
       }
       int nv = 0;
       for (int r = 0; r <= a.R; ++r) {
         e[r] = e[r] / T;
-        if (r > 0 && s_valid[r - 1]) { s_rows[nv] = r - 1; s_w[nv] = e[r]; ++nv; }
+        if (r > 0 && ((vmask >> (r - 1)) & 1ull)) { s_rows[nv] = r - 1; s_w[nv] = e[r]; ++nv; }
       }
       s_nv = nv;
       a.shift[n] = shift;    // the gate head is finished in k_softmax_topk (needs the att_ga projection)
@@ -248,6 +289,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   }
   __syncthreads();
 
+  TICK();
   // weighted sum over sentinel + valid regions: each thread owns two float4 columns, 4 rows x 2 columns
   // (8 independent 128-bit loads) in flight
   float* out = a.att + (size_t)n * a.ld_att;
@@ -287,6 +329,12 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
       store_pair(a.att_b, o1 + 2, acc1.z); store_pair(a.att_b, o1 + 3, acc1.w);
     }
   }
+  TICK();
+#ifdef VSR_DBG_CLK
+  if (lane == 0 && (n == 7 || n == 301) && (warp == 0 || warp == 5))
+    printf("attend n=%d warp=%d nv=%d: setup %lld  wait+bar %lld  scores %lld  bar+softmax+bar %lld  wsum %lld\n", n, warp, nv,
+           tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4]);
+#endif
 }
 
 // ---------------------------------------------------------------- log-softmax + gate head + verb forcing + top-k
@@ -353,13 +401,12 @@ __device__ __forceinline__ void warp_argbest_redux(float v, int i, unsigned& kbe
 __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a) {
   constexpr int THREADS = SM_THREADS;
   constexpr int NW = THREADS / 32;
-  __shared__ float red_m[NW], red_s[NW];
+  __shared__ float red_m[NW], red_s[NW], red_g[NW];
   __shared__ float wl_v[NW][VSR_MAX_BEAM];      // per-warp top-k lists
   __shared__ int wl_i[NW][VSR_MAX_BEAM];
   __shared__ int wl_second[NW][VSR_MAX_BEAM];
   __shared__ float red_v[2][NW];
   __shared__ int red_i[2][NW];
-  __shared__ float s_stay;
   __shared__ int s_forced, s_slow;
   __shared__ int s_pick[VSR_MAX_BEAM];
   const int n = blockIdx.x;
@@ -377,6 +424,13 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
       verb = load_verb(a.verbs, a.verbs_dtype, (size_t)(n / a.cur_beam) * a.L + a.ptr[n]);
   }
 
+  // stay-gate logit att_g . tanh(ga + ha): every thread takes a slice (loads issued before the row scan)
+  float stay_part = 0.f;
+  {
+    const float* ha = a.ha + (size_t)n * a.ld_ha;
+    const float* ga = a.ga + (size_t)n * a.ld_ga;
+    for (int i = tid; i < a.A; i += THREADS) stay_part += a.v_g[i] * fast_tanh(ga[i] + ha[i]);
+  }
   float v1 = -INFINITY, v2 = -INFINITY; int i1 = 0x7fffffff, i2 = 0x7fffffff;   // this thread's two best
   float m = -INFINITY, ssum = 0.f;
   constexpr int PRE = 5;
@@ -417,7 +471,8 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
   {
     const float wm = warp_max(m);
     const float ws = warp_sum(m > -INFINITY ? ssum * expf(m - wm) : 0.f);
-    if (lane == 0) { red_m[warp] = wm; red_s[warp] = ws; }
+    const float wg = warp_sum(stay_part);
+    if (lane == 0) { red_m[warp] = wm; red_s[warp] = ws; red_g[warp] = wg; }
   }
   // warp-level top-k of the warp's 64 candidates
   {
@@ -433,15 +488,6 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     }
   }
   if (tid == 0) s_slow = 0;
-  // stay-gate logit (last warp)
-  if (warp == NW - 1) {
-    const float* ha = a.ha + (size_t)n * a.ld_ha;
-    const float* ga = a.ga + (size_t)n * a.ld_ga;
-    float acc = 0.f;
-    for (int i = lane; i < a.A; i += 32) acc += a.v_g[i] * fast_tanh(ga[i] + ha[i]);
-    acc = warp_sum(acc);
-    if (lane == 0) s_stay = acc;
-  }
   __syncthreads();
 
   float mx = red_m[0];
@@ -512,7 +558,9 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     float g0, g1;
     if (forced >= 0) { g0 = -1e3f; g1 = 0.f; }
     else {
-      const float stay = s_stay;
+      float stay = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) stay += red_g[w];
       const float gm = fmaxf(stay, shift_logit);
       const float ls = logf(expf(stay - gm) + expf(shift_logit - gm));
       g0 = (stay - gm) - ls; g1 = (shift_logit - gm) - ls;
@@ -642,14 +690,20 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   {
     PhaseScope ps(c, PH_ATTEND, st);
     AttendArgs a{};
-    a.det_seqs = c->det_seqs; a.P = c->P; a.seq_valid = c->seq_valid; a.ptr = c->ptr;
+    a.det_seqs = c->det_seqs; a.P = c->P; a.slot_mask = c->slot_mask; a.ptr = c->ptr;
     a.sent = c->sent; a.ld_sent = c->NB1; a.o_sa = c->oB1_sa;
     a.hb = c->hb; a.ld_hb = c->NB2; a.o_ha = c->oB2_ha;
     a.v_a = c->v_a; a.v_s = c->v_s;
     a.att = c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.shift = c->shift;
     a.rows = rows; a.cur_beam = io.cur_beam; a.L = c->L; a.R = c->R; a.F = c->F; a.A = c->A; a.H = H;
     a.ldP = c->NVA;
-    const size_t smem = sizeof(float) * (size_t)(c->A + c->R + 1);
+    const size_t smem = sizeof(float) * ((size_t)c->A + (size_t)c->R * c->A + c->R + 1);
+    static bool attr_set = false;
+    if (!attr_set) {
+      VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    VSR_REQUIRE(smem <= 200 * 1024, VSR_EINVAL, "attention tile (R=%d x A=%d) does not fit shared memory", c->R, c->A);
     k_attend<<<rows, ATT_THREADS, smem, st>>>(a);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
