@@ -419,6 +419,137 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   }
 }
 
+// ---------------------------------------------------------------- persistent variant
+// One CTA per SM walks the tile list (tile = blockIdx.x + i * gridDim.x).  The smem ring keeps running
+// across tiles and the accumulator is double-buffered in TMEM, so the epilogue of tile i (TMEM -> registers
+// -> global, incl. the fused LSTM / gate math) overlaps the TMA + MMA main loop of tile i+1, and the
+// per-CTA set-up (barrier init, TMEM allocation, descriptor prefetch, pipeline fill) is paid once.
+__device__ __forceinline__ bool tile_all_padding(const uint8_t* row_skip, int m0, int M, int lane) {
+  if (row_skip == nullptr) return false;
+  int any = 0;
+  for (int r = lane; r < BM; r += 32) if (m0 + r < M) any |= row_skip[m0 + r];
+  return !__any_sync(0xffffffffu, any);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int BN, int KB>
+__global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constant__ TcParams params) {
+  using Cfg = TcCfg<BN, KB>;
+  constexpr int kAccCols = (BN <= 128) ? 128 : 256;     // TMEM column stride between the two accumulators
+  constexpr int kTmemCols = 2 * kAccCols;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles0 = params.pr[0].n_tiles * params.pr[0].m_tiles;
+  const int total_tiles = tiles0 + (params.nprob > 1 ? params.pr[1].n_tiles * params.pr[1].m_tiles : 0);
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  if (warp == 0 && lane == 0) {
+    for (int q = 0; q < params.nprob; ++q) {
+      const TcProblem& p = params.pr[q];
+      for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); }
+      prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  // every role walks the same tile list and skips the same (all-padding) tiles
+  int it = 0;        // running k-block counter -> smem ring stage / phase
+  int ti = 0;        // running (non-skipped) tile counter -> accumulator buffer / phase
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int pi = (params.nprob > 1 && tile >= tiles0) ? 1 : 0;
+    const int t = tile - pi * tiles0;
+    const TcProblem& p = params.pr[pi];
+    const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
+    const int m0 = m_tile * BM, n0 = n_tile * BN;
+    if (tile_all_padding(p.row_skip, m0, p.M, lane)) continue;
+    int total_kb = 0;
+    for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+    const int acc = ti & 1;
+    const uint32_t aph = (ti >> 1) & 1;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * kAccCols);
+
+    if (warp == 0) {
+      if (lane == 0) {
+        int seg = 0, kk = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int st = (it + kb) % Cfg::kStages;
+          const uint32_t ph = ((it + kb) / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* base = smem + st * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+          tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
+          tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
+          tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+          tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
+          if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = make_idesc<BN>();
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);       // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int st = (it + kb) % Cfg::kStages;
+          const uint32_t ph = ((it + kb) / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
+          const uint64_t ah = make_kmajor_desc<KB>(base), al = make_kmajor_desc<KB>(base + Cfg::kABytes);
+          const uint64_t wh = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes);
+          const uint64_t wl = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes);
+#pragma unroll
+          for (int k = 0; k < KB / UMMA_K; ++k) {
+            const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
+            umma_f16(tmem_acc, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16(tmem_acc, ah + off, wl + off, idesc, 1u);
+            umma_f16(tmem_acc, al + off, wh + off, idesc, 1u);
+          }
+          umma_commit(&empty_bar[st]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+      __syncwarp();
+    } else {
+      mbar_wait(&tmem_full_bar[acc], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tc_epilogue<BN>(p, tmem_acc, m0, n0, n_tile, warp, lane);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // 4 epilogue warps -> accumulator free again
+    }
+    it += total_kb;
+    ++ti;
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
 // Two CTAs of a cluster (one TPC) compute a 256 x BN tile: each CTA stages its own 128 rows of A and HALF
 // of the W tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both
@@ -647,6 +778,9 @@ int tc_gemm_init() {
   TC_SET_SMEM(256, 64); TC_SET_SMEM(192, 64); TC_SET_SMEM(128, 64);
   TC_SET_SMEM(256, 32); TC_SET_SMEM(192, 32); TC_SET_SMEM(128, 32);
   TC_SET_SMEM(144, 64); TC_SET_SMEM(240, 32);
+#define TCP_SET_SMEM(BN_, KB_) VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tcp<BN_, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_, KB_>::kSmemBytes))
+  TCP_SET_SMEM(128, 64); TCP_SET_SMEM(144, 64); TCP_SET_SMEM(192, 32); TCP_SET_SMEM(192, 64); TCP_SET_SMEM(128, 32);
+#undef TCP_SET_SMEM
 #undef TC_SET_SMEM
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<256>::kSmemBytes));
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<192>::kSmemBytes));
@@ -738,6 +872,25 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
     VSR_TRY(fill_problem(&p.pr[1], *g2, BN, false, kb));
     p.nprob = 2;
     tiles += p.pr[1].n_tiles * p.pr[1].m_tiles;
+  }
+  static int persist = -1, sms = 148;
+  if (persist < 0) {
+    const char* e = getenv("VSRDEC_PERSIST");
+    persist = (e == nullptr) ? 1 : atoi(e);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  }
+  // persistent tiles pay off only when a CTA gets more than one tile (epilogue / main-loop overlap);
+  // for single-wave launches the plain kernel measured 5-10 % faster
+  // (and measured neutral-to-worse for the grouped two-problem launch, whose tiles are uneven)
+  if (persist && tiles > sms && g2 == nullptr && (BN == 128 || BN == 144 || BN == 192)) {
+    const int grid = tiles < sms ? tiles : sms;
+#define TCP_LAUNCH(BN_, KB_) k_gemm_tcp<BN_, KB_><<<grid, TC_THREADS, TcCfg<BN_, KB_>::kSmemBytes, st>>>(p)
+    if (BN == 144) TCP_LAUNCH(144, 64);
+    else if (BN == 192) { if (kb == 32) TCP_LAUNCH(192, 32); else TCP_LAUNCH(192, 64); }
+    else { if (kb == 32) TCP_LAUNCH(128, 32); else TCP_LAUNCH(128, 64); }
+#undef TCP_LAUNCH
+    VSR_CHECK_CUDA(cudaGetLastError());
+    return VSR_OK;
   }
 #define TC_LAUNCH(BN_, KB_) k_gemm_tc<BN_, KB_><<<tiles, TC_THREADS, TcCfg<BN_, KB_>::kSmemBytes, st>>>(p)
   if (BN == 144) TC_LAUNCH(144, 64);
