@@ -248,35 +248,46 @@ __global__ void k_greedy_pick(const int32_t* cand, const float* gate_lp, int32_t
 }
 
 // final ordering of the beams by accumulated score (stable, descending) and unroll of the
-// back-pointers (CaptioningModel.py:182-194 / 279-293).  One thread per caption.
-__global__ void k_backtrack(int b, int k, int T, int out_size, const float* seq_lp,
-                            const int32_t* hist_parent, const int32_t* hist_word,
-                            const int32_t* hist_gate, const float* hist_lpw, const float* hist_lpg,
-                            int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= b) return;
+// back-pointers (CaptioningModel.py:182-194 / 279-293).  One CTA per caption: the caption's [T][k] history is
+// staged in shared memory with coalesced loads, so the serial pointer chase never waits on global memory.
+constexpr int BT_MAX_T = 64;
+__global__ void __launch_bounds__(64) k_backtrack(int b, int k, int T, int out_size, const float* seq_lp,
+                                                  const int32_t* hist_parent, const int32_t* hist_word,
+                                                  const int32_t* hist_gate, const float* hist_lpw, const float* hist_lpg,
+                                                  int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates) {
+  __shared__ int32_t s_par[BT_MAX_T * VSR_MAX_BEAM], s_wrd[BT_MAX_T * VSR_MAX_BEAM], s_gat[BT_MAX_T * VSR_MAX_BEAM];
+  __shared__ float s_lpw[BT_MAX_T * VSR_MAX_BEAM], s_lpg[BT_MAX_T * VSR_MAX_BEAM];
+  __shared__ float s_seq[VSR_MAX_BEAM];
+  const int c = blockIdx.x;
+  for (int i = threadIdx.x; i < T * k; i += blockDim.x) {
+    const int t = i / k, j = i - t * k;
+    const size_t hi = ((size_t)t * b + c) * k + j;
+    s_par[i] = hist_parent[hi]; s_wrd[i] = hist_word[hi]; s_gat[i] = hist_gate[hi];
+    s_lpw[i] = hist_lpw[hi]; s_lpg[i] = hist_lpg[hi];
+  }
+  if (threadIdx.x < k) s_seq[threadIdx.x] = seq_lp[c * k + threadIdx.x];
+  __syncthreads();
+  const int o = threadIdx.x;
+  if (o >= out_size) return;
   int order[VSR_MAX_BEAM];
   for (int i = 0; i < k; ++i) order[i] = i;
   for (int i = 1; i < k; ++i) {   // insertion sort, stable, descending
     const int oi = order[i];
-    const float v = seq_lp[c * k + oi];
+    const float v = s_seq[oi];
     int j = i - 1;
-    while (j >= 0 && seq_lp[c * k + order[j]] < v) { order[j + 1] = order[j]; --j; }
+    while (j >= 0 && s_seq[order[j]] < v) { order[j + 1] = order[j]; --j; }
     order[j + 1] = oi;
   }
-  for (int o = 0; o < out_size; ++o) {
-    const int final_slot = order[o];
-    int slot = final_slot;
-    const size_t ob = ((size_t)c * out_size + o) * T;
-    for (int t = T - 1; t >= 0; --t) {
-      const size_t hi = ((size_t)t * b + c) * k;
-      out_words[ob + t] = hist_word[hi + slot];
-      out_gates[ob + t] = hist_gate[hi + slot];
-      // log-probs are NOT back-tracked: slot order at step t, permuted by the final sort only
-      lp_words[ob + t] = hist_lpw[hi + final_slot];
-      lp_gates[ob + t] = hist_lpg[hi + final_slot];
-      slot = hist_parent[hi + slot];
-    }
+  const int final_slot = order[o];
+  int slot = final_slot;
+  const size_t ob = ((size_t)c * out_size + o) * T;
+  for (int t = T - 1; t >= 0; --t) {
+    out_words[ob + t] = s_wrd[t * k + slot];
+    out_gates[ob + t] = s_gat[t * k + slot];
+    // log-probs are NOT back-tracked: slot order at step t, permuted by the final sort only
+    lp_words[ob + t] = s_lpw[t * k + final_slot];
+    lp_gates[ob + t] = s_lpg[t * k + final_slot];
+    slot = s_par[t * k + slot];
   }
 }
 
@@ -378,7 +389,8 @@ int launch_greedy_pick(Ctx* c, int rows, int t, int T, int64_t* out_words, int64
 int launch_backtrack(Ctx* c, int b, int k, int T, int out_size, int64_t* out_words,
                      int64_t* out_gates, float* lp_words, float* lp_gates, cudaStream_t st) {
   PhaseScope ps(c, PH_FINAL, st);
-  k_backtrack<<<(b + 63) / 64, 64, 0, st>>>(b, k, T, out_size, c->seq_lp, c->hist_parent, c->hist_word,
+  VSR_REQUIRE(T <= BT_MAX_T, VSR_EINVAL, "seq_len=%d > %d unsupported by the back-track kernel", T, BT_MAX_T);
+  k_backtrack<<<b, 64, 0, st>>>(b, k, T, out_size, c->seq_lp, c->hist_parent, c->hist_word,
                                             c->hist_gate, c->hist_lpw, c->hist_lpg, out_words, out_gates,
                                             lp_words, lp_gates);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;

@@ -180,12 +180,10 @@ struct TcProblem {
   int ld_state;
   // fused g_t = sig(gq + acc) * tanh(c1') on the tiles with n0 < gt_cols (plain epilogue elsewhere)
   int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; __half* g_hi; __half* g_lo;
-  int dbg_nostore;   // debugging only: skip the plain epilogue's global stores (timing experiment)
 };
 struct TcParams {
   TcProblem pr[2];
   int nprob;
-  int dbg_passes;   // debugging only: 1 = issue only the hi*hi MMA (results wrong, timing experiment)
 };
 
 // Fused LSTM cell epilogue.  Every 32-unit chunk of the tile is NG*32 columns laid out as 4 sub-blocks of
@@ -303,7 +301,7 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
             const float4 b = __ldg(reinterpret_cast<const float4*>(gath + n + j));
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          if (!p.dbg_nostore) *reinterpret_cast<float4*>(crow + n + j) = o;
+          *reinterpret_cast<float4*>(crow + n + j) = o;
         }
       }
     } else {
@@ -696,10 +694,8 @@ k_gemm_tc2(const __grid_constant__ TcParams params) {
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
           umma_f16_pair(tmem_base, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
-          if (params.dbg_passes != 1) {
-            umma_f16_pair(tmem_base, ah + off, wl + off, idesc, 1u);
-            umma_f16_pair(tmem_base, al + off, wh + off, idesc, 1u);
-          }
+          umma_f16_pair(tmem_base, ah + off, wl + off, idesc, 1u);
+          umma_f16_pair(tmem_base, al + off, wh + off, idesc, 1u);
         }
         umma_commit_pair(&empty_bar[st]);     // frees this stage in BOTH CTAs
       }
@@ -804,7 +800,6 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
   p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
   p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
   p->gather = g.gather; p->ld_gather = g.ld_gather; p->gather_idx = g.gather_idx;
-  if (const char* e = getenv("VSRDEC_DBG_NOSTORE")) p->dbg_nostore = atoi(e);
   const FusedCell& f = g.cell;
   p->mode = f.mode;
   if (f.mode != 0) {
@@ -829,7 +824,6 @@ static int launch_gemm_tc_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream
   memset(&p, 0, sizeof(p));
   VSR_TRY(fill_problem(&p.pr[0], g, BN, true));
   p.nprob = 1;
-  if (const char* e = getenv("VSRDEC_DBG_PASSES")) p.dbg_passes = atoi(e);
   int pairs = p.pr[0].n_tiles * ((p.pr[0].m_tiles + 1) / 2);
   if (g2 != nullptr) {
     VSR_TRY(fill_problem(&p.pr[1], *g2, BN, true));

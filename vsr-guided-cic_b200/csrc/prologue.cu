@@ -96,10 +96,18 @@ __global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D,
   const float* p = det + (size_t)g * img_stride + f;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
-  for (int d = 0; d < D; ++d) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)d * F));
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    cnt += valid[g * D + d];
+  for (int d0 = 0; d0 < D; d0 += 8) {     // 8 independent row loads in flight; same summation order
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = d0 + u < D ? __ldg(reinterpret_cast<const float4*>(p + (size_t)(d0 + u) * F)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (d0 + u < D) {
+        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
+        cnt += valid[g * D + d0 + u];
+      }
+    }
   }
   const float n = (float)cnt;
   const float4 o = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
