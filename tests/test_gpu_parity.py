@@ -340,3 +340,56 @@ def test_two_gpu_sharded_decode_matches_single_gpu():
     assert torch.equal(torch.cat([x[0] for x in outs]), o[0].cpu())
     assert torch.equal(torch.cat([x[1] for x in outs]), o[1].cpu())
     assert torch.equal(torch.cat([x[2] for x in outs]), lp[0].cpu())
+
+
+# ----------------------------------------------------------------------------- f1: sample_rl, odd dimensions
+def test_sample_rl_logprobs_are_consistent():
+    """sample_rl (CaptioningModel.py:54-76) draws from the device step's distributions; whatever it draws,
+    the returned log-probs must be the oracle's step log-probs of exactly those tokens."""
+    from gpu_common import make_model
+    fx = load_golden("small_a.pt")
+    d, W = fx["dims_obj"], fx["weights"]
+    m = make_model(d, W, fx["verb_table"])
+    det, ds = fx["det"], fx["det_seqs"]
+    torch.manual_seed(0)
+    (words, gates), (lpw, lpg) = m.sample_rl(*_cuda(det, ds))
+    torch.cuda.synchronize()
+    words, gates, lpw, lpg = words.cpu(), gates.cpu(), lpw.cpu(), lpg.cpu()
+    assert words.shape == gates.shape == lpw.shape == lpg.shape == (det.size(0), d.seq_len)
+    state = O.init_state(d, det.size(0))
+    prev = None
+    with torch.no_grad():
+        for t in range(d.seq_len):
+            (out, gate), state = O.decoder_step(W, d, t, state, prev, (det, ds), None, "feedback")
+            assert rel_close(lpw[:, t], out.gather(1, words[:, t:t + 1]).squeeze(1), REL, ABS)
+            assert rel_close(lpg[:, t], gate.gather(1, gates[:, t:t + 1]).squeeze(1), REL, ABS)
+            prev = (words[:, t], gates[:, t])
+
+
+@pytest.mark.parametrize("dims", [
+    dict(vocab_size=97, det_feat_size=64, input_encoding_size=30, rnn_size=33, att_size=12),
+    dict(vocab_size=513, det_feat_size=132, input_encoding_size=64, rnn_size=130, att_size=36, h2_first_lstm=False),
+    dict(vocab_size=300, det_feat_size=256, input_encoding_size=17, rnn_size=64, att_size=64, img_second_lstm=True),
+])
+def test_odd_dimensions_against_oracle(dims):
+    """Padding / tiling logic on dimensions that are not multiples of any tile (hidden size 33, vocab 97, ...)."""
+    from gpu_common import make_model, device_beam
+    d = O.Dims(seq_len=8, bos_idx=2, **dims)
+    W = O.init_weights(d, seed=5)
+    W["out_fc.weight"] = W["out_fc.weight"] * 30.0
+    m = make_model(d, W)
+    det, ds, verbs = O.synth_inputs(7, 9, 5, 6, d.det_feat_size, seed=21, vocab_size=d.vocab_size, n_det_range=(3, 9),
+                                    real_slots=(2, 5), verb_slots=(1,), verb_vocab_id=11)
+    (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(det, ds, verbs), [3, -1], 4, 2, True, True)
+    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 4, hist, True, True, None,
+                                          extra["step_out"], extra["step_gate"])
+    print("odd dims", dims, v.summary())
+    assert not v.violations, v.violations[:5]
+    assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0
+    assert torch.equal(w.cpu(), o_outs[0][:, :2]) and torch.equal(g.cpu(), o_outs[1][:, :2])
+    caps = torch.randint(0, d.vocab_size, (7, 5), generator=torch.Generator().manual_seed(1))
+    ctrl = ds[:, :5].contiguous()
+    out, gate = m((det.to(DEV),), (caps.to(DEV), ctrl.to(DEV)))
+    with torch.no_grad():
+        ro, rg = O.forward_teacher(W, d, (det,), (caps, ctrl))
+    assert rel_close(out.cpu(), ro, REL, ABS) and rel_close(gate.cpu(), rg, REL, ABS)
