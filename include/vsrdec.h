@@ -118,6 +118,18 @@ int vsr_prologue(vsr_handle h, const float* det, int64_t det_batch_stride, int32
                  const float* det_seqs, int32_t b, int32_t L, int32_t R,
                  const void* verbs, int32_t verbs_dtype, void* stream);
 
+/* Index form of the prologue (an ADDITIONAL fast entry point, not part of the reference's
+ * call signature).  The reference's fields materialise every slot tile by copying detection rows
+ * (data/field.py:461-541); here a slot is described by indices instead:
+ *   slot_index (b, L, R) int32:  d >= 0  region = det[caption's image, d, :]
+ *                                -2      region = mean of the image's valid detections (verb slots, field.py:460,517)
+ *                                -1      padding
+ * 10x fewer input bytes than det_seqs (b, L, R, F) and the att_va projection is computed once per detection row
+ * instead of once per slot row.  Every decode entry point works unchanged after either prologue. */
+int vsr_prologue_indexed(vsr_handle h, const float* det, int64_t det_batch_stride, int32_t D,
+                         const int32_t* slot_index, int32_t b, int32_t L, int32_t R,
+                         const void* verbs, int32_t verbs_dtype, void* stream);
+
 /* One decoder step for the b prologue captions, one row per caption
  * (ControllableCaptioningModel.step / step_v, controllable_captioning.py:117-190 / 192-297).
  *   h1,c1,h2,c2 (b,H) state in;  slot (b) int64 = slot index the row attends to (feedback:

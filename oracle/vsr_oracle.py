@@ -441,4 +441,4 @@ def new_trace() -> BeamTrace:
 import os as _os
 import sys as _sys
 _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))))
-from tools.synth import synth_inputs, synth_verb_table  # noqa: E402,F401
+from tools.synth import synth_inputs, synth_verb_table, synth_inputs_indexed, materialize_slots  # noqa: E402,F401

@@ -149,3 +149,23 @@ def test_sharded_decode_world2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_materialize_slots_semantics():
+    """Index form -> tiles: detection copies, mean-of-valid row for -2, zeros for -1 (data only, CPU)."""
+    from tools.synth import synth_inputs_indexed, materialize_slots
+    det, idx, verbs = synth_inputs_indexed(4, 9, 6, 5, 16, seed=3, n_det_range=(3, 9), real_slots=(2, 5))
+    ds = materialize_slots(det, idx)
+    assert ds.shape == (4, 6, 5, 16)
+    for i in range(4):
+        valid = det[i][det[i].sum(-1) != 0]
+        for l in range(6):
+            for r in range(5):
+                k = int(idx[i, l, r])
+                if k >= 0:
+                    assert torch.equal(ds[i, l, r], det[i, k])
+                elif k == -2:
+                    assert torch.allclose(ds[i, l, r], valid.mean(0))
+                else:
+                    assert float(ds[i, l, r].abs().sum()) == 0.0
+    assert bool((idx[:, :, 0][verbs != -1] == -2).all())      # verb slots are mean-row slots (repeated tail slots carry verb -1)

@@ -393,3 +393,33 @@ def test_odd_dimensions_against_oracle(dims):
     with torch.no_grad():
         ro, rg = O.forward_teacher(W, d, (det,), (caps, ctrl))
     assert rel_close(out.cpu(), ro, REL, ABS) and rel_close(gate.cpu(), rg, REL, ABS)
+
+
+# ----------------------------------------------------------------------------- f3: index-form slot input
+@pytest.mark.parametrize("shared_image", [False, True])
+def test_indexed_slot_input_matches_oracle_on_materialised_tiles(shared_image):
+    """vsr_prologue_indexed / beam_search_v_indexed: slots as indices into the detections.  The oracle runs on the
+    tiles the reference's fields would have materialised for the same indices."""
+    from gpu_common import make_model
+    d = O.Dims()
+    W = O.init_weights(d, seed=1234)
+    W["out_fc.weight"] = W["out_fc.weight"] * 100.0
+    m = make_model(d, W)
+    det, idx, verbs = O.synth_inputs_indexed(24, 50, 10, 20, 2048, seed=1006, n_det_range=(10, 50))
+    if shared_image:      # eval_coco.py:243: one image expanded over its captions
+        det = det[:1].expand(24, 50, 2048)
+        idx = idx.clamp(max=int((det[0].sum(-1) != 0).sum()) - 1)
+    ds = O.materialize_slots(det, idx)
+    dev = (det.to(DEV) if not shared_image else det[:1].to(DEV).expand(24, 50, 2048), idx.to(DEV), verbs.to(DEV))
+    (w, g), (lw, lg) = m.beam_search_v_indexed(dev, [3, -1], 5, 1, gt=True)
+    hist = m._eng.history()
+    torch.cuda.synchronize()
+    v, o_outs, o_lps = verify_device_beam(W, d, (det.contiguous(), ds, verbs), [3, -1], 5, hist, True, True)
+    print("indexed slots shared_image=%s" % shared_image, v.summary())
+    assert not v.violations, v.violations[:5]
+    assert torch.equal(w.cpu(), o_outs[0][:, 0]) and torch.equal(g.cpu(), o_outs[1][:, 0])
+    assert rel_close(lw.cpu(), o_lps[0][:, 0], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, 0], REL, ABS)
+    # and the materialised entry point on the same data gives the same captions
+    o2, _ = m.beam_search_v((dev[0], ds.to(DEV), dev[2]), [3, -1], 5, 1, gt=True)
+    torch.cuda.synchronize()
+    print("captions identical to the materialised entry point:", _match_fraction(o2[0], w))

@@ -57,3 +57,48 @@ def synth_verb_table(n_verbs: int, vocab_size: int, seed: int) -> Dict[str, List
         n = 0 if r == 1 else int(torch.randint(1, 7, (1,), generator=g))
         table[str(v)] = [int(x) for x in torch.randint(0, vocab_size, (n,), generator=g)]
     return table
+
+
+def synth_inputs_indexed(b: int, D: int, L: int, R: int, Fd: int, seed: int, n_det_range: Tuple[int, int] = None,
+                         real_slots: Tuple[int, int] = (4, 8), verb_slots: Sequence[int] = (2,),
+                         verb_vocab_id: Optional[int] = 17):
+    """Index form of synth_inputs: det (b,D,F) f32, slot_index (b,L,R) int32 (>= 0 detection row, -2 image mean
+    row, -1 padding), verbs (b,L) f64.  Slots after the last real one repeat it, as in eval_coco.py:231-237."""
+    g = torch.Generator().manual_seed(seed)
+    det = torch.relu(torch.randn((b, D, Fd), generator=g))
+    n_det = torch.full((b,), D, dtype=torch.long)
+    if n_det_range is not None:
+        n_det = torch.randint(n_det_range[0], n_det_range[1] + 1, (b,), generator=g)
+        for i in range(b):
+            det[i, int(n_det[i]):] = 0
+    idx = -torch.ones((b, L, R), dtype=torch.int32)
+    verbs = -torch.ones((b, L), dtype=torch.float64)
+    n_real = torch.randint(real_slots[0], min(real_slots[1], L) + 1, (b,), generator=g)
+    for i in range(b):
+        nr = int(n_real[i])
+        for l in range(nr):
+            if l in verb_slots:
+                idx[i, l, 0] = -2
+                verbs[i, l] = float(verb_vocab_id)
+            else:
+                nv = int(torch.randint(1, R + 1, (1,), generator=g))
+                idx[i, l, :nv] = torch.randint(0, int(n_det[i]), (nv,), generator=g).to(torch.int32)
+        idx[i, nr:] = idx[i, nr - 1]
+    return det, idx, verbs
+
+
+def materialize_slots(det: torch.Tensor, slot_index: torch.Tensor) -> torch.Tensor:
+    """det_seqs (b,L,R,F) that the reference's fields would have built for these indices
+    (data/field.py:461-541): copies of detection rows, the mean of the valid detections for -2, zeros for -1."""
+    b, L, R = slot_index.shape
+    Fd = det.size(2)
+    out = torch.zeros((b, L, R, Fd), dtype=det.dtype)
+    for i in range(b):
+        valid = det[i][det[i].sum(-1) != 0]
+        mean = valid.mean(0) if valid.size(0) > 0 else torch.zeros(Fd)
+        sel = slot_index[i].long()
+        rows = det[i][sel.clamp(min=0)]
+        rows = torch.where((sel >= 0).unsqueeze(-1), rows, torch.zeros_like(rows))
+        rows = torch.where((sel == -2).unsqueeze(-1), mean.expand_as(rows), rows)
+        out[i] = rows
+    return out

@@ -239,20 +239,24 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   return VSR_OK;
 }
 
-static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, const float* det_seqs, int b,
-                         int L, int R, const void* verbs, int verbs_dtype, cudaStream_t st) {
-  VSR_REQUIRE(det != nullptr && det_seqs != nullptr, VSR_EINVAL, "vsr_prologue: null input");
+static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, const float* det_seqs,
+                         const int32_t* slot_index, int b, int L, int R, const void* verbs, int verbs_dtype,
+                         cudaStream_t st) {
+  VSR_REQUIRE(det != nullptr && (det_seqs != nullptr || slot_index != nullptr), VSR_EINVAL, "vsr_prologue: null input");
   VSR_REQUIRE(b > 0 && D > 0 && L > 0 && R > 0, VSR_EINVAL, "vsr_prologue: bad shape b=%d D=%d L=%d R=%d", b, D, L, R);
   VSR_REQUIRE(R <= 64, VSR_EINVAL, "vsr_prologue: R=%d regions per slot > 64 unsupported", R);
   VSR_REQUIRE(det_stride == 0 || det_stride >= (int64_t)D * c->F, VSR_EINVAL, "vsr_prologue: bad det_batch_stride");
   VSR_REQUIRE(verbs == nullptr || (verbs_dtype >= 0 && verbs_dtype <= 2), VSR_EINVAL, "vsr_prologue: bad verbs dtype");
+  VSR_REQUIRE(slot_index == nullptr || det_stride == 0 || det_stride == (int64_t)D * c->F, VSR_EINVAL,
+              "vsr_prologue_indexed: detections must be dense (b, D, F) or one shared image");
   VSR_REQUIRE(((uintptr_t)det % 16) == 0 && ((uintptr_t)det_seqs % 16) == 0 && (det_stride % 4) == 0, VSR_EINVAL,
               "vsr_prologue: feature tensors must be 16-byte aligned");
   c->have_prologue = false;
   if (c->profiling) reset_phases(c);   // a decode job starts here
   c->b = b; c->D = D; c->L = L; c->R = R;
   c->n_img = det_stride == 0 ? 1 : b;
-  c->det_seqs = det_seqs; c->verbs = verbs; c->verbs_dtype = verbs_dtype;
+  c->det_seqs = det_seqs; c->slot_index = slot_index; c->det = det; c->det_stride = det_stride;
+  c->verbs = verbs; c->verbs_dtype = verbs_dtype;
   const size_t n_img_pad = round_up(c->n_img, MPAD);
   if (n_img_pad > c->cap_img) {
     dev_free(c, c->img); dev_free(c, c->U); dev_free(c, c->U2);
@@ -262,16 +266,22 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     VSR_TRY(alloc_pair(c, &c->img_b, (int)n_img_pad, c->Fp, MPAD));
     c->cap_img = n_img_pad;
   }
-  const size_t prow = (size_t)b * L * R;
-  if (prow > c->cap_P) {
+  // rows of the projection buffer: one per slot row (materialised form) or one per detection row plus one
+  // per image, each block padded to whole 128-row tiles (index form)
+  const size_t prow = slot_index == nullptr
+                          ? (size_t)b * L * R
+                          : (size_t)round_up(c->n_img * D, MPAD) + round_up(c->n_img, MPAD);
+  if (prow > c->cap_P || (size_t)b * L + 1 > c->cap_slots) {
+    const size_t need_rows = std::max(prow, c->cap_P), need_slots = std::max((size_t)b * L + 1, c->cap_slots);
     dev_free(c, c->P); dev_free(c, c->seq_valid); dev_free(c, c->slot_mask);
-    c->P = nullptr; c->seq_valid = nullptr; c->slot_mask = nullptr; c->cap_P = 0;
-    ALLOC_F(c->P, round_up((int)prow, MPAD) * (size_t)c->NVA);
-    VSR_TRY(dev_alloc(c, (void**)&c->seq_valid, round_up((int)prow, MPAD)));
-    VSR_TRY(dev_alloc(c, (void**)&c->slot_mask, sizeof(unsigned long long) * ((size_t)b * L + 1)));
-    VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)prow, MPAD), c->Fp, MPAD));
-    c->cap_P = prow;
+    c->P = nullptr; c->seq_valid = nullptr; c->slot_mask = nullptr; c->cap_P = 0; c->cap_slots = 0;
+    ALLOC_F(c->P, round_up((int)need_rows, MPAD) * (size_t)c->NVA);
+    VSR_TRY(dev_alloc(c, (void**)&c->seq_valid, round_up((int)need_rows, MPAD)));
+    VSR_TRY(dev_alloc(c, (void**)&c->slot_mask, sizeof(unsigned long long) * need_slots));
+    VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)need_rows, MPAD), c->Fp, MPAD));
+    c->cap_P = need_rows; c->cap_slots = need_slots;
   }
+  c->Pmean = slot_index != nullptr ? c->P + (size_t)round_up(c->n_img * D, MPAD) * c->NVA : nullptr;
   const size_t dvr = (size_t)c->n_img * D;
   if (dvr > c->cap_detv) {
     dev_free(c, c->det_valid); c->det_valid = nullptr; c->cap_detv = 0;
@@ -279,7 +289,8 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     c->cap_detv = dvr;
   }
   VSR_TRY(ensure_rows(c, b));
-  VSR_TRY(run_prologue(c, det, det_stride, st));
+  if (slot_index == nullptr) VSR_TRY(run_prologue(c, det, det_stride, st));
+  else VSR_TRY(run_prologue_indexed(c, det, det_stride, st));
   c->have_prologue = true;
   return VSR_OK;
 }
@@ -477,7 +488,15 @@ int vsr_set_verb_table(vsr_handle h, const int64_t* keys, const int32_t* offsets
 int vsr_prologue(vsr_handle h, const float* det, int64_t det_batch_stride, int32_t D, const float* det_seqs,
                  int32_t b, int32_t L, int32_t R, const void* verbs, int32_t verbs_dtype, void* stream) {
   if (!h) { vsr::set_error("vsr_prologue: null handle"); return VSR_EINVAL; }
-  return vsr::prologue_impl((Ctx*)h, det, det_batch_stride, D, det_seqs, b, L, R, verbs, verbs_dtype,
+  return vsr::prologue_impl((Ctx*)h, det, det_batch_stride, D, det_seqs, nullptr, b, L, R, verbs, verbs_dtype,
+                            (cudaStream_t)stream);
+}
+
+int vsr_prologue_indexed(vsr_handle h, const float* det, int64_t det_batch_stride, int32_t D,
+                         const int32_t* slot_index, int32_t b, int32_t L, int32_t R, const void* verbs,
+                         int32_t verbs_dtype, void* stream) {
+  if (!h || !slot_index) { vsr::set_error("vsr_prologue_indexed: null argument"); return VSR_EINVAL; }
+  return vsr::prologue_impl((Ctx*)h, det, det_batch_stride, D, nullptr, slot_index, b, L, R, verbs, verbs_dtype,
                             (cudaStream_t)stream);
 }
 

@@ -183,7 +183,10 @@ struct Ctx {
   // prologue products (per batch)
   bool have_prologue = false;
   int b = 0, D = 0, L = 0, R = 0, n_img = 0;
-  const float* det_seqs = nullptr;
+  const float* det_seqs = nullptr;       // materialised slot tiles (b,L,R,F), or null in index form
+  const int32_t* slot_index = nullptr;   // index form: (b,L,R) detection row / -2 mean row / -1 padding
+  const float* det = nullptr; int64_t det_stride = 0;   // index form: detections (n_img, D, F)
+  float* Pmean = nullptr;                // index form: att_va projection of the image mean rows [n_img][NVA]
   const void* verbs = nullptr; int verbs_dtype = 0;
   float* img = nullptr;        // [n_img_alloc][Fp]
   float* U = nullptr;          // [n_img_alloc][NA]
@@ -192,7 +195,7 @@ struct Ctx {
   uint8_t* seq_valid = nullptr;  // [b*L*R]
   unsigned long long* slot_mask = nullptr;  // [b*L] bit r set = region r of the slot is a real (non-padding) row
   uint8_t* det_valid = nullptr;  // [n_img*D]
-  size_t cap_img = 0, cap_P = 0, cap_detv = 0;
+  size_t cap_img = 0, cap_P = 0, cap_detv = 0, cap_slots = 0;
   // per-row workspace (rows = captions * beam), capacity cap_rows (multiple of MPAD)
   int cap_rows = 0;
   float *h1, *c1, *h2, *c2;          // current state [rows][Hp]
@@ -241,6 +244,7 @@ struct PhaseScope {  // records start/stop events around a phase when profiling 
 // ---------------------------------------------------------------- kernels (defined in *.cu)
 int pack_weights(Ctx* c, const float* const* w, cudaStream_t st);
 int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st);
+int run_prologue_indexed(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st);
 int ensure_rows(Ctx* c, int rows);
 int ensure_beam_ws(Ctx* c, int caps, int T);
 

@@ -87,6 +87,24 @@ __global__ void k_slot_masks(const uint8_t* __restrict__ valid, int R, int n_slo
   mask[s] = m;
 }
 
+// index form: validity mask of a slot from its detection indices (-2 = image mean row, valid iff the image
+// has any valid detection; -1 = padding)
+__global__ void k_slot_masks_indexed(const int32_t* __restrict__ slot_index, const uint8_t* __restrict__ det_valid,
+                                     int R, int L, int D, int n_slots, int img_mul, unsigned long long* __restrict__ mask) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slots) return;
+  const int img = (s / L) * img_mul;
+  int any = 0;
+  for (int d = 0; d < D; ++d) any |= det_valid[img * D + d];
+  unsigned long long m = 0;
+  for (int r = 0; r < R; ++r) {
+    const int idx = slot_index[(size_t)s * R + r];
+    const bool v = idx >= 0 ? (idx < D && det_valid[img * D + idx]) : (idx == -2 && any);
+    if (v) m |= 1ull << r;
+  }
+  mask[s] = m;
+}
+
 // img[g][f] = sum_d det[g][d][f] / count(valid rows of g); one thread per float4 column.
 __global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D, int F,
                        const uint8_t* __restrict__ valid, float* __restrict__ img, int ld_img, PairOut split) {
@@ -303,6 +321,60 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     g.row_skip = c->seq_valid;
     VSR_TRY(launch_gemm(c, g, st));
     c->launches++;
+  }
+  return VSR_OK;
+}
+
+// Index form (vsr_prologue_indexed): projections per DETECTION row + one per image mean row; slot tiles are
+// never materialised.
+int run_prologue_indexed(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) {
+  PhaseScope ps(c, PH_PROLOGUE, st);
+  const int F = c->F, D = c->D, b = c->b, L = c->L, R = c->R;
+  const int n_img = c->n_img;
+  const int rows = n_img * D;
+  {
+    const PairOut dsp{c->use_tc ? (__half*)c->ds_b.hi : nullptr, (__half*)c->ds_b.lo, c->Fp};
+    k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, dsp);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    k_slot_masks_indexed<<<(b * L + 127) / 128, 128, 0, st>>>(c->slot_index, c->det_valid, R, L, D, b * L,
+                                                              n_img == 1 ? 0 : 1, c->slot_mask);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    dim3 grid((F / 4 + 127) / 128, n_img);
+    const PairOut ip{c->use_tc ? (__half*)c->img_b.hi : nullptr, (__half*)c->img_b.lo, c->Fp};
+    k_pool<<<grid, 128, 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
+    VSR_CHECK_CUDA(cudaGetLastError());
+    c->launches += 3;
+  }
+  {
+    GemmArgs g{};
+    g.nseg = 1; g.seg[0] = {c->img, c->Fp, c->Fp, c->Fp, &c->img_b};
+    g.w = c->WU; g.ldw = c->Fp; g.bias = c->bU; g.wb = &c->WU_b;
+    g.c = c->U; g.ldc = c->NA; g.M = n_img; g.N = c->NA;
+    VSR_TRY(launch_gemm(c, g, st));
+    c->launches++;
+    if (c->d.img_second_lstm) {
+      GemmArgs g2{};
+      g2.nseg = 1; g2.seg[0] = {c->img, c->Fp, c->Fp, c->Fp, &c->img_b};
+      g2.w = c->WU2; g2.ldw = c->Fp; g2.wb = &c->WU2_b;
+      g2.c = c->U2; g2.ldc = c->ND; g2.M = n_img; g2.N = c->ND;
+      VSR_TRY(launch_gemm(c, g2, st));
+      c->launches++;
+    }
+  }
+  {  // P per detection row, and per image mean row
+    GemmArgs g{};
+    // the fp32 FFMA twin reads the detections in place; their rows are contiguous only when images are dense
+    g.nseg = 1; g.seg[0] = {det, F, c->Fp, F, &c->ds_b};
+    g.w = c->Wva; g.ldw = c->Fp; g.wb = &c->Wva_b;
+    g.c = c->P; g.ldc = c->NVA; g.M = rows; g.N = c->NVA;
+    g.row_skip = c->det_valid;
+    VSR_TRY(launch_gemm(c, g, st));
+    GemmArgs gm{};
+    gm.nseg = 1; gm.seg[0] = {c->img, c->Fp, c->Fp, c->Fp, &c->img_b};
+    gm.w = c->Wva; gm.ldw = c->Fp; gm.wb = &c->Wva_b;
+    gm.c = c->Pmean; gm.ldc = c->NVA; gm.M = n_img; gm.N = c->NVA;
+    VSR_TRY(launch_gemm(c, gm, st));
+    c->launches += 2;
   }
   return VSR_OK;
 }

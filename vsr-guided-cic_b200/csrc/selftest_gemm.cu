@@ -49,7 +49,7 @@ static int run_case(int M, int N, int nseg, const int* ks, bool extras, int BN, 
   F16Pair ab[3];
   for (int s = 0; s < nseg; ++s) {
     float* A = dev_rand((size_t)Mp * ks[s], 1.0f, 10 + s);
-    memset(&ab[s], 0, sizeof(F16Pair));
+    ab[s] = F16Pair{};
     make_pair(&ab[s], A, Mp, ks[s], 128);
     g.seg[s] = {A, ks[s], ks[s], ks[s], &ab[s]};
   }

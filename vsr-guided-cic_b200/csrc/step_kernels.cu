@@ -103,8 +103,11 @@ constexpr int ATT_THREADS = 256;
 constexpr int ATT_MAX_R = 64;
 
 struct AttendArgs {
-  const float* det_seqs;   // (b, L, R, F)
-  const float* P;          // [b*L*R][ldP]
+  const float* det_seqs;   // (b, L, R, F) materialised slot tiles, or null in index form
+  const float* P;          // materialised: [b*L*R][ldP]; index form: [n_img*D][ldP] (per detection row)
+  // index form (vsr_prologue_indexed): region = det[img][idx] (idx >= 0) or the image mean row (idx == -2)
+  const int32_t* slot_index; const float* det; int64_t det_stride; int D;
+  const float* img; int ld_img; const float* Pmean; int img_mul;
   const unsigned long long* slot_mask;  // [b*L] validity bits of each slot tile
   const int32_t* ptr;      // [rows]
   const float* sent; int ld_sent; int o_sa;   // sentinel (F) at 0 | sa (A) at o_sa
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   __shared__ int s_rows[ATT_MAX_R];     // compacted valid region rows and their weights
   __shared__ float s_w[ATT_MAX_R];
   __shared__ int s_nv;
+  __shared__ const float* s_feat[ATT_MAX_R];   // feature row of every region of the slot
 
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -165,20 +169,33 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
     vmask = a.slot_mask[(size_t)cap * a.L + slot];
   }
   const size_t tile_row0 = ((size_t)cap * a.L + slot) * a.R;
-  const float* tile = a.det_seqs + tile_row0 * a.F;
-  const float* Pt = a.P + tile_row0 * a.ldP;
+  const int imgi = cap * a.img_mul;
 
   // stage the valid regions' projections with cp.async (16-byte chunks, no registers held) and pull the
   // valid feature rows towards L2 while the scores are computed; one warp per region row, no divisions
   for (int r = warp; r < a.R; r += nwarp) {
     if (!((vmask >> r) & 1ull)) continue;
-    const float* prow = Pt + (size_t)r * a.ldP;
+    const float* prow;
+    const float* frow;
+    if (a.slot_index == nullptr) {
+      prow = a.P + (tile_row0 + r) * a.ldP;
+      frow = a.det_seqs + (tile_row0 + r) * a.F;
+    } else {
+      const int idx = a.slot_index[tile_row0 + r];
+      if (idx >= 0) {
+        prow = a.P + ((size_t)imgi * a.D + idx) * a.ldP;
+        frow = a.det + (size_t)imgi * a.det_stride + (size_t)idx * a.F;
+      } else {
+        prow = a.Pmean + (size_t)imgi * a.ldP;
+        frow = a.img + (size_t)imgi * a.ld_img;
+      }
+    }
+    if (lane == 0) s_feat[r] = frow;
     float* pdst = Ps + (size_t)r * a.A;
     for (int ch = lane * 4; ch < a.A; ch += 128) {
       const unsigned dst = (unsigned)__cvta_generic_to_shared(pdst + ch);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(prow + ch) : "memory");
     }
-    const float* frow = tile + (size_t)r * a.F;
     for (int f = lane * 32; f < a.F; f += 32 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(frow + f));
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -306,8 +323,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
       float4 v0[4], v1[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int r = s_rows[min(i + u, nv - 1)];
-        const float* rp = tile + (size_t)r * a.F;
+        const float* rp = s_feat[s_rows[min(i + u, nv - 1)]];
         v0[u] = __ldg(reinterpret_cast<const float4*>(rp + f0));
         v1[u] = two ? __ldg(reinterpret_cast<const float4*>(rp + f1)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
@@ -691,6 +707,8 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     PhaseScope ps(c, PH_ATTEND, st);
     AttendArgs a{};
     a.det_seqs = c->det_seqs; a.P = c->P; a.slot_mask = c->slot_mask; a.ptr = c->ptr;
+    a.slot_index = c->slot_index; a.det = c->det; a.det_stride = c->det_stride; a.D = c->D;
+    a.img = c->img; a.ld_img = c->Fp; a.Pmean = c->Pmean; a.img_mul = (c->n_img == 1 ? 0 : 1);
     a.sent = c->sent; a.ld_sent = c->NB1; a.o_sa = c->oB1_sa;
     a.hb = c->hb; a.ld_hb = c->NB2; a.o_ha = c->oB2_ha;
     a.v_a = c->v_a; a.v_s = c->v_s;

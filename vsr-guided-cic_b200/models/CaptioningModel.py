@@ -95,6 +95,22 @@ class CaptioningModel(nn.Module):
             log_probs = [lp.squeeze(1) for lp in log_probs]
         return outputs, log_probs
 
+    def beam_search_v_indexed(self, statics, eos_idxs, beam_size, out_size=1, *args, gt=False):
+        """Extension: beam_search_v with the slots given as INDICES into the detections instead
+        of materialised feature tiles: statics = (detections (b,D,F), slot_index (b,L,R) int, verbs (b,L) or None);
+        slot_index >= 0 picks a detection row, -2 the mean of the image's valid detections, -1 is padding.
+        Same return structure as beam_search_v; 10x fewer input bytes."""
+        eng = self._engine()
+        verbs = statics[2] if len(statics) > 2 else None
+        eng.prologue_indexed(statics[0], statics[1], verbs)
+        self._prologue_key = None
+        (words, gates), (lpw, lpg), _ = eng.beam_search(beam_size, out_size, eos_idxs, use_verbs=verbs is not None, gt=gt)
+        outputs, log_probs = [words, gates], [lpw, lpg]
+        if out_size == 1:
+            outputs = [o.squeeze(1) for o in outputs]
+            log_probs = [lp.squeeze(1) for lp in log_probs]
+        return outputs, log_probs
+
     def beam_search(self, statics, eos_idxs, beam_size, out_size=1, *args):
         """Joint (word, gate) beam search (reference CaptioningModel.py:116-195)."""
         return self._beam(statics[:2], eos_idxs, beam_size, out_size, False, False)

@@ -136,6 +136,39 @@ class DecoderEngine:
                 self.handle, det_k.data_ptr(), stride, D, ds.data_ptr(), b, self.L, self.R,
                 vb.data_ptr() if vb is not None else None, vdt, _stream_ptr(self.device)))
 
+    def prologue_indexed(self, det: torch.Tensor, slot_index: torch.Tensor, verbs: Optional[torch.Tensor] = None):
+        """Index form of the prologue (vsr_prologue_indexed): slot_index (b, L, R) holds, per region, a
+        detection row of the caption's image (>= 0), -2 for the image's mean row, or -1 for padding."""
+        _req_cuda(det, "detections", torch.float32)
+        _req_cuda(slot_index, "slot_index")
+        if det.dim() != 3 or slot_index.dim() != 3 or det.size(0) != slot_index.size(0):
+            raise VsrError(f"bad static shapes {tuple(det.shape)} / {tuple(slot_index.shape)}")
+        F = self.dims["det_feat_size"]
+        if det.size(2) != F:
+            raise VsrError("feature width does not match det_feat_size")
+        b, D = det.size(0), det.size(1)
+        if b > 1 and det.stride(0) == 0 and det[0].is_contiguous():
+            det_k, stride = det[0], 0
+        else:
+            det_k = det.contiguous()
+            stride = D * F
+        idx = slot_index.to(torch.int32).contiguous()
+        vb, vdt = None, 0
+        if verbs is not None:
+            _req_cuda(verbs, "verbs")
+            if verbs.dtype not in _VERB_DT:
+                verbs = verbs.double()
+            if tuple(verbs.shape) != (b, idx.size(1)):
+                raise VsrError(f"verbs shape {tuple(verbs.shape)} != {(b, idx.size(1))}")
+            vb = verbs.contiguous()
+            vdt = _VERB_DT[vb.dtype]
+        self._keep = (det_k, idx, vb)
+        self.b, self.L, self.R = b, idx.size(1), idx.size(2)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.vsr_prologue_indexed(
+                self.handle, det_k.data_ptr(), stride, D, idx.data_ptr(), b, self.L, self.R,
+                vb.data_ptr() if vb is not None else None, vdt, _stream_ptr(self.device)))
+
     # ------------------------------------------------------------------ single step
     def step(self, h1, c1, h2, c2, slot, word, use_verbs=False, gt=False):
         b, H, V = self.b, self.dims["rnn_size"], self.dims["vocab_size"]
