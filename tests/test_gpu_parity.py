@@ -36,13 +36,16 @@ def test_small_model_beam_search_cases(name):
         ("bs_freeze_k4", (det, ds), False, False, slice(None)),
         ("bsv_gt_b1", (det[:1], ds[:1], fx["verbs_gt"][:1]), True, True, slice(0, 1)),
     ]
-    for cname, statics, use_verbs, gt, _ in cases:
+    # trace=True: full log-prob rows are produced (log-softmax kernel); trace=False: the production path, where the
+    # vocabulary GEMM's epilogue and k_vocab_merge replace the logits tensor
+    for (cname, statics, use_verbs, gt, _), trace in [(c, tr) for c in cases for tr in (True, False)]:
         c = fx["cases"][cname]
         k, osz = c["beam"], c["out_size"]
-        (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(*statics), c["eos"], k, osz, use_verbs, gt)
+        (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(*statics), c["eos"], k, osz, use_verbs, gt, trace=trace)
         v, o_outs, o_lps = verify_device_beam(W, d, statics, c["eos"], k, hist, use_verbs, gt, fx["verb_table"],
-                                              extra["step_out"], extra["step_gate"])
-        print(cname, v.summary())
+                                              extra.get("step_out") if extra else None,
+                                              extra.get("step_gate") if extra else None)
+        print(cname, "trace" if trace else "fused-head", v.summary())
         assert not v.violations, v.violations[:5]
         assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0    # fraction of (1e-3*|x| + 1e-4)
         # along the device's own trajectory the oracle reproduces the device's outputs exactly
@@ -311,13 +314,15 @@ def test_edge_cases_ragged_and_empty_slots():
     ds[3] = torch.relu(torch.randn(ds[3].shape, generator=torch.Generator().manual_seed(3))) + 0.1   # all valid
     for sl in (slice(None), slice(0, 1)):
         statics = (det[sl], ds[sl], verbs[sl])
-        (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(*statics), [3, -1], 3, 2, True, True)
-        v, o_outs, o_lps = verify_device_beam(W, d, statics, [3, -1], 3, hist, True, True, fx["verb_table"],
-                                              extra["step_out"], extra["step_gate"])
-        print("edge cases", v.summary())
-        assert not v.violations, v.violations[:5]
-        assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0
-        assert torch.equal(w.cpu(), o_outs[0][:, :2]) and torch.equal(g.cpu(), o_outs[1][:, :2])
+        for trace in (True, False):
+            (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(*statics), [3, -1], 3, 2, True, True, trace=trace)
+            v, o_outs, o_lps = verify_device_beam(W, d, statics, [3, -1], 3, hist, True, True, fx["verb_table"],
+                                                  extra.get("step_out") if extra else None,
+                                                  extra.get("step_gate") if extra else None)
+            print("edge cases", v.summary())
+            assert not v.violations, v.violations[:5]
+            assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0
+            assert torch.equal(w.cpu(), o_outs[0][:, :2]) and torch.equal(g.cpu(), o_outs[1][:, :2])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -380,13 +385,16 @@ def test_odd_dimensions_against_oracle(dims):
     m = make_model(d, W)
     det, ds, verbs = O.synth_inputs(7, 9, 5, 6, d.det_feat_size, seed=21, vocab_size=d.vocab_size, n_det_range=(3, 9),
                                     real_slots=(2, 5), verb_slots=(1,), verb_vocab_id=11)
-    (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(det, ds, verbs), [3, -1], 4, 2, True, True)
-    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 4, hist, True, True, None,
-                                          extra["step_out"], extra["step_gate"])
-    print("odd dims", dims, v.summary())
-    assert not v.violations, v.violations[:5]
-    assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0
-    assert torch.equal(w.cpu(), o_outs[0][:, :2]) and torch.equal(g.cpu(), o_outs[1][:, :2])
+    for trace in (True, False):
+        (w, g), (lw, lg), hist, extra = device_beam(m, _cuda(det, ds, verbs), [3, -1], 4, 2, True, True, trace=trace)
+        v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], 4, hist, True, True, None,
+                                              extra.get("step_out") if extra else None,
+                                              extra.get("step_gate") if extra else None)
+        print("odd dims", dims, "trace" if trace else "fused-head", v.summary())
+        assert not v.violations, v.violations[:5]
+        assert v.max_out_rel <= 1.0 and v.max_gate_rel <= 1.0
+        assert torch.equal(w.cpu(), o_outs[0][:, :2]) and torch.equal(g.cpu(), o_outs[1][:, :2])
+        assert rel_close(lw.cpu(), o_lps[0][:, :2], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, :2], REL, ABS)
     caps = torch.randint(0, d.vocab_size, (7, 5), generator=torch.Generator().manual_seed(1))
     ctrl = ds[:, :5].contiguous()
     out, gate = m((det.to(DEV),), (caps.to(DEV), ctrl.to(DEV)))

@@ -109,7 +109,7 @@ int ensure_rows(Ctx* c, int rows) {
   const int cap = round_up(rows, MPAD);
   float** bufs[] = {&c->h1, &c->c1, &c->h2, &c->c2, &c->h1n, &c->c1n, &c->h2n, &c->c2n, &c->pre1,
                     &c->s_t, &c->g_t, &c->gq, &c->sent, &c->hb, &c->ga, &c->att, &c->pre2, &c->logits, &c->gate_lp,
-                    &c->row_max, &c->row_lsum, &c->shift};
+                    &c->row_max, &c->row_lsum, &c->shift, &c->vpart};
   for (float** p : bufs) { dev_free(c, *p); *p = nullptr; }
   dev_free(c, c->word_idx);
   dev_free(c, c->ptr); dev_free(c, c->ptrn); dev_free(c, c->forced); dev_free(c, c->cand); dev_free(c, c->word_in);
@@ -123,6 +123,7 @@ int ensure_rows(Ctx* c, int rows) {
   ALLOC_F(c->sent, n * c->NB1); ALLOC_F(c->hb, n * c->NB2); ALLOC_F(c->ga, n * c->NC);
   ALLOC_F(c->att, n * c->Fp); ALLOC_F(c->pre2, n * c->ND); ALLOC_F(c->logits, n * c->NE);
   ALLOC_F(c->gate_lp, n * 2); ALLOC_F(c->row_max, n); ALLOC_F(c->row_lsum, n); ALLOC_F(c->shift, n);
+  ALLOC_F(c->vpart, n * (size_t)(c->NE / 128 + 1) * VOCAB_REC);
   VSR_TRY(dev_alloc(c, (void**)&c->ptr, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->ptrn, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));

@@ -99,7 +99,11 @@ struct FusedCell {
   // plain mode only: on output columns [0, gt_cols) write g_t = sig(gq + acc) * tanh(c1') instead of acc
   int gt_cols = 0; const float* gt_gq = nullptr; const float* gt_c1n = nullptr;
   float* g_t = nullptr; void *g_hi = nullptr, *g_lo = nullptr;
+  // mode 3 (vocabulary head): besides the logits, per (row, N tile) records of VOCAB_REC floats
+  // {tile max, sum exp(x - max), max of each 16-column chunk}.  *vocab_tiles_out / *vocab_bn_out = tiling of the launch.
+  float* vocab_part = nullptr; int* vocab_tiles_out = nullptr; int* vocab_bn_out = nullptr;
 };
+constexpr int VOCAB_REC = 16;
 
 struct GemmArgs {
   GemmSeg seg[3];
@@ -216,6 +220,7 @@ struct Ctx {
   float *row_max, *row_lsum;         // [rows]
   int32_t *forced;                   // [rows] forced vocab idx or -1
   int32_t *cand;                     // [rows][VSR_MAX_BEAM]
+  float *vpart;                      // [rows][NE / 128 + 1][VOCAB_REC] per-tile softmax records of the vocabulary GEMM
   // beam workspace
   int cap_caps = 0, cap_T = 0;
   float *seq_lp, *seq_lp_n;          // [caps][beam]

@@ -158,7 +158,7 @@ __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
-enum { EPI_PLAIN = 0, EPI_LSTM1 = 1, EPI_LSTM2 = 2 };
+enum { EPI_PLAIN = 0, EPI_LSTM1 = 1, EPI_LSTM2 = 2, EPI_VOCAB = 3 };
 
 // One GEMM problem.  Up to two independent problems (same tile shape) share a launch.
 struct TcProblem {
@@ -180,6 +180,8 @@ struct TcProblem {
   int ld_state;
   // fused g_t = sig(gq + acc) * tanh(c1') on the tiles with n0 < gt_cols (plain epilogue elsewhere)
   int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; __half* g_hi; __half* g_lo;
+  // EPI_VOCAB: per (row, N tile) softmax / top-k partial records instead of (or besides, when c != null) the logits
+  float* vpart; int n_valid;
 };
 struct TcParams {
   TcProblem pr[2];
@@ -248,6 +250,57 @@ __device__ __forceinline__ void cell_epilogue(const TcProblem& p, uint32_t tlane
   }
 }
 
+// Vocabulary-head epilogue: besides storing the logits (acc + bias) the thread that owns a row folds its BN
+// columns into one record {tile max, sum exp(x - max), max of every 16-column chunk}.  k_vocab_merge
+// (step_kernels.cu) finishes log-softmax and top-k from the records and re-reads only the few chunks that can hold
+// a top-k element, so the 20 MB logits tensor is written but never scanned.
+template <int BN>
+__device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0, int n_tile) {
+  static_assert(BN / 16 <= VOCAB_REC - 2, "record too small for this tile");
+  float m = -INFINITY, ssum = 0.f;
+  float cmx[VOCAB_REC - 2];
+#pragma unroll
+  for (int k = 0; k < VOCAB_REC - 2; ++k) cmx[k] = -INFINITY;
+  float* crow = p.c + (size_t)row * p.ldc;
+#pragma unroll
+  for (int ch = 0; ch < BN / 16; ++ch) {
+    uint32_t r[16];
+    tmem_ld16(tlane + (uint32_t)(ch * 16), r);
+    const int n = n0 + ch * 16;
+    if (live) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+        *reinterpret_cast<float4*>(crow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (n + 16 > p.n_valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) if (n + j >= p.n_valid) v[j] = -INFINITY;
+      }
+      float cm = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
+      cm = fmaxf(cm, fmaxf(fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11])), fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]))));
+      cmx[ch] = cm;
+      if (cm > m) { ssum *= __expf(m - cm); m = cm; }
+      if (m > -INFINITY) {
+        float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;     // exp(-inf) = 0 on masked columns
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          e0 += __expf(v[j] - m); e1 += __expf(v[j + 1] - m); e2 += __expf(v[j + 2] - m); e3 += __expf(v[j + 3] - m);
+        }
+        ssum += (e0 + e1) + (e2 + e3);
+      }
+    }
+  }
+  if (!live) return;
+  float4* rec = reinterpret_cast<float4*>(p.vpart + ((size_t)row * p.n_tiles + n_tile) * VOCAB_REC);
+  rec[0] = make_float4(m, ssum, cmx[0], cmx[1]);
+#pragma unroll
+  for (int q = 1; q < VOCAB_REC / 4; ++q) rec[q] = make_float4(cmx[4 * q - 2], cmx[4 * q - 1], cmx[4 * q], cmx[4 * q + 1]);
+}
+
 template <int BN>
 __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int n_tile,
                                             int warp, int lane) {
@@ -260,7 +313,9 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
     const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
     const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
 
-    if (p.mode == EPI_PLAIN) {
+    if (p.mode == EPI_VOCAB) {
+      if constexpr (BN / 16 <= VOCAB_REC - 2) vocab_epilogue<BN>(p, tlane, row, live, n0, n_tile);   // host checks the tile
+    } else if (p.mode == EPI_PLAIN) {
       float* crow = p.c + (size_t)row * p.ldc;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 16; ++ch) {       // 16 accumulator columns per TMEM load: any BN % 16 == 0
@@ -802,7 +857,13 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
   p->gather = g.gather; p->ld_gather = g.ld_gather; p->gather_idx = g.gather_idx;
   const FusedCell& f = g.cell;
   p->mode = f.mode;
-  if (f.mode != 0) {
+  if (f.mode == EPI_VOCAB) {
+    VSR_REQUIRE(f.vocab_part != nullptr && g.bias != nullptr && g.c != nullptr && BN / 16 <= VOCAB_REC - 2, VSR_EINVAL,
+                "launch_gemm_tc: vocabulary epilogue needs a bias, an output and a record buffer (N tile %d)", BN);
+    p->vpart = f.vocab_part; p->n_valid = g.wb->n_valid;
+    if (f.vocab_tiles_out != nullptr) *f.vocab_tiles_out = p->n_tiles;
+    if (f.vocab_bn_out != nullptr) *f.vocab_bn_out = BN;
+  } else if (f.mode != 0) {
     VSR_REQUIRE((f.mode == EPI_LSTM1 && BN % 192 == 0) || (f.mode == EPI_LSTM2 && BN % 128 == 0), VSR_EINVAL,
                 "launch_gemm_tc: fused cell mode %d does not fit N tile %d", f.mode, BN);
     p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_hi = (__half*)f.h_hi; p->h_lo = (__half*)f.h_lo;
@@ -848,7 +909,7 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   VSR_REQUIRE(g2 == nullptr || g2->wb->kb == kb, VSR_EINVAL, "launch_gemm_tc: grouped problems need one k-block size");
   // Tile choice: operand delivery bounds these GEMMs, so a tile costs ~ (BM + BN) and a launch costs
   // waves(tiles / 148 SMs) * (BM + BN).  Take the alternative N tile when that is cheaper.
-  if (g.wb->alt_bn > 0 && g.cell.mode == 0 && (g2 == nullptr || (g2->wb->alt_bn == g.wb->alt_bn && g2->cell.mode == 0))) {
+  if (g.wb->alt_bn > 0 && (g.cell.mode == 0 || g.cell.mode == EPI_VOCAB) && (g2 == nullptr || (g2->wb->alt_bn == g.wb->alt_bn && g2->cell.mode == 0))) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int mt = (g.M + BM - 1) / BM;
@@ -857,7 +918,9 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
       if (g2 != nullptr) tiles += ((g2->M + BM - 1) / BM) * ((g2->wb->n_valid + bn - 1) / bn);
       return ((tiles + sms - 1) / sms) * (BM + bn);
     };
-    if (cost(g.wb->alt_bn) < cost(BN)) { BN = g.wb->alt_bn; kb = g.wb->alt_kb; }
+    // (the vocabulary head always takes the alternative tile: its per-tile records, and with them the summation
+    //  order of the row's log-sum-exp, must not depend on how many rows the launch has)
+    if (cost(g.wb->alt_bn) < cost(BN) || g.cell.mode == EPI_VOCAB) { BN = g.wb->alt_bn; kb = g.wb->alt_kb; }
   }
   VSR_TRY(fill_problem(&p.pr[0], g, BN, false, kb));
   p.nprob = 1;

@@ -7,6 +7,7 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace vsr {
@@ -638,6 +639,181 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
   }
 }
 
+// ---------------------------------------------------------------- fused vocabulary head: finish from the per-tile records
+// The vocabulary GEMM's epilogue (gemm_tc.cu: vocab_epilogue) leaves, per (row, N tile), {max, sum exp, max of every
+// 16-column chunk}.  One WARP per row: row max / log-sum-exp from the records; then the topk tiles by max, the topk
+// chunks among them by max, and only those topk * 16 logits are re-read and their topk picked.
+// Exact: if an element e of group C (tile or chunk) were in the row's top-k without C being among the topk groups
+// in (max desc, position asc) order, each of the topk groups ahead of C would hold an element ordered before e
+// (larger, or equal with a smaller index).
+// Also the gate head and verb forcing, exactly as k_softmax_topk; same outputs.
+constexpr int VM_WARPS = 4;
+
+__global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs a, const float* __restrict__ vpart,
+                                                                int n_tiles, int nch) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * VM_WARPS + (threadIdx.x >> 5);
+  if (n >= a.rows) return;
+  const int V = a.V, topk = a.topk;
+  const float* rec0 = vpart + (size_t)n * n_tiles * VOCAB_REC;
+  const float* x = a.logits + (size_t)n * a.ld;
+
+  int64_t verb = -1; float shift_logit = 0.f;
+  if (lane == 0) {
+    shift_logit = a.shift[n];
+    if (a.use_verbs && a.verbs != nullptr)
+      verb = load_verb(a.verbs, a.verbs_dtype, (size_t)(n / a.cur_beam) * a.L + a.ptr[n]);
+  }
+  // (max, sum exp) of this lane's tiles
+  float m = -INFINITY, ssum = 0.f;
+  for (int t = lane; t < n_tiles; t += 32) {
+    const float2 ms = *reinterpret_cast<const float2*>(rec0 + (size_t)t * VOCAB_REC);
+    if (ms.x > m) { ssum *= __expf(m - ms.x); m = ms.x; }
+    if (ms.x > -INFINITY) ssum += ms.y * __expf(ms.x - m);
+  }
+  // stay-gate logit att_g . tanh(ga + ha)
+  float stay = 0.f;
+  {
+    const float4* ha = reinterpret_cast<const float4*>(a.ha + (size_t)n * a.ld_ha);
+    const float4* ga = reinterpret_cast<const float4*>(a.ga + (size_t)n * a.ld_ga);
+    const float4* vg = reinterpret_cast<const float4*>(a.v_g);
+    for (int i = lane; i < a.A / 4; i += 32) {
+      const float4 h = ha[i], g = ga[i], w = __ldg(vg + i);
+      stay += (w.x * fast_tanh(g.x + h.x) + w.y * fast_tanh(g.y + h.y)) + (w.z * fast_tanh(g.z + h.z) + w.w * fast_tanh(g.w + h.w));
+    }
+  }
+  const float mx = warp_max(m);
+  const float se = warp_sum(m > -INFINITY ? ssum * expf(m - mx) : 0.f);
+  const float lsum = logf(se);
+  stay = warp_sum(stay);
+
+  // Hierarchical exact selection, every level in (value desc, position asc) order with composite keys
+  // orderable(value) : ~position, so "ordered before" is a plain unsigned 64-bit '>':
+  //   1. the topk TILES by tile max (round j: every lane's best key strictly below the previous winner, then a
+  //      warp arg-best; lane j keeps winner j),
+  //   2. the topk 16-column CHUNKS among those tiles' chunk maxima,
+  //   3. the topk ELEMENTS among those chunks' logits.
+  unsigned long long prev = ~0ull;
+  int my_tile = -1;
+  for (int j = 0; j < topk; ++j) {
+    unsigned long long best = 0ull;
+    for (int t = lane; t < n_tiles; t += 32) {
+      const float tm = rec0[(size_t)t * VOCAB_REC];
+      const unsigned long long key = ((unsigned long long)orderable(tm) << 32) | (unsigned)(~(unsigned)t);
+      if (tm > -INFINITY && key < prev && key > best) best = key;
+    }
+    const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
+    const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
+    prev = ((unsigned long long)hi << 32) | lo;
+    if (hi == 0u && lo == 0u) break;          // fewer tiles than topk (uniform)
+    if (lane == j) my_tile = (int)(~lo);
+  }
+  constexpr int CQ = (VSR_MAX_BEAM * (VOCAB_REC - 2) + 31) / 32;
+  float kv[CQ]; int kc[CQ];
+#pragma unroll
+  for (int q = 0; q < CQ; ++q) {
+    const int e = lane + 32 * q;
+    const int tsel = e / nch, ch = e - tsel * nch;
+    const int tile = __shfl_sync(0xffffffffu, my_tile, tsel & 31);
+    kv[q] = -INFINITY; kc[q] = 0x7fffffff;
+    if (tsel < topk && tile >= 0) {
+      const float cm = rec0[(size_t)tile * VOCAB_REC + 2 + ch];
+      if (cm > -INFINITY) { kv[q] = cm; kc[q] = tile * nch + ch; }
+    }
+  }
+  int my_chunk = -1;
+  for (int j = 0; j < topk; ++j) {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) if (before(kv[q], kc[q], bv, bi)) { bv = kv[q]; bi = kc[q]; }
+    unsigned kb; int ib;
+    warp_argbest_redux(bv, bi, kb, ib);
+#pragma unroll
+    for (int q = 0; q < CQ; ++q) if (kc[q] == ib) { kv[q] = -INFINITY; kc[q] = 0x7fffffff; }
+    if (lane == j && ib != 0x7fffffff) my_chunk = ib;
+  }
+
+  // candidates: the 16 logits of each selected chunk; lane owns elements e = lane + 32 * q of the topk * 16
+  constexpr int EQ = VSR_MAX_BEAM * 16 / 32;
+  float cv[EQ]; int ci[EQ];
+#pragma unroll
+  for (int q = 0; q < EQ; ++q) {
+    const int e = lane + 32 * q;
+    const int chunk = __shfl_sync(0xffffffffu, my_chunk, (e >> 4) & 31);
+    cv[q] = -INFINITY; ci[q] = 0x7fffffff;
+    if (e < topk * 16 && chunk >= 0) {
+      const int col = chunk * 16 + (e & 15);
+      if (col < V) { cv[q] = x[col]; ci[q] = col; }
+    }
+  }
+  int my_pick = 0x7fffffff;
+  for (int j = 0; j < topk; ++j) {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < EQ; ++q) if (before(cv[q], ci[q], bv, bi)) { bv = cv[q]; bi = ci[q]; }
+    unsigned kb; int ib;
+    warp_argbest_redux(bv, bi, kb, ib);
+#pragma unroll
+    for (int q = 0; q < EQ; ++q) if (ci[q] == ib) { cv[q] = -INFINITY; ci[q] = 0x7fffffff; }
+    if (lane == j) my_pick = ib;
+  }
+
+  int forced = -1;
+  if (lane == 0) {
+    // verb forcing (:271-295): which vocabulary index does the current slot force, if any
+    if (verb != -1) {
+      if (a.gt) {
+        forced = (int)verb;
+      } else {
+        forced = 0;   // key missing or empty list -> vocabulary index 0 (:291-292)
+        int lo = 0, hi = a.vt_n - 1, pos = -1;
+        while (lo <= hi) {
+          const int mid = (lo + hi) >> 1;
+          const int64_t k = a.vt_keys[mid];
+          if (k == verb) { pos = mid; break; }
+          if (k < verb) lo = mid + 1; else hi = mid - 1;
+        }
+        if (pos >= 0 && a.vt_off[pos + 1] > a.vt_off[pos]) {
+          float best = -1e6f; int best_i = -1;    // strict '>' : first maximum wins (:284-289)
+          for (int qq = a.vt_off[pos]; qq < a.vt_off[pos + 1]; ++qq) {
+            const int idx = a.vt_idx[qq];
+            const float lp = (x[idx] - mx) - lsum;
+            if (lp > best) { best = lp; best_i = idx; }
+          }
+          forced = best_i < 0 ? V - 1 : best_i;   // python index -1 == last vocabulary entry
+        }
+      }
+      forced = min(max(forced, 0), V - 1);
+    }
+    a.row_max[n] = mx;
+    a.row_lsum[n] = lsum;
+    a.forced[n] = forced;
+    // gate head: log_softmax([stay, shift]) (:187-188), or [-1e3, 0] on a verb slot (:295)
+    float g0, g1;
+    if (forced >= 0) { g0 = -1e3f; g1 = 0.f; }
+    else {
+      const float gm = fmaxf(stay, shift_logit);
+      const float ls = logf(expf(stay - gm) + expf(shift_logit - gm));
+      g0 = (stay - gm) - ls; g1 = (shift_logit - gm) - ls;
+    }
+    a.gate_lp[(size_t)n * 2] = g0; a.gate_lp[(size_t)n * 2 + 1] = g1;
+    if (a.gate_out != nullptr) {
+      a.gate_out[(size_t)n * a.gate_stride + 0] = g0;
+      a.gate_out[(size_t)n * a.gate_stride + 1] = g1;
+    }
+  }
+  forced = __shfl_sync(0xffffffffu, forced, 0);
+  if (lane < topk) {
+    if (forced >= 0) {
+      // forced word first, then the lowest other indices (all tied at -1e6)
+      int w = forced;
+      if (lane > 0) { w = lane - 1; if (w >= forced) ++w; w = min(w, V - 1); }
+      my_pick = w;
+    }
+    a.cand[(size_t)n * VSR_MAX_BEAM + lane] = my_pick;
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- one decoder step (host side)
@@ -753,12 +929,20 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     k_lstm2<<<pw_grid, 128, 0, st>>>(c->pre2, c->ND, c->c2, c->h2n, c->c2n, pair_out(c, c->h2n_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
+  // Fused vocabulary head (tensor-core path, nobody needs full log-prob rows): the GEMM epilogue also reduces
+  // every tile to a softmax record and k_vocab_merge finishes the row without scanning the logits.
+  static const bool fuse_enabled = [] { const char* e = getenv("VSRDEC_FUSE_VOCAB"); return e == nullptr || atoi(e) != 0; }();
+  const bool fuse_vocab = fuse_enabled && fused && io.out_logp == nullptr && io.topk > 0;
+  int vocab_tiles = 0, vocab_bn = 0;
   {  // E: logits = out_fc . h2' + b
     PhaseScope ps(c, PH_GEMM_E, st);
     GemmArgs g{};
     g.nseg = 1; g.seg[0] = {c->h2n, c->Hp, c->Hp, c->Hp, &c->h2n_b};
     g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE; g.wb = &c->WE_b;
     g.c = c->logits; g.ldc = c->NE; g.M = rows; g.N = c->NE;
+    if (fuse_vocab) {
+      g.cell.mode = 3; g.cell.vocab_part = c->vpart; g.cell.vocab_tiles_out = &vocab_tiles; g.cell.vocab_bn_out = &vocab_bn;
+    }
     VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
   {
@@ -773,7 +957,13 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.row_max = c->row_max; a.row_lsum = c->row_lsum; a.forced = c->forced; a.cand = c->cand;
     a.gate_lp = c->gate_lp; a.out_logp = io.out_logp; a.out_stride = io.out_stride;
     a.gate_out = io.gate_out; a.gate_stride = io.gate_stride;
-    k_softmax_topk<<<rows, SM_THREADS, 0, st>>>(a);
+    if (fuse_vocab) {
+      VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
+                  "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);
+      k_vocab_merge<<<(rows + VM_WARPS - 1) / VM_WARPS, VM_WARPS * 32, 0, st>>>(a, c->vpart, vocab_tiles, vocab_bn / 16);
+    } else {
+      k_softmax_topk<<<rows, SM_THREADS, 0, st>>>(a);
+    }
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   return VSR_OK;
