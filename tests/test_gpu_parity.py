@@ -431,3 +431,43 @@ def test_indexed_slot_input_matches_oracle_on_materialised_tiles(shared_image):
     o2, _ = m.beam_search_v((dev[0], ds.to(DEV), dev[2]), [3, -1], 5, 1, gt=True)
     torch.cuda.synchronize()
     print("captions identical to the materialised entry point:", _match_fraction(o2[0], w))
+
+
+# ----------------------------------------------------------------------------- CUDA-graph replay of the decode
+def test_graph_replay_is_bit_identical_and_tracks_new_inputs():
+    """The library replays a repeated beam search (same buffers, same parameters) from a CUDA graph: call 1 runs
+    eagerly, call 2 captures, later calls replay.  All must agree bit for bit, count the same launches, and a
+    replay must see new data written into the same input buffers (the prologue is not part of the graph)."""
+    from gpu_common import make_model
+    d = O.Dims()
+    W = O.init_weights(d, seed=1234)
+    W["out_fc.weight"] = W["out_fc.weight"] * 100.0
+    m = make_model(d, W)
+    det, ds, verbs = _config2_inputs(b=16)
+    bufs = _cuda(det, ds, verbs)
+    runs, launches = [], []
+    for _ in range(4):
+        l0 = m._engine().launch_count()
+        (w, g), (lw, lg) = m.beam_search_v(bufs, [3, -1], 5, 1, gt=True)
+        torch.cuda.synchronize()
+        launches.append(m._engine().launch_count() - l0)
+        runs.append((w.clone(), g.clone(), lw.clone(), lg.clone(), [h.clone() for h in m._eng.history()]))
+    for r in runs[1:]:
+        for a, b_ in zip(r[:4], runs[0][:4]):
+            assert torch.equal(a, b_)
+        for a, b_ in zip(r[4], runs[0][4]):
+            assert torch.equal(a, b_)
+    assert len(set(launches)) == 1 and launches[0] > 100, launches
+    # new inputs in the SAME device buffers: the replayed graph must decode them, checked against the oracle
+    det2, ds2, verbs2 = _config2_inputs(b=16, seed=77)
+    for dst, src in zip(bufs, (det2, ds2, verbs2)):
+        dst.copy_(src.to(DEV))
+    (w, g), (lw, lg) = m.beam_search_v(bufs, [3, -1], 5, 1, gt=True)
+    hist = m._eng.history()
+    torch.cuda.synchronize()
+    assert not torch.equal(w, runs[0][0])
+    v, o_outs, o_lps = verify_device_beam(W, d, (det2, ds2, verbs2), [3, -1], 5, hist, True, True)
+    print("graph replay on new inputs", v.summary())
+    assert not v.violations, v.violations[:5]
+    assert torch.equal(w.cpu(), o_outs[0][:, 0]) and torch.equal(g.cpu(), o_outs[1][:, 0])
+    assert rel_close(lw.cpu(), o_lps[0][:, 0], REL, ABS)

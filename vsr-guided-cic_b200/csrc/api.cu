@@ -29,6 +29,7 @@ int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero) {
     return VSR_ENOMEM;
   }
   c->owned.push_back(*p);
+  c->epoch++;
   if (zero) VSR_CHECK_CUDA(cudaMemset(*p, 0, bytes));
   return VSR_OK;
 }
@@ -37,6 +38,7 @@ static void dev_free(Ctx* c, void* p) {
   if (p == nullptr) return;
   auto it = std::find(c->owned.begin(), c->owned.end(), p);
   if (it != c->owned.end()) c->owned.erase(it);
+  c->epoch++;
   cudaFree(p);
 }
 
@@ -225,6 +227,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128.
   // CTA-pair kernel (default; VSRDEC_2CTA=0 disables): 256 x 192 tiles for A, 256 x 256 elsewhere.
   if (const char* e = getenv("VSRDEC_2CTA")) c->use_pair = atoi(e) != 0;
+  if (const char* e = getenv("VSRDEC_GRAPH")) c->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
   VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 96)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, 128, c->NB1v));
@@ -351,19 +354,10 @@ static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, 
   return VSR_OK;
 }
 
-static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int use_verbs, int gt,
-                            int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
-                            const VsrTrace* tr, cudaStream_t st) {
-  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_beam_search: call vsr_prologue first");
-  VSR_REQUIRE(k >= 1 && k <= VSR_MAX_BEAM, VSR_EINVAL, "vsr_beam_search: beam_size=%d not in [1,%d]", k, VSR_MAX_BEAM);
-  VSR_REQUIRE(out_size >= 1 && out_size <= k, VSR_EINVAL, "vsr_beam_search: out_size=%d not in [1,beam]", out_size);
-  VSR_REQUIRE(2 * c->V >= k, VSR_EINVAL, "vsr_beam_search: vocabulary smaller than the beam");
-  VSR_REQUIRE(eos && out_words && out_gates && lp_words && lp_gates, VSR_EINVAL, "vsr_beam_search: null argument");
-  VSR_REQUIRE(!use_verbs || c->verbs != nullptr, VSR_EINVAL, "vsr_beam_search: use_verbs without a verbs tensor");
+// state init + T x (decoder step, beam selection + reorder): everything of a beam search except the back-track
+static int enqueue_beam_steps(Ctx* c, int k, const int64_t* eos, int use_verbs, int gt, const VsrTrace* tr,
+                              cudaStream_t st) {
   const int b = c->b, T = c->d.seq_len;
-  VSR_TRY(ensure_rows(c, b * k));
-  VSR_TRY(ensure_beam_ws(c, b, T));
-  c->hist_T = T; c->hist_b = b; c->hist_k = k;
   VSR_TRY(launch_state_init(c, b, st));
   const bool have_forced = tr && tr->forced_beam && tr->forced_word && tr->forced_gate;
   for (int t = 0; t < T; ++t) {
@@ -379,6 +373,85 @@ static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int
                              have_forced ? tr->forced_word + fo : nullptr,
                              have_forced ? tr->forced_gate + fo : nullptr, t + 1 < T, st));
   }
+  return VSR_OK;
+}
+
+static void drop_graphs(Ctx* c) {
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
+  c->graph_seen.clear();
+}
+
+// The steps of a beam search through the graph cache: first sighting of a key runs eagerly, the second captures
+// the same enqueue sequence on the library's capture stream and instantiates it, later ones replay it on `st`.
+static int beam_steps_graphed(Ctx* c, int k, const int64_t* eos, int use_verbs, int gt, cudaStream_t st) {
+  Ctx::GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.epoch = c->epoch; key.det = c->det; key.det_seqs = c->det_seqs; key.slot_index = c->slot_index; key.verbs = c->verbs;
+  key.det_stride = c->det_stride; key.eos0 = eos[0]; key.eos1 = eos[1];
+  key.b = c->b; key.D = c->D; key.L = c->L; key.R = c->R; key.n_img = c->n_img; key.verbs_dtype = c->verbs_dtype;
+  key.k = k; key.use_verbs = use_verbs; key.gt = gt; key.T = c->d.seq_len;
+  if (!c->graphs.empty() && c->graphs[0].key.epoch != c->epoch) drop_graphs(c);   // buffers moved: all stale
+  ++c->graph_clock;
+  for (auto& g : c->graphs)
+    if (memcmp(&g.key, &key, sizeof(key)) == 0) {
+      VSR_CHECK_CUDA(cudaGraphLaunch(g.exec, st));
+      c->launches += g.launches; g.last_use = c->graph_clock;
+      return VSR_OK;
+    }
+  bool seen = false;
+  for (auto& s : c->graph_seen) seen = seen || memcmp(&s, &key, sizeof(key)) == 0;
+  if (!seen) {
+    if (c->graph_seen.size() >= 8) c->graph_seen.erase(c->graph_seen.begin());
+    c->graph_seen.push_back(key);
+    return enqueue_beam_steps(c, k, eos, use_verbs, gt, nullptr, st);
+  }
+  if (c->cap_stream == nullptr) VSR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+  const int64_t l0 = c->launches;
+  VSR_CHECK_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_beam_steps(c, k, eos, use_verbs, gt, nullptr, c->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+  const int64_t n_launch = c->launches - l0;
+  c->launches = l0;
+  if (rc != VSR_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  VSR_CHECK_CUDA(ce);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  VSR_CHECK_CUDA(ie);
+  if (c->graphs.size() >= 4) {      // evict the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(c->graphs[lru].exec);
+    c->graphs.erase(c->graphs.begin() + lru);
+  }
+  c->graphs.push_back({key, exec, n_launch, c->graph_clock});
+  VSR_CHECK_CUDA(cudaGraphLaunch(exec, st));
+  c->launches += n_launch;
+  return VSR_OK;
+}
+
+static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int use_verbs, int gt,
+                            int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
+                            const VsrTrace* tr, cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_beam_search: call vsr_prologue first");
+  VSR_REQUIRE(k >= 1 && k <= VSR_MAX_BEAM, VSR_EINVAL, "vsr_beam_search: beam_size=%d not in [1,%d]", k, VSR_MAX_BEAM);
+  VSR_REQUIRE(out_size >= 1 && out_size <= k, VSR_EINVAL, "vsr_beam_search: out_size=%d not in [1,beam]", out_size);
+  VSR_REQUIRE(2 * c->V >= k, VSR_EINVAL, "vsr_beam_search: vocabulary smaller than the beam");
+  VSR_REQUIRE(eos && out_words && out_gates && lp_words && lp_gates, VSR_EINVAL, "vsr_beam_search: null argument");
+  VSR_REQUIRE(!use_verbs || c->verbs != nullptr, VSR_EINVAL, "vsr_beam_search: use_verbs without a verbs tensor");
+  const int b = c->b, T = c->d.seq_len;
+  VSR_TRY(ensure_rows(c, b * k));
+  VSR_TRY(ensure_beam_ws(c, b, T));
+  c->hist_T = T; c->hist_b = b; c->hist_k = k;
+  // graph replay unless a trace is requested, the phase profiler is on, or the caller is capturing itself
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+  if (c->use_graphs && tr == nullptr && !c->profiling && cap == cudaStreamCaptureStatusNone)
+    VSR_TRY(beam_steps_graphed(c, k, eos, use_verbs, gt, st));
+  else
+    VSR_TRY(enqueue_beam_steps(c, k, eos, use_verbs, gt, tr, st));
   VSR_TRY(launch_backtrack(c, b, k, T, out_size, out_words, out_gates, lp_words, lp_gates, st));
   return VSR_OK;
 }
@@ -455,6 +528,8 @@ void vsr_destroy(vsr_handle h) {
   Ctx* c = (Ctx*)h;
   cudaDeviceSynchronize();
   vsr::reset_phases(c);
+  vsr::drop_graphs(c);
+  if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   for (void* p : c->owned) cudaFree(p);
   delete c;
 }

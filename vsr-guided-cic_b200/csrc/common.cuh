@@ -236,6 +236,21 @@ struct Ctx {
   bool profiling = false;
   Phase phases[PH_COUNT];
   std::vector<void*> owned;          // every cudaMalloc'd pointer (freed in destroy)
+  // CUDA-graph cache of whole beam searches (api.cu).  A decode is ~140 launches with no host decision in
+  // between; replaying it as one graph removes the per-launch cost (and its sensitivity to PCIe traffic).
+  // Key = every value baked into the kernels' arguments; `epoch` changes whenever a device buffer is (re)allocated.
+  struct GraphKey {
+    uint64_t epoch;
+    const void *det, *det_seqs, *slot_index, *verbs;
+    int64_t det_stride, eos0, eos1;
+    int32_t b, D, L, R, n_img, verbs_dtype, k, use_verbs, gt, T;
+  };
+  struct GraphEntry { GraphKey key; cudaGraphExec_t exec; int64_t launches; uint64_t last_use; };
+  std::vector<GraphEntry> graphs;
+  std::vector<GraphKey> graph_seen;  // keys decoded once eagerly; the second sighting captures
+  uint64_t epoch = 0, graph_clock = 0;
+  cudaStream_t cap_stream = nullptr;
+  bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
 };
 
 int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero = true);
