@@ -228,6 +228,8 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // CTA-pair kernel (default; VSRDEC_2CTA=0 disables): 256 x 192 tiles for A, 256 x 256 elsewhere.
   if (const char* e = getenv("VSRDEC_2CTA")) c->use_pair = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_GRAPH")) c->use_graphs = atoi(e) != 0;
+  if (const char* e = getenv("VSRDEC_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("VSRDEC_PDL_MODE")) c->pdl_mode = atoi(e);
   if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
   VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 96)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, 128, c->NB1v));

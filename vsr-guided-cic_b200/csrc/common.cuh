@@ -89,6 +89,29 @@ __host__ __device__ inline int cell_col(int g, int u, int ng) {
 
 // Optional epilogue fusion of the tensor-core GEMM (ignored by the FFMA twin, whose callers run the
 // stand-alone pointwise kernels instead).
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The kernels of a decoder step form one dependency chain.  Launched with the programmatic-serialization attribute,
+// kernel N+1 may become resident while kernel N drains: it runs its own set-up (barrier init, TMEM allocation,
+// descriptor prefetch, WEIGHT tile prefetch) and then blocks in pdl_wait() until kernel N has completed and its
+// writes are visible.  Rule for every such kernel: before pdl_wait() touch nothing but launch arguments and data
+// that is constant over the whole decode (weights, prologue products); write nothing.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
+
 struct FusedCell {
   int mode = 0;                 // 0 = plain, 1 = LSTM cell 1 (+ sentinel gate, 6 gates), 2 = LSTM cell 2 (4 gates)
   const float* c_old = nullptr; float* c_new = nullptr; float* h_new = nullptr;
@@ -123,6 +146,8 @@ struct GemmArgs {
   const int32_t* gather_idx = nullptr;
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
   const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
+  bool pdl = false;             // launch with programmatic dependent launch (decoder-step GEMMs only)
+  int pdl_flags = 0;            // bit 0: weight tiles before the dependency wait; bit 1: trigger after the main loop
   FusedCell cell;               // epilogue fusion (tensor-core path only)
 };
 struct Ctx;
@@ -251,6 +276,11 @@ struct Ctx {
   uint64_t epoch = 0, graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
   bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
+  bool use_pdl = true;               // VSRDEC_PDL=0: plain stream serialization between the step kernels
+  // VSRDEC_PDL_MODE bits: 1 = GEMM launches, 2 = small kernels, 4 = weight prefetch before the wait, 8 = GEMMs
+  // trigger after their main loop.  Measured inside the decode graph (ms per decode): off 4.07, 1: 4.02, 1|4: 4.00,
+  // 1|2|4: 4.18 (early-resident CTAs of the many-CTA kernels pile up on the SMs that drain first), 1|2|8: 4.08.
+  int pdl_mode = 5;
 };
 
 int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero = true);

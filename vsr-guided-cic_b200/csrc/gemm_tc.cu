@@ -186,6 +186,7 @@ struct TcProblem {
 struct TcParams {
   TcProblem pr[2];
   int nprob;
+  int pdl_flags;
 };
 
 // Fused LSTM cell epilogue.  Every 32-unit chunk of the tile is NG*32 columns laid out as 4 sub-blocks of
@@ -388,7 +389,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   const int m_tile = t % p.m_tiles, n_tile = t / p.m_tiles;
   const int m0 = m_tile * BM, n0 = n_tile * BN;
 
+  if (!(params.pdl_flags & 2)) pdl_trigger();
   if (p.row_skip != nullptr) {   // all-padding row tiles produce nothing (block-uniform)
+    pdl_wait();                  // the flags come from the previous kernel
     int any = 0;
     if (threadIdx.x < BM && m0 + (int)threadIdx.x < p.M) any = p.row_skip[m0 + threadIdx.x];
     if (!__syncthreads_or(any)) return;
@@ -420,16 +423,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
+      // the WEIGHT halves of the first ring pass do not depend on the previous kernel: fetch them, then wait
+      const int pre = !(params.pdl_flags & 1) ? 0 : (total_kb < Cfg::kStages ? total_kb : Cfg::kStages);
+      for (int kb = 0; kb < pre; ++kb) {
+        uint8_t* base = smem + kb * Cfg::kStageBytes;
+        mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+        tma_load_2d(&p.w_hi, &full_bar[kb], base + 2 * Cfg::kABytes, kb * KB, n0);
+        tma_load_2d(&p.w_lo, &full_bar[kb], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+      }
+      pdl_wait();
       int seg = 0, kk = 0;
       for (int kb = 0; kb < total_kb; ++kb) {
         const int st = kb % Cfg::kStages;
         const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
         uint8_t* base = smem + st * Cfg::kStageBytes;
-        mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+        if (kb >= pre) {
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+          tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
+          tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+        }
         tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
-        tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
-        tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
         tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
         if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
       }
@@ -457,9 +471,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         umma_commit(&empty_bar[st]);          // frees the smem slot once these MMAs have read it
       }
       umma_commit(&tmem_full_bar);            // accumulator complete -> epilogue
+      if (params.pdl_flags & 2) pdl_trigger();
     }
     __syncwarp();
   } else {
+    pdl_wait();
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     tc_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane);
@@ -504,6 +520,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
   const int total_tiles = tiles0 + (params.nprob > 1 ? params.pr[1].n_tiles * params.pr[1].m_tiles : 0);
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 
+  if (!(params.pdl_flags & 2)) pdl_trigger();
+  bool pdl_waited = false;
+  for (int q = 0; q < params.nprob; ++q)
+    if (params.pr[q].row_skip != nullptr) pdl_waited = true;     // tile skipping reads the previous kernel's flags
+  if (pdl_waited || warp >= 2) pdl_wait();                        // epilogue warps: before any global access
   if (warp == 0 && lane == 0) {
     for (int q = 0; q < params.nprob; ++q) {
       const TcProblem& p = params.pr[q];
@@ -544,16 +565,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
 
     if (warp == 0) {
       if (lane == 0) {
+        // first tile of this CTA: weight halves of the first ring pass before the dependency wait (see k_gemm_tc)
+        int pre = 0;
+        if (!pdl_waited) {
+          pre = !(params.pdl_flags & 1) ? 0 : (total_kb < Cfg::kStages ? total_kb : Cfg::kStages);
+          for (int kb = 0; kb < pre; ++kb) {
+            uint8_t* base = smem + kb * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
+            tma_load_2d(&p.w_hi, &full_bar[kb], base + 2 * Cfg::kABytes, kb * KB, n0);
+            tma_load_2d(&p.w_lo, &full_bar[kb], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+          }
+          pdl_wait();
+          pdl_waited = true;
+        }
         int seg = 0, kk = 0;
         for (int kb = 0; kb < total_kb; ++kb) {
           const int st = (it + kb) % Cfg::kStages;
           const uint32_t ph = ((it + kb) / Cfg::kStages) & 1;
-          mbar_wait(&empty_bar[st], ph ^ 1);
           uint8_t* base = smem + st * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+          if (kb >= pre) {
+            mbar_wait(&empty_bar[st], ph ^ 1);
+            mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+            tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
+            tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+          }
           tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
-          tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
-          tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
           tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
           if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
         }
@@ -583,6 +619,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
           umma_commit(&empty_bar[st]);
         }
         umma_commit(&tmem_full_bar[acc]);
+        if ((params.pdl_flags & 2) && tile + (int)gridDim.x >= total_tiles) pdl_trigger();   // last tile of this CTA
       }
       __syncwarp();
     } else {
@@ -924,6 +961,7 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   }
   VSR_TRY(fill_problem(&p.pr[0], g, BN, false, kb));
   p.nprob = 1;
+  p.pdl_flags = g.pdl_flags;
   int tiles = p.pr[0].n_tiles * p.pr[0].m_tiles;
   if (g2 != nullptr) {
     VSR_TRY(fill_problem(&p.pr[1], *g2, BN, false, kb));
@@ -941,7 +979,7 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   // (and measured neutral-to-worse for the grouped two-problem launch, whose tiles are uneven)
   if (persist && tiles > sms && g2 == nullptr && (BN == 128 || BN == 144 || BN == 192)) {
     const int grid = tiles < sms ? tiles : sms;
-#define TCP_LAUNCH(BN_, KB_) k_gemm_tcp<BN_, KB_><<<grid, TC_THREADS, TcCfg<BN_, KB_>::kSmemBytes, st>>>(p)
+#define TCP_LAUNCH(BN_, KB_) VSR_CHECK_CUDA(launch_k(k_gemm_tcp<BN_, KB_>, dim3(grid), dim3(TC_THREADS), TcCfg<BN_, KB_>::kSmemBytes, st, g.pdl, p))
     if (BN == 144) TCP_LAUNCH(144, 64);
     else if (BN == 192) { if (kb == 32) TCP_LAUNCH(192, 32); else TCP_LAUNCH(192, 64); }
     else { if (kb == 32) TCP_LAUNCH(128, 32); else TCP_LAUNCH(128, 64); }
@@ -949,7 +987,7 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
     VSR_CHECK_CUDA(cudaGetLastError());
     return VSR_OK;
   }
-#define TC_LAUNCH(BN_, KB_) k_gemm_tc<BN_, KB_><<<tiles, TC_THREADS, TcCfg<BN_, KB_>::kSmemBytes, st>>>(p)
+#define TC_LAUNCH(BN_, KB_) VSR_CHECK_CUDA(launch_k(k_gemm_tc<BN_, KB_>, dim3(tiles), dim3(TC_THREADS), TcCfg<BN_, KB_>::kSmemBytes, st, g.pdl, p))
   if (BN == 144) TC_LAUNCH(144, 64);
   else if (BN == 240) TC_LAUNCH(240, 32);
   else if (kb == 32) {

@@ -142,6 +142,8 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
 #define TICK() do {} while (0)
 #endif
   TICK();
+  pdl_trigger();
+  pdl_wait();          // every input of this kernel comes from the step's earlier kernels
   const int cap = n / a.cur_beam;
   const float* sent = a.sent + (size_t)n * a.ld_sent;   // sentinel feature row
   const float* sa = sent + a.o_sa;
@@ -428,6 +430,8 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
   __shared__ int s_pick[VSR_MAX_BEAM];
   const int n = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_trigger();
+  pdl_wait();
   const float* x = a.logits + (size_t)n * a.ld;
   const int V = a.V;
   const int n4 = (V + 3) >> 2;
@@ -653,6 +657,8 @@ __global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs
                                                                 int n_tiles, int nch) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * VM_WARPS + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (n >= a.rows) return;
   const int V = a.V, topk = a.topk;
   const float* rec0 = vpart + (size_t)n * n_tiles * VOCAB_REC;
@@ -843,6 +849,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.gather = c->X; g.ld_gather = c->NA; g.gather_idx = c->word_idx;
     g.rowadd = c->U; g.ld_rowadd = c->NA; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
+    g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     fused = gemm_uses_tc(c, g);
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
       g.cell.mode = 1; g.cell.c_old = c->c1; g.cell.c_new = c->c1n; g.cell.h_new = c->h1n;
@@ -872,6 +879,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
       g2.cell.gt_cols = c->oB2_ha; g2.cell.gt_gq = c->gq; g2.cell.gt_c1n = c->c1n; g2.cell.g_t = c->g_t;
       g2.cell.g_hi = c->g_t_b.hi; g2.cell.g_lo = c->g_t_b.lo; g2.cell.ld_state = c->Hp;
     }
+    g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     VSR_TRY(launch_gemm(c, g, st, &g2)); c->launches += fused ? 1 : 2;   // one grouped launch on tensor cores
   }
   if (!fused) {
@@ -898,7 +906,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
       attr_set = true;
     }
     VSR_REQUIRE(smem <= 200 * 1024, VSR_EINVAL, "attention tile (R=%d x A=%d) does not fit shared memory", c->R, c->A);
-    k_attend<<<rows, ATT_THREADS, smem, st>>>(a);
+    VSR_CHECK_CUDA(launch_k(k_attend, dim3(rows), dim3(ATT_THREADS), smem, st, c->use_pdl && (c->pdl_mode & 2), a));
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // D: pre2 = pre2_h1 + WD . [att | h2_old] + b (+ U2[img]);  C: ga = att_ga . g_t rides in the same launch
@@ -922,6 +930,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
       g.cell.mode = 2; g.cell.c_old = c->c2; g.cell.c_new = c->c2n; g.cell.h_new = c->h2n;
       g.cell.h_hi = c->h2n_b.hi; g.cell.h_lo = c->h2n_b.lo; g.cell.ld_state = c->Hp;
     }
+    g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     VSR_TRY(launch_gemm(c, g, st, &gc)); c->launches += fused ? 1 : 2;
   }
   if (!fused) {
@@ -940,6 +949,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.nseg = 1; g.seg[0] = {c->h2n, c->Hp, c->Hp, c->Hp, &c->h2n_b};
     g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE; g.wb = &c->WE_b;
     g.c = c->logits; g.ldc = c->NE; g.M = rows; g.N = c->NE;
+    g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     if (fuse_vocab) {
       g.cell.mode = 3; g.cell.vocab_part = c->vpart; g.cell.vocab_tiles_out = &vocab_tiles; g.cell.vocab_bn_out = &vocab_bn;
     }
@@ -960,9 +970,10 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     if (fuse_vocab) {
       VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
                   "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);
-      k_vocab_merge<<<(rows + VM_WARPS - 1) / VM_WARPS, VM_WARPS * 32, 0, st>>>(a, c->vpart, vocab_tiles, vocab_bn / 16);
+      VSR_CHECK_CUDA(launch_k(k_vocab_merge, dim3((rows + VM_WARPS - 1) / VM_WARPS), dim3(VM_WARPS * 32), 0, st, c->use_pdl && (c->pdl_mode & 2),
+                              a, (const float*)c->vpart, vocab_tiles, vocab_bn / 16));
     } else {
-      k_softmax_topk<<<rows, SM_THREADS, 0, st>>>(a);
+      VSR_CHECK_CUDA(launch_k(k_softmax_topk, dim3(rows), dim3(SM_THREADS), 0, st, c->use_pdl && (c->pdl_mode & 2), a));
     }
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
