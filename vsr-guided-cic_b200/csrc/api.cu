@@ -505,6 +505,15 @@ static int greedy_impl(Ctx* c, int64_t* out_words, int64_t* out_gates, cudaStrea
 // ============================================================================ C ABI
 using vsr::Ctx;
 
+// Every entry point runs on the handle's device regardless of the caller's current device (restored on return).
+struct DeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit DeviceGuard(const vsr::Ctx* c) {
+    if (c != nullptr && cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
 extern "C" {
 
 const char* vsr_last_error(void) { return vsr::g_err; }
@@ -522,12 +531,14 @@ int vsr_create(const VsrDims* dims, const float* const* weights, vsr_handle* out
 
 int vsr_load_weights(vsr_handle h, const float* const* weights, void* stream) {
   if (!h || !weights) { vsr::set_error("vsr_load_weights: null argument"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::pack_weights((Ctx*)h, weights, (cudaStream_t)stream);
 }
 
 void vsr_destroy(vsr_handle h) {
   if (!h) return;
   Ctx* c = (Ctx*)h;
+  DeviceGuard dg(c);
   cudaDeviceSynchronize();
   vsr::reset_phases(c);
   vsr::drop_graphs(c);
@@ -539,6 +550,7 @@ void vsr_destroy(vsr_handle h) {
 int vsr_set_verb_table(vsr_handle h, const int64_t* keys, const int32_t* offsets, const int32_t* vocab_idx,
                        int32_t n_keys) {
   if (!h) { vsr::set_error("vsr_set_verb_table: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   Ctx* c = (Ctx*)h;
   VSR_CHECK_CUDA(cudaDeviceSynchronize());
   vsr::dev_free(c, c->vt_keys); vsr::dev_free(c, c->vt_off); vsr::dev_free(c, c->vt_idx);
@@ -566,6 +578,7 @@ int vsr_set_verb_table(vsr_handle h, const int64_t* keys, const int32_t* offsets
 int vsr_prologue(vsr_handle h, const float* det, int64_t det_batch_stride, int32_t D, const float* det_seqs,
                  int32_t b, int32_t L, int32_t R, const void* verbs, int32_t verbs_dtype, void* stream) {
   if (!h) { vsr::set_error("vsr_prologue: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::prologue_impl((Ctx*)h, det, det_batch_stride, D, det_seqs, nullptr, b, L, R, verbs, verbs_dtype,
                             (cudaStream_t)stream);
 }
@@ -574,6 +587,7 @@ int vsr_prologue_indexed(vsr_handle h, const float* det, int64_t det_batch_strid
                          const int32_t* slot_index, int32_t b, int32_t L, int32_t R, const void* verbs,
                          int32_t verbs_dtype, void* stream) {
   if (!h || !slot_index) { vsr::set_error("vsr_prologue_indexed: null argument"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::prologue_impl((Ctx*)h, det, det_batch_stride, D, nullptr, slot_index, b, L, R, verbs, verbs_dtype,
                             (cudaStream_t)stream);
 }
@@ -582,6 +596,7 @@ int vsr_step(vsr_handle h, const float* h1, const float* c1, const float* h2, co
              const int64_t* slot, const int64_t* word, int32_t use_verbs, int32_t gt, float* h1o, float* c1o,
              float* h2o, float* c2o, float* out_logp, float* gate_logp, void* stream) {
   if (!h) { vsr::set_error("vsr_step: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::step_impl((Ctx*)h, h1, c1, h2, c2, slot, word, use_verbs, gt, h1o, c1o, h2o, c2o, out_logp,
                         gate_logp, (cudaStream_t)stream);
 }
@@ -590,12 +605,14 @@ int vsr_beam_search(vsr_handle h, int32_t beam_size, int32_t out_size, const int
                     int32_t use_verbs, int32_t gt, int64_t* out_words, int64_t* out_gates, float* lp_words,
                     float* lp_gates, const VsrTrace* trace, void* stream) {
   if (!h) { vsr::set_error("vsr_beam_search: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::beam_search_impl((Ctx*)h, beam_size, out_size, eos_idxs, use_verbs, gt, out_words, out_gates,
                                lp_words, lp_gates, trace, (cudaStream_t)stream);
 }
 
 int vsr_get_history(vsr_handle h, int32_t* parent, int32_t* word, int32_t* gate, float* score, void* stream) {
   if (!h) { vsr::set_error("vsr_get_history: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   Ctx* c = (Ctx*)h;
   VSR_REQUIRE(c->hist_T > 0, VSR_ESTATE, "vsr_get_history: no beam search has run on this handle");
   const size_t n = (size_t)c->hist_T * c->hist_b * c->hist_k;
@@ -609,11 +626,13 @@ int vsr_get_history(vsr_handle h, int32_t* parent, int32_t* word, int32_t* gate,
 
 int vsr_forward_teacher(vsr_handle h, const int64_t* captions, int32_t T, float* out, float* gate, void* stream) {
   if (!h) { vsr::set_error("vsr_forward_teacher: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::forward_impl((Ctx*)h, captions, T, out, gate, (cudaStream_t)stream);
 }
 
 int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* stream) {
   if (!h) { vsr::set_error("vsr_greedy: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   return vsr::greedy_impl((Ctx*)h, out_words, out_gates, (cudaStream_t)stream);
 }
 
@@ -634,6 +653,7 @@ int vsr_set_profiling(vsr_handle h, int32_t enabled) {
 
 int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* launches, int32_t cap) {
   if (!h) { vsr::set_error("vsr_get_phase_times: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
   Ctx* c = (Ctx*)h;
   VSR_CHECK_CUDA(cudaDeviceSynchronize());
   int n = 0;

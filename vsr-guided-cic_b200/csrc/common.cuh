@@ -275,6 +275,7 @@ struct Ctx {
   std::vector<GraphKey> graph_seen;  // keys decoded once eagerly; the second sighting captures
   uint64_t epoch = 0, graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
+  bool attend_attr_set = false;
   bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
   bool use_pdl = true;               // VSRDEC_PDL=0: plain stream serialization between the step kernels
   // VSRDEC_PDL_MODE bits: 1 = GEMM launches, 2 = small kernels, 4 = weight prefetch before the wait, 8 = GEMMs

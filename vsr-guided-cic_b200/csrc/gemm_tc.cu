@@ -860,7 +860,11 @@ int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t 
 }
 
 int tc_gemm_init() {
-  static bool done = false;
+  // function attributes are per device: track which devices of this process have been set up
+  static unsigned long long done_mask = 0ull;
+  int dev = 0;
+  VSR_CHECK_CUDA(cudaGetDevice(&dev));
+  const bool done = dev < 64 && ((done_mask >> dev) & 1ull);
   if (done) return VSR_OK;
 #define TC_SET_SMEM(BN_, KB_) VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc<BN_, KB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<BN_, KB_>::kSmemBytes))
   TC_SET_SMEM(256, 64); TC_SET_SMEM(192, 64); TC_SET_SMEM(128, 64);
@@ -872,7 +876,7 @@ int tc_gemm_init() {
 #undef TC_SET_SMEM
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<256>::kSmemBytes));
   VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<192>::kSmemBytes));
-  done = true;
+  if (dev < 64) done_mask |= 1ull << dev;
   return VSR_OK;
 }
 
