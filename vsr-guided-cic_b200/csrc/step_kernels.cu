@@ -219,7 +219,6 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   TICK();
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
-  if (lane == 0) e[0] += 0.f;   // (consumer of the barrier for the debug clock)
   TICK();
 
   // scores: job 0 = sentinel, 1 = padding-row score, 2.. = valid regions; one warp per job
