@@ -141,11 +141,11 @@ def gemm_flops_per_row_step(dims):
     """Algorithmic FLOPs (2*K*N_out) of the per-step dense contractions this implementation executes:
     SURVEY.md §8d's hoisted formulation (95.54 MFLOP per row-step) minus the xt part of GEMM-A
     (2*E*6H = 12 MFLOP), which is a per-word table lookup here: A = h2->6H + h1->5H,
-    B = s_t->(F+A) + h1'->(H+A+4H), D = [att|h2]->4H (+ C = g_t->A in the same launch), E = h2'->V."""
+    B = s_t->(F+A) + h1'->(H+A), D = [att|h2|h1']->4H (+ C = g_t->A in the same launch), E = h2'->V."""
     H, E, F, A, V = dims["H"], dims["E"], dims["F"], dims["A"], dims["V"]
     return {"gemm_a_lstm1_gates": 2 * (H * 6 * H + H * 5 * H),
-            "gemm_b_sentinel_h1proj": 2 * (H * (F + A) + H * (H + A + 4 * H)),
-            "gemm_d_lstm2_gates": 2 * (F + H) * 4 * H + 2 * H * A,
+            "gemm_b_sentinel_h1proj": 2 * (H * (F + A) + H * (H + A)),
+            "gemm_d_lstm2_gates": 2 * (F + 2 * H) * 4 * H + 2 * H * A,
             "gemm_e_vocab": 2 * H * V}
 
 
@@ -299,6 +299,31 @@ def main_ours(args, rank, world, local_rank):
         decode_indexed(dev_idx)
     idx_total_ms, _, _, _ = timed(lambda: decode_indexed(dev_idx), args.steps)
 
+    # ---- secondary workload: teacher-forced forward, B=100, T=20, D=100 (train.py:99-103 shape)
+    fwd = None
+    if rank == 0:
+        gq = torch.Generator().manual_seed(1005)
+        f_det = torch.relu(torch.randn((100, 100, w["F"]), generator=gq)).to(dev)
+        f_caps = torch.randint(0, w["V"], (100, w["T"]), generator=gq).to(dev)
+        f_ctrl = torch.relu(torch.randn((100, w["T"], w["R"], w["F"]), generator=gq))
+        f_nv = torch.randint(1, w["R"] + 1, (100, w["T"]), generator=gq)
+        f_ctrl = (f_ctrl * (torch.arange(w["R"])[None, None, :] < f_nv[:, :, None]).unsqueeze(-1)).to(dev)
+        for _ in range(2):
+            model((f_det,), (f_caps, f_ctrl))
+        torch.cuda.synchronize(dev)
+        fe0, fe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_fwd = 5
+        fe0.record()
+        for _ in range(n_fwd):
+            model((f_det,), (f_caps, f_ctrl))
+        fe1.record()
+        torch.cuda.synchronize(dev)
+        f_ms = fe0.elapsed_time(fe1) / n_fwd
+        fwd = {"workload": "xe_forward(config5): B=100, T=20, D=100, full (B,T,V) log-prob output", "ms_per_forward": f_ms,
+               "row_steps_per_s": 100 * w["T"] / (f_ms * 1e-3), "n_gpus": 1}
+        del f_det, f_caps, f_ctrl
+    barrier()
+
     # ---- per-kernel times: the same K steps repeated with the library's CUDA-event phase profiler
     # (events on the launching stream around every phase of every decoder step)
     phase_acc, prof_ms = {}, None
@@ -385,6 +410,7 @@ def main_ours(args, rank, world, local_rank):
                                 "device_resident_value": world * w["b"] * args.steps / (idx_total_ms * 1e-3),
                                 "entry": "beam_search_v_indexed / vsr_prologue_indexed: slots as int32 indices into the "
                                          "detections (same workload shape, extension to the reference signature)"},
+                "forward_teacher": fwd,
                 "roofline": roofline, "roofline_attend": roofline_att,
                 "phases_ms_per_decode": {n: v[0] / n_prof for n, v in phase_acc.items()},
                 "profiled_ms_per_step": prof_ms,

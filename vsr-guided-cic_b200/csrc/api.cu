@@ -195,14 +195,14 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   c->NB1 = pad_rows(c->NB1v, 128, 0);
   c->oB2_ha = c->Hp;
   c->oB2_p2 = c->oB2_ha + c->Ap;
-  c->NB2v = c->oB2_p2 + 4 * c->Hp;
+  c->NB2v = c->oB2_p2;                     // (h1' -> LSTM2 gates lives in GEMM-D as a third K segment)
   c->NB2 = pad_rows(c->NB2v, 128, 0);
   c->NC = round_up(c->A, NPAD);
   c->ND = 4 * c->Hp;                       // gate-interleaved: 4 gates x Hp units (multiple of 256)
   c->NE = pad_rows(c->V, 128, 144);
   c->NVA = round_up(c->A, NPAD);
   c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Hp;
-  c->KD = c->Fp + c->Hp;
+  c->KD = c->Fp + 2 * c->Hp;
   for (int i = 0; i < PH_COUNT; ++i) c->phases[i].name = kPhaseNames[i];
   *out = c;   // from here on vsr_destroy can clean up a half-built context
   ALLOC_F(c->WA, (size_t)c->NA * c->KA); ALLOC_F(c->WU, (size_t)c->NA * c->Fp); ALLOC_F(c->bU, c->NA);

@@ -180,16 +180,16 @@ struct Ctx {
   int NA, NB1, NB2, NC, ND, NE;  // padded output widths of the stacked GEMMs
   int NB1v, NB2v;                // their un-padded widths
   int KA;                      // [h2 (Hp, if h2_first) | h1 (Hp)]  (the xt part is a per-word table, see X)
-  int KD;                      // [att (Fp) | h2 (Hp)]
+  int KD;                      // [att (Fp) | h2 (Hp) | h1' (Hp)]
   // column offsets of the stacked output blocks (KPAD-aligned so float4 epilogues stay aligned)
   int oB1_sa;                  // sent:  sentinel at 0 (F) | sa at oB1_sa (A)
-  int oB2_ha, oB2_p2;          // hb:    hg at 0 (H) | ha at oB2_ha (A) | pre2_h1 at oB2_p2 (4H)
+  int oB2_ha, oB2_p2;          // hb:    hg at 0 (H) | ha at oB2_ha (A) ; oB2_p2 = end of the valid columns
   // packed weights
   float *WA, *WU, *bU;         // [NA][KA], [NA][Fp], [NA]   rows: i,f,g,o (4H) | s (H) | g (H)
   float *WB1, *bB1;            // [NB1][Hp]: s_fc (F) | att_sa (A)
-  float *WB2;                  // [NB2][Hp]: W1_hg (H) | att_ha (A) | lstm2.W_ih[:, :H] (4H)
+  float *WB2;                  // [NB2][Hp]: W1_hg (H) | att_ha (A)
   float *WC;                   // [NC][Hp]: att_ga
-  float *WD, *bD;              // [ND][KD]: lstm2.W_ih[:, H:H+F] | lstm2.W_hh ; b_ih2 + b_hh2
+  float *WD, *bD;              // [ND][KD]: lstm2.W_ih[:, H:H+F] | lstm2.W_hh | lstm2.W_ih[:, :H] ; b_ih2 + b_hh2
   float *WU2;                  // [ND][Fp]: lstm2.W_ih[:, H+F:H+2F] (img_second_lstm) or null
   float *WE, *bE;              // [NE][Hp]: out_fc
   float *Wva;                  // [Ap128][Fp]: att_va

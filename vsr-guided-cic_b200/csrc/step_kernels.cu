@@ -864,7 +864,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
                                      pair_out(c, c->s_t_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
-  {  // B: [sentinel | sa] = WB1 . s_t + b ;  [hg | ha | pre2_h1] = WB2 . h1'
+  {  // B: [sentinel | sa] = WB1 . s_t + b ;  [hg | ha] = WB2 . h1'
     PhaseScope ps(c, PH_GEMM_B, st);
     GemmArgs g{};
     g.nseg = 1; g.seg[0] = {c->s_t, c->Hp, c->Hp, c->Hp, &c->s_t_b};
@@ -907,7 +907,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     VSR_CHECK_CUDA(launch_k(k_attend, dim3(rows), dim3(ATT_THREADS), smem, st, c->use_pdl && (c->pdl_mode & 2), a));
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
-  {  // D: pre2 = pre2_h1 + WD . [att | h2_old] + b (+ U2[img]);  C: ga = att_ga . g_t rides in the same launch
+  {  // D: pre2 = WD . [att | h2_old | h1'] + b (+ U2[img]);  C: ga = att_ga . g_t rides in the same launch
      // (the stay-gate logit that needs ga is finished in k_softmax_topk, off the attention's critical path)
     PhaseScope ps(c, PH_GEMM_D, st);
     GemmArgs gc{};
@@ -915,11 +915,11 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b;
     gc.c = c->ga; gc.ldc = c->NC; gc.M = rows; gc.N = c->NC;
     GemmArgs g{};
-    g.nseg = 2;
+    g.nseg = 3;
     g.seg[0] = {c->att, c->Fp, c->Fp, c->Fp, &c->att_b};
     g.seg[1] = {c->h2, c->Hp, c->Hp, c->Hp, &c->h2_b};
+    g.seg[2] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
     g.w = c->WD; g.ldw = c->KD; g.bias = c->bD; g.wb = &c->WD_b;
-    g.cadd = c->hb + c->oB2_p2; g.ld_cadd = c->NB2;
     if (c->d.img_second_lstm) {
       g.rowadd = c->U2; g.ld_rowadd = c->ND; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     }
