@@ -80,11 +80,11 @@ struct GemmSeg {
   int k_valid;      // readable columns of a (multiple of 4, <= k); the rest reads as zero
   const F16Pair* b = nullptr;   // fp16 hi/lo twin of a (tensor-core path), or null
 };
-// Column of (gate g, hidden unit u) in a gate-interleaved LSTM pre-activation row with NG gates:
-// 32-unit chunks, each laid out as 4 sub-blocks of [gate][8 units], so that one 128 x (NG*32) tensor-core
-// tile holds every gate of its 32 units and the cell math can run in the GEMM epilogue.
+// Column of (gate g, hidden unit u) in a gate-interleaved LSTM pre-activation row with NG gates: 32-unit chunks,
+// each laid out as [gate][32 units], so that one 128 x (NG*32) tensor-core tile holds every gate of its 32 units
+// (the cell math runs in the GEMM epilogue) and the 32 units of a gate are 128 contiguous bytes (coalesced operands).
 __host__ __device__ inline int cell_col(int g, int u, int ng) {
-  return (u >> 5) * (ng * 32) + ((u >> 3) & 3) * (ng * 8) + g * 8 + (u & 7);
+  return (u >> 5) * (ng * 32) + g * 32 + (u & 31);
 }
 
 // Optional epilogue fusion of the tensor-core GEMM (ignored by the FFMA twin, whose callers run the

@@ -31,7 +31,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                 // fp16 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+// warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.  TMEM lane quarter q is readable by the warps
+// with (warp & 3) == q, so every quarter has two epilogue warps (hsel = 0 / 1).
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
+constexpr int TC2_THREADS = 192;          // CTA-pair experiment: four epilogue warps, row-wise plain epilogue only
 
 // KB = fp16 elements per k-block: 64 (one 128-byte swizzle row) or 32 (64-byte swizzle).  The smaller
 // block halves the stage size, i.e. doubles the ring depth that fits in 227 KB of shared memory — these
@@ -43,7 +48,12 @@ template <int BN, int KB> struct TcCfg {
   static constexpr int kABytes = BM * KB * 2;            // 16 / 8 KB
   static constexpr int kWBytes = BN * KB * 2;
   static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;   // + alignment slack
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  // epilogue tile: one TMEM lane quarter (32 rows x BN fp32) staged through shared memory (tile_epilogue)
+  static constexpr bool kTileEpi = (BN == 128 || BN == 192);
+  // (the vocabulary epilogue's 4 KB exchange buffer lives in the same place; the two are never used together)
+  static constexpr int kEpiBytes = kTileEpi ? 32 * BN * 4 : 4096;
+  static constexpr int kSmemBytes = kRingBytes + 1024 + kEpiBytes;   // + alignment slack
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,12 +126,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// tcgen05.ld of 8 consecutive fp32 columns of this warp's 32 TMEM lanes (no wait)
-__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -131,32 +135,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 
-// 8 consecutive fp32 values -> fp32 store + fp16 hi/lo stores (16-byte vectors)
-__device__ __forceinline__ void store8(float* f32, __half* hi, __half* lo, size_t off, const float (&v)[8]) {
-  if (f32 != nullptr) {
-    *reinterpret_cast<float4*>(f32 + off) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(f32 + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-  if (hi != nullptr) {
-    __align__(16) __half h[8];
-    __align__(16) __half l[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float x = fminf(fmaxf(v[j], -65504.f), 65504.f);
-      h[j] = __float2half_rn(x);
-      l[j] = __float2half_rn(x - __half2float(h[j]));
-    }
-    *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<const uint4*>(h);
-    *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<const uint4*>(l);
-  }
-}
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
 
 enum { EPI_PLAIN = 0, EPI_LSTM1 = 1, EPI_LSTM2 = 2, EPI_VOCAB = 3 };
 
@@ -189,66 +169,200 @@ struct TcParams {
   int pdl_flags;
 };
 
-// Fused LSTM cell epilogue.  Every 32-unit chunk of the tile is NG*32 columns laid out as 4 sub-blocks of
-// [gate][8 units] (cell_col()).  LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq), LSTM2: NG = 4.
-// pre = acc + bias + rowadd + cadd + gather ; then the cell math of nn.LSTMCell.
-template <int BN, int NG>
-__device__ __forceinline__ void cell_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0, int n_tile,
-                                              const float* radd, const float* cadd, const float* gath) {
-  constexpr int CH = BN / (NG * 32);
-#pragma unroll 1
-  for (int chunk = 0; chunk < CH; ++chunk) {
-    const int cbase = chunk * NG * 32;               // first tile column of this chunk
-    const int ubase = (n_tile * CH + chunk) * 32;     // first hidden unit of this chunk
-#pragma unroll 1
-      for (int sub = 0; sub < 4; ++sub) {
-        uint32_t r[NG][8];
+// ---------------------------------------------------------------- epilogues
+// The accumulator leaves TMEM one ROW per thread.  An epilogue that touches global memory in that layout issues 32
+// scattered 16-byte requests per warp instruction — one L1 wavefront each — and measured (clock64 + ablation) the
+// fused LSTM epilogue of GEMM-A at 15 us of a 47 us kernel, two thirds of it LSU wavefronts (loads 7.7k cycles,
+// stores 9.1k, math 9k).  tile_epilogue therefore stages one TMEM lane quarter at a time (32 rows x BN fp32,
+// swizzled) in shared memory and lets all eight epilogue warps work on it with lanes running ALONG a row:
+// every global load / store of a warp is then 128 contiguous bytes per row.
+__device__ __forceinline__ void epi_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(TC_EPI_THREADS) : "memory"); }
+__device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// float offset of 16-byte piece c4 of tile row r (XOR swizzle inside aligned groups of 8 pieces: conflict-free both for
+// the row-per-thread dump and for the row-major read-back)
+template <int BN>
+__device__ __forceinline__ int tile_slot(int r, int c4) { return r * BN + ((c4 ^ (r & 7)) << 2); }
+
+// fp32 + optional fp16 hi/lo twins of four consecutive values
+__device__ __forceinline__ void store4(float* f32, __half* hi, __half* lo, size_t off, const float4 v) {
+  if (f32 != nullptr) *reinterpret_cast<float4*>(f32 + off) = v;
+  if (hi != nullptr) {
+    const float x[4] = {fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f),
+                        fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f)};
+    __align__(8) __half h[4];
+    __align__(8) __half l[4];
 #pragma unroll
-        for (int g = 0; g < NG; ++g) tmem_ld8_nowait(tlane + (uint32_t)(cbase + sub * NG * 8 + g * 8), r[g]);
-        tmem_ld_wait();
-        if (!live) continue;
-        const int ncol = n0 + cbase + sub * NG * 8;                 // first output column of this sub-block
-        const int unit0 = ubase + sub * 8;            // first hidden unit of this sub-block
-        float pre[NG][8];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-          float add[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) pre[g][u] = __uint_as_float(r[g][u]);
-          if (p.bias != nullptr) { load8(p.bias + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-          if (radd != nullptr) { load8(radd + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-          if (cadd != nullptr) { load8(cadd + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-          if (gath != nullptr) { load8(gath + ncol + g * 8, add);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) pre[g][u] += add[u]; }
-        }
-        const size_t so = (size_t)row * p.ld_state + unit0;
-        float cold[8], cn[8], hn[8];
-        load8(p.c_old + so, cold);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float ig = fast_sigmoid(pre[0][u]), fg = fast_sigmoid(pre[1][u]), gg = fast_tanh(pre[2][u]),
-                      og = fast_sigmoid(pre[3][u]);
-          cn[u] = fg * cold[u] + ig * gg;
-          hn[u] = og * fast_tanh(cn[u]);
-        }
-        store8(p.c_new, nullptr, nullptr, so, cn);
-        store8(p.h_new, p.h_hi, p.h_lo, so, hn);
-        if constexpr (NG == 6) {
-          float sv[8], gq[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) { sv[u] = fast_sigmoid(pre[4][u]) * fast_tanh(cn[u]); gq[u] = pre[5][u]; }
-          store8(p.s_new, p.s_hi, p.s_lo, so, sv);
-          store8(p.gq, nullptr, nullptr, so, gq);
-        }
-      }
+    for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); l[j] = __float2half_rn(x[j] - __half2float(h[j])); }
+    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<const uint2*>(l);
   }
+}
+
+// TMEM -> tile: the two warps of quarter q write their 32 rows, each one half of the columns
+template <int BN>
+__device__ __forceinline__ void tile_dump(uint32_t tlane, float* tile, int hsel, int lane) {
+  constexpr int NCH = BN / 16;
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    if ((ch < NCH / 2) != (hsel == 0)) continue;
+    uint32_t r[16];
+    tmem_ld16(tlane + (uint32_t)(ch * 16), r);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(tile + tile_slot<BN>(lane, ch * 4 + j)) =
+          make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  }
+}
+
+// plain tiles: C = acc + bias + rowadd + cadd + gather, or g_t = sig(gq + acc) * tanh(c1') on the columns < gt_cols
+template <int BN>
+__device__ __forceinline__ void tile_plain(const TcProblem& p, const float* tile, const float* s_bias, int rowq, int n0, int te) {
+  constexpr int P4 = BN / 4, ITEMS = 32 * P4 / TC_EPI_THREADS;     // 16-byte pieces per row, pieces per thread
+  float4 acc[ITEMS], x0[ITEMS], x1[ITEMS], x2[ITEMS];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {        // all loads first: one round trip for the thread's pieces
+    const int idx = te + k * TC_EPI_THREADS;
+    const int r = idx / P4, c4 = idx - r * P4;
+    const int row = rowq + r, n = n0 + 4 * c4;
+    acc[k] = *reinterpret_cast<const float4*>(tile + tile_slot<BN>(r, c4));
+    x0[k] = zero; x1[k] = zero; x2[k] = zero;
+    if (row < p.M) {
+      if (n < p.gt_cols) {
+        x0[k] = *reinterpret_cast<const float4*>(p.gt_gq + (size_t)row * p.ld_state + n);
+        x1[k] = *reinterpret_cast<const float4*>(p.gt_c1n + (size_t)row * p.ld_state + n);
+      } else {
+        if (p.rowadd != nullptr)
+          x0[k] = __ldg(reinterpret_cast<const float4*>(p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd + n));
+        if (p.cadd != nullptr) x1[k] = *reinterpret_cast<const float4*>(p.cadd + (size_t)row * p.ld_cadd + n);
+        if (p.gather != nullptr) x2[k] = __ldg(reinterpret_cast<const float4*>(p.gather + (size_t)p.gather_idx[row] * p.ld_gather + n));
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ITEMS; ++k) {
+    const int idx = te + k * TC_EPI_THREADS;
+    const int r = idx / P4, c4 = idx - r * P4;
+    const int row = rowq + r, n = n0 + 4 * c4;
+    if (row >= p.M) continue;
+    if (n < p.gt_cols) {
+      // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
+      const float4 o = make_float4(fast_sigmoid(x0[k].x + acc[k].x) * fast_tanh(x1[k].x), fast_sigmoid(x0[k].y + acc[k].y) * fast_tanh(x1[k].y),
+                                   fast_sigmoid(x0[k].z + acc[k].z) * fast_tanh(x1[k].z), fast_sigmoid(x0[k].w + acc[k].w) * fast_tanh(x1[k].w));
+      store4(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n, o);
+    } else {
+      float4 o = acc[k];
+      add4(o, *reinterpret_cast<const float4*>(s_bias + 4 * c4));
+      add4(o, x0[k]); add4(o, x1[k]); add4(o, x2[k]);
+      *reinterpret_cast<float4*>(p.c + (size_t)row * p.ldc + n) = o;
+    }
+  }
+}
+
+// Fused LSTM cell.  The tile's BN = NG*32 columns hold NG gates x 32 units as [gate][32 units] (cell_col()).
+// LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq), LSTM2: NG = 4.  One item = 4 units of one row:
+// pre = acc + bias + rowadd + cadd + gather, then the cell math of nn.LSTMCell.  256 items = one per epilogue thread.
+template <int BN, int NG>
+__device__ __forceinline__ void tile_cell(const TcProblem& p, const float* tile, const float* s_bias, int rowq, int n0, int n_tile,
+                                          int te) {
+  static_assert(BN == NG * 32, "one 32-unit chunk per tile");
+  const int r = te >> 3, uq = te & 7;
+  const int row = rowq + r;
+  if (row >= p.M) return;
+  const int unit = n_tile * 32 + uq * 4;
+  const size_t so = (size_t)row * p.ld_state + unit;
+  float4 pre[NG], x0[NG], x1[NG], x2[NG];
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#ifdef VSR_DBG_CLK
+  const long long k0 = clock64();
+#endif
+  const float4 cold = *reinterpret_cast<const float4*>(p.c_old + so);
+  const float* radd = p.rowadd != nullptr ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd + n0 + uq * 4 : nullptr;
+  const float* cadd = p.cadd != nullptr ? p.cadd + (size_t)row * p.ld_cadd + n0 + uq * 4 : nullptr;
+  const float* gath = p.gather != nullptr ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather + n0 + uq * 4 : nullptr;
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    pre[g] = *reinterpret_cast<const float4*>(tile + tile_slot<BN>(r, g * 8 + uq));
+    x0[g] = radd != nullptr ? __ldg(reinterpret_cast<const float4*>(radd + g * 32)) : zero;
+    x1[g] = cadd != nullptr ? *reinterpret_cast<const float4*>(cadd + g * 32) : zero;
+    x2[g] = gath != nullptr ? __ldg(reinterpret_cast<const float4*>(gath + g * 32)) : zero;
+  }
+#pragma unroll
+  for (int g = 0; g < NG; ++g) {
+    add4(pre[g], *reinterpret_cast<const float4*>(s_bias + g * 32 + uq * 4));
+    add4(pre[g], x0[g]); add4(pre[g], x1[g]); add4(pre[g], x2[g]);
+  }
+#ifdef VSR_DBG_CLK
+  const long long k1 = clock64();
+#endif
+  const float pi[4] = {pre[0].x, pre[0].y, pre[0].z, pre[0].w}, pf[4] = {pre[1].x, pre[1].y, pre[1].z, pre[1].w};
+  const float pg[4] = {pre[2].x, pre[2].y, pre[2].z, pre[2].w}, po[4] = {pre[3].x, pre[3].y, pre[3].z, pre[3].w};
+  const float co[4] = {cold.x, cold.y, cold.z, cold.w};
+  float cn[4], hn[4], tc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float ig = fast_sigmoid(pi[u]), fg = fast_sigmoid(pf[u]), gg = fast_tanh(pg[u]), og = fast_sigmoid(po[u]);
+    cn[u] = fg * co[u] + ig * gg;
+    tc[u] = fast_tanh(cn[u]);
+    hn[u] = og * tc[u];
+  }
+#ifdef VSR_DBG_CLK
+  const long long k2 = clock64();
+#endif
+  store4(p.c_new, nullptr, nullptr, so, make_float4(cn[0], cn[1], cn[2], cn[3]));
+  store4(p.h_new, p.h_hi, p.h_lo, so, make_float4(hn[0], hn[1], hn[2], hn[3]));
+  if constexpr (NG == 6) {
+    const float ps[4] = {pre[4].x, pre[4].y, pre[4].z, pre[4].w};
+    store4(p.s_new, p.s_hi, p.s_lo, so, make_float4(fast_sigmoid(ps[0]) * tc[0], fast_sigmoid(ps[1]) * tc[1],
+                                                     fast_sigmoid(ps[2]) * tc[2], fast_sigmoid(ps[3]) * tc[3]));
+    store4(p.gq, nullptr, nullptr, so, pre[5]);
+  }
+#ifdef VSR_DBG_CLK
+  if ((te == 0 || te == 200) && blockIdx.x == 5 && p.M > 200 && (rowq & 127) == 0)
+    printf("cell NG=%d te=%d: loads+adds %lld math %lld stores %lld\n", NG, te, k1 - k0, k2 - k1, clock64() - k2);
+#endif
+}
+
+// all eight epilogue warps: quarter by quarter, dump -> barrier -> cooperative pass -> barrier
+template <int BN>
+__device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int n_tile, int warp, int lane,
+                                              const float* s_bias, float* tile) {
+  const int q = warp & 3, hsel = (warp - 2) >> 2, te = (warp - 2) * 32 + lane;
+  const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+#ifdef VSR_DBG_CLK
+  long long td = 0, tb1 = 0, tp = 0, tb2 = 0;
+#endif
+#pragma unroll 1
+  for (int qq = 0; qq < 4; ++qq) {
+    if (m0 + qq * 32 >= p.M) break;                 // no live row in this or any later quarter (uniform)
+#ifdef VSR_DBG_CLK
+    const long long c0 = clock64();
+#endif
+    if (q == qq) tile_dump<BN>(tlane, tile, hsel, lane);
+#ifdef VSR_DBG_CLK
+    const long long c1 = clock64();
+#endif
+    epi_bar(3);
+#ifdef VSR_DBG_CLK
+    const long long c2 = clock64();
+#endif
+    const int rowq = m0 + qq * 32;
+    if (p.mode == EPI_PLAIN) tile_plain<BN>(p, tile, s_bias, rowq, n0, te);
+    if constexpr (BN == 192) { if (p.mode == EPI_LSTM1) tile_cell<BN, 6>(p, tile, s_bias, rowq, n0, n_tile, te); }
+    if constexpr (BN == 128) { if (p.mode == EPI_LSTM2) tile_cell<BN, 4>(p, tile, s_bias, rowq, n0, n_tile, te); }
+#ifdef VSR_DBG_CLK
+    const long long c3 = clock64();
+#endif
+    epi_bar(4);
+#ifdef VSR_DBG_CLK
+    td += c1 - c0; tb1 += c2 - c1; tp += c3 - c2; tb2 += clock64() - c3;
+#endif
+  }
+#ifdef VSR_DBG_CLK
+  if (lane == 0 && (warp == 2 || warp == 4 || warp == 9) && blockIdx.x == 5 && p.M > 200)
+    printf("epi BN=%d mode=%d warp=%d: dump %lld bar1 %lld process %lld bar2 %lld\n", BN, p.mode, warp, td, tb1, tp, tb2);
+#endif
 }
 
 // Vocabulary-head epilogue: besides storing the logits (acc + bias) the thread that owns a row folds its BN
@@ -256,15 +370,19 @@ __device__ __forceinline__ void cell_epilogue(const TcProblem& p, uint32_t tlane
 // (step_kernels.cu) finishes log-softmax and top-k from the records and re-reads only the few chunks that can hold
 // a top-k element, so the 20 MB logits tensor is written but never scanned.
 template <int BN>
-__device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0, int n_tile) {
+__device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0, int n_tile,
+                                               const float* s_bias, float (*s_vx)[8], int hsel, int lane) {
   static_assert(BN / 16 <= VOCAB_REC - 2, "record too small for this tile");
+  constexpr int NCH = BN / 16, H0 = (NCH + 1) / 2;      // chunks [0, H0) -> first warp of the quarter, [H0, NCH) -> second
+  static_assert(NCH - H0 <= 6, "exchange record too small");
   float m = -INFINITY, ssum = 0.f;
   float cmx[VOCAB_REC - 2];
 #pragma unroll
   for (int k = 0; k < VOCAB_REC - 2; ++k) cmx[k] = -INFINITY;
   float* crow = p.c + (size_t)row * p.ldc;
 #pragma unroll
-  for (int ch = 0; ch < BN / 16; ++ch) {
+  for (int ch = 0; ch < NCH; ++ch) {
+    if ((ch < H0) != (hsel == 0)) continue;
     uint32_t r[16];
     tmem_ld16(tlane + (uint32_t)(ch * 16), r);
     const int n = n0 + ch * 16;
@@ -272,7 +390,7 @@ __device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlan
       float v[16];
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        const float4 b = *reinterpret_cast<const float4*>(s_bias + ch * 16 + j);
         v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
         v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
         *reinterpret_cast<float4*>(crow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -295,79 +413,114 @@ __device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlan
       }
     }
   }
-  if (!live) return;
+  // the quarter's second warp hands {max, sum, its chunk maxima} of the row to the first one through shared memory
+  if (hsel != 0) {
+    float* x = s_vx[lane];
+    x[0] = m; x[1] = ssum;
+#pragma unroll
+    for (int k = 0; k < NCH - H0; ++k) x[2 + k] = cmx[H0 + k];
+  }
+  epi_bar(2);
+  if (hsel != 0 || !live) return;
+  {
+    const float* x = s_vx[lane];
+    const float m2 = x[0], s2 = x[1];
+#pragma unroll
+    for (int k = 0; k < NCH - H0; ++k) cmx[H0 + k] = x[2 + k];
+    const float mm = fmaxf(m, m2);
+    float tot = 0.f;
+    if (m > -INFINITY) tot += ssum * __expf(m - mm);
+    if (m2 > -INFINITY) tot += s2 * __expf(m2 - mm);
+    m = mm; ssum = tot;
+  }
   float4* rec = reinterpret_cast<float4*>(p.vpart + ((size_t)row * p.n_tiles + n_tile) * VOCAB_REC);
   rec[0] = make_float4(m, ssum, cmx[0], cmx[1]);
 #pragma unroll
   for (int q = 1; q < VOCAB_REC / 4; ++q) rec[q] = make_float4(cmx[4 * q - 2], cmx[4 * q - 1], cmx[4 * q], cmx[4 * q + 1]);
 }
 
+// Before the accumulator is complete (i.e. behind the main loop), by all epilogue warps: the tile's bias -> shared
+// memory, and for the fused cell epilogues an L2 prefetch of the per-row operands the four quarter passes will read.
+// The per-word rows of GEMM-A come out of a 246 MB table (one random 768-byte segment per row and tile): a cold
+// read costs ~2 us per pass (HBM + TLB miss) when it is first touched inside the pass.
 template <int BN>
-__device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int n_tile,
-                                            int warp, int lane) {
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool live = row < p.M;
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float* radd = (p.rowadd != nullptr && live)
-                            ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
-    const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
-    const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
-
-    if (p.mode == EPI_VOCAB) {
-      if constexpr (BN / 16 <= VOCAB_REC - 2) vocab_epilogue<BN>(p, tlane, row, live, n0, n_tile);   // host checks the tile
-    } else if (p.mode == EPI_PLAIN) {
-      float* crow = p.c + (size_t)row * p.ldc;
-#pragma unroll 1
-      for (int ch = 0; ch < BN / 16; ++ch) {       // 16 accumulator columns per TMEM load: any BN % 16 == 0
-        uint32_t r[16];
-        tmem_ld16(tlane + (uint32_t)(ch * 16), r);
-        const int n = n0 + ch * 16;
-        if (!live) continue;
-        if (n < p.gt_cols) {
-          // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
+__device__ __forceinline__ void epi_bias(const TcProblem& p, int m0, int n0, int n_tile, int warp, int lane, float* s_bias,
+                                         bool reuse) {
+  if (reuse) epi_bar(1);                             // previous tile's readers are done
+  const int te = (warp - 2) * 32 + lane;
+  for (int i = te; i < BN; i += TC_EPI_THREADS) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.f;
+  if (p.mode == EPI_LSTM1 || p.mode == EPI_LSTM2) {
+    const int r = te >> 3, g = te & 7;               // thread (row, gate): one 128-byte line per quarter pass
 #pragma unroll
-          for (int j = 0; j < 16; j += 8) {
-            float gq[8], cc[8], o[8];
-            load8(p.gt_gq + (size_t)row * p.ld_state + n + j, gq);
-            load8(p.gt_c1n + (size_t)row * p.ld_state + n + j, cc);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) o[u] = fast_sigmoid(gq[u] + __uint_as_float(r[j + u])) * fast_tanh(cc[u]);
-            store8(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n + j, o);
-          }
-          continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3]));
-          if (p.bias != nullptr) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (radd != nullptr) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(radd + n + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (cadd != nullptr) {
-            const float4 b = *reinterpret_cast<const float4*>(cadd + n + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (gath != nullptr) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(gath + n + j));
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          *reinterpret_cast<float4*>(crow + n + j) = o;
-        }
+    for (int qq = 0; qq < 4; ++qq) {
+      const int row = m0 + qq * 32 + r;
+      if (row >= p.M) break;
+      const float* line = nullptr;
+      if (g < BN / 32) {
+        if (p.gather != nullptr) line = p.gather + (size_t)p.gather_idx[row] * p.ld_gather + n0 + g * 32;
+      } else if (g == 6) {
+        line = p.c_old + (size_t)row * p.ld_state + n_tile * 32;
+      } else if (p.rowadd != nullptr) {
+        line = p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd + n0;     // first of the caption row's lines
       }
-    } else {
-      // Fused LSTM cell.  The tile's BN = NG*32 columns hold NG gates x 32 units as 4 sub-blocks of
-      // [gate][8 units] (cell_col()).  LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq),
-      // LSTM2: NG = 4.  pre = acc + bias + rowadd + cadd ; then the cell math of nn.LSTMCell.
-      // (a tile may hold several such 32-unit chunks: BN = chunks * NG * 32)
-      if constexpr (BN % 192 == 0) { if (p.mode == EPI_LSTM1) cell_epilogue<BN, 6>(p, tlane, row, live, n0, n_tile, radd, cadd, gath); }
-      if constexpr (BN % 128 == 0) { if (p.mode == EPI_LSTM2) cell_epilogue<BN, 4>(p, tlane, row, live, n0, n_tile, radd, cadd, gath); }
+      if (line != nullptr) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
     }
+  }
+  epi_bar(1);
+}
+
+// row-per-thread plain epilogue (tiles without a staging buffer, and the CTA-pair experiment); `nsplit` warps share a
+// TMEM lane quarter and take the column chunks [hsel * NCH / nsplit, ...)
+template <int BN>
+__device__ __forceinline__ void rowwise_plain(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int warp, int lane,
+                                              int hsel, int nsplit) {
+  const int q = warp & 3;
+  const int row = m0 + q * 32 + lane;
+  const bool live = row < p.M;
+  const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+  const float* radd = (p.rowadd != nullptr && live)
+                          ? p.rowadd + (size_t)((row / p.row_div) * p.rowadd_mul) * p.ld_rowadd : nullptr;
+  const float* cadd = (p.cadd != nullptr && live) ? p.cadd + (size_t)row * p.ld_cadd : nullptr;
+  const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
+  float* crow = p.c + (size_t)row * p.ldc;
+  constexpr int NCH = BN / 16;
+  const int c_lo = hsel * NCH / nsplit, c_hi = (hsel + 1) * NCH / nsplit;
+#pragma unroll 1
+  for (int ch = c_lo; ch < c_hi; ++ch) {       // 16 accumulator columns per TMEM load: any BN % 16 == 0
+    uint32_t r[16];
+    tmem_ld16(tlane + (uint32_t)(ch * 16), r);
+    const int n = n0 + ch * 16;
+    if (!live) continue;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                             __uint_as_float(r[j + 3]));
+      if (p.bias != nullptr) add4(o, __ldg(reinterpret_cast<const float4*>(p.bias + n + j)));
+      if (radd != nullptr) add4(o, __ldg(reinterpret_cast<const float4*>(radd + n + j)));
+      if (cadd != nullptr) add4(o, *reinterpret_cast<const float4*>(cadd + n + j));
+      if (gath != nullptr) add4(o, __ldg(reinterpret_cast<const float4*>(gath + n + j)));
+      *reinterpret_cast<float4*>(crow + n + j) = o;
+    }
+  }
+}
+
+// epilogue of the single-CTA kernels (eight epilogue warps)
+template <int BN, int KB>
+__device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int n_tile,
+                                            int warp, int lane, const float* s_bias, float* tile) {
+  using Cfg = TcCfg<BN, KB>;
+  float (*s_vx)[32][8] = reinterpret_cast<float (*)[32][8]>(tile);     // vocabulary mode: exchange buffer instead of a tile
+  const int q = warp & 3, hsel = (warp - 2) >> 2;
+  if (p.mode == EPI_VOCAB) {
+    if constexpr (BN / 16 <= VOCAB_REC - 2) {
+      const int row = m0 + q * 32 + lane;
+      vocab_epilogue<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16), row, row < p.M, n0, n_tile, s_bias, s_vx[q], hsel, lane);
+    }
+  } else if constexpr (Cfg::kTileEpi) {
+    tile_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane, s_bias, tile);
+  } else {
+    rowwise_plain<BN>(p, tmem_base, m0, n0, warp, lane, hsel, 2);     // host: plain mode only on these tiles
+  }
 }
 
 template <int BN, int KB>
@@ -378,6 +531,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile of this CTA: problems back to back; consecutive CTAs walk the M tiles of one W tile (L2 reuse)
@@ -476,9 +630,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
     __syncwarp();
   } else {
     pdl_wait();
+#ifdef VSR_DBG_CLK
+    const long long tk0 = clock64();
+#endif
+    epi_bias<BN>(p, m0, n0, n_tile, warp, lane, s_bias, false);
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane);
+#ifdef VSR_DBG_CLK
+    const long long tk1 = clock64();
+#endif
+    tc_epilogue<BN, KB>(p, tmem_base, m0, n0, n_tile, warp, lane, s_bias, reinterpret_cast<float*>(smem + Cfg::kRingBytes));
+#ifdef VSR_DBG_CLK
+    if (lane == 0 && warp == 2 && (blockIdx.x == 5 || blockIdx.x == 100) && p.M > 200)
+      printf("gemm BN=%d KB=%d grid=%d cta=%d mode=%d kblocks=%d: main loop %lld cyc, epilogue %lld cyc\n", BN, KB, (int)gridDim.x,
+             (int)blockIdx.x, p.mode, total_kb, tk1 - tk0, clock64() - tk1);
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -514,6 +680,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[BN];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles0 = params.pr[0].n_tiles * params.pr[0].m_tiles;
@@ -535,7 +702,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], TC_EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -623,12 +790,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
       }
       __syncwarp();
     } else {
+      epi_bias<BN>(p, m0, n0, n_tile, warp, lane, s_bias, ti != 0);
       mbar_wait(&tmem_full_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tc_epilogue<BN>(p, tmem_acc, m0, n0, n_tile, warp, lane);
+      tc_epilogue<BN, KB>(p, tmem_acc, m0, n0, n_tile, warp, lane, s_bias, reinterpret_cast<float*>(smem + Cfg::kRingBytes));
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // 4 epilogue warps -> accumulator free again
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);   // every epilogue warp -> accumulator free again
     }
     it += total_kb;
     ++ti;
@@ -696,7 +864,7 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc_pair(
 }
 
 template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 k_gemm_tc2(const __grid_constant__ TcParams params) {
   using Cfg = Tc2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -720,7 +888,7 @@ k_gemm_tc2(const __grid_constant__ TcParams params) {
 
   if (p.row_skip != nullptr) {   // pair-uniform: skip only when all 256 rows of the pair are padding
     int any = 0;
-    for (int r = threadIdx.x; r < 2 * BM; r += TC_THREADS) {
+    for (int r = threadIdx.x; r < 2 * BM; r += TC2_THREADS) {
       const int row = m_pair * 2 * BM + r;
       if (row < p.M) any |= p.row_skip[row];
     }
@@ -797,7 +965,7 @@ k_gemm_tc2(const __grid_constant__ TcParams params) {
   } else {
     mbar_wait(&tmem_full_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    tc_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane);
+    rowwise_plain<BN>(p, tmem_base, m0, n0, warp, lane, 0, 1);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   // neither CTA may release TMEM / exit while the pair's MMAs or the other epilogue are still running
@@ -905,11 +1073,13 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
     if (f.vocab_tiles_out != nullptr) *f.vocab_tiles_out = p->n_tiles;
     if (f.vocab_bn_out != nullptr) *f.vocab_bn_out = BN;
   } else if (f.mode != 0) {
-    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN % 192 == 0) || (f.mode == EPI_LSTM2 && BN % 128 == 0), VSR_EINVAL,
-                "launch_gemm_tc: fused cell mode %d does not fit N tile %d", f.mode, BN);
+    VSR_REQUIRE(!pair && ((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && BN == 128)), VSR_EINVAL,
+                "launch_gemm_tc: fused cell mode %d does not fit N tile %d%s", f.mode, BN, pair ? " (CTA-pair kernel: plain only)" : "");
     p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_hi = (__half*)f.h_hi; p->h_lo = (__half*)f.h_lo;
     p->s_new = f.s_new; p->s_hi = (__half*)f.s_hi; p->s_lo = (__half*)f.s_lo; p->gq = f.gq;
   }
+  VSR_REQUIRE(f.gt_cols == 0 || (!pair && (BN == 128 || BN == 192)), VSR_EINVAL, "launch_gemm_tc: g_t fusion needs a 128- or 192-wide tile");
+  VSR_REQUIRE(f.mode != EPI_VOCAB || !pair, VSR_EINVAL, "launch_gemm_tc: vocabulary epilogue is not available in the CTA-pair kernel");
   p->ld_state = f.ld_state;
   p->gt_cols = f.gt_cols; p->gt_gq = f.gt_gq; p->gt_c1n = f.gt_c1n; p->g_t = f.g_t;
   p->g_hi = (__half*)f.g_hi; p->g_lo = (__half*)f.g_lo;
@@ -932,8 +1102,8 @@ static int launch_gemm_tc_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream
     p.nprob = 2;
     pairs += p.pr[1].n_tiles * ((p.pr[1].m_tiles + 1) / 2);
   }
-  if (BN == 256) k_gemm_tc2<256><<<2 * pairs, TC_THREADS, Tc2Cfg<256>::kSmemBytes, st>>>(p);
-  else k_gemm_tc2<192><<<2 * pairs, TC_THREADS, Tc2Cfg<192>::kSmemBytes, st>>>(p);
+  if (BN == 256) k_gemm_tc2<256><<<2 * pairs, TC2_THREADS, Tc2Cfg<256>::kSmemBytes, st>>>(p);
+  else k_gemm_tc2<192><<<2 * pairs, TC2_THREADS, Tc2Cfg<192>::kSmemBytes, st>>>(p);
   VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }

@@ -849,7 +849,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.rowadd = c->U; g.ld_rowadd = c->NA; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
-    fused = gemm_uses_tc(c, g);
+    fused = gemm_uses_tc(c, g) && !c->use_pair;    // the CTA-pair experiment has plain epilogues only
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
       g.cell.mode = 1; g.cell.c_old = c->c1; g.cell.c_new = c->c1n; g.cell.h_new = c->h1n;
       g.cell.h_hi = c->h1n_b.hi; g.cell.h_lo = c->h1n_b.lo;
