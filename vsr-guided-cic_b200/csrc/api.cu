@@ -348,6 +348,7 @@ static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, 
   StepIO io{};
   io.rows = b; io.cur_beam = 1; io.use_verbs = use_verbs != 0; io.gt = gt != 0;
   io.out_logp = out_logp; io.out_stride = c->V; io.gate_out = gate_logp; io.gate_stride = 2; io.topk = 0;
+  io.need_h32 = true;
   VSR_TRY(run_step(c, io, st));
   if (h1o) VSR_TRY(copy2d(c, h1o, H, c->h1n, c->Hp, H, b, st));
   if (c1o) VSR_TRY(copy2d(c, c1o, H, c->c1n, c->Hp, H, b, st));

@@ -164,9 +164,11 @@ struct AdvanceArgs {
 __device__ __forceinline__ void advance_row(const AdvanceArgs& a, int n, int p, int64_t w, int gate_shift) {
   const size_t so = (size_t)p * a.Hp, dof = (size_t)n * a.Hp;
   for (int i = threadIdx.x * 4; i < a.Hp; i += blockDim.x * 4) {
-    *reinterpret_cast<float4*>(a.h1 + dof + i) = *reinterpret_cast<const float4*>(a.h1n + so + i);
+    if (a.h1n != nullptr) {        // fp32 h only where somebody reads it (FFMA twin)
+      *reinterpret_cast<float4*>(a.h1 + dof + i) = *reinterpret_cast<const float4*>(a.h1n + so + i);
+      *reinterpret_cast<float4*>(a.h2 + dof + i) = *reinterpret_cast<const float4*>(a.h2n + so + i);
+    }
     *reinterpret_cast<float4*>(a.c1 + dof + i) = *reinterpret_cast<const float4*>(a.c1n + so + i);
-    *reinterpret_cast<float4*>(a.h2 + dof + i) = *reinterpret_cast<const float4*>(a.h2n + so + i);
     *reinterpret_cast<float4*>(a.c2 + dof + i) = *reinterpret_cast<const float4*>(a.c2n + so + i);
   }
   w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
@@ -317,7 +319,7 @@ int launch_words(Ctx* c, const int64_t* words, int rows, cudaStream_t st) {
 
 static void fill_advance(Ctx* c, AdvanceArgs& a) {
   a.L = c->L; a.Hp = c->Hp; a.Ep = c->Ep; a.V = c->V;
-  a.h1n = c->h1n; a.c1n = c->c1n; a.h2n = c->h2n; a.c2n = c->c2n;
+  a.h1n = c->state_h32 ? c->h1n : nullptr; a.c1n = c->c1n; a.h2n = c->state_h32 ? c->h2n : nullptr; a.c2n = c->c2n;
   a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2;
   a.ptr = c->ptr; a.ptrn = c->ptrn; a.word_idx = c->word_idx;
   if (c->use_tc) {

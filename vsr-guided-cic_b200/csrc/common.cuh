@@ -276,6 +276,7 @@ struct Ctx {
   uint64_t epoch = 0, graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
   bool attend_attr_set = false;
+  bool state_h32 = true;             // the last step wrote fp32 h1'/h2' (always on the FFMA twin)
   bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
   bool use_pdl = true;               // VSRDEC_PDL=0: plain stream serialization between the step kernels
   // VSRDEC_PDL_MODE bits: 1 = GEMM launches, 2 = small kernels, 4 = weight prefetch before the wait, 8 = GEMMs
@@ -308,6 +309,7 @@ struct StepIO {
   float* gate_out;   // optional (rows,2) post-forcing gate log-probs
   int64_t gate_stride;
   int topk;          // number of word candidates to extract per row (0 = none)
+  bool need_h32;     // the caller reads the fp32 h1'/h2' (vsr_step); the tensor-core path itself only needs the fp16 twins
 };
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st);
 

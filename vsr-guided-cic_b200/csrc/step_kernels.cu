@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   TICK();
   // weighted sum over sentinel + valid regions: each thread owns two float4 columns, 4 rows x 2 columns
   // (8 independent 128-bit loads) in flight
-  float* out = a.att + (size_t)n * a.ld_att;
+  float* out = a.att != nullptr ? a.att + (size_t)n * a.ld_att : nullptr;
   const float a_s = e[0];
   const int nv = s_nv;
   for (int f0 = tid * 4; f0 < a.F; f0 += ATT_THREADS * 8) {
@@ -336,12 +336,12 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
         acc1.x += w * v1[u].x; acc1.y += w * v1[u].y; acc1.z += w * v1[u].z; acc1.w += w * v1[u].w;
       }
     }
-    *reinterpret_cast<float4*>(out + f0) = acc0;
+    if (out != nullptr) *reinterpret_cast<float4*>(out + f0) = acc0;
     const size_t o0 = (size_t)n * a.ld_att + f0;
     store_pair(a.att_b, o0, acc0.x); store_pair(a.att_b, o0 + 1, acc0.y);
     store_pair(a.att_b, o0 + 2, acc0.z); store_pair(a.att_b, o0 + 3, acc0.w);
     if (two) {
-      *reinterpret_cast<float4*>(out + f1) = acc1;
+      if (out != nullptr) *reinterpret_cast<float4*>(out + f1) = acc1;
       const size_t o1 = (size_t)n * a.ld_att + f1;
       store_pair(a.att_b, o1, acc1.x); store_pair(a.att_b, o1 + 1, acc1.y);
       store_pair(a.att_b, o1 + 2, acc1.z); store_pair(a.att_b, o1 + 3, acc1.w);
@@ -850,10 +850,13 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     fused = gemm_uses_tc(c, g) && !c->use_pair;    // the CTA-pair experiment has plain epilogues only
+    c->state_h32 = !fused || io.need_h32;
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
-      g.cell.mode = 1; g.cell.c_old = c->c1; g.cell.c_new = c->c1n; g.cell.h_new = c->h1n;
+      // fp32 copies of h1', s_t (and g_t, att, h2' below) feed only the FFMA twin and vsr_step's outputs: the
+      // tensor-core GEMMs read the fp16 hi/lo twins, so those stores (and their reorder copies) are skipped
+      g.cell.mode = 1; g.cell.c_old = c->c1; g.cell.c_new = c->c1n; g.cell.h_new = io.need_h32 ? c->h1n : nullptr;
       g.cell.h_hi = c->h1n_b.hi; g.cell.h_lo = c->h1n_b.lo;
-      g.cell.s_new = c->s_t; g.cell.s_hi = c->s_t_b.hi; g.cell.s_lo = c->s_t_b.lo;
+      g.cell.s_new = nullptr; g.cell.s_hi = c->s_t_b.hi; g.cell.s_lo = c->s_t_b.lo;
       g.cell.gq = c->gq; g.cell.ld_state = c->Hp;
     }
     VSR_TRY(launch_gemm(c, g, st)); c->launches++;
@@ -875,7 +878,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b;
     g2.c = c->hb; g2.ldc = c->NB2; g2.M = rows; g2.N = c->NB2;
     if (fused) {   // g_t = sig(gq + W1_hg.h1') * tanh(c1') on the hg column block of the h1' projection
-      g2.cell.gt_cols = c->oB2_ha; g2.cell.gt_gq = c->gq; g2.cell.gt_c1n = c->c1n; g2.cell.g_t = c->g_t;
+      g2.cell.gt_cols = c->oB2_ha; g2.cell.gt_gq = c->gq; g2.cell.gt_c1n = c->c1n; g2.cell.g_t = nullptr;
       g2.cell.g_hi = c->g_t_b.hi; g2.cell.g_lo = c->g_t_b.lo; g2.cell.ld_state = c->Hp;
     }
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
@@ -895,7 +898,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.sent = c->sent; a.ld_sent = c->NB1; a.o_sa = c->oB1_sa;
     a.hb = c->hb; a.ld_hb = c->NB2; a.o_ha = c->oB2_ha;
     a.v_a = c->v_a; a.v_s = c->v_s;
-    a.att = c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.shift = c->shift;
+    a.att = fused ? nullptr : c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.shift = c->shift;
     a.rows = rows; a.cur_beam = io.cur_beam; a.L = c->L; a.R = c->R; a.F = c->F; a.A = c->A; a.H = H;
     a.ldP = c->NVA;
     const size_t smem = sizeof(float) * ((size_t)c->A + (size_t)c->R * c->A + c->R + 1);
@@ -925,7 +928,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     }
     g.c = c->pre2; g.ldc = c->ND; g.M = rows; g.N = c->ND;
     if (fused) {   // LSTM cell 2 in the epilogue
-      g.cell.mode = 2; g.cell.c_old = c->c2; g.cell.c_new = c->c2n; g.cell.h_new = c->h2n;
+      g.cell.mode = 2; g.cell.c_old = c->c2; g.cell.c_new = c->c2n; g.cell.h_new = io.need_h32 ? c->h2n : nullptr;
       g.cell.h_hi = c->h2n_b.hi; g.cell.h_lo = c->h2n_b.lo; g.cell.ld_state = c->Hp;
     }
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
