@@ -428,9 +428,9 @@ def eng_gemm_kind(kind):
     """Roofline annotation of the GEMM path the handle runs (vsr_gemm_kind)."""
     if kind.startswith("tcgen05"):
         # dram__bytes_read+write of the largest single launch (GEMM-A, grid 128) from the committed
-        # `ncu --set full` capture profiles/r01e_gemm_step_ncu_summary.md
+        # `ncu --set full` capture profiles/r01l_ncu_summary.md (61.9 MB read + 2.4 MB written)
         return {"kernel": "k_gemm_tc (tcgen05.mma kind::f16, f16x3 hi/lo split, TMA + TMEM; all per-step GEMM phases)",
-                "passes": 3, "traffic": 63.7e6}
+                "passes": 3, "traffic": 64.3e6}
     return {"kernel": "k_gemm_simt (fp32 FFMA, all five per-step GEMM phases)", "passes": 1, "traffic": None}
 
 
