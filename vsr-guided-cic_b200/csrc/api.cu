@@ -279,11 +279,14 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
                           : (size_t)round_up(c->n_img * D, MPAD) + round_up(c->n_img, MPAD);
   if (prow > c->cap_P || (size_t)b * L + 1 > c->cap_slots) {
     const size_t need_rows = std::max(prow, c->cap_P), need_slots = std::max((size_t)b * L + 1, c->cap_slots);
-    dev_free(c, c->P); dev_free(c, c->seq_valid); dev_free(c, c->slot_mask);
-    c->P = nullptr; c->seq_valid = nullptr; c->slot_mask = nullptr; c->cap_P = 0; c->cap_slots = 0;
+    dev_free(c, c->P); dev_free(c, c->seq_valid); dev_free(c, c->slot_mask); dev_free(c, c->slot_base); dev_free(c, c->comp_valid);
+    c->P = nullptr; c->seq_valid = nullptr; c->slot_mask = nullptr; c->slot_base = nullptr; c->comp_valid = nullptr;
+    c->cap_P = 0; c->cap_slots = 0;
     ALLOC_F(c->P, round_up((int)need_rows, MPAD) * (size_t)c->NVA);
     VSR_TRY(dev_alloc(c, (void**)&c->seq_valid, round_up((int)need_rows, MPAD)));
     VSR_TRY(dev_alloc(c, (void**)&c->slot_mask, sizeof(unsigned long long) * need_slots));
+    VSR_TRY(dev_alloc(c, (void**)&c->slot_base, sizeof(int32_t) * need_slots));
+    VSR_TRY(dev_alloc(c, (void**)&c->comp_valid, round_up((int)need_rows, MPAD)));
     VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)need_rows, MPAD), c->Fp, MPAD));
     c->cap_P = need_rows; c->cap_slots = need_slots;
   }

@@ -223,6 +223,11 @@ struct Ctx {
   float* P = nullptr;          // [b*L*R (alloc)][NVA] att_va projections
   uint8_t* seq_valid = nullptr;  // [b*L*R]
   unsigned long long* slot_mask = nullptr;  // [b*L] bit r set = region r of the slot is a real (non-padding) row
+  // tensor-core path, materialised slots: only the valid rows are split to fp16 and projected; the valid rows of
+  // slot s occupy P rows slot_base[s] .. slot_base[s] + popcount(slot_mask[s]) - 1 (null = P row == slot row)
+  int32_t* slot_base = nullptr;             // [b*L]
+  uint8_t* comp_valid = nullptr;            // [rows of P] 1 for the rows in use (tile skipping of the projection GEMM)
+  bool p_compact = false;
   uint8_t* det_valid = nullptr;  // [n_img*D]
   size_t cap_img = 0, cap_P = 0, cap_detv = 0, cap_slots = 0;
   // per-row workspace (rows = captions * beam), capacity cap_rows (multiple of MPAD)

@@ -87,6 +87,50 @@ __global__ void k_slot_masks(const uint8_t* __restrict__ valid, int R, int n_slo
   mask[s] = m;
 }
 
+// Compaction of the valid slot rows (tensor-core path): exclusive scan of the slots' valid-row counts -> first P row
+// of every slot, and the in-use flags of the compact rows.  One block; n_slots is ~1000.
+__global__ void __launch_bounds__(1024) k_slot_scan(const unsigned long long* __restrict__ mask, int n_slots,
+                                                    int32_t* __restrict__ slot_base, uint8_t* __restrict__ comp_valid,
+                                                    int comp_rows) {
+  __shared__ int s_part[1024];
+  __shared__ int s_total;
+  const int tid = threadIdx.x;
+  const int per = (n_slots + 1023) / 1024;
+  const int lo = tid * per, hi = min(lo + per, n_slots);
+  int cnt = 0;
+  for (int s = lo; s < hi; ++s) cnt += __popcll(mask[s]);
+  s_part[tid] = cnt;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {       // Hillis-Steele inclusive scan
+    const int v = tid >= off ? s_part[tid - off] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int base = s_part[tid] - cnt;
+  for (int s = lo; s < hi; ++s) { slot_base[s] = base; base += __popcll(mask[s]); }
+  if (tid == 1023) s_total = s_part[1023];
+  __syncthreads();
+  const int total = s_total;
+  for (int i = tid; i < comp_rows; i += 1024) comp_valid[i] = i < total ? 1 : 0;
+}
+
+// one warp per source row: valid rows are split to fp16 hi/lo at their compact position
+__global__ void k_split_compact(const float* __restrict__ x, int R, int total_rows, int F,
+                                const unsigned long long* __restrict__ mask, const int32_t* __restrict__ slot_base,
+                                PairOut split) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= total_rows) return;
+  const int s = row / R, r = row - s * R;
+  const unsigned long long m = mask[s];
+  if (!((m >> r) & 1ull)) return;
+  const int dst = slot_base[s] + __popcll(m & ((1ull << r) - 1ull));
+  const float* p = x + (size_t)row * F;
+  for (int f = lane * 4; f < F; f += 128)
+    store_pair4(split, (size_t)dst * split.ld + f, __ldg(reinterpret_cast<const float4*>(p + f)));
+}
+
 // index form: validity mask of a slot from its detection indices (-2 = image mean row, valid iff the image
 // has any valid detection; -1 = padding)
 __global__ void k_slot_masks_indexed(const int32_t* __restrict__ slot_index, const uint8_t* __restrict__ det_valid,
@@ -105,29 +149,44 @@ __global__ void k_slot_masks_indexed(const int32_t* __restrict__ slot_index, con
   mask[s] = m;
 }
 
-// img[g][f] = sum_d det[g][d][f] / count(valid rows of g); one thread per float4 column.
-__global__ void k_pool(const float* __restrict__ det, int64_t img_stride, int D, int F,
+// img[g][f] = sum_d det[g][d][f] / count(valid rows of g).  Block (128, POOL_Y): thread (x, y) sums the rows
+// d = y, y + POOL_Y, ... of float4 column x; the POOL_Y partial sums are combined in a fixed order (deterministic).
+constexpr int POOL_Y = 4;
+__global__ void __launch_bounds__(128 * POOL_Y) k_pool(const float* __restrict__ det, int64_t img_stride, int D, int F,
                        const uint8_t* __restrict__ valid, float* __restrict__ img, int ld_img, PairOut split) {
+  __shared__ float4 s_part[POOL_Y][128];
+  __shared__ int s_cnt;
   const int g = blockIdx.y;
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (f >= F) return;
-  const float* p = det + (size_t)g * img_stride + f;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int f = (blockIdx.x * 128 + tx) * 4;
+  if (tx == 0 && ty == 0) s_cnt = 0;
+  __syncthreads();
+  {   // valid-row count of the image
+    int c = 0;
+    for (int d = ty * 128 + tx; d < D; d += 128 * POOL_Y) c += valid[g * D + d];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tx & 31) == 0 && c != 0) atomicAdd(&s_cnt, c);
+  }
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-  int cnt = 0;
-  for (int d0 = 0; d0 < D; d0 += 8) {     // 8 independent row loads in flight; same summation order
-    float4 v[8];
+  if (f < F) {
+    const float* p = det + (size_t)g * img_stride + f;
+    for (int d0 = ty; d0 < D; d0 += 8 * POOL_Y) {     // 8 independent row loads in flight
+      float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      v[u] = d0 + u < D ? __ldg(reinterpret_cast<const float4*>(p + (size_t)(d0 + u) * F)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      if (d0 + u < D) {
-        s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w;
-        cnt += valid[g * D + d0 + u];
+      for (int u = 0; u < 8; ++u) {
+        const int d = d0 + u * POOL_Y;
+        v[u] = d < D ? __ldg(reinterpret_cast<const float4*>(p + (size_t)d * F)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
     }
   }
-  const float n = (float)cnt;
+  s_part[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || f >= F) return;
+#pragma unroll
+  for (int y = 1; y < POOL_Y; ++y) { const float4 q = s_part[y][tx]; s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
+  const float n = (float)s_cnt;
   const float4 o = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
   *reinterpret_cast<float4*>(img + (size_t)g * ld_img + f) = o;
   if (split.hi != nullptr) store_pair4(split, (size_t)g * split.ld + f, o);
@@ -279,19 +338,29 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, none);
     VSR_CHECK_CUDA(cudaGetLastError());
     const int srows = b * L * R;
-    const PairOut dsp{c->use_tc ? (__half*)c->ds_b.hi : nullptr, (__half*)c->ds_b.lo, c->Fp};
     k_row_valid<<<(int)(((size_t)srows * 32 + 255) / 256), 256, 0, st>>>(c->det_seqs, (int64_t)L * R * F, L * R,
-                                                                          srows, F, c->seq_valid, dsp);
+                                                                          srows, F, c->seq_valid, none);
     VSR_CHECK_CUDA(cudaGetLastError());
     k_slot_masks<<<(b * L + 127) / 128, 128, 0, st>>>(c->seq_valid, R, b * L, c->slot_mask);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches += 3;
+    c->p_compact = c->use_tc;
+    if (c->p_compact) {
+      // about half of the slot rows are padding: only the valid ones are split to fp16 and projected
+      const PairOut dsp{(__half*)c->ds_b.hi, (__half*)c->ds_b.lo, c->Fp};
+      k_slot_scan<<<1, 1024, 0, st>>>(c->slot_mask, b * L, c->slot_base, c->comp_valid, round_up(srows, MPAD));
+      VSR_CHECK_CUDA(cudaGetLastError());
+      k_split_compact<<<(int)(((size_t)srows * 32 + 255) / 256), 256, 0, st>>>(c->det_seqs, R, srows, F, c->slot_mask,
+                                                                               c->slot_base, dsp);
+      VSR_CHECK_CUDA(cudaGetLastError());
+      c->launches += 2;
+    }
   }
   // image descriptor
   {
     dim3 grid((F / 4 + 127) / 128, n_img);
     const PairOut ip{c->use_tc ? (__half*)c->img_b.hi : nullptr, (__half*)c->img_b.lo, c->Fp};
-    k_pool<<<grid, 128, 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
+    k_pool<<<grid, dim3(128, POOL_Y), 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches++;
   }
@@ -318,7 +387,7 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     g.nseg = 1; g.seg[0] = {c->det_seqs, F, c->Fp, F, &c->ds_b};
     g.w = c->Wva; g.ldw = c->Fp; g.wb = &c->Wva_b;
     g.c = c->P; g.ldc = c->NVA; g.M = b * L * R; g.N = c->NVA;
-    g.row_skip = c->seq_valid;
+    g.row_skip = c->p_compact ? c->comp_valid : c->seq_valid;     // compact: the tiles past the last valid row are skipped
     VSR_TRY(launch_gemm(c, g, st));
     c->launches++;
   }
@@ -332,6 +401,7 @@ int run_prologue_indexed(Ctx* c, const float* det, int64_t det_stride, cudaStrea
   const int F = c->F, D = c->D, b = c->b, L = c->L, R = c->R;
   const int n_img = c->n_img;
   const int rows = n_img * D;
+  c->p_compact = false;
   {
     const PairOut dsp{c->use_tc ? (__half*)c->ds_b.hi : nullptr, (__half*)c->ds_b.lo, c->Fp};
     k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, dsp);
@@ -341,7 +411,7 @@ int run_prologue_indexed(Ctx* c, const float* det, int64_t det_stride, cudaStrea
     VSR_CHECK_CUDA(cudaGetLastError());
     dim3 grid((F / 4 + 127) / 128, n_img);
     const PairOut ip{c->use_tc ? (__half*)c->img_b.hi : nullptr, (__half*)c->img_b.lo, c->Fp};
-    k_pool<<<grid, 128, 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
+    k_pool<<<grid, dim3(128, POOL_Y), 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches += 3;
   }

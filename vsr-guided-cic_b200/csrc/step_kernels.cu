@@ -110,6 +110,7 @@ struct AttendArgs {
   const int32_t* slot_index; const float* det; int64_t det_stride; int D;
   const float* img; int ld_img; const float* Pmean; int img_mul;
   const unsigned long long* slot_mask;  // [b*L] validity bits of each slot tile
+  const int32_t* slot_base;             // [b*L] first P row of the slot when only valid rows were projected, or null
   const int32_t* ptr;      // [rows]
   const float* sent; int ld_sent; int o_sa;   // sentinel (F) at 0 | sa (A) at o_sa
   const float* hb; int ld_hb; int o_ha;       // hg (H) at 0 | ha (A) at o_ha | ...
@@ -163,13 +164,17 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
   // all L slot masks of the caption are fetched alongside the slot pointer; the right one is picked by shuffle
   unsigned long long vmask;
   int slot;
+  int pbase = -1;                       // compact form: P row of the slot's first valid region
   if (a.L <= 32) {
     const unsigned long long ml = lane < a.L ? a.slot_mask[(size_t)cap * a.L + lane] : 0ull;
+    const int bl = (a.slot_base != nullptr && lane < a.L) ? a.slot_base[(size_t)cap * a.L + lane] : -1;
     slot = a.ptr[n];
     vmask = __shfl_sync(0xffffffffu, ml, slot);
+    pbase = __shfl_sync(0xffffffffu, bl, slot);
   } else {
     slot = a.ptr[n];
     vmask = a.slot_mask[(size_t)cap * a.L + slot];
+    if (a.slot_base != nullptr) pbase = a.slot_base[(size_t)cap * a.L + slot];
   }
   const size_t tile_row0 = ((size_t)cap * a.L + slot) * a.R;
   const int imgi = cap * a.img_mul;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
     const float* prow;
     const float* frow;
     if (a.slot_index == nullptr) {
-      prow = a.P + (tile_row0 + r) * a.ldP;
+      prow = a.P + (pbase >= 0 ? (size_t)(pbase + __popcll(vmask & ((1ull << r) - 1ull))) : tile_row0 + r) * a.ldP;
       frow = a.det_seqs + (tile_row0 + r) * a.F;
     } else {
       const int idx = a.slot_index[tile_row0 + r];
@@ -893,6 +898,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     PhaseScope ps(c, PH_ATTEND, st);
     AttendArgs a{};
     a.det_seqs = c->det_seqs; a.P = c->P; a.slot_mask = c->slot_mask; a.ptr = c->ptr;
+    a.slot_base = c->p_compact ? c->slot_base : nullptr;
     a.slot_index = c->slot_index; a.det = c->det; a.det_stride = c->det_stride; a.D = c->D;
     a.img = c->img; a.ld_img = c->Fp; a.Pmean = c->Pmean; a.img_mul = (c->n_img == 1 ? 0 : 1);
     a.sent = c->sent; a.ld_sent = c->NB1; a.o_sa = c->oB1_sa;
