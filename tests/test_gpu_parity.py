@@ -471,3 +471,26 @@ def test_graph_replay_is_bit_identical_and_tracks_new_inputs():
     assert not v.violations, v.violations[:5]
     assert torch.equal(w.cpu(), o_outs[0][:, 0]) and torch.equal(g.cpu(), o_outs[1][:, 0])
     assert rel_close(lw.cpu(), o_lps[0][:, 0], REL, ABS)
+
+
+# ----------------------------------------------------------------------------- launch shapes beyond the bench workload
+@pytest.mark.parametrize("b,k,out_size,vocab", [(160, 5, 1, 10000), (12, 8, 8, 10201), (40, 1, 1, 10000)])
+def test_other_launch_shapes_against_oracle(b, k, out_size, vocab):
+    """Shapes that take other kernel variants than the bench workload: 800 rows (7 row tiles: every step GEMM runs more
+    than one wave, the persistent kernel carries the fused LSTM epilogue), the maximum beam 8 with out_size 8 and a
+    vocabulary that is not a multiple of any tile, and beam 1."""
+    from gpu_common import make_model, device_beam
+    d = O.Dims(vocab_size=vocab)
+    W = O.init_weights(d, seed=1234)
+    W["out_fc.weight"] = W["out_fc.weight"] * 100.0
+    m = make_model(d, W)
+    det, ds, verbs = O.synth_inputs(b, 50, 10, 20, 2048, seed=2000 + b, vocab_size=vocab, n_det_range=(10, 50),
+                                    verb_slots=(2,), verb_vocab_id=17)
+    (w, g), (lw, lg), hist, _ = device_beam(m, _cuda(det, ds, verbs), [3, -1], k, out_size, True, True, trace=False)
+    v, o_outs, o_lps = verify_device_beam(W, d, (det, ds, verbs), [3, -1], k, hist, True, True)
+    print("shape b=%d k=%d V=%d" % (b, k, vocab), v.summary())
+    assert not v.violations, v.violations[:5]
+    T = d.seq_len
+    ref = [x.reshape(b, -1, T)[:, :out_size] for x in (o_outs[0], o_outs[1], o_lps[0], o_lps[1])]   # (a beam of 1 comes back squeezed)
+    assert torch.equal(w.cpu().reshape(b, out_size, T), ref[0]) and torch.equal(g.cpu().reshape(b, out_size, T), ref[1])
+    assert rel_close(lw.cpu().reshape(b, out_size, T), ref[2], REL, ABS) and rel_close(lg.cpu().reshape(b, out_size, T), ref[3], REL, ABS)
