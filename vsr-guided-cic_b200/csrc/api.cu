@@ -245,6 +245,75 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   return VSR_OK;
 }
 
+static void drop_graphs(Ctx* c) {
+  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
+  c->graphs.clear();
+  c->graph_seen.clear();
+}
+
+// The steps of a beam search through the graph cache: first sighting of a key runs eagerly, the second captures
+// the same enqueue sequence on the library's capture stream and instantiates it, later ones replay it on `st`.
+// A launch sequence through the graph cache: first sighting of a key runs eagerly, the second captures the same
+// enqueue sequence on the library's capture stream and instantiates it, later ones replay it on `st`.
+template <typename Enqueue>
+static int run_graphed(Ctx* c, const Ctx::GraphKey& key, cudaStream_t st, Enqueue enqueue) {
+  if (!c->graphs.empty() && c->graphs[0].key.epoch != c->epoch) drop_graphs(c);   // buffers moved: all stale
+  ++c->graph_clock;
+  for (auto& g : c->graphs)
+    if (memcmp(&g.key, &key, sizeof(key)) == 0) {
+      VSR_CHECK_CUDA(cudaGraphLaunch(g.exec, st));
+      c->launches += g.launches; g.last_use = c->graph_clock;
+      return VSR_OK;
+    }
+  bool seen = false;
+  for (auto& s : c->graph_seen) seen = seen || memcmp(&s, &key, sizeof(key)) == 0;
+  if (!seen) {
+    if (c->graph_seen.size() >= 16) c->graph_seen.erase(c->graph_seen.begin());
+    c->graph_seen.push_back(key);
+    return enqueue(st);
+  }
+  if (c->cap_stream == nullptr) VSR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
+  const int64_t l0 = c->launches;
+  VSR_CHECK_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue(c->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
+  const int64_t n_launch = c->launches - l0;
+  c->launches = l0;
+  if (rc != VSR_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+  VSR_CHECK_CUDA(ce);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  VSR_CHECK_CUDA(ie);
+  if (c->graphs.size() >= 8) {      // evict the least recently used
+    size_t lru = 0;
+    for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
+    cudaGraphExecDestroy(c->graphs[lru].exec);
+    c->graphs.erase(c->graphs.begin() + lru);
+  }
+  c->graphs.push_back({key, exec, n_launch, c->graph_clock});
+  VSR_CHECK_CUDA(cudaGraphLaunch(exec, st));
+  c->launches += n_launch;
+  return VSR_OK;
+}
+
+static Ctx::GraphKey graph_key(const Ctx* c, int kind) {
+  Ctx::GraphKey key;
+  memset(&key, 0, sizeof(key));
+  key.kind = kind;
+  key.epoch = c->epoch; key.det = c->det; key.det_seqs = c->det_seqs; key.slot_index = c->slot_index; key.verbs = c->verbs;
+  key.det_stride = c->det_stride;
+  key.b = c->b; key.D = c->D; key.L = c->L; key.R = c->R; key.n_img = c->n_img; key.verbs_dtype = c->verbs_dtype;
+  return key;
+}
+
+static bool graphs_usable(Ctx* c, cudaStream_t st) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
+  return c->use_graphs && !c->profiling && cap == cudaStreamCaptureStatusNone;
+}
+
 static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, const float* det_seqs,
                          const int32_t* slot_index, int b, int L, int R, const void* verbs, int verbs_dtype,
                          cudaStream_t st) {
@@ -298,8 +367,13 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     c->cap_detv = dvr;
   }
   VSR_TRY(ensure_rows(c, b));
-  if (slot_index == nullptr) VSR_TRY(run_prologue(c, det, det_stride, st));
-  else VSR_TRY(run_prologue_indexed(c, det, det_stride, st));
+  c->p_compact = slot_index == nullptr && c->use_tc;    // materialised slots on tensor cores: only valid rows are projected
+  // the prologue's launch sequence goes through the same graph cache as the steps (kind 1)
+  auto enqueue = [&](cudaStream_t s) {
+    return slot_index == nullptr ? run_prologue(c, det, det_stride, s) : run_prologue_indexed(c, det, det_stride, s);
+  };
+  if (graphs_usable(c, st)) VSR_TRY(run_graphed(c, graph_key(c, 1), st, enqueue));
+  else VSR_TRY(enqueue(st));
   c->have_prologue = true;
   return VSR_OK;
 }
@@ -382,60 +456,12 @@ static int enqueue_beam_steps(Ctx* c, int k, const int64_t* eos, int use_verbs, 
   return VSR_OK;
 }
 
-static void drop_graphs(Ctx* c) {
-  for (auto& g : c->graphs) cudaGraphExecDestroy(g.exec);
-  c->graphs.clear();
-  c->graph_seen.clear();
-}
-
-// The steps of a beam search through the graph cache: first sighting of a key runs eagerly, the second captures
-// the same enqueue sequence on the library's capture stream and instantiates it, later ones replay it on `st`.
+// the steps of a beam search (kind 0)
 static int beam_steps_graphed(Ctx* c, int k, const int64_t* eos, int use_verbs, int gt, cudaStream_t st) {
-  Ctx::GraphKey key;
-  memset(&key, 0, sizeof(key));
-  key.epoch = c->epoch; key.det = c->det; key.det_seqs = c->det_seqs; key.slot_index = c->slot_index; key.verbs = c->verbs;
-  key.det_stride = c->det_stride; key.eos0 = eos[0]; key.eos1 = eos[1];
-  key.b = c->b; key.D = c->D; key.L = c->L; key.R = c->R; key.n_img = c->n_img; key.verbs_dtype = c->verbs_dtype;
+  Ctx::GraphKey key = graph_key(c, 0);
+  key.eos0 = eos[0]; key.eos1 = eos[1];
   key.k = k; key.use_verbs = use_verbs; key.gt = gt; key.T = c->d.seq_len;
-  if (!c->graphs.empty() && c->graphs[0].key.epoch != c->epoch) drop_graphs(c);   // buffers moved: all stale
-  ++c->graph_clock;
-  for (auto& g : c->graphs)
-    if (memcmp(&g.key, &key, sizeof(key)) == 0) {
-      VSR_CHECK_CUDA(cudaGraphLaunch(g.exec, st));
-      c->launches += g.launches; g.last_use = c->graph_clock;
-      return VSR_OK;
-    }
-  bool seen = false;
-  for (auto& s : c->graph_seen) seen = seen || memcmp(&s, &key, sizeof(key)) == 0;
-  if (!seen) {
-    if (c->graph_seen.size() >= 8) c->graph_seen.erase(c->graph_seen.begin());
-    c->graph_seen.push_back(key);
-    return enqueue_beam_steps(c, k, eos, use_verbs, gt, nullptr, st);
-  }
-  if (c->cap_stream == nullptr) VSR_CHECK_CUDA(cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking));
-  const int64_t l0 = c->launches;
-  VSR_CHECK_CUDA(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
-  const int rc = enqueue_beam_steps(c, k, eos, use_verbs, gt, nullptr, c->cap_stream);
-  cudaGraph_t graph = nullptr;
-  const cudaError_t ce = cudaStreamEndCapture(c->cap_stream, &graph);
-  const int64_t n_launch = c->launches - l0;
-  c->launches = l0;
-  if (rc != VSR_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-  VSR_CHECK_CUDA(ce);
-  cudaGraphExec_t exec = nullptr;
-  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-  cudaGraphDestroy(graph);
-  VSR_CHECK_CUDA(ie);
-  if (c->graphs.size() >= 4) {      // evict the least recently used
-    size_t lru = 0;
-    for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
-    cudaGraphExecDestroy(c->graphs[lru].exec);
-    c->graphs.erase(c->graphs.begin() + lru);
-  }
-  c->graphs.push_back({key, exec, n_launch, c->graph_clock});
-  VSR_CHECK_CUDA(cudaGraphLaunch(exec, st));
-  c->launches += n_launch;
-  return VSR_OK;
+  return run_graphed(c, key, st, [&](cudaStream_t s) { return enqueue_beam_steps(c, k, eos, use_verbs, gt, nullptr, s); });
 }
 
 static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int use_verbs, int gt,
@@ -452,9 +478,7 @@ static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int
   VSR_TRY(ensure_beam_ws(c, b, T));
   c->hist_T = T; c->hist_b = b; c->hist_k = k;
   // graph replay unless a trace is requested, the phase profiler is on, or the caller is capturing itself
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusActive; }
-  if (c->use_graphs && tr == nullptr && !c->profiling && cap == cudaStreamCaptureStatusNone)
+  if (tr == nullptr && graphs_usable(c, st))
     VSR_TRY(beam_steps_graphed(c, k, eos, use_verbs, gt, st));
   else
     VSR_TRY(enqueue_beam_steps(c, k, eos, use_verbs, gt, tr, st));

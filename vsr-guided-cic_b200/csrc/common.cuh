@@ -271,6 +271,7 @@ struct Ctx {
   // Key = every value baked into the kernels' arguments; `epoch` changes whenever a device buffer is (re)allocated.
   struct GraphKey {
     uint64_t epoch;
+    int64_t kind;                    // 0 = steps of a beam search, 1 = prologue
     const void *det, *det_seqs, *slot_index, *verbs;
     int64_t det_stride, eos0, eos1;
     int32_t b, D, L, R, n_img, verbs_dtype, k, use_verbs, gt, T;

@@ -344,7 +344,6 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     k_slot_masks<<<(b * L + 127) / 128, 128, 0, st>>>(c->seq_valid, R, b * L, c->slot_mask);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches += 3;
-    c->p_compact = c->use_tc;
     if (c->p_compact) {
       // about half of the slot rows are padding: only the valid ones are split to fp16 and projected
       const PairOut dsp{(__half*)c->ds_b.hi, (__half*)c->ds_b.lo, c->Fp};
@@ -401,7 +400,6 @@ int run_prologue_indexed(Ctx* c, const float* det, int64_t det_stride, cudaStrea
   const int F = c->F, D = c->D, b = c->b, L = c->L, R = c->R;
   const int n_img = c->n_img;
   const int rows = n_img * D;
-  c->p_compact = false;
   {
     const PairOut dsp{c->use_tc ? (__half*)c->ds_b.hi : nullptr, (__half*)c->ds_b.lo, c->Fp};
     k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, dsp);
