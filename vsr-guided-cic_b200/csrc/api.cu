@@ -229,6 +229,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   if (const char* e = getenv("VSRDEC_2CTA")) c->use_pair = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_GRAPH")) c->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("VSRDEC_ZERO_STATE")) c->zero_state_opt = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL_MODE")) c->pdl_mode = atoi(e);
   if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
@@ -445,6 +446,7 @@ static int enqueue_beam_steps(Ctx* c, int k, const int64_t* eos, int use_verbs, 
     const int rows = b * cur;
     StepIO io{};
     io.rows = rows; io.cur_beam = cur; io.use_verbs = use_verbs != 0; io.gt = gt != 0; io.topk = k;
+    io.zero_state = t == 0 && c->zero_state_opt;
     if (tr && tr->step_out) { io.out_logp = tr->step_out + (size_t)t * b * k * c->V; io.out_stride = c->V; }
     if (tr && tr->step_gate) { io.gate_out = tr->step_gate + (size_t)t * b * k * 2; io.gate_stride = 2; }
     VSR_TRY(run_step(c, io, st));
@@ -503,6 +505,7 @@ static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, floa
     }
     StepIO io{};
     io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 0;
+    io.zero_state = t == 0 && c->zero_state_opt;
     io.out_logp = out + (size_t)t * c->V; io.out_stride = (int64_t)T * c->V;
     io.gate_out = gate + (size_t)t * 2; io.gate_stride = (int64_t)T * 2;
     VSR_TRY(run_step(c, io, st));
@@ -521,6 +524,7 @@ static int greedy_impl(Ctx* c, int64_t* out_words, int64_t* out_gates, cudaStrea
   for (int t = 0; t < T; ++t) {
     StepIO io{};
     io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 1;
+    io.zero_state = t == 0 && c->zero_state_opt;
     VSR_TRY(run_step(c, io, st));
     VSR_TRY(launch_greedy_pick(c, b, t, T, out_words, out_gates, st));
     if (t + 1 < T) VSR_TRY(launch_commit_identity(c, b, nullptr, 0, -1, st));

@@ -147,6 +147,7 @@ struct GemmArgs {
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
   const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
   bool pdl = false;             // launch with programmatic dependent launch (decoder-step GEMMs only)
+  bool zero_acc = false;        // every A operand is known to be zero (h = 0 at t = 0): skip the main loop, acc := 0
   int pdl_flags = 0;            // bit 0: weight tiles before the dependency wait; bit 1: trigger after the main loop
   FusedCell cell;               // epilogue fusion (tensor-core path only)
 };
@@ -180,7 +181,7 @@ struct Ctx {
   int NA, NB1, NB2, NC, ND, NE;  // padded output widths of the stacked GEMMs
   int NB1v, NB2v;                // their un-padded widths
   int KA;                      // [h2 (Hp, if h2_first) | h1 (Hp)]  (the xt part is a per-word table, see X)
-  int KD;                      // [att (Fp) | h2 (Hp) | h1' (Hp)]
+  int KD;                      // [att (Fp) | h1' (Hp) | h2 (Hp)]  (h2 last: dropped at t = 0 where it is zero)
   // column offsets of the stacked output blocks (KPAD-aligned so float4 epilogues stay aligned)
   int oB1_sa;                  // sent:  sentinel at 0 (F) | sa at oB1_sa (A)
   int oB2_ha, oB2_p2;          // hb:    hg at 0 (H) | ha at oB2_ha (A) ; oB2_p2 = end of the valid columns
@@ -284,6 +285,7 @@ struct Ctx {
   bool attend_attr_set = false;
   bool state_h32 = true;             // the last step wrote fp32 h1'/h2' (always on the FFMA twin)
   bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
+  bool zero_state_opt = true;        // VSRDEC_ZERO_STATE=0: run the h-dependent GEMM parts at t = 0 although h = 0
   bool use_pdl = true;               // VSRDEC_PDL=0: plain stream serialization between the step kernels
   // VSRDEC_PDL_MODE bits: 1 = GEMM launches, 2 = small kernels, 4 = weight prefetch before the wait, 8 = GEMMs
   // trigger after their main loop.  Measured inside the decode graph (ms per decode): off 4.07, 1: 4.02, 1|4: 4.00,
@@ -315,6 +317,7 @@ struct StepIO {
   float* gate_out;   // optional (rows,2) post-forcing gate log-probs
   int64_t gate_stride;
   int topk;          // number of word candidates to extract per row (0 = none)
+  bool zero_state;   // h1 = h2 = 0 on entry (first step after init_state): their GEMM contributions are skipped
   bool need_h32;     // the caller reads the fp32 h1'/h2' (vsr_step); the tensor-core path itself only needs the fp16 twins
 };
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st);

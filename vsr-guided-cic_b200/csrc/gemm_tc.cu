@@ -162,6 +162,7 @@ struct TcProblem {
   int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; __half* g_hi; __half* g_lo;
   // EPI_VOCAB: per (row, N tile) softmax / top-k partial records instead of (or besides, when c != null) the logits
   float* vpart; int n_valid;
+  int zero_acc;     // k_gemm_tc only: no main loop, the accumulator is taken as zero
 };
 struct TcParams {
   TcProblem pr[2];
@@ -201,13 +202,18 @@ __device__ __forceinline__ void store4(float* f32, __half* hi, __half* lo, size_
 
 // TMEM -> tile: the two warps of quarter q write their 32 rows, each one half of the columns
 template <int BN>
-__device__ __forceinline__ void tile_dump(uint32_t tlane, float* tile, int hsel, int lane) {
+__device__ __forceinline__ void tile_dump(uint32_t tlane, float* tile, int hsel, int lane, bool zero_acc) {
   constexpr int NCH = BN / 16;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if ((ch < NCH / 2) != (hsel == 0)) continue;
     uint32_t r[16];
-    tmem_ld16(tlane + (uint32_t)(ch * 16), r);
+    if (zero_acc) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[j] = 0u;
+    } else {
+      tmem_ld16(tlane + (uint32_t)(ch * 16), r);
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<float4*>(tile + tile_slot<BN>(lane, ch * 4 + j)) =
@@ -339,7 +345,7 @@ __device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_
 #ifdef VSR_DBG_CLK
     const long long c0 = clock64();
 #endif
-    if (q == qq) tile_dump<BN>(tlane, tile, hsel, lane);
+    if (q == qq) tile_dump<BN>(tlane, tile, hsel, lane, p.zero_acc != 0);
 #ifdef VSR_DBG_CLK
     const long long c1 = clock64();
 #endif
@@ -574,6 +580,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
 
   int total_kb = 0;
   for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+
+  if (p.zero_acc) total_kb = 0;          // operands known to be zero: nothing to load or multiply
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1080,6 +1088,7 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
   }
   VSR_REQUIRE(f.gt_cols == 0 || (!pair && (BN == 128 || BN == 192)), VSR_EINVAL, "launch_gemm_tc: g_t fusion needs a 128- or 192-wide tile");
   VSR_REQUIRE(f.mode != EPI_VOCAB || !pair, VSR_EINVAL, "launch_gemm_tc: vocabulary epilogue is not available in the CTA-pair kernel");
+  p->zero_acc = g.zero_acc ? 1 : 0;
   p->ld_state = f.ld_state;
   p->gt_cols = f.gt_cols; p->gt_gq = f.gt_gq; p->gt_c1n = f.gt_c1n; p->g_t = f.g_t;
   p->g_hi = (__half*)f.g_hi; p->g_lo = (__half*)f.g_lo;

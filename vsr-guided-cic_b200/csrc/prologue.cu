@@ -274,7 +274,7 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   // ---- S5 -> WC: att_ga
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WC, 0, sizeof(float) * (size_t)c->NC * Hp, st));
   VSR_TRY(pack_block(c, c->WC, Hp, 0, 0, w[26], H, 0, A, H, st));
-  // ---- S6 -> WD: lstm2.W_ih[:, H:H+F] (att) | lstm2.W_hh (h2) | lstm2.W_ih[:, 0:H] (h1') ; bias b_ih2 + b_hh2
+  // ---- S6 -> WD: lstm2.W_ih[:, H:H+F] (att) | lstm2.W_ih[:, 0:H] (h1') | lstm2.W_hh (h2) ; bias b_ih2 + b_hh2
   // (h1' rides in GEMM-D rather than in the h1' projection GEMM-B: B then fits one wave of 148 CTAs)
   VSR_CHECK_CUDA(cudaMemsetAsync(c->WD, 0, sizeof(float) * (size_t)c->ND * c->KD, st));
   VSR_CHECK_CUDA(cudaMemsetAsync(c->bD, 0, sizeof(float) * (size_t)c->ND, st));
@@ -282,8 +282,8 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
   for (int g = 0; g < 4; ++g) {
     const float* wi = w[14] + (size_t)g * H * in2;
     VSR_TRY(pack_perm(c, c->WD, c->KD, 0, 0, wi, in2, H, H, F, g, 4, st));
-    VSR_TRY(pack_perm(c, c->WD, c->KD, 0, c->Fp, w[15] + (size_t)g * H * H, H, 0, H, H, g, 4, st));
-    VSR_TRY(pack_perm(c, c->WD, c->KD, 0, c->Fp + Hp, wi, in2, 0, H, H, g, 4, st));
+    VSR_TRY(pack_perm(c, c->WD, c->KD, 0, c->Fp, wi, in2, 0, H, H, g, 4, st));
+    VSR_TRY(pack_perm(c, c->WD, c->KD, 0, c->Fp + Hp, w[15] + (size_t)g * H * H, H, 0, H, H, g, 4, st));
     VSR_TRY(pack_bias_perm(c, c->bD, w[16] + g * H, w[17] + g * H, H, g, 4, st));
     if (img2) VSR_TRY(pack_perm(c, c->WU2, c->Fp, 0, 0, wi, in2, H + F, H, F, g, 4, st));
   }

@@ -853,6 +853,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.gather = c->X; g.ld_gather = c->NA; g.gather_idx = c->word_idx;
     g.rowadd = c->U; g.ld_rowadd = c->NA; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
+    g.zero_acc = io.zero_state;           // [h2 | h1] = 0 at t = 0: pre1 = U[caption] + X[bos], no main loop
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     fused = gemm_uses_tc(c, g) && !c->use_pair;    // the CTA-pair experiment has plain epilogues only
     c->state_h32 = !fused || io.need_h32;
@@ -924,10 +925,10 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b;
     gc.c = c->ga; gc.ldc = c->NC; gc.M = rows; gc.N = c->NC;
     GemmArgs g{};
-    g.nseg = 3;
+    g.nseg = io.zero_state ? 2 : 3;       // h2 = 0 at t = 0: its K segment (last in WD) is not read
     g.seg[0] = {c->att, c->Fp, c->Fp, c->Fp, &c->att_b};
-    g.seg[1] = {c->h2, c->Hp, c->Hp, c->Hp, &c->h2_b};
-    g.seg[2] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
+    g.seg[1] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
+    g.seg[2] = {c->h2, c->Hp, c->Hp, c->Hp, &c->h2_b};
     g.w = c->WD; g.ldw = c->KD; g.bias = c->bD; g.wb = &c->WD_b;
     if (c->d.img_second_lstm) {
       g.rowadd = c->U2; g.ld_rowadd = c->ND; g.row_div = io.cur_beam; g.rowadd_mul = (c->n_img == 1 ? 0 : 1);
