@@ -156,9 +156,8 @@ def main_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries exactly one JSON line: NCCL logs (its version banner at NCCL_DEBUG=VERSION/WARN) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
 
