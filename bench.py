@@ -157,6 +157,9 @@ def main_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         # stdout carries exactly one JSON line: NCCL logs (its version banner at NCCL_DEBUG=VERSION/WARN) go to stderr
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so that level is dropped instead)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            del os.environ["NCCL_DEBUG"]
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
