@@ -217,12 +217,9 @@ def main_ours(args, rank, world, local_rank):
     l0 = eng.launch_count()
     total_ms, per_ms, t0, t1 = timed(lambda: decode(dev_in), args.steps)
     launches = eng.launch_count() - l0
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
     ms_per_step = total_ms / args.steps
     value = world * w["b"] * args.steps / (total_ms * 1e-3)
 
-    # ---- e2e: host (pinned) inputs -> H2D -> decode through the public API -> D2H of the captions, every
-    # step.  Double-buffered: the H2D copy of step i+1 runs on a copy stream while step i decodes.
     # ---- two decodes in flight: a second engine (same weights) on a second stream.  Consecutive batches are
     # independent, so while one decode sits in its latency-bound small kernels the other one's GEMMs use the SMs.
     model2 = ControllableCaptioningModel(w["T"], w["V"], 2, verb_tables=({}, {})).to(dev).eval()
@@ -261,7 +258,10 @@ def main_ours(args, rank, world, local_rank):
             ms = float(tt)
         return ms
     two_lane_timed(6)                                  # per lane: eager, graph capture, replay
+    l2 = model._eng.launch_count() + model2._eng.launch_count()
     two_ms = two_lane_timed(args.steps)
+    two_launches = model._eng.launch_count() + model2._eng.launch_count() - l2
+    clocks = sampler.stop(t0, time.time()) if rank == 0 else None      # both timed regions (one lane, two lanes)
 
     result = {}
     copy_stream = torch.cuda.Stream(dev)
@@ -455,25 +455,29 @@ def main_ours(args, rank, world, local_rank):
                         "bytes_per_decode": att_bytes, "ms_per_decode": att_ms,
                         "note": "beams of one caption mostly share a slot tile, so L2 serves the repeats"}
         cpu_cps, cpu_ms, cores = run_cpu_port(1, 1, CPU_SAMPLE_B) if world == 1 and not args.no_cpu_baseline else (None, None, None)
-        line = {"metric": METRIC, "value": value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        # headline: the K timed steps with two decodes in flight (two engines, two streams); the classic one-decode-
+        # at-a-time measurement (which the per-kernel analysis below refers to) is reported next to it
+        two_value = world * w["b"] * args.steps / (two_ms * 1e-3)
+        line = {"metric": METRIC, "value": two_value, "unit": "captions/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": two_ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": w["name"], "captions_per_gpu": w["b"], "beam": w["beam"], "vocab": w["V"],
                            "decoder_steps": w["T"], "detections": w["D"], "slots": w["L"], "regions_per_slot": w["R"],
                            "parallelism": f"caption-sharded x{world} (weights replicated, one all_gather of captions)",
+                           "concurrency": "2 batches in flight per GPU (two engines on two streams, steps alternate); "
+                                          "one_at_a_time has the single-stream figures",
                            "l2": "per-step working set (inputs 0.21 GB + weights 0.29 GB) exceeds the 126 MB L2; no flush"},
                 "p50_step_latency_ms": statistics.median(per_ms) / w["T"],
                 "p50_decode_ms": statistics.median(per_ms),
-                "gpu_launches": int(launches) * world,
+                "gpu_launches": int(two_launches) * world,
+                "one_at_a_time": {"value": value, "unit": "captions/s", "ms_per_step": ms_per_step,
+                                  "gpu_launches": int(launches) * world,
+                                  "note": "same K steps on one engine and one stream; p50_* and the per-kernel blocks refer to it"},
                 "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e2e_s / args.steps,
                         "pipeline": "two lanes (engine + stream each): H2D of step i+1 (copy stream), the decode of step i-1 on the "
                                     "other lane and the host read of its result (async D2H into pinned memory) overlap the "
                                     "decode of step i; every step's H2D, D2H and host read are inside the timed region"},
-                "two_streams": {"value": world * w["b"] * args.steps / (two_ms * 1e-3), "unit": "captions/s",
-                                "ms_per_step": two_ms / args.steps,
-                                "note": "device-resident inputs, K decodes alternating over two engines on two streams "
-                                        "(two batches in flight); `value` above is one decode at a time"},
                 "e2e_indexed": {"value": world * w["b"] * args.steps / e2e_idx_s, "unit": "captions/s",
                                 "h2d_bytes_per_step": h2d_idx_bytes, "d2h_bytes_per_step": d2h_bytes,
                                 "ms_per_step": 1e3 * e2e_idx_s / args.steps,

@@ -14,6 +14,6 @@ import json
 d=json.load(open("gpurun_out/bench_$R.json")); r=json.load(open("gpurun_out/bench_ref_$R.json"))
 print("value", d["value"], "ms/step", d["ms_per_step"], "e2e", d["e2e"]["value"], "launches", d["gpu_launches"])
 print("roofline", d["roofline"]["achieved"], d["roofline"]["frac"], d["roofline"]["issued_frac"], "attend", d["roofline_attend"]["achieved"], d["roofline_attend"]["frac"])
-print("e2e_indexed", d["e2e_indexed"]["value"], d["e2e_indexed"]["device_resident_value"], d["e2e_indexed"]["h2d_bytes_per_step"])
+print("one_at_a_time", d["one_at_a_time"]["value"], d["one_at_a_time"]["ms_per_step"]); print("e2e_indexed", d["e2e_indexed"]["value"], d["e2e_indexed"]["device_resident_value"], d["e2e_indexed"]["h2d_bytes_per_step"])
 print("cpu", d.get("cpu_baseline",{}).get("value"), "ref arm", r["value"], r["cpu_baseline"]["cores"], "clocks", d["clocks"])
 PY
