@@ -1,4 +1,4 @@
-"""Throughput of two independent decodes in flight (two engines, two streams) versus one (diagnostic)."""
+"""Throughput of 1..4 independent decodes in flight (one engine and one stream each) (diagnostic)."""
 import os
 import sys
 import time
@@ -14,7 +14,7 @@ def main(b=100, k=5, D=50, L=10, R=20, V=10000, iters=20):
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     models, statics, streams = [], [], []
-    for s in range(2):
+    for s in range(4):
         m = ControllableCaptioningModel(20, V, 2, verb_tables=({}, {})).to(dev).eval()
         g = torch.Generator(device=dev).manual_seed(1 + s)
         det = torch.relu(torch.randn((b, D, 2048), device=dev, generator=g))
@@ -42,10 +42,8 @@ def main(b=100, k=5, D=50, L=10, R=20, V=10000, iters=20):
         n = iters * n_streams
         print(f"{n_streams} stream(s): {1e3 * dt / n:.3f} ms per decode -> {n * b / dt:.1f} captions/s", flush=True)
 
-    run(1)
-    run(2)
-    run(1)
-    run(2)
+    for n in (1, 2, 3, 4, 2, 3):
+        run(n)
 
 
 if __name__ == "__main__":
