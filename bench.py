@@ -264,56 +264,16 @@ def main_ours(args, rank, world, local_rank):
     clocks = sampler.stop(t0, time.time()) if rank == 0 else None      # both timed regions (one lane, two lanes)
 
     result = {}
-    copy_stream = torch.cuda.Stream(dev)
 
-    def e2e_measure(host_in, decode_fns):
-        NB = 4                                         # input buffers: two per lane, so the copy engine runs ahead
-        bufs = [tuple(torch.empty_like(t, device=dev) for t in host_in) for _ in range(NB)]
-        ready = [torch.cuda.Event() for _ in range(NB)]
-        freed = [torch.cuda.Event() for _ in range(NB)]
-
-        def stage(i):                                  # enqueue the H2D copies of step i into buffer i % NB
-            slot = i % NB
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(freed[slot])    # the decode that last read this buffer has finished
-                for d_t, h_t in zip(bufs[slot], host_in):
-                    d_t.copy_(h_t, non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        pinned = [None] * NB
-        done = [torch.cuda.Event() for _ in range(NB)]
-
-        def collect(slot):                             # host read of a finished step's result
-            done[slot].synchronize()
-            result["words"] = pinned[slot][0].clone()
-            result["gates"] = pinned[slot][1].clone()
+    def e2e_measure(host_in, indexed):
+        """K steps through vsrdec.DecodePipeline (the package's public throughput loop): two lanes, four input buffers
+        fed from pinned host memory by a copy stream, results read back through pinned memory one step later."""
+        from vsrdec import DecodePipeline
+        pipe = DecodePipeline(lane_models, w["eos"], w["beam"], 1, gt=w["gt"], indexed=indexed, buffers=4, post=gather)
 
         def e2e_run(steps):
-            # Step i: buffer i % NB, lane i % 2 (own stream and engine), so two consecutive steps decode concurrently
-            # while the copy engine fills the buffers of the steps after them.
-            cur = torch.cuda.current_stream(dev)
-            for ev in freed:
-                ev.record(cur)
-            stage(0)
-            stage(1)
-            for i in range(steps):
-                slot = i % NB
-                lane = lanes[i % 2]
-                if i + 2 < steps:
-                    stage(i + 2)
-                lane.wait_event(ready[slot])
-                with torch.cuda.stream(lane):
-                    words, gates, lpw = decode_fns[i % 2](bufs[slot])
-                    freed[slot].record(lane)
-                    if pinned[slot] is None:
-                        pinned[slot] = (torch.empty(words.shape, dtype=words.dtype).pin_memory(),
-                                        torch.empty(gates.shape, dtype=gates.dtype).pin_memory())
-                    pinned[slot][0].copy_(words, non_blocking=True)      # device->host read of the step's result
-                    pinned[slot][1].copy_(gates, non_blocking=True)
-                    done[slot].record(lane)
-                if i > 0:
-                    collect((i - 1) % NB)
-            collect((steps - 1) % NB)
+            for words, gates, lpw, lpg in pipe.run(host_in for _ in range(steps)):
+                result["words"], result["gates"], result["lps"] = words, gates, (lpw, lpg)
         e2e_run(12)                                    # every (lane, buffer) pair: eager, graph capture, replay
         barrier()
         t_e0 = time.perf_counter()
@@ -326,9 +286,9 @@ def main_ours(args, rank, world, local_rank):
             secs = float(tt)
         return secs
 
-    e2e_s = e2e_measure(host, [lane_decode(0), lane_decode(1)])
+    e2e_s = e2e_measure(host, False)
     e2e_value = world * w["b"] * args.steps / e2e_s
-    d2h_bytes = int(result["words"].numel() * 8 + result["gates"].numel() * 8)
+    d2h_bytes = int(sum(t.numel() * t.element_size() for t in (result["words"], result["gates"]) + result["lps"]))
 
     # ---- the same e2e loop through the index-form entry point (vsr_prologue_indexed): the slots
     # arrive as int32 indices into the detections instead of materialised (b,L,R,F) tiles.  Extra key only; the
@@ -344,7 +304,7 @@ def main_ours(args, rank, world, local_rank):
             return gather(words), gates, lpw
         return fn
     decode_indexed = lane_decode_indexed(0)
-    e2e_idx_s = e2e_measure(host_i, [lane_decode_indexed(0), lane_decode_indexed(1)])
+    e2e_idx_s = e2e_measure(host_i, True)
     h2d_idx_bytes = sum(t.numel() * t.element_size() for t in host_i)
     dev_idx = tuple(t.to(dev) for t in host_i)
     for _ in range(3):

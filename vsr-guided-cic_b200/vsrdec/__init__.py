@@ -2,3 +2,4 @@
 from ._lib import load_library, library_path, VsrError, EXPORTED_SYMBOLS  # noqa: F401
 from .engine import DecoderEngine, PARAM_NAMES  # noqa: F401
 from .sharding import shard_range, decode_sharded  # noqa: F401
+from .pipeline import DecodePipeline  # noqa: F401
