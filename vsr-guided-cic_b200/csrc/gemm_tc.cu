@@ -11,12 +11,16 @@
 // the path's operands (|x| << 65504: gates in [-1,1], Xavier weights, pooled CNN features) fit its
 // range, lo parts of small values degrade gracefully through fp16 subnormals (abs error <= 2^-25).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
-//   warp 0   : TMA producer   cp.async.bulk.tensor.2d -> 128B-swizzled smem tiles, mbarrier expect_tx
+// Structure (one 128 x BN output tile per CTA, 320 threads):
+//   warp 0   : TMA producer   cp.async.bulk.tensor.2d -> swizzled smem tiles, mbarrier expect_tx; the weight halves of
+//              the first ring pass are fetched before the programmatic-dependent-launch wait
 //   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (kind::f16, M=128, N=BN, K=16)
-//   warps 2-5: epilogue       tcgen05.ld TMEM -> registers -> (+bias, +per-caption row, +matrix) -> global
-// smem ring: kStages x {A_hi, A_lo (128 x 64 fp16), W_hi, W_lo (BN x 64 fp16)}, full/empty mbarriers;
-// the accumulator hand-off to the epilogue is a tcgen05.commit on a third mbarrier.
+//   warps 2-9: epilogue (two warps per TMEM lane quarter): bias -> smem behind the main loop; then one lane quarter at
+//              a time TMEM -> swizzled smem tile -> all eight warps with lanes along a row (coalesced operands and
+//              outputs): plain / g_t / fused LSTM cells; the vocabulary head keeps the row-per-thread form
+// smem ring: kStages x {A_hi, A_lo (128 x KB fp16), W_hi, W_lo (BN x KB fp16)}, full/empty mbarriers; the accumulator
+// hand-off to the epilogue is a tcgen05.commit on a third mbarrier.  k_gemm_tcp is the persistent variant
+// (double-buffered TMEM accumulator), k_gemm_tc2 the CTA-pair experiment.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
