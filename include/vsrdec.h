@@ -144,7 +144,11 @@ int vsr_step(vsr_handle h, const float* h1, const float* c1, const float* h2, co
 /* Whole beam search over the prologue batch without host synchronisation
  * (CaptioningModel.beam_search / beam_search_v, CaptioningModel.py:116-195 / 197-294).
  *   out_words,out_gates (b,out_size,T) int64;  lp_words,lp_gates (b,out_size,T) fp32
- *   eos_idxs[2] [host];  trace may be NULL. */
+ *   eos_idxs[2] [host];  trace may be NULL.
+ * Repeated calls with identical arguments (same prologue inputs, shapes and flags; trace == NULL) are replayed from a
+ * CUDA graph that the library captures on an internal stream at the second such call and launches on `stream`
+ * (vsr_prologue / vsr_prologue_indexed likewise).  If `stream` is itself being captured the work is enqueued as plain
+ * launches.  VSRDEC_GRAPH=0 in the environment at vsr_create() time disables this. */
 int vsr_beam_search(vsr_handle h, int32_t beam_size, int32_t out_size, const int64_t* eos_idxs,
                     int32_t use_verbs, int32_t gt,
                     int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
