@@ -222,10 +222,13 @@ def main_ours(args, rank, world, local_rank):
 
     # ---- two decodes in flight: a second engine (same weights) on a second stream.  Consecutive batches are
     # independent, so while one decode sits in its latency-bound small kernels the other one's GEMMs use the SMs.
-    model2 = ControllableCaptioningModel(w["T"], w["V"], 2, verb_tables=({}, {})).to(dev).eval()
-    model2.load_state_dict(model.state_dict())
-    lanes = [torch.cuda.Stream(dev) for _ in range(2)]
-    lane_models = [model, model2]
+    n_lanes = max(1, args.lanes)
+    lane_models = [model]
+    for _ in range(n_lanes - 1):
+        replica = ControllableCaptioningModel(w["T"], w["V"], 2, verb_tables=({}, {})).to(dev).eval()
+        replica.load_state_dict(model.state_dict())
+        lane_models.append(replica)
+    lanes = [torch.cuda.Stream(dev) for _ in range(n_lanes)]
 
     def lane_decode(which):
         def fn(statics):
@@ -243,8 +246,8 @@ def main_ours(args, rank, world, local_rank):
         for ln in lanes:
             ln.wait_event(e0)
         for i in range(steps):
-            with torch.cuda.stream(lanes[i % 2]):
-                lane_decode(i % 2)(dev_in)
+            with torch.cuda.stream(lanes[i % n_lanes]):
+                lane_decode(i % n_lanes)(dev_in)
         for ln in lanes:
             ev = torch.cuda.Event()
             ev.record(ln)
@@ -257,10 +260,10 @@ def main_ours(args, rank, world, local_rank):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt)
         return ms
-    two_lane_timed(6)                                  # per lane: eager, graph capture, replay
-    l2 = model._eng.launch_count() + model2._eng.launch_count()
+    two_lane_timed(3 * n_lanes)                        # per lane: eager, graph capture, replay
+    l2 = sum(m._eng.launch_count() for m in lane_models)
     two_ms = two_lane_timed(args.steps)
-    two_launches = model._eng.launch_count() + model2._eng.launch_count() - l2
+    two_launches = sum(m._eng.launch_count() for m in lane_models) - l2
     clocks = sampler.stop(t0, time.time()) if rank == 0 else None      # both timed regions (one lane, two lanes)
 
     result = {}
@@ -269,12 +272,12 @@ def main_ours(args, rank, world, local_rank):
         """K steps through vsrdec.DecodePipeline (the package's public throughput loop): two lanes, four input buffers
         fed from pinned host memory by a copy stream, results read back through pinned memory one step later."""
         from vsrdec import DecodePipeline
-        pipe = DecodePipeline(lane_models, w["eos"], w["beam"], 1, gt=w["gt"], indexed=indexed, buffers=4, post=gather)
+        pipe = DecodePipeline(lane_models, w["eos"], w["beam"], 1, gt=w["gt"], indexed=indexed, buffers=2 * n_lanes, post=gather)
 
         def e2e_run(steps):
             for words, gates, lpw, lpg in pipe.run(host_in for _ in range(steps)):
                 result["words"], result["gates"], result["lps"] = words, gates, (lpw, lpg)
-        e2e_run(12)                                    # every (lane, buffer) pair: eager, graph capture, replay
+        e2e_run(6 * n_lanes)                           # every (lane, buffer) pair: eager, graph capture, replay
         barrier()
         t_e0 = time.perf_counter()
         e2e_run(args.steps)
@@ -424,7 +427,7 @@ def main_ours(args, rank, world, local_rank):
                 "config": {"workload": w["name"], "captions_per_gpu": w["b"], "beam": w["beam"], "vocab": w["V"],
                            "decoder_steps": w["T"], "detections": w["D"], "slots": w["L"], "regions_per_slot": w["R"],
                            "parallelism": f"caption-sharded x{world} (weights replicated, one all_gather of captions)",
-                           "concurrency": "2 batches in flight per GPU (two engines on two streams, steps alternate); "
+                           "concurrency": f"{n_lanes} batches in flight per GPU (one engine and one stream each, steps alternate); "
                                           "one_at_a_time has the single-stream figures",
                            "l2": "per-step working set (inputs 0.21 GB + weights 0.29 GB) exceeds the 126 MB L2; no flush"},
                 "p50_step_latency_ms": statistics.median(per_ms) / w["T"],
@@ -435,9 +438,10 @@ def main_ours(args, rank, world, local_rank):
                                   "note": "same K steps on one engine and one stream; p50_* and the per-kernel blocks refer to it"},
                 "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e2e_s / args.steps,
-                        "pipeline": "two lanes (engine + stream each): H2D of step i+1 (copy stream), the decode of step i-1 on the "
-                                    "other lane and the host read of its result (async D2H into pinned memory) overlap the "
-                                    "decode of step i; every step's H2D, D2H and host read are inside the timed region"},
+                        "pipeline": f"vsrdec.DecodePipeline, {n_lanes} lanes (engine + stream each), {2 * n_lanes} input buffers: the "
+                                    "H2D of later steps (copy stream), the decodes on the other lanes and the host read of "
+                                    "finished results (async D2H into pinned memory) overlap the decode of step i; every "
+                                    "step's H2D, D2H and host read are inside the timed region"},
                 "e2e_indexed": {"value": world * w["b"] * args.steps / e2e_idx_s, "unit": "captions/s",
                                 "h2d_bytes_per_step": h2d_idx_bytes, "d2h_bytes_per_step": d2h_bytes,
                                 "ms_per_step": 1e3 * e2e_idx_s / args.steps,
@@ -475,6 +479,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=3, help="decodes in flight per GPU (engines on their own streams)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
