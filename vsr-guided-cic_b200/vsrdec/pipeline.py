@@ -47,6 +47,10 @@ class DecodePipeline:
         bufs = self._bufs[slot]
         if bufs is None or any(b.shape != h.shape or b.dtype != h.dtype for b, h in zip(bufs, host_batch)):
             bufs = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_batch)
+            for t in bufs:                                      # written on the copy stream, read on the lanes: a buffer
+                t.record_stream(self.copy_stream)               # dropped later (shape change) must not be recycled early
+                for ln in self.lanes:
+                    t.record_stream(ln)
             self._bufs[slot] = bufs
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._freed[slot])      # the decode that last read this buffer has finished
