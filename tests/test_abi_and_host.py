@@ -169,3 +169,16 @@ def test_materialize_slots_semantics():
                 else:
                     assert float(ds[i, l, r].abs().sum()) == 0.0
     assert bool((idx[:, :, 0][verbs != -1] == -2).all())      # verb slots are mean-row slots (repeated tail slots carry verb -1)
+
+
+def test_decode_pipeline_refuses_cpu_models():
+    """The throughput loop has no CPU path either: models on the CPU are rejected up front."""
+    import pytest
+    from models import ControllableCaptioningModel
+    from vsrdec import DecodePipeline
+    m = ControllableCaptioningModel(6, 40, 2, det_feat_size=16, input_encoding_size=8, rnn_size=8, att_size=8,
+                                    verb_tables=({}, {}))
+    with pytest.raises(RuntimeError):
+        DecodePipeline([m], [3, -1], 3)
+    with pytest.raises(ValueError):
+        DecodePipeline([], [3, -1], 3)
