@@ -41,6 +41,7 @@ extern "C" {
 #define VSR_ESTATE (-4)  /* call order violated (e.g. decode before prologue)     */
 
 #define VSR_MAX_BEAM 8   /* largest beam_size supported by the fused top-k        */
+#define VSR_MAX_SEQ_LEN 256 /* largest seq_len of the beam-search back-track kernel  */
 #define VSR_NUM_WEIGHTS 28
 
 /* dtype tags for the `verbs` tensor (eval_coco.py:240 hands float64 from numpy) */

@@ -58,6 +58,12 @@ class BeamVerdict:
         self.max_gate_rel = 0.0     #   |dev - oracle| / (1e-3*|oracle| + 1e-4); <= 1 passes
         self.max_out_abs = 0.0
         self.max_gate_abs = 0.0
+        self.band_caption = None    # bool (b,): the caption had at least one decision (or its final ordering) inside the band
+
+    def decisive_captions(self):
+        """Captions whose every top-k decision AND final beam ordering were outside the tie band: on these the device's
+        tokens must equal the free-running reference's, bit for bit."""
+        return ~self.band_caption
 
     def summary(self):
         return (f"decisions={self.decisions} in_tie_band={self.in_band} set_mismatch={self.set_mismatch} "
@@ -92,7 +98,13 @@ def verify_device_beam(W, d, statics, eos, k, hist, use_verbs=False, gt=False, v
         kth, nxt = top[:, k - 1], top[:, k]
         band = band_abs + band_rel * kth.abs()
         v.decisions += b
+        inb = (kth - nxt) <= band
+        # the ORDER of the selected candidates matters too (slot order decides the final sort's tie-breaks and which
+        # beam is "best"): adjacent selected scores closer than the band make the caption non-decisive
+        if k > 1:
+            inb = inb | ((top[:, :k - 1] - top[:, 1:k]) <= band.unsqueeze(1)).any(1)
         v.in_band += int(((kth - nxt) <= band).sum())
+        v.band_caption = inb.clone() if v.band_caption is None else (v.band_caption | inb)
         oracle_sel = torch.topk(flat, k, dim=1).indices
         v.set_mismatch += int((oracle_sel.sort(1).values != sel.sort(1).values).any(1).sum())
         low = sel_sc < (kth - band).unsqueeze(1)

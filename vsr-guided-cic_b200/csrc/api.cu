@@ -77,8 +77,8 @@ static int pad_rows(int n_valid, int bn, int alt_bn) {
   return round_up(r, 128);
 }
 
-int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int half_rows = 0, int n_valid = 0,
-               int alt_bn = 0, int alt_kb = 64) {
+int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int n_valid = 0,
+               int alt_bn = 0, int alt_kb = 64, bool scaled = false) {
   dev_free(c, b->hi); dev_free(c, b->lo);
   b->hi = b->lo = nullptr;
   if (!c->use_tc) return VSR_OK;
@@ -97,12 +97,7 @@ int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int half_rows
     VSR_TRY(make_tmap_f16(b->alt_lo, b->lo, rows, ld, ld, alt_bn, alt_kb));
     b->alt_bn = alt_bn; b->alt_kb = alt_kb;
   }
-  b->half_rows = 0;
-  if (half_rows > 0 && c->use_pair && rows % (2 * half_rows) == 0) {
-    VSR_TRY(make_tmap_f16(b->half_hi, b->hi, rows, ld, ld, half_rows));
-    VSR_TRY(make_tmap_f16(b->half_lo, b->lo, rows, ld, ld, half_rows));
-    b->half_rows = half_rows;
-  }
+  if (scaled && b->scale == nullptr) VSR_TRY(dev_alloc(c, (void**)&b->scale, 2 * sizeof(float)));
   return VSR_OK;
 }
 
@@ -225,22 +220,21 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   int bn = 128;
   if (const char* e = getenv("VSRDEC_BN")) bn = atoi(e) == 256 ? 256 : 128;
   // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128.
-  // CTA-pair kernel (default; VSRDEC_2CTA=0 disables): 256 x 192 tiles for A, 256 x 256 elsewhere.
-  if (const char* e = getenv("VSRDEC_2CTA")) c->use_pair = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_GRAPH")) c->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL")) c->use_pdl = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_ZERO_STATE")) c->zero_state_opt = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL_MODE")) c->pdl_mode = atoi(e);
   if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 96)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, 128, c->NB1v));
-  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, 128, c->NB2v)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, 128));
-  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, 128)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, 128, c->V, 144, 64));
+  // weight pairs are power-of-two scaled per tensor (F16Pair::scale)
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 0, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, c->NB1v, 0, 64, true));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, c->NB2v, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, 0, 0, 64, true));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, 0, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, c->V, 144, 64, true));
   // GEMM-A's 192-wide tile only fits 2 ring stages with 64-element k-blocks; 32-element blocks give 5
   c->WA_b.kb = 32;
   if (const char* e = getenv("VSRDEC_KB_A")) c->WA_b.kb = atoi(e) == 32 ? 32 : 64;
-  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128, 128)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn, 128));
-  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128, 128));
+  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128, 0, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn, 0, 0, 64, true));
+  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128, 0, 0, 64, true));
   VSR_TRY(pack_weights(c, w, 0));
   VSR_CHECK_CUDA(cudaStreamSynchronize(0));
   return VSR_OK;
@@ -472,7 +466,10 @@ static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int
   VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_beam_search: call vsr_prologue first");
   VSR_REQUIRE(k >= 1 && k <= VSR_MAX_BEAM, VSR_EINVAL, "vsr_beam_search: beam_size=%d not in [1,%d]", k, VSR_MAX_BEAM);
   VSR_REQUIRE(out_size >= 1 && out_size <= k, VSR_EINVAL, "vsr_beam_search: out_size=%d not in [1,beam]", out_size);
-  VSR_REQUIRE(2 * c->V >= k, VSR_EINVAL, "vsr_beam_search: vocabulary smaller than the beam");
+  VSR_REQUIRE(c->V >= k, VSR_EINVAL, "vsr_beam_search: vocabulary (%d) smaller than the beam (%d): a row has fewer than "
+              "beam distinct word candidates", c->V, k);
+  VSR_REQUIRE(c->d.seq_len <= VSR_MAX_SEQ_LEN, VSR_EINVAL, "vsr_beam_search: seq_len=%d > %d unsupported by the back-track kernel",
+              c->d.seq_len, VSR_MAX_SEQ_LEN);
   VSR_REQUIRE(eos && out_words && out_gates && lp_words && lp_gates, VSR_EINVAL, "vsr_beam_search: null argument");
   VSR_REQUIRE(!use_verbs || c->verbs != nullptr, VSR_EINVAL, "vsr_beam_search: use_verbs without a verbs tensor");
   const int b = c->b, T = c->d.seq_len;
@@ -564,6 +561,8 @@ int vsr_create(const VsrDims* dims, const float* const* weights, vsr_handle* out
 int vsr_load_weights(vsr_handle h, const float* const* weights, void* stream) {
   if (!h || !weights) { vsr::set_error("vsr_load_weights: null argument"); return VSR_EINVAL; }
   DeviceGuard dg((const vsr::Ctx*)h);
+  // the hoisted projections (U / U2 / P / img) were made with the old att_va / W_ih: the prologue must be re-run
+  ((Ctx*)h)->have_prologue = false;
   return vsr::pack_weights((Ctx*)h, weights, (cudaStream_t)stream);
 }
 

@@ -254,13 +254,16 @@ __global__ void k_greedy_pick(const int32_t* cand, const float* gate_lp, int32_t
 // final ordering of the beams by accumulated score (stable, descending) and unroll of the
 // back-pointers (CaptioningModel.py:182-194 / 279-293).  One CTA per caption: the caption's [T][k] history is
 // staged in shared memory with coalesced loads, so the serial pointer chase never waits on global memory.
-constexpr int BT_MAX_T = 64;
 __global__ void __launch_bounds__(64) k_backtrack(int b, int k, int T, int out_size, const float* seq_lp,
                                                   const int32_t* hist_parent, const int32_t* hist_word,
                                                   const int32_t* hist_gate, const float* hist_lpw, const float* hist_lpg,
                                                   int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates) {
-  __shared__ int32_t s_par[BT_MAX_T * VSR_MAX_BEAM], s_wrd[BT_MAX_T * VSR_MAX_BEAM], s_gat[BT_MAX_T * VSR_MAX_BEAM];
-  __shared__ float s_lpw[BT_MAX_T * VSR_MAX_BEAM], s_lpg[BT_MAX_T * VSR_MAX_BEAM];
+  extern __shared__ __align__(16) unsigned char bt_smem[];      // 5 arrays of T*k 4-byte entries (<= 40 KB)
+  int32_t* s_par = reinterpret_cast<int32_t*>(bt_smem);
+  int32_t* s_wrd = s_par + T * k;
+  int32_t* s_gat = s_wrd + T * k;
+  float* s_lpw = reinterpret_cast<float*>(s_gat + T * k);
+  float* s_lpg = s_lpw + T * k;
   __shared__ float s_seq[VSR_MAX_BEAM];
   const int c = blockIdx.x;
   for (int i = threadIdx.x; i < T * k; i += blockDim.x) {
@@ -393,8 +396,10 @@ int launch_greedy_pick(Ctx* c, int rows, int t, int T, int64_t* out_words, int64
 int launch_backtrack(Ctx* c, int b, int k, int T, int out_size, int64_t* out_words,
                      int64_t* out_gates, float* lp_words, float* lp_gates, cudaStream_t st) {
   PhaseScope ps(c, PH_FINAL, st);
-  VSR_REQUIRE(T <= BT_MAX_T, VSR_EINVAL, "seq_len=%d > %d unsupported by the back-track kernel", T, BT_MAX_T);
-  k_backtrack<<<b, 64, 0, st>>>(b, k, T, out_size, c->seq_lp, c->hist_parent, c->hist_word,
+  VSR_REQUIRE(T <= VSR_MAX_SEQ_LEN, VSR_EINVAL, "seq_len=%d > %d unsupported by the back-track kernel", T, VSR_MAX_SEQ_LEN);
+  // final scores come from the history slice of the last step, NOT from the ping-pong buffer c->seq_lp: a replayed
+  // CUDA graph bakes in the ping-pong parity of its capture, which need not be the host's current one (odd seq_len)
+  k_backtrack<<<b, 64, (size_t)T * k * 20, st>>>(b, k, T, out_size, c->hist_score + (size_t)(T - 1) * b * k, c->hist_parent, c->hist_word,
                                             c->hist_gate, c->hist_lpw, c->hist_lpg, out_words, out_gates,
                                             lp_words, lp_gates);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;

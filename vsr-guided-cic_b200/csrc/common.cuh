@@ -57,12 +57,13 @@ struct F16Pair {
   void* hi = nullptr;   // __half [rows][ld]
   void* lo = nullptr;
   int rows = 0, ld = 0, box_rows = 0;
-  int half_rows = 0;    // > 0 (weights only): CTA-pair GEMM, each CTA loads half_rows of a 2*half_rows-wide W tile
+  // (weights only) device [2] = {s, 1/s}: the pair holds x * s with s the power of two that brings max|x| to 2^13..2^14,
+  // so lo parts of small weights stay out of the fp16 subnormals; the GEMM epilogue multiplies the accumulator by 1/s
+  // (exact).  Null = unscaled (activations: |x| ~ 1).
+  float* scale = nullptr;
   int kb = 64;          // (weights only) k-block of the GEMMs that use this weight: 64 (128B swizzle) or 32 (64B)
   alignas(64) unsigned char map_hi[128];
   alignas(64) unsigned char map_lo[128];
-  alignas(64) unsigned char half_hi[128];
-  alignas(64) unsigned char half_lo[128];
   alignas(64) unsigned char map32_hi[128];   // 32-element k-blocks, 64-byte swizzle
   alignas(64) unsigned char map32_lo[128];
   // (weights only) alternative N tile, chosen per launch when it needs fewer waves over the 148 SMs
@@ -158,7 +159,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st);
 bool gemm_uses_tc(const Ctx* c, const GemmArgs& g);
 int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows, int kb = 64);
-int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st);
+int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st, float* scale = nullptr);
 
 // ---------------------------------------------------------------- context
 struct Phase {
@@ -203,7 +204,6 @@ struct Ctx {
   bool use_tc = true;
   bool use_alt_tiles = true;     // per-launch choice between the default and the alternative N tile (VSRDEC_ALT_TILES=0)
   int gemm_kb = 64;              // k-block of the tensor-core GEMMs (VSRDEC_KB=32: 64-byte swizzle, deeper ring)
-  bool use_pair = false;         // CTA-pair (cta_group::2) GEMM tiles: correct but measured slower (VSRDEC_2CTA=1)
   F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b;
   F16Pair WU_b, WU2_b, Wva_b;   // prologue weights
   F16Pair ds_b, img_b;          // prologue activations: slot rows [b*L*R][Fp], image descriptors [n_img][Fp]

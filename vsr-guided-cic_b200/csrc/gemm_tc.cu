@@ -40,7 +40,6 @@ constexpr int UMMA_K = 16;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_EPI_THREADS = 32 * TC_EPI_WARPS;
 constexpr int TC_THREADS = 64 + TC_EPI_THREADS;
-constexpr int TC2_THREADS = 192;          // CTA-pair experiment: four epilogue warps, row-wise plain epilogue only
 
 // KB = fp16 elements per k-block: 64 (one 128-byte swizzle row) or 32 (64-byte swizzle).  The smaller
 // block halves the stage size, i.e. doubles the ring depth that fits in 227 KB of shared memory — these
@@ -167,6 +166,7 @@ struct TcProblem {
   // EPI_VOCAB: per (row, N tile) softmax / top-k partial records instead of (or besides, when c != null) the logits
   float* vpart; int n_valid;
   int zero_acc;     // k_gemm_tc only: no main loop, the accumulator is taken as zero
+  const float* acc_scale;   // device scalar 1/s undoing the power-of-two scale of the weight's fp16 pair, or null
 };
 struct TcParams {
   TcProblem pr[2];
@@ -206,7 +206,7 @@ __device__ __forceinline__ void store4(float* f32, __half* hi, __half* lo, size_
 
 // TMEM -> tile: the two warps of quarter q write their 32 rows, each one half of the columns
 template <int BN>
-__device__ __forceinline__ void tile_dump(uint32_t tlane, float* tile, int hsel, int lane, bool zero_acc) {
+__device__ __forceinline__ void tile_dump(uint32_t tlane, float* tile, int hsel, int lane, bool zero_acc, float sc) {
   constexpr int NCH = BN / 16;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
@@ -221,7 +221,8 @@ __device__ __forceinline__ void tile_dump(uint32_t tlane, float* tile, int hsel,
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       *reinterpret_cast<float4*>(tile + tile_slot<BN>(lane, ch * 4 + j)) =
-          make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          make_float4(__uint_as_float(r[4 * j]) * sc, __uint_as_float(r[4 * j + 1]) * sc, __uint_as_float(r[4 * j + 2]) * sc,
+                      __uint_as_float(r[4 * j + 3]) * sc);
   }
 }
 
@@ -340,6 +341,7 @@ __device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_
                                               const float* s_bias, float* tile) {
   const int q = warp & 3, hsel = (warp - 2) >> 2, te = (warp - 2) * 32 + lane;
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+  const float sc = p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f;
 #ifdef VSR_DBG_CLK
   long long td = 0, tb1 = 0, tp = 0, tb2 = 0;
 #endif
@@ -349,7 +351,7 @@ __device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_
 #ifdef VSR_DBG_CLK
     const long long c0 = clock64();
 #endif
-    if (q == qq) tile_dump<BN>(tlane, tile, hsel, lane, p.zero_acc != 0);
+    if (q == qq) tile_dump<BN>(tlane, tile, hsel, lane, p.zero_acc != 0, sc);
 #ifdef VSR_DBG_CLK
     const long long c1 = clock64();
 #endif
@@ -390,6 +392,7 @@ __device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlan
 #pragma unroll
   for (int k = 0; k < VOCAB_REC - 2; ++k) cmx[k] = -INFINITY;
   float* crow = p.c + (size_t)row * p.ldc;
+  const float sc = p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if ((ch < H0) != (hsel == 0)) continue;
@@ -401,8 +404,8 @@ __device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlan
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         const float4 b = *reinterpret_cast<const float4*>(s_bias + ch * 16 + j);
-        v[j] = __uint_as_float(r[j]) + b.x; v[j + 1] = __uint_as_float(r[j + 1]) + b.y;
-        v[j + 2] = __uint_as_float(r[j + 2]) + b.z; v[j + 3] = __uint_as_float(r[j + 3]) + b.w;
+        v[j] = __uint_as_float(r[j]) * sc + b.x; v[j + 1] = __uint_as_float(r[j + 1]) * sc + b.y;
+        v[j + 2] = __uint_as_float(r[j + 2]) * sc + b.z; v[j + 3] = __uint_as_float(r[j + 3]) * sc + b.w;
         *reinterpret_cast<float4*>(crow + n + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
       if (n + 16 > p.n_valid) {
@@ -494,6 +497,7 @@ __device__ __forceinline__ void rowwise_plain(const TcProblem& p, uint32_t tmem_
   const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
   float* crow = p.c + (size_t)row * p.ldc;
   constexpr int NCH = BN / 16;
+  const float sc = p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f;
   const int c_lo = hsel * NCH / nsplit, c_hi = (hsel + 1) * NCH / nsplit;
 #pragma unroll 1
   for (int ch = c_lo; ch < c_hi; ++ch) {       // 16 accumulator columns per TMEM load: any BN % 16 == 0
@@ -503,8 +507,8 @@ __device__ __forceinline__ void rowwise_plain(const TcProblem& p, uint32_t tmem_
     if (!live) continue;
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                             __uint_as_float(r[j + 3]));
+      float4 o = make_float4(__uint_as_float(r[j]) * sc, __uint_as_float(r[j + 1]) * sc, __uint_as_float(r[j + 2]) * sc,
+                             __uint_as_float(r[j + 3]) * sc);
       if (p.bias != nullptr) add4(o, __ldg(reinterpret_cast<const float4*>(p.bias + n + j)));
       if (radd != nullptr) add4(o, __ldg(reinterpret_cast<const float4*>(radd + n + j)));
       if (cadd != nullptr) add4(o, *reinterpret_cast<const float4*>(cadd + n + j));
@@ -820,180 +824,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
   }
 }
 
-// ---------------------------------------------------------------- CTA-pair variant (cta_group::2)
-// Two CTAs of a cluster (one TPC) compute a 256 x BN tile: each CTA stages its own 128 rows of A and HALF
-// of the W tile (BN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) which reads both
-// halves, and each CTA ends up with its 128 x BN accumulator half in its own TMEM.  Operand bytes pulled
-// from L2 per output drop by ~2x versus the 128 x 128 single-CTA tile, which is what bounds these skinny
-// three-pass GEMMs (measured: the single-CTA kernel saturates the L2->SM fabric, not the tensor pipe).
-template <int BN> struct Tc2Cfg {
-  static constexpr int kStages = 3;
-  static constexpr int kABytes = BM * BK * 2;                 // 16 KB   (this CTA's 128 rows)
-  static constexpr int kWBytes = (BN / 2) * BK * 2;           // 12/16 KB (this CTA's half of the W tile)
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
-  static constexpr int kTmemCols = 256;
-};
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive (count 1) on the same mbarrier of CTA `rank` of this cluster
-__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
-  asm volatile(
-      "{\n\t"
-      ".reg .b32 ra;\n\t"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
-}
-// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-// commit: arrive on the same mbarrier in BOTH CTAs of the pair once the issued MMAs have completed
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc_pair() {   // M = 256
-  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-}
-
-template <int BN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
-k_gemm_tc2(const __grid_constant__ TcParams params) {
-  using Cfg = Tc2Cfg<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];     // used in the leader CTA only
-  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
-  __shared__ uint32_t tmem_base_slot;
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();         // 0 = leader (issues the MMAs), 1 = peer
-  // pair tile of this cluster: problems back to back; consecutive clusters walk the M pairs of one W tile
-  int t = blockIdx.x >> 1;
-  const int m_pairs0 = (params.pr[0].m_tiles + 1) >> 1;
-  const int tiles0 = params.pr[0].n_tiles * m_pairs0;
-  const int pi = (params.nprob > 1 && t >= tiles0) ? 1 : 0;
-  t -= pi * tiles0;
-  const TcProblem& p = params.pr[pi];
-  const int m_pairs = (p.m_tiles + 1) >> 1;
-  const int m_pair = t % m_pairs, n_tile = t / m_pairs;
-  const int m0 = (m_pair * 2 + (int)rank) * BM, n0 = n_tile * BN;
-
-  if (p.row_skip != nullptr) {   // pair-uniform: skip only when all 256 rows of the pair are padding
-    int any = 0;
-    for (int r = threadIdx.x; r < 2 * BM; r += TC2_THREADS) {
-      const int row = m_pair * 2 * BM + r;
-      if (row < p.M) any |= p.row_skip[row];
-    }
-    if (!__syncthreads_or(any)) return;
-  }
-
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); }
-    prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
-  }
-  if (warp == 1) {
-    if (lane == 0) {
-      for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-      mbar_init(&tmem_full_bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  cluster_sync_all();            // barriers of both CTAs initialised, TMEM allocated in both
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = tmem_base_slot;
-
-  int total_kb = 0;
-  for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
-
-  if (warp == 0) {
-    if (lane == 0) {
-      int seg = 0, kk = 0;
-      const int wrow = n0 + (int)rank * (BN / 2);     // this CTA's half of the W tile
-      for (int kb = 0; kb < total_kb; ++kb) {
-        const int st = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[st], ph ^ 1);
-        uint8_t* base = smem + st * Cfg::kStageBytes;
-        if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
-        tma_load_2d_pair(&p.a_hi[seg], &full_bar[st], base, kk * BK, m0);
-        tma_load_2d_pair(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * BK, wrow);
-        tma_load_2d_pair(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * BK, wrow);
-        tma_load_2d_pair(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * BK, m0);
-        if (rank != 0) mbar_arrive_cluster(&full_bar[st], 0);
-        if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
-      constexpr uint32_t idesc = make_idesc_pair<BN>();
-      for (int kb = 0; kb < total_kb; ++kb) {
-        const int st = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[st], ph);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
-        const uint64_t ah = make_sw128_desc(base), al = make_sw128_desc(base + Cfg::kABytes);
-        const uint64_t wh = make_sw128_desc(base + 2 * Cfg::kABytes);
-        const uint64_t wl = make_sw128_desc(base + 2 * Cfg::kABytes + Cfg::kWBytes);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
-          umma_f16_pair(tmem_base, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_f16_pair(tmem_base, ah + off, wl + off, idesc, 1u);
-          umma_f16_pair(tmem_base, al + off, wh + off, idesc, 1u);
-        }
-        umma_commit_pair(&empty_bar[st]);     // frees this stage in BOTH CTAs
-      }
-      umma_commit_pair(&tmem_full_bar);       // accumulators complete in both CTAs -> epilogues
-    }
-    __syncwarp();
-  } else {
-    mbar_wait(&tmem_full_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    rowwise_plain<BN>(p, tmem_base, m0, n0, warp, lane, 0, 1);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  // neither CTA may release TMEM / exit while the pair's MMAs or the other epilogue are still running
-  cluster_sync_all();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
-  }
-}
-
 // x -> (fp16 hi, fp16 lo) with lo = fp16(x - hi)
+// scale != null: x is multiplied by the power of two scale[0] first (weights, see F16Pair::scale)
 __global__ void k_split_f16(const float* __restrict__ x, __half* __restrict__ hi,
-                             __half* __restrict__ lo, size_t n) {
+                             __half* __restrict__ lo, size_t n, const float* __restrict__ scale) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = fminf(fmaxf(x[i], -65504.f), 65504.f);   // saturate instead of overflowing to inf
+  const float s = scale != nullptr ? scale[0] : 1.f;
+  const float v = fminf(fmaxf(x[i] * s, -65504.f), 65504.f);   // saturate instead of overflowing to inf
   const __half h = __float2half_rn(v);
   hi[i] = h;
   lo[i] = __float2half_rn(v - __half2float(h));
@@ -1032,9 +870,34 @@ int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, i
   return VSR_OK;
 }
 
-int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st) {
+// max |x| as the bit pattern of a non-negative float (monotone as unsigned)
+__global__ void k_absmax(const float* __restrict__ x, size_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(x[i]);
+    if (v == v && v < INFINITY) m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+// scale[0] = 2^e with max|x| * 2^e in (2^13, 2^14]  (1 for an all-zero tensor), scale[1] = 2^-e
+__global__ void k_pick_scale(float* scale) {
+  const float m = __uint_as_float(*reinterpret_cast<unsigned*>(scale));
+  int e = 0;
+  if (m > 0.f) { int ex; frexpf(m, &ex); e = 14 - ex; }     // m = f * 2^ex, f in [0.5, 1)
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  scale[0] = ldexpf(1.f, e);
+  scale[1] = ldexpf(1.f, -e);
+}
+
+int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st, float* scale) {
   if (n == 0) return VSR_OK;
-  k_split_f16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (__half*)hi, (__half*)lo, n);
+  if (scale != nullptr) {
+    VSR_CHECK_CUDA(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
+    k_absmax<<<296, 256, 0, st>>>(x, n, reinterpret_cast<unsigned*>(scale));
+    k_pick_scale<<<1, 1, 0, st>>>(scale);
+  }
+  k_split_f16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (__half*)hi, (__half*)lo, n, scale);
   VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }
@@ -1054,13 +917,11 @@ int tc_gemm_init() {
   TCP_SET_SMEM(128, 64); TCP_SET_SMEM(144, 64); TCP_SET_SMEM(192, 32); TCP_SET_SMEM(192, 64); TCP_SET_SMEM(128, 32);
 #undef TCP_SET_SMEM
 #undef TC_SET_SMEM
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<256>::kSmemBytes));
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_tc2<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<192>::kSmemBytes));
   if (dev < 64) done_mask |= 1ull << dev;
   return VSR_OK;
 }
 
-static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = false, int kb = 64) {
+static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64) {
   VSR_REQUIRE(g.M > 0 && g.N >= round_up(g.wb->n_valid, BN), VSR_EINVAL, "launch_gemm_tc: N=%d too small for N tile %d", g.N, BN);
   p->nseg = g.nseg;
   for (int s = 0; s < g.nseg; ++s) {
@@ -1069,9 +930,10 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
     memcpy(&p->a_lo[s], kb == 32 ? g.seg[s].b->map32_lo : g.seg[s].b->map_lo, sizeof(CUtensorMap));
     p->kblocks[s] = g.seg[s].k / kb;
   }
-  const bool alt = !pair && BN == g.wb->alt_bn && BN != g.wb->box_rows;
-  memcpy(&p->w_hi, pair ? g.wb->half_hi : alt ? g.wb->alt_hi : (kb == 32 ? g.wb->map32_hi : g.wb->map_hi), sizeof(CUtensorMap));
-  memcpy(&p->w_lo, pair ? g.wb->half_lo : alt ? g.wb->alt_lo : (kb == 32 ? g.wb->map32_lo : g.wb->map_lo), sizeof(CUtensorMap));
+  const bool alt = BN == g.wb->alt_bn && BN != g.wb->box_rows;
+  memcpy(&p->w_hi, alt ? g.wb->alt_hi : (kb == 32 ? g.wb->map32_hi : g.wb->map_hi), sizeof(CUtensorMap));
+  memcpy(&p->w_lo, alt ? g.wb->alt_lo : (kb == 32 ? g.wb->map32_lo : g.wb->map_lo), sizeof(CUtensorMap));
+  p->acc_scale = g.wb->scale != nullptr ? g.wb->scale + 1 : nullptr;
   p->n_tiles = (g.wb->n_valid + BN - 1) / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
   p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
   p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
@@ -1085,13 +947,12 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
     if (f.vocab_tiles_out != nullptr) *f.vocab_tiles_out = p->n_tiles;
     if (f.vocab_bn_out != nullptr) *f.vocab_bn_out = BN;
   } else if (f.mode != 0) {
-    VSR_REQUIRE(!pair && ((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && BN == 128)), VSR_EINVAL,
-                "launch_gemm_tc: fused cell mode %d does not fit N tile %d%s", f.mode, BN, pair ? " (CTA-pair kernel: plain only)" : "");
+    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && BN == 128), VSR_EINVAL,
+                "launch_gemm_tc: fused cell mode %d does not fit N tile %d", f.mode, BN);
     p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_hi = (__half*)f.h_hi; p->h_lo = (__half*)f.h_lo;
     p->s_new = f.s_new; p->s_hi = (__half*)f.s_hi; p->s_lo = (__half*)f.s_lo; p->gq = f.gq;
   }
-  VSR_REQUIRE(f.gt_cols == 0 || (!pair && (BN == 128 || BN == 192)), VSR_EINVAL, "launch_gemm_tc: g_t fusion needs a 128- or 192-wide tile");
-  VSR_REQUIRE(f.mode != EPI_VOCAB || !pair, VSR_EINVAL, "launch_gemm_tc: vocabulary epilogue is not available in the CTA-pair kernel");
+  VSR_REQUIRE(f.gt_cols == 0 || BN == 128 || BN == 192, VSR_EINVAL, "launch_gemm_tc: g_t fusion needs a 128- or 192-wide tile");
   p->zero_acc = g.zero_acc ? 1 : 0;
   p->ld_state = f.ld_state;
   p->gt_cols = f.gt_cols; p->gt_gq = f.gt_gq; p->gt_c1n = f.gt_c1n; p->g_t = f.g_t;
@@ -1100,30 +961,8 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, bool pair = fal
 }
 
 // g2 (optional) is an independent problem with the same N tile that shares the launch
-// CTA-pair launch: 256 x BN2 tiles, BN2 = 2 * (rows of the weight's half-tile tensor map)
-static int launch_gemm_tc_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
-  const int BN = 2 * g.wb->half_rows;
-  VSR_REQUIRE(BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc_pair: unsupported N tile %d", BN);
-  VSR_REQUIRE(g2 == nullptr || 2 * g2->wb->half_rows == BN, VSR_EINVAL, "launch_gemm_tc_pair: grouped problems need one tile shape");
-  TcParams p;
-  memset(&p, 0, sizeof(p));
-  VSR_TRY(fill_problem(&p.pr[0], g, BN, true));
-  p.nprob = 1;
-  int pairs = p.pr[0].n_tiles * ((p.pr[0].m_tiles + 1) / 2);
-  if (g2 != nullptr) {
-    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, true));
-    p.nprob = 2;
-    pairs += p.pr[1].n_tiles * ((p.pr[1].m_tiles + 1) / 2);
-  }
-  if (BN == 256) k_gemm_tc2<256><<<2 * pairs, TC2_THREADS, Tc2Cfg<256>::kSmemBytes, st>>>(p);
-  else k_gemm_tc2<192><<<2 * pairs, TC2_THREADS, Tc2Cfg<192>::kSmemBytes, st>>>(p);
-  VSR_CHECK_CUDA(cudaGetLastError());
-  return VSR_OK;
-}
-
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   VSR_TRY(tc_gemm_init());
-  if (g.wb->half_rows > 0 && (g2 == nullptr || g2->wb->half_rows > 0)) return launch_gemm_tc_pair(g, g2, st);
   int BN = g.wb->box_rows;
   VSR_REQUIRE(BN == 128 || BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc: unsupported N tile %d", BN);
   VSR_REQUIRE(g2 == nullptr || g2->wb->box_rows == BN, VSR_EINVAL, "launch_gemm_tc: grouped problems need one tile shape");
@@ -1146,12 +985,12 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
     //  order of the row's log-sum-exp, must not depend on how many rows the launch has)
     if (cost(g.wb->alt_bn) < cost(BN) || g.cell.mode == EPI_VOCAB) { BN = g.wb->alt_bn; kb = g.wb->alt_kb; }
   }
-  VSR_TRY(fill_problem(&p.pr[0], g, BN, false, kb));
+  VSR_TRY(fill_problem(&p.pr[0], g, BN, kb));
   p.nprob = 1;
   p.pdl_flags = g.pdl_flags;
   int tiles = p.pr[0].n_tiles * p.pr[0].m_tiles;
   if (g2 != nullptr) {
-    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, false, kb));
+    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, kb));
     p.nprob = 2;
     tiles += p.pr[1].n_tiles * p.pr[1].m_tiles;
   }

@@ -321,8 +321,8 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
                    {c->WD, &c->WD_b, (size_t)c->ND * c->KD}, {c->WE, &c->WE_b, (size_t)c->NE * Hp}};
   for (const Tw& t : tw) {
     if (t.b->hi == nullptr || t.f == nullptr) continue;
-    VSR_TRY(launch_split_f16(t.f, t.b->hi, t.b->lo, t.n, st));
-    c->launches++;
+    VSR_TRY(launch_split_f16(t.f, t.b->hi, t.b->lo, t.n, st, t.b->scale));
+    c->launches += t.b->scale != nullptr ? 3 : 1;
   }
   return VSR_OK;
 }

@@ -855,7 +855,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
     g.zero_acc = io.zero_state;           // [h2 | h1] = 0 at t = 0: pre1 = U[caption] + X[bos], no main loop
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
-    fused = gemm_uses_tc(c, g) && !c->use_pair;    // the CTA-pair experiment has plain epilogues only
+    fused = gemm_uses_tc(c, g);
     c->state_h32 = !fused || io.need_h32;
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
       // fp32 copies of h1', s_t (and g_t, att, h2' below) feed only the FFMA twin and vsr_step's outputs: the

@@ -31,8 +31,10 @@ class DecodePipeline:
         self.post = post
         self.n_lanes = len(self.models)
         self.n_buf = buffers if buffers is not None else 2 * self.n_lanes
-        if self.n_buf < self.n_lanes:
-            raise ValueError("DecodePipeline needs at least one input buffer per lane")
+        # results are staged per input slot and collected one step late: with a single slot step s+1 would overwrite
+        # (and re-record the event of) step s before it has been handed out
+        if self.n_buf < max(2, self.n_lanes):
+            raise ValueError("DecodePipeline needs at least two input buffers and at least one per lane")
         self.lanes = [torch.cuda.Stream(self.device) for _ in range(self.n_lanes)]
         self.copy_stream = torch.cuda.Stream(self.device)
         self._bufs: List[Optional[Tuple[torch.Tensor, ...]]] = [None] * self.n_buf
