@@ -183,6 +183,10 @@ const char* vsr_gemm_kind(vsr_handle h);
  * returns the number of phases written, or a negative error. */
 int vsr_set_profiling(vsr_handle h, int32_t enabled);
 int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* launches, int32_t cap);
+/* Device time of every decoder step (decoder step + beam selection/reorder) of the last vsr_beam_search run with
+ * profiling enabled: CUDA events between the steps on the launching stream (SURVEY.md 8d "p50 per-step latency").
+ * ms is a [host] array of capacity cap; returns the number of steps written, or a negative error. */
+int vsr_get_step_times(vsr_handle h, float* ms, int32_t cap);
 
 #ifdef __cplusplus
 }

@@ -211,8 +211,21 @@ def _full_check(tag, d, W, m, statics, k, use_verbs, gt, table=None, min_identic
     (w, g), (lw, lg), hist, _ = device_beam(m, _cuda(*statics), [3, -1], k, 1, use_verbs, gt, trace=False)
     v, o_outs, o_lps = verify_device_beam(W, d, statics, [3, -1], k, hist, use_verbs, gt, table)
     assert not v.violations, v.violations[:5]
-    assert torch.equal(w.cpu(), o_outs[0][:, :1]) and torch.equal(g.cpu(), o_outs[1][:, :1])
-    assert rel_close(lw.cpu(), o_lps[0][:, :1], REL, ABS) and rel_close(lg.cpu(), o_lps[1][:, :1], REL, ABS)
+    # Returned caption: the oracle, replaying the device's trajectory, unrolls all k final beams sorted by ITS scores.
+    # The device's best beam must be the oracle's best one, or one whose final score ties with it inside the band
+    # (raw random-init weights: final scores of different beams routinely agree to ~1e-5 at |score| ~ 170).
+    b = w.shape[0]
+    T = d.seq_len
+    ow, og = o_outs[0].reshape(b, -1, T), o_outs[1].reshape(b, -1, T)
+    olw, olg = o_lps[0].reshape(b, -1, T), o_lps[1].reshape(b, -1, T)
+    dev_final = hist[3][-1].cpu().sort(1, descending=True).values
+    for c in range(b):
+        hit = [r for r in range(ow.size(1)) if torch.equal(ow[c, r], w[c, 0].cpu()) and torch.equal(og[c, r], g[c, 0].cpu())]
+        assert hit, f"{tag}: caption {c} is not the unroll of any final beam of its own trajectory"
+        r = hit[0]
+        band = 2e-3 + 2e-5 * float(dev_final[c, 0].abs())
+        assert r == 0 or float(dev_final[c, 0] - dev_final[c, r]) <= band, f"{tag}: caption {c} returned beam {r}"
+        assert rel_close(lw[c, 0].cpu(), olw[c, r], REL, ABS) and rel_close(lg[c, 0].cpu(), olg[c, r], REL, ABS)
     with torch.no_grad():
         ref_o, _ = O.beam_search(W, d, statics, [3, -1], k, 1, use_verbs=use_verbs, gt=gt, verb_table=table)
     same_w = (ref_o[0].reshape(w.shape[0], -1) == w.cpu().reshape(w.shape[0], -1)).all(1)
@@ -569,10 +582,11 @@ def test_other_launch_shapes_against_oracle(b, k, out_size, vocab):
 
 
 # ----------------------------------------------------------------------------- throughput pipeline (host loop)
-@pytest.mark.parametrize("indexed", [False, True])
-def test_decode_pipeline_matches_direct_calls(indexed):
-    """vsrdec.DecodePipeline (two lanes, four input buffers, async read-back) must hand out, in order, exactly what
-    direct beam_search_v[_indexed] calls return for the same batches — seven different batches through four buffers."""
+@pytest.mark.parametrize("indexed,stack", [(False, 1), (True, 1), (False, 3), (True, 2)])
+def test_decode_pipeline_matches_direct_calls(indexed, stack):
+    """vsrdec.DecodePipeline (two lanes, four input buffers, async read-back, `stack` batches per decode call) must hand
+    out, per batch and in order, exactly what direct beam_search_v[_indexed] calls return for the same batches — seven
+    different batches through four buffers (with stacking: groups of `stack`, the last one partial)."""
     from gpu_common import make_model
     from vsrdec import DecodePipeline
     d = O.Dims()
@@ -587,7 +601,9 @@ def test_decode_pipeline_matches_direct_calls(indexed):
             batches.append(O.synth_inputs(12, 50, 10, 20, 2048, seed=3000 + i, vocab_size=d.vocab_size, n_det_range=(10, 50),
                                           verb_slots=(2,), verb_vocab_id=17))
     pinned = [tuple(t.pin_memory() for t in b_) for b_ in batches]
-    pipe = DecodePipeline(models, [3, -1], 5, 1, gt=True, indexed=indexed, buffers=4)
+    pipe = DecodePipeline(models, [3, -1], 5, 1, gt=True, indexed=indexed, buffers=4, stack=stack)
+    with pytest.raises(ValueError):
+        DecodePipeline(models[:1], [3, -1], 5, 1, gt=True, buffers=1)     # results are collected one decode late
     got = list(pipe.run(iter(pinned)))
     assert len(got) == len(batches)
     fn = models[0].beam_search_v_indexed if indexed else models[0].beam_search_v

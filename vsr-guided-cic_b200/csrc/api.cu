@@ -222,6 +222,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128.
   if (const char* e = getenv("VSRDEC_GRAPH")) c->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL")) c->use_pdl = atoi(e) != 0;
+  if (const char* e = getenv("VSRDEC_FUSE_TAIL")) c->fuse_tail = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_ZERO_STATE")) c->zero_state_opt = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL_MODE")) c->pdl_mode = atoi(e);
   if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
@@ -263,7 +264,7 @@ static int run_graphed(Ctx* c, const Ctx::GraphKey& key, cudaStream_t st, Enqueu
   bool seen = false;
   for (auto& s : c->graph_seen) seen = seen || memcmp(&s, &key, sizeof(key)) == 0;
   if (!seen) {
-    if (c->graph_seen.size() >= 16) c->graph_seen.erase(c->graph_seen.begin());
+    if (c->graph_seen.size() >= 32) c->graph_seen.erase(c->graph_seen.begin());
     c->graph_seen.push_back(key);
     return enqueue(st);
   }
@@ -281,7 +282,7 @@ static int run_graphed(Ctx* c, const Ctx::GraphKey& key, cudaStream_t st, Enqueu
   const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
   VSR_CHECK_CUDA(ie);
-  if (c->graphs.size() >= 8) {      // evict the least recently used
+  if (c->graphs.size() >= 16) {     // evict the least recently used
     size_t lru = 0;
     for (size_t i = 1; i < c->graphs.size(); ++i) if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
     cudaGraphExecDestroy(c->graphs[lru].exec);
@@ -435,12 +436,21 @@ static int enqueue_beam_steps(Ctx* c, int k, const int64_t* eos, int use_verbs, 
   const int b = c->b, T = c->d.seq_len;
   VSR_TRY(launch_state_init(c, b, st));
   const bool have_forced = tr && tr->forced_beam && tr->forced_word && tr->forced_gate;
+  if (c->profiling) {          // per-step latency: one event before every step and one after the last
+    for (cudaEvent_t e : c->step_ev) cudaEventDestroy(e);
+    c->step_ev.clear();
+  }
   for (int t = 0; t < T; ++t) {
+    if (c->profiling) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); c->step_ev.push_back(e); }
+    }
     const int cur = t == 0 ? 1 : k;
     const int rows = b * cur;
     StepIO io{};
     io.rows = rows; io.cur_beam = cur; io.use_verbs = use_verbs != 0; io.gt = gt != 0; io.topk = k;
     io.zero_state = t == 0 && c->zero_state_opt;
+    io.defer_head = c->fuse_tail;
     if (tr && tr->step_out) { io.out_logp = tr->step_out + (size_t)t * b * k * c->V; io.out_stride = c->V; }
     if (tr && tr->step_gate) { io.gate_out = tr->step_gate + (size_t)t * b * k * 2; io.gate_stride = 2; }
     VSR_TRY(run_step(c, io, st));
@@ -448,6 +458,10 @@ static int enqueue_beam_steps(Ctx* c, int k, const int64_t* eos, int use_verbs, 
     VSR_TRY(launch_beam_step(c, t, b, cur, k, eos[0], eos[1], have_forced ? tr->forced_beam + fo : nullptr,
                              have_forced ? tr->forced_word + fo : nullptr,
                              have_forced ? tr->forced_gate + fo : nullptr, t + 1 < T, st));
+  }
+  if (c->profiling) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) { cudaEventRecord(e, st); c->step_ev.push_back(e); }
   }
   return VSR_OK;
 }
@@ -572,6 +586,7 @@ void vsr_destroy(vsr_handle h) {
   DeviceGuard dg(c);
   cudaDeviceSynchronize();
   vsr::reset_phases(c);
+  for (cudaEvent_t e : c->step_ev) cudaEventDestroy(e);
   vsr::drop_graphs(c);
   if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
   for (void* p : c->owned) cudaFree(p);
@@ -699,6 +714,20 @@ int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* la
     if (ms) ms[n] = total;
     if (launches) launches[n] = c->phases[i].launches;
     ++n;
+  }
+  return n;
+}
+
+int vsr_get_step_times(vsr_handle h, float* ms, int32_t cap) {
+  if (!h) { vsr::set_error("vsr_get_step_times: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
+  Ctx* c = (Ctx*)h;
+  VSR_CHECK_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (size_t j = 0; j + 1 < c->step_ev.size() && n < cap; ++j, ++n) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, c->step_ev[j], c->step_ev[j + 1]) != cudaSuccess) t = -1.f;
+    if (ms) ms[n] = t;
   }
   return n;
 }

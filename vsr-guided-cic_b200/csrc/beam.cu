@@ -8,14 +8,11 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "vocab_head.cuh"
 
 namespace vsr {
 
 namespace {
-
-__device__ __forceinline__ bool before(float v1, int i1, float v2, int i2) {
-  return v1 > v2 || (v1 == v2 && i1 < i2);
-}
 
 // log-prob of vocabulary entry `word` in row `row` as returned by the step (post verb forcing)
 __device__ __forceinline__ float row_logp(const float* logits, int ld, const float* row_max,
@@ -24,6 +21,15 @@ __device__ __forceinline__ float row_logp(const float* logits, int ld, const flo
   if (f >= 0) return word == f ? 0.f : -1e6f;
   return (logits[(size_t)row * ld + word] - row_max[row]) - row_lsum[row];
 }
+
+// Heads of a caption's rows left in shared memory by the merge warps of the fused tail kernel (k_tail): the selection
+// then needs no global round trip for the candidates, their log-probs, the gate log-probs and the row statistics.
+struct HeadSmem {
+  float mx[VSR_MAX_BEAM], ls[VSR_MAX_BEAM], gate[VSR_MAX_BEAM][2];
+  int forced[VSR_MAX_BEAM];
+  int cand[VSR_MAX_BEAM][VSR_MAX_BEAM];
+  float wlp[VSR_MAX_BEAM][VSR_MAX_BEAM];      // post-forcing word log-prob of every candidate
+};
 
 struct BeamArgs {
   int t, b, cur, k, V;
@@ -38,7 +44,20 @@ struct BeamArgs {
   int32_t *hist_parent, *hist_word, *hist_gate;    // [T][b][k] slices for step t
   float *hist_score, *hist_lpw, *hist_lpg;
   const int32_t *f_beam, *f_word, *f_gate;        // forced selections for step t or null
+  const HeadSmem* hs;                              // k_tail: the rows' heads in shared memory (else read from global)
 };
+
+// post-forcing word log-prob of `word` in beam row j (global row `row`) of the caption
+__device__ __forceinline__ float pick_logp(const BeamArgs& a, int row, int j, int word) {
+  if (a.hs == nullptr) return row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+  const int f = a.hs->forced[j];
+  if (f >= 0) return word == f ? 0.f : -1e6f;
+  for (int i = 0; i < a.k; ++i) if (a.hs->cand[j][i] == word) return a.hs->wlp[j][i];
+  return (a.logits[(size_t)row * a.ld + word] - a.hs->mx[j]) - a.hs->ls[j];     // trajectory replay / frozen beams
+}
+__device__ __forceinline__ float gate_logp(const BeamArgs& a, int row, int j, int g) {
+  return a.hs == nullptr ? a.gate_lp[row * 2 + g] : a.hs->gate[j][g];
+}
 
 constexpr int MAXC = 2 * VSR_MAX_BEAM * VSR_MAX_BEAM;  // 128 candidates per caption
 
@@ -79,9 +98,13 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
         const int row = c * cur + j;
         int word; float sc;
         if (s_full[j]) {
-          word = a.cand[row * VSR_MAX_BEAM + i];
-          const float wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
-          sc = __fadd_rn(s_seq[j], __fadd_rn(wl, a.gate_lp[row * 2 + g]));   // seq + (word + gate), :139
+          float wl;
+          if (a.hs != nullptr) { word = a.hs->cand[j][i]; wl = a.hs->wlp[j][i]; }
+          else {
+            word = a.cand[row * VSR_MAX_BEAM + i];
+            wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+          }
+          sc = __fadd_rn(s_seq[j], __fadd_rn(wl, gate_logp(a, row, j, g)));   // seq + (word + gate), :139
         } else {
           // frozen beam: old score at word 0 (both gates), -999 elsewhere (:146-150)
           word = i;
@@ -117,8 +140,8 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
     const int row = c * cur + j;
     float sc;
     if (s_full[j]) {
-      const float wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
-      sc = __fadd_rn(s_seq[j], __fadd_rn(wl, a.gate_lp[row * 2 + g]));
+      const float wl = pick_logp(a, row, j, word);
+      sc = __fadd_rn(s_seq[j], __fadd_rn(wl, gate_logp(a, row, j, g)));
     } else {
       sc = (word == 0) ? s_seq[j] : -999.f;
     }
@@ -131,8 +154,8 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
     const int row = c * cur + j;
     const int o = c * k + lane;
     // per-token log-probs of the pick, in slot order, masked by the parent's sticky masks (:145,175-177)
-    float lw = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
-    float lg = a.gate_lp[row * 2 + g];
+    float lw = pick_logp(a, row, j, word);
+    float lg = gate_logp(a, row, j, g);
     if (a.t > 0) { lw *= s_m0[j]; lg *= s_m1[j]; }
     a.sel_beam[o] = j; a.sel_word[o] = word; a.sel_gate[o] = g;
     a.seq_lp_n[o] = s_ps[lane];
@@ -211,6 +234,69 @@ __global__ void __launch_bounds__(256) k_beam_step(const BeamArgs b, const Advan
   __syncthreads();
   if (!do_advance) return;
   advance_row(a, c * b.k + i, c * b.cur + sh.pb[i], (int64_t)sh.pw[i], sh.pg[i]);
+}
+
+// Fused tail of a beam-search step, one CTA per CAPTION: warp j finishes the vocabulary head of beam row j (merge_row:
+// softmax statistics, exact top-k words, gate head, verb forcing), warp 0 then selects the caption's k best (parent,
+// word, gate) candidates out of shared memory, and the whole CTA moves the k new beam rows' states.  One launch instead
+// of k_vocab_merge + k_beam_step, no global round trip between merge and selection, one merge per row.
+constexpr int TAIL_THREADS = 512;
+__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const SoftmaxArgs m, const float* __restrict__ vpart, int n_tiles,
+                                                       int nch, BeamArgs b, const AdvanceArgs a, int do_advance) {
+  __shared__ BeamSmem sh;
+  __shared__ HeadSmem hs;
+  const int c = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  pdl_trigger();
+  pdl_wait();
+  if (warp < b.cur) {
+    RowHead h;
+    merge_row(m, vpart, n_tiles, nch, c * b.cur + warp, lane, h);
+    if (lane == 0) {
+      hs.mx[warp] = h.mx; hs.ls[warp] = h.lsum; hs.forced[warp] = h.forced;
+      hs.gate[warp][0] = h.g0; hs.gate[warp][1] = h.g1;
+    }
+    if (lane < m.topk) {
+      hs.cand[warp][lane] = h.pick;
+      hs.wlp[warp][lane] = h.forced >= 0 ? (h.pick == h.forced ? 0.f : -1e6f) : (h.pick_logit - h.mx) - h.lsum;
+    }
+  }
+  __syncthreads();
+  b.hs = &hs;
+  if (warp == 0) beam_select_warp(b, sh, c, lane, true);
+  __syncthreads();
+  if (!do_advance) return;
+  // move the k new rows: (row i, 16-byte piece) flattened over the CTA
+  const int k = b.k, Hp = a.Hp;
+  const int p4 = Hp / 4;                      // float4 pieces of an fp32 state row
+  for (int idx = threadIdx.x; idx < k * p4; idx += TAIL_THREADS) {
+    const int i = idx / p4, e = (idx - i * p4) * 4;
+    const size_t so = (size_t)(c * b.cur + sh.pb[i]) * Hp + e, dof = (size_t)(c * k + i) * Hp + e;
+    if (a.h1n != nullptr) {
+      *reinterpret_cast<float4*>(a.h1 + dof) = *reinterpret_cast<const float4*>(a.h1n + so);
+      *reinterpret_cast<float4*>(a.h2 + dof) = *reinterpret_cast<const float4*>(a.h2n + so);
+    }
+    *reinterpret_cast<float4*>(a.c1 + dof) = *reinterpret_cast<const float4*>(a.c1n + so);
+    *reinterpret_cast<float4*>(a.c2 + dof) = *reinterpret_cast<const float4*>(a.c2n + so);
+  }
+  if (a.h1_hi != nullptr) {
+    const int p8 = Hp / 8;                    // uint4 pieces of an fp16 row
+    for (int idx = threadIdx.x; idx < k * p8; idx += TAIL_THREADS) {
+      const int i = idx / p8, e = idx - i * p8;
+      const size_t sv = (size_t)(c * b.cur + sh.pb[i]) * p8 + e, dv = (size_t)(c * k + i) * p8 + e;
+      a.h1_hi[dv] = a.h1n_hi[sv]; a.h1_lo[dv] = a.h1n_lo[sv];
+      a.h2_hi[dv] = a.h2n_hi[sv]; a.h2_lo[dv] = a.h2n_lo[sv];
+    }
+  }
+  if (threadIdx.x < k) {
+    const int i = threadIdx.x, n = c * k + i, p = c * b.cur + sh.pb[i];
+    int w = sh.pw[i];
+    w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
+    a.word_idx[n] = w;
+    int s = a.ptr[p] + sh.pg[i];                                   // ctrl_det_idxs + prev gate, clamped (:139-140)
+    s = s < 0 ? 0 : (s > a.L - 1 ? a.L - 1 : s);
+    a.ptrn[n] = s;
+  }
 }
 
 // zero state, slot 0, input word = bos   (init_state, controllable_captioning.py:109-115, :136)
@@ -352,7 +438,14 @@ int launch_beam_step(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t
   AdvanceArgs ad{};
   ad.rows_new = b * k; ad.cur = cur; ad.k = k; ad.fixed_slot = -1;
   fill_advance(c, ad);
-  VSR_CHECK_CUDA(launch_k(k_beam_step, dim3(b, advance ? k : 1), dim3(256), 0, st, c->use_pdl && (c->pdl_mode & 2), a, ad, advance ? 1 : 0));
+  if (c->head_deferred) {      // the step left its vocabulary head to this launch (run_step, StepIO::defer_head)
+    SoftmaxArgs m = make_softmax_args(c, b * cur, cur, k, c->head_use_verbs, c->head_gt);
+    VSR_CHECK_CUDA(launch_k(k_tail, dim3(b), dim3(TAIL_THREADS), 0, st, c->use_pdl && (c->pdl_mode & 2), m, (const float*)c->vpart,
+                            c->head_tiles, c->head_nch, a, ad, advance ? 1 : 0));
+    c->head_deferred = false;
+  } else {
+    VSR_CHECK_CUDA(launch_k(k_beam_step, dim3(b, advance ? k : 1), dim3(256), 0, st, c->use_pdl && (c->pdl_mode & 2), a, ad, advance ? 1 : 0));
+  }
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   std::swap(c->sel_beam, c->sel_beam_n);
   std::swap(c->sel_word, c->sel_word_n);

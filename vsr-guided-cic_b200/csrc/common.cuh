@@ -266,6 +266,7 @@ struct Ctx {
   int64_t launches = 0;
   bool profiling = false;
   Phase phases[PH_COUNT];
+  std::vector<cudaEvent_t> step_ev;  // profiling: one event before every step of the last beam search + one after it
   std::vector<void*> owned;          // every cudaMalloc'd pointer (freed in destroy)
   // CUDA-graph cache of whole beam searches (api.cu).  A decode is ~140 launches with no host decision in
   // between; replaying it as one graph removes the per-launch cost (and its sensitivity to PCIe traffic).
@@ -283,9 +284,12 @@ struct Ctx {
   uint64_t epoch = 0, graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
   bool attend_attr_set = false;
+  // the step's vocabulary head was left to the fused tail kernel of the beam search (run_step -> launch_beam_step)
+  bool head_deferred = false; int head_tiles = 0, head_nch = 0; bool head_use_verbs = false, head_gt = false;
   bool state_h32 = true;             // the last step wrote fp32 h1'/h2' (always on the FFMA twin)
   bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
   bool zero_state_opt = true;        // VSRDEC_ZERO_STATE=0: run the h-dependent GEMM parts at t = 0 although h = 0
+  bool fuse_tail = true;             // VSRDEC_FUSE_TAIL=0: separate k_vocab_merge + k_beam_step launches (round-1 layout)
   bool use_pdl = true;               // VSRDEC_PDL=0: plain stream serialization between the step kernels
   // VSRDEC_PDL_MODE bits: 1 = GEMM launches, 2 = small kernels, 4 = weight prefetch before the wait, 8 = GEMMs
   // trigger after their main loop.  Measured inside the decode graph (ms per decode): off 4.07, 1: 4.02, 1|4: 4.00,
@@ -318,6 +322,7 @@ struct StepIO {
   int64_t gate_stride;
   int topk;          // number of word candidates to extract per row (0 = none)
   bool zero_state;   // h1 = h2 = 0 on entry (first step after init_state): their GEMM contributions are skipped
+  bool defer_head;   // beam search: leave the vocabulary head (softmax statistics, top-k, gate head) to the tail kernel
   bool need_h32;     // the caller reads the fp32 h1'/h2' (vsr_step); the tensor-core path itself only needs the fp16 twins
 };
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st);

@@ -8,7 +8,9 @@
 #include <cuda_fp16.h>
 
 #include <cstdlib>
+#include <cstring>
 #include "common.cuh"
+#include "vocab_head.cuh"
 
 namespace vsr {
 
@@ -26,16 +28,6 @@ __device__ __forceinline__ void store_pair(const PairOut& o, size_t i, float v) 
   o.lo[i] = __float2half_rn(v - __half2float(h));
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 
 // ---------------------------------------------------------------- LSTM cell 1 + sentinel gate
 // (FFMA-twin path; the tensor-core path runs this math in the GEMM-A epilogue.)
@@ -102,6 +94,7 @@ __global__ void k_lstm2(const float* __restrict__ pre2, int ld_pre, const float*
 //   gate  = log_softmax([att_g . tanh(ga + ha), sum_{valid r} e_r])            :184-188
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_MAX_R = 64;
+constexpr int ATC_MAX_TR = VSR_MAX_BEAM * ATT_MAX_R;     // tile rows of a caption, worst case
 
 struct AttendArgs {
   const float* det_seqs;   // (b, L, R, F) materialised slot tiles, or null in index form
@@ -360,46 +353,283 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
 #endif
 }
 
+// ---------------------------------------------------------------- slot attention, one CTA per CAPTION
+// The k beam rows of a caption mostly sit on the same slot, so the row-per-CTA kernel above re-fetches one slot tile k
+// times through L2 behind a ptr -> mask -> P -> scores -> softmax -> features dependency chain (ncu: 13 % of HBM peak,
+// 63 % L2 hits, latency-bound).  Here a CTA owns all rows of a caption:
+//   * the rows are grouped by slot pointer; the valid regions of every distinct slot form a flat list of "tile rows";
+//   * each tile row's att_va projection is staged ONCE in shared memory (cp.async) and scored against every row of its
+//     group (one warp per (row, tile row) job: v_a . tanh(P + ha_row));
+//   * the weighted sum streams each tile row's feature row ONCE from global memory (one float4 column per thread, up to
+//     eight independent 128-bit loads in flight) and accumulates it into the K per-row accumulators with the row's
+//     softmax weight (0 for rows of another group).
+// Same math and the same per-row summation order as k_attend; outputs identical buffers.
+constexpr int ATC_THREADS = 512;
+constexpr int ATC_CAP = 24;           // tile rows whose projections are staged per scoring pass
+
+template <int K>
+__global__ void __launch_bounds__(ATC_THREADS, 1) k_attend_cap(const AttendArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int NW = ATC_THREADS / 32;
+  const int A = a.A, R = a.R, k = a.cur_beam;
+  const int max_tr = k * R;                         // worst case: every row on its own slot, all regions valid
+  const float** s_feat = reinterpret_cast<const float**>(sm);   // [max_tr] feature row of every tile row
+  const float** s_prow = s_feat + max_tr;                        // [max_tr] its att_va projection row
+  float* ha = reinterpret_cast<float*>(s_prow + max_tr);         // [K][A]   (16-byte aligned: 16 * max_tr bytes before it)
+  float* va = ha + K * A;                           // [A] att_a weights
+  float* vs = va + A;                               // [A] att_s weights
+  float* Ps = vs + A;                               // [ATC_CAP][A]
+  float* e = Ps + ATC_CAP * A;                      // [K][R + 2]: 0 = sentinel, 1 = padding score, 2 + r = region r
+  float* wmat = e + K * (R + 2);                    // [max_tr][K] softmax weight of tile row t for row j
+  __shared__ float s_red[K][NW];
+  __shared__ float s_as[K];                         // sentinel weight per row
+  __shared__ int s_slot[K], s_grp[K], s_goff[K + 1], s_gslot[K];
+  __shared__ unsigned long long s_gmask[K];
+  __shared__ unsigned char s_tgrp[ATC_MAX_TR];      // group of tile row t
+  __shared__ unsigned char s_treg[ATC_MAX_TR];      // region index of tile row t
+  __shared__ int s_ngrp;
+
+  const int cap = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = cap * k;
+  pdl_trigger();
+  pdl_wait();
+  const int imgi = cap * a.img_mul;
+
+  // ---- loads that depend only on the row index first: sentinel columns (registers), ha rows, attention vectors
+  float4 sent_v[K];
+  const int f0 = tid * 4;                           // F <= 4 * ATC_THREADS columns per pass (host checks the loop bound)
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    sent_v[j] = (j < k && f0 < a.F) ? *reinterpret_cast<const float4*>(a.sent + (size_t)(row0 + j) * a.ld_sent + f0)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < k * A; i += ATC_THREADS) {
+    const int j = i / A, c = i - j * A;
+    ha[j * A + c] = a.hb[(size_t)(row0 + j) * a.ld_hb + a.o_ha + c];
+  }
+  for (int i = tid; i < A; i += ATC_THREADS) { va[i] = __ldg(a.v_a + i); vs[i] = __ldg(a.v_s + i); }
+
+  // ---- warp 0: slot pointers -> groups of rows that share a slot -> tile-row offsets
+  if (warp == 0) {
+    int slot = -1;
+    if (lane < k) slot = a.ptr[row0 + lane];
+    unsigned long long mask = 0ull;
+    if (lane < k) mask = a.slot_mask[(size_t)cap * a.L + slot];
+    const unsigned same = __match_any_sync(0xffffffffu, slot);
+    const int leader = __ffs(same) - 1;
+    const bool is_leader = lane < k && leader == lane;
+    const unsigned lead_ballot = __ballot_sync(0xffffffffu, is_leader);
+    const int my_grp = __popc(lead_ballot & ((1u << leader) - 1u));      // group id = rank of the leader lane
+    if (lane < k) { s_slot[lane] = slot; s_grp[lane] = my_grp; }
+    if (is_leader) { s_gmask[my_grp] = mask; s_gslot[my_grp] = slot; }
+    __syncwarp();
+    if (lane == 0) {
+      const int ng = __popc(lead_ballot);
+      int off = 0;
+      for (int g = 0; g < ng; ++g) { s_goff[g] = off; off += __popcll(s_gmask[g]); }
+      s_goff[ng] = off;
+      s_ngrp = ng;
+    }
+  }
+  __syncthreads();
+  const int ngrp = s_ngrp, n_tr = s_goff[ngrp];
+
+  // ---- tile-row table: (group, region) -> projection row / feature row pointers
+  for (int t = tid; t < n_tr; t += ATC_THREADS) {
+    int g = 0;
+    while (t >= s_goff[g + 1]) ++g;
+    const unsigned long long m = s_gmask[g];
+    int idx = t - s_goff[g];
+    unsigned long long mm = m;                      // region = position of the idx-th set bit of m
+    for (int q = 0; q < idx; ++q) mm &= mm - 1ull;
+    const int r = __ffsll((long long)mm) - 1;
+    const int slot = s_gslot[g];
+    const size_t tile_row0 = ((size_t)cap * a.L + slot) * R;
+    const float* prow;
+    const float* frow;
+    if (a.slot_index == nullptr) {
+      const int pbase = a.slot_base != nullptr ? a.slot_base[(size_t)cap * a.L + slot] : -1;
+      prow = a.P + (pbase >= 0 ? (size_t)(pbase + idx) : tile_row0 + r) * a.ldP;
+      frow = a.det_seqs + (tile_row0 + r) * a.F;
+    } else {
+      const int di = a.slot_index[tile_row0 + r];
+      if (di >= 0) {
+        prow = a.P + ((size_t)imgi * a.D + di) * a.ldP;
+        frow = a.det + (size_t)imgi * a.det_stride + (size_t)di * a.F;
+      } else {
+        prow = a.Pmean + (size_t)imgi * a.ldP;
+        frow = a.img + (size_t)imgi * a.ld_img;
+      }
+    }
+    s_tgrp[t] = (unsigned char)g; s_treg[t] = (unsigned char)r;
+    s_feat[t] = frow; s_prow[t] = prow;
+  }
+  // sum of every sentinel row (its validity is computed like any region row's, :159)
+  {
+    float ss[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) ss[j] = (sent_v[j].x + sent_v[j].y) + (sent_v[j].z + sent_v[j].w);
+    for (int f = f0 + ATC_THREADS * 4; f < a.F; f += ATC_THREADS * 4) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) if (j < k) {
+        const float4 v = *reinterpret_cast<const float4*>(a.sent + (size_t)(row0 + j) * a.ld_sent + f);
+        ss[j] += (v.x + v.y) + (v.z + v.w);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) { const float w = warp_sum(ss[j]); if (lane == 0) s_red[j][warp] = w; }
+  }
+  __syncthreads();
+
+  // ---- scores.  Pass p stages the projections of tile rows [p*CAP, p*CAP+CAP) and scores them against the rows of
+  // their groups; pass 0 also does the 2k row-only jobs (sentinel: att_s . tanh(sa + ha); padding rows: att_a . tanh(ha))
+  for (int t0 = 0; t0 == 0 || t0 < n_tr; t0 += ATC_CAP) {
+    const int nt = min(ATC_CAP, n_tr - t0);
+    if (t0 > 0) __syncthreads();                      // previous pass's readers of Ps are done
+    for (int i = tid; i < nt * (A / 4); i += ATC_THREADS) {
+      const int t = i / (A / 4), ch = (i - t * (A / 4)) * 4;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Ps + (size_t)t * A + ch);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s_prow[t0 + t] + ch) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (t0 == 0) {
+      // pull the feature rows towards L2 while the scores are computed
+      for (int i = tid; i < n_tr * (a.F / 32); i += ATC_THREADS) {
+        const int t = i / (a.F / 32), c = i - t * (a.F / 32);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s_feat[t] + c * 32));
+      }
+      for (int job = warp; job < 2 * k; job += NW) {   // row-only jobs need no staged data
+        const int j = job >> 1;
+        const bool is_sent = (job & 1) == 0;
+        const float* sa = a.sent + (size_t)(row0 + j) * a.ld_sent + a.o_sa;
+        const float* vec = is_sent ? vs : va;
+        float acc = 0.f;
+        for (int i = lane * 4; i < A; i += 128) {
+          const float4 hv = *reinterpret_cast<const float4*>(ha + j * A + i);
+          const float4 pv = is_sent ? *reinterpret_cast<const float4*>(sa + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 vv = *reinterpret_cast<const float4*>(vec + i);
+          acc += vv.x * fast_tanh(pv.x + hv.x) + vv.y * fast_tanh(pv.y + hv.y) + vv.z * fast_tanh(pv.z + hv.z) + vv.w * fast_tanh(pv.w + hv.w);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) e[j * (R + 2) + (is_sent ? 0 : 1)] = acc;
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    for (int job = warp; job < nt * k; job += NW) {
+      const int t = job / k, j = job - t * k;
+      if (s_grp[j] != (int)s_tgrp[t0 + t]) continue;   // warp-uniform
+      const float* pr = Ps + (size_t)t * A;
+      float acc = 0.f;
+      for (int i = lane * 4; i < A; i += 128) {
+        const float4 hv = *reinterpret_cast<const float4*>(ha + j * A + i);
+        const float4 pv = *reinterpret_cast<const float4*>(pr + i);
+        const float4 vv = *reinterpret_cast<const float4*>(va + i);
+        acc += vv.x * fast_tanh(pv.x + hv.x) + vv.y * fast_tanh(pv.y + hv.y) + vv.z * fast_tanh(pv.z + hv.z) + vv.w * fast_tanh(pv.w + hv.w);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) e[j * (R + 2) + 2 + (int)s_treg[t0 + t]] = acc;
+    }
+  }
+  __syncthreads();
+
+  // ---- masked softmax per row (one warp per row): softmax over [sentinel, R regions] -> mask -> renormalise (:167-169)
+  for (int j = warp; j < k; j += NW) {
+    float sent_sum = 0.f;
+    for (int w = 0; w < NW; ++w) sent_sum += s_red[j][w];
+    const int g = s_grp[j];
+    const unsigned long long vmask = s_gmask[g];
+    const float* ej = e + j * (R + 2);
+    const float e_pad = ej[1];
+    // entry x in [0, R]: 0 = sentinel, x >= 1 = region x-1; lanes stride the entries
+    float m = -INFINITY;
+    for (int x = lane; x <= R; x += 32) {
+      const bool valid = x == 0 ? true : (((vmask >> (x - 1)) & 1ull) != 0);
+      m = fmaxf(m, (x == 0 || valid) ? ej[x == 0 ? 0 : x + 1] : e_pad);
+    }
+    m = warp_max(m);
+    float S = 0.f;
+    for (int x = lane; x <= R; x += 32) {
+      const bool valid = x == 0 ? true : (((vmask >> (x - 1)) & 1ull) != 0);
+      S += expf(((x == 0 || valid) ? ej[x == 0 ? 0 : x + 1] : e_pad) - m);
+    }
+    S = warp_sum(S);
+    float T = 0.f, shift = 0.f;
+    for (int x = lane; x <= R; x += 32) {
+      const bool valid = x == 0 ? (sent_sum != 0.f) : (((vmask >> (x - 1)) & 1ull) != 0);
+      if (valid) {
+        const float ev = ej[x == 0 ? 0 : x + 1];
+        T += expf(ev - m) / S;
+        if (x > 0) shift += ev;
+      }
+    }
+    T = warp_sum(T);
+    shift = warp_sum(shift);
+    // weights of this row: its group's tile rows get alpha, every other tile row 0
+    for (int t = lane; t < n_tr; t += 32) {
+      float w = 0.f;
+      if ((int)s_tgrp[t] == g) w = (expf(ej[2 + (int)s_treg[t]] - m) / S) / T;
+      wmat[(size_t)t * K + j] = w;
+    }
+    if (lane == 0) {
+      s_as[j] = (sent_sum != 0.f) ? (expf(ej[0] - m) / S) / T : 0.f;
+      a.shift[row0 + j] = shift;
+    }
+  }
+  __syncthreads();
+
+  // ---- weighted sum: att_j = alpha_s * sentinel_j + sum_t w[t][j] * feature row t; every feature row is read once
+  for (int fb = f0; fb < a.F; fb += ATC_THREADS * 4) {
+    float4 acc[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      float4 sv = sent_v[j];
+      if (fb != f0 && j < k) sv = *reinterpret_cast<const float4*>(a.sent + (size_t)(row0 + j) * a.ld_sent + fb);
+      const float as = j < k ? s_as[j] : 0.f;
+      acc[j] = make_float4(as * sv.x, as * sv.y, as * sv.z, as * sv.w);
+    }
+    constexpr int U = 8;
+    for (int t = 0; t < n_tr; t += U) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(s_feat[min(t + u, n_tr - 1)] + fb));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (t + u < n_tr) {
+          const float* wr = wmat + (size_t)(t + u) * K;
+#pragma unroll
+          for (int j = 0; j < K; ++j) {
+            const float w = wr[j];
+            acc[j].x += w * v[u].x; acc[j].y += w * v[u].y; acc[j].z += w * v[u].z; acc[j].w += w * v[u].w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (j >= k) break;
+      const size_t o = (size_t)(row0 + j) * a.ld_att + fb;
+      if (a.att != nullptr) *reinterpret_cast<float4*>(a.att + o) = acc[j];
+      if (a.att_b.hi != nullptr) {
+        const float x[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
+        __align__(8) __half h[4];
+        __align__(8) __half l[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float xv = fminf(fmaxf(x[q], -65504.f), 65504.f);
+          h[q] = __float2half_rn(xv); l[q] = __float2half_rn(xv - __half2float(h[q]));
+        }
+        *reinterpret_cast<uint2*>(a.att_b.hi + o) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(a.att_b.lo + o) = *reinterpret_cast<const uint2*>(l);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- log-softmax + gate head + verb forcing + top-k
 // One CTA per row; the row's logits are read ONCE into registers.  Also finishes the
 // shift-gate head (stay logit = att_g . tanh(ga + ha), controllable_captioning.py:184-188) so the
 // att_ga projection is off the attention kernel's critical path, and applies verb forcing (:271-295).
-
-__device__ __forceinline__ int64_t load_verb(const void* verbs, int dtype, size_t i) {
-  if (dtype == VSR_DT_F64) return (int64_t) reinterpret_cast<const double*>(verbs)[i];
-  if (dtype == VSR_DT_F32) return (int64_t) reinterpret_cast<const float*>(verbs)[i];
-  return reinterpret_cast<const int64_t*>(verbs)[i];
-}
-
-// (value desc, index asc) total order: is (v1,i1) before (v2,i2)?
-__device__ __forceinline__ bool before(float v1, int i1, float v2, int i2) {
-  return v1 > v2 || (v1 == v2 && i1 < i2);
-}
-__device__ __forceinline__ void warp_argbest(float& bv, int& bi) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
-  }
-}
-
-struct SoftmaxArgs {
-  const float* logits; int ld;   // [rows][ld]
-  int rows, V, cur_beam, L, topk;
-  const int32_t* ptr;
-  const void* verbs; int verbs_dtype; int use_verbs, gt;
-  const int64_t* vt_keys; const int32_t* vt_off; const int32_t* vt_idx; int vt_n;
-  // gate head inputs
-  const float* ha; int ld_ha;     // [rows] att_ha . h1'   (A wide)
-  const float* ga; int ld_ga;     // [rows] att_ga . g_t
-  const float* v_g; int A;
-  const float* shift;             // [rows] sum of the valid region scores (from the attention kernel)
-  float* row_max; float* row_lsum; int32_t* forced; int32_t* cand;  // cand [rows][VSR_MAX_BEAM]
-  float* gate_lp;                 // [rows][2] post-forcing gate log-probs
-  float* out_logp; int64_t out_stride;   // optional full rows
-  float* gate_out; int64_t gate_stride;  // optional copy of the gate rows
-};
 
 // One pass over the row (each thread: its float4s in register batches): online (max, sum exp) per thread,
 // merged block-wide, plus the thread's two best elements.  Every warp then picks the top-k of its 64
@@ -409,17 +639,6 @@ struct SoftmaxArgs {
 // take the slow exact path: k rounds of block arg-best with the owner rescanning its elements.
 // Serial single-warp sections are kept to a few hundred cycles: they dominated earlier versions.
 constexpr int SM_THREADS = 256;
-
-__device__ __forceinline__ unsigned orderable(float v) {     // monotone float -> unsigned
-  const unsigned u = __float_as_uint(v);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-// warp arg-best in (value desc, index asc) order with two redux.sync; every lane gets the winner
-__device__ __forceinline__ void warp_argbest_redux(float v, int i, unsigned& kbest, int& ibest) {
-  const unsigned key = orderable(v);
-  kbest = __reduce_max_sync(0xffffffffu, key);
-  ibest = (int)__reduce_min_sync(0xffffffffu, key == kbest ? (unsigned)i : 0xffffffffu);
-}
 
 __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a) {
   constexpr int THREADS = SM_THREADS;
@@ -647,16 +866,8 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
   }
 }
 
-// ---------------------------------------------------------------- fused vocabulary head: finish from the per-tile records
-// The vocabulary GEMM's epilogue (gemm_tc.cu: vocab_epilogue) leaves, per (row, N tile), {max, sum exp, max of every
-// 16-column chunk}.  One WARP per row: row max / log-sum-exp from the records; then the topk tiles by max, the topk
-// chunks among them by max, and only those topk * 16 logits are re-read and their topk picked.
-// Exact: if an element e of group C (tile or chunk) were in the row's top-k without C being among the topk groups
-// in (max desc, position asc) order, each of the topk groups ahead of C would hold an element ordered before e
-// (larger, or equal with a smaller index).
-// Also the gate head and verb forcing, exactly as k_softmax_topk; same outputs.
 constexpr int VM_WARPS = 4;
-
+// k_vocab_merge: vocab_head.cuh (merge_row) — one warp per row finishes the vocabulary head from the GEMM's records
 __global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs a, const float* __restrict__ vpart,
                                                                 int n_tiles, int nch) {
   const int lane = threadIdx.x & 31;
@@ -664,164 +875,17 @@ __global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs
   pdl_trigger();
   pdl_wait();
   if (n >= a.rows) return;
-  const int V = a.V, topk = a.topk;
-  const float* rec0 = vpart + (size_t)n * n_tiles * VOCAB_REC;
-  const float* x = a.logits + (size_t)n * a.ld;
-
-  int64_t verb = -1; float shift_logit = 0.f;
+  RowHead h;
+  merge_row(a, vpart, n_tiles, nch, n, lane, h);
   if (lane == 0) {
-    shift_logit = a.shift[n];
-    if (a.use_verbs && a.verbs != nullptr)
-      verb = load_verb(a.verbs, a.verbs_dtype, (size_t)(n / a.cur_beam) * a.L + a.ptr[n]);
-  }
-  // (max, sum exp) of this lane's tiles
-  float m = -INFINITY, ssum = 0.f;
-  for (int t = lane; t < n_tiles; t += 32) {
-    const float2 ms = *reinterpret_cast<const float2*>(rec0 + (size_t)t * VOCAB_REC);
-    if (ms.x > m) { ssum *= __expf(m - ms.x); m = ms.x; }
-    if (ms.x > -INFINITY) ssum += ms.y * __expf(ms.x - m);
-  }
-  // stay-gate logit att_g . tanh(ga + ha)
-  float stay = 0.f;
-  {
-    const float4* ha = reinterpret_cast<const float4*>(a.ha + (size_t)n * a.ld_ha);
-    const float4* ga = reinterpret_cast<const float4*>(a.ga + (size_t)n * a.ld_ga);
-    const float4* vg = reinterpret_cast<const float4*>(a.v_g);
-    for (int i = lane; i < a.A / 4; i += 32) {
-      const float4 h = ha[i], g = ga[i], w = __ldg(vg + i);
-      stay += (w.x * fast_tanh(g.x + h.x) + w.y * fast_tanh(g.y + h.y)) + (w.z * fast_tanh(g.z + h.z) + w.w * fast_tanh(g.w + h.w));
-    }
-  }
-  const float mx = warp_max(m);
-  const float se = warp_sum(m > -INFINITY ? ssum * expf(m - mx) : 0.f);
-  const float lsum = logf(se);
-  stay = warp_sum(stay);
-
-  // Hierarchical exact selection, every level in (value desc, position asc) order with composite keys
-  // orderable(value) : ~position, so "ordered before" is a plain unsigned 64-bit '>':
-  //   1. the topk TILES by tile max (round j: every lane's best key strictly below the previous winner, then a
-  //      warp arg-best; lane j keeps winner j),
-  //   2. the topk 16-column CHUNKS among those tiles' chunk maxima,
-  //   3. the topk ELEMENTS among those chunks' logits.
-  unsigned long long prev = ~0ull;
-  int my_tile = -1;
-  for (int j = 0; j < topk; ++j) {
-    unsigned long long best = 0ull;
-    for (int t = lane; t < n_tiles; t += 32) {
-      const float tm = rec0[(size_t)t * VOCAB_REC];
-      const unsigned long long key = ((unsigned long long)orderable(tm) << 32) | (unsigned)(~(unsigned)t);
-      if (tm > -INFINITY && key < prev && key > best) best = key;
-    }
-    const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
-    const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
-    prev = ((unsigned long long)hi << 32) | lo;
-    if (hi == 0u && lo == 0u) break;          // fewer tiles than topk (uniform)
-    if (lane == j) my_tile = (int)(~lo);
-  }
-  constexpr int CQ = (VSR_MAX_BEAM * (VOCAB_REC - 2) + 31) / 32;
-  float kv[CQ]; int kc[CQ];
-#pragma unroll
-  for (int q = 0; q < CQ; ++q) {
-    const int e = lane + 32 * q;
-    const int tsel = e / nch, ch = e - tsel * nch;
-    const int tile = __shfl_sync(0xffffffffu, my_tile, tsel & 31);
-    kv[q] = -INFINITY; kc[q] = 0x7fffffff;
-    if (tsel < topk && tile >= 0) {
-      const float cm = rec0[(size_t)tile * VOCAB_REC + 2 + ch];
-      if (cm > -INFINITY) { kv[q] = cm; kc[q] = tile * nch + ch; }
-    }
-  }
-  int my_chunk = -1;
-  for (int j = 0; j < topk; ++j) {
-    float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < CQ; ++q) if (before(kv[q], kc[q], bv, bi)) { bv = kv[q]; bi = kc[q]; }
-    unsigned kb; int ib;
-    warp_argbest_redux(bv, bi, kb, ib);
-#pragma unroll
-    for (int q = 0; q < CQ; ++q) if (kc[q] == ib) { kv[q] = -INFINITY; kc[q] = 0x7fffffff; }
-    if (lane == j && ib != 0x7fffffff) my_chunk = ib;
-  }
-
-  // candidates: the 16 logits of each selected chunk; lane owns elements e = lane + 32 * q of the topk * 16
-  constexpr int EQ = VSR_MAX_BEAM * 16 / 32;
-  float cv[EQ]; int ci[EQ];
-#pragma unroll
-  for (int q = 0; q < EQ; ++q) {
-    const int e = lane + 32 * q;
-    const int chunk = __shfl_sync(0xffffffffu, my_chunk, (e >> 4) & 31);
-    cv[q] = -INFINITY; ci[q] = 0x7fffffff;
-    if (e < topk * 16 && chunk >= 0) {
-      const int col = chunk * 16 + (e & 15);
-      if (col < V) { cv[q] = x[col]; ci[q] = col; }
-    }
-  }
-  int my_pick = 0x7fffffff;
-  for (int j = 0; j < topk; ++j) {
-    float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < EQ; ++q) if (before(cv[q], ci[q], bv, bi)) { bv = cv[q]; bi = ci[q]; }
-    unsigned kb; int ib;
-    warp_argbest_redux(bv, bi, kb, ib);
-#pragma unroll
-    for (int q = 0; q < EQ; ++q) if (ci[q] == ib) { cv[q] = -INFINITY; ci[q] = 0x7fffffff; }
-    if (lane == j) my_pick = ib;
-  }
-
-  int forced = -1;
-  if (lane == 0) {
-    // verb forcing (:271-295): which vocabulary index does the current slot force, if any
-    if (verb != -1) {
-      if (a.gt) {
-        forced = (int)verb;
-      } else {
-        forced = 0;   // key missing or empty list -> vocabulary index 0 (:291-292)
-        int lo = 0, hi = a.vt_n - 1, pos = -1;
-        while (lo <= hi) {
-          const int mid = (lo + hi) >> 1;
-          const int64_t k = a.vt_keys[mid];
-          if (k == verb) { pos = mid; break; }
-          if (k < verb) lo = mid + 1; else hi = mid - 1;
-        }
-        if (pos >= 0 && a.vt_off[pos + 1] > a.vt_off[pos]) {
-          float best = -1e6f; int best_i = -1;    // strict '>' : first maximum wins (:284-289)
-          for (int qq = a.vt_off[pos]; qq < a.vt_off[pos + 1]; ++qq) {
-            const int idx = a.vt_idx[qq];
-            const float lp = (x[idx] - mx) - lsum;
-            if (lp > best) { best = lp; best_i = idx; }
-          }
-          forced = best_i < 0 ? V - 1 : best_i;   // python index -1 == last vocabulary entry
-        }
-      }
-      forced = min(max(forced, 0), V - 1);
-    }
-    a.row_max[n] = mx;
-    a.row_lsum[n] = lsum;
-    a.forced[n] = forced;
-    // gate head: log_softmax([stay, shift]) (:187-188), or [-1e3, 0] on a verb slot (:295)
-    float g0, g1;
-    if (forced >= 0) { g0 = -1e3f; g1 = 0.f; }
-    else {
-      const float gm = fmaxf(stay, shift_logit);
-      const float ls = logf(expf(stay - gm) + expf(shift_logit - gm));
-      g0 = (stay - gm) - ls; g1 = (shift_logit - gm) - ls;
-    }
-    a.gate_lp[(size_t)n * 2] = g0; a.gate_lp[(size_t)n * 2 + 1] = g1;
+    a.row_max[n] = h.mx; a.row_lsum[n] = h.lsum; a.forced[n] = h.forced;
+    a.gate_lp[(size_t)n * 2] = h.g0; a.gate_lp[(size_t)n * 2 + 1] = h.g1;
     if (a.gate_out != nullptr) {
-      a.gate_out[(size_t)n * a.gate_stride + 0] = g0;
-      a.gate_out[(size_t)n * a.gate_stride + 1] = g1;
+      a.gate_out[(size_t)n * a.gate_stride + 0] = h.g0;
+      a.gate_out[(size_t)n * a.gate_stride + 1] = h.g1;
     }
   }
-  forced = __shfl_sync(0xffffffffu, forced, 0);
-  if (lane < topk) {
-    if (forced >= 0) {
-      // forced word first, then the lowest other indices (all tied at -1e6)
-      int w = forced;
-      if (lane > 0) { w = lane - 1; if (w >= forced) ++w; w = min(w, V - 1); }
-      my_pick = w;
-    }
-    a.cand[(size_t)n * VSR_MAX_BEAM + lane] = my_pick;
-  }
+  if (lane < a.topk) a.cand[(size_t)n * VSR_MAX_BEAM + lane] = h.pick;
 }
 
 }  // namespace
@@ -908,13 +972,39 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.att = fused ? nullptr : c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.shift = c->shift;
     a.rows = rows; a.cur_beam = io.cur_beam; a.L = c->L; a.R = c->R; a.F = c->F; a.A = c->A; a.H = H;
     a.ldP = c->NVA;
-    const size_t smem = sizeof(float) * ((size_t)c->A + (size_t)c->R * c->A + c->R + 1);
-    if (!c->attend_attr_set) {     // per device, hence per handle
-      VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      c->attend_attr_set = true;
+    static const bool per_row = [] { const char* e = getenv("VSRDEC_ATTEND"); return e != nullptr && strcmp(e, "row") == 0; }();
+    if (per_row) {      // the round-1 kernel (one CTA per row), kept for A/B measurements
+      const size_t smem = sizeof(float) * ((size_t)c->A + (size_t)c->R * c->A + c->R + 1);
+      if (!c->attend_attr_set) {     // per device, hence per handle
+        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->attend_attr_set = true;
+      }
+      VSR_REQUIRE(smem <= 200 * 1024, VSR_EINVAL, "attention tile (R=%d x A=%d) does not fit shared memory", c->R, c->A);
+      VSR_CHECK_CUDA(launch_k(k_attend, dim3(rows), dim3(ATT_THREADS), smem, st, c->use_pdl && (c->pdl_mode & 2), a));
+    } else {            // one CTA per caption: every slot tile is fetched once for all the beams that sit on it
+      const int k = io.cur_beam, KK = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 6 ? 6 : 8;
+      const size_t max_tr = (size_t)k * c->R;
+      const size_t smem = 2 * sizeof(float*) * max_tr +
+                          sizeof(float) * ((size_t)KK * c->A + 2 * (size_t)c->A + (size_t)ATC_CAP * c->A + (size_t)KK * (c->R + 2) + max_tr * KK);
+      VSR_REQUIRE(smem <= 200 * 1024 && rows % k == 0, VSR_EINVAL, "attention workspace (beam %d, R=%d, A=%d) does not fit shared memory", k, c->R, c->A);
+      if (!c->attend_attr_set) {
+        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        c->attend_attr_set = true;
+      }
+      const bool pdl = c->use_pdl && (c->pdl_mode & 2);
+      const dim3 grid(rows / k), block(ATC_THREADS);
+      switch (KK) {
+        case 1: VSR_CHECK_CUDA(launch_k(k_attend_cap<1>, grid, block, smem, st, pdl, a)); break;
+        case 2: VSR_CHECK_CUDA(launch_k(k_attend_cap<2>, grid, block, smem, st, pdl, a)); break;
+        case 4: VSR_CHECK_CUDA(launch_k(k_attend_cap<4>, grid, block, smem, st, pdl, a)); break;
+        case 6: VSR_CHECK_CUDA(launch_k(k_attend_cap<6>, grid, block, smem, st, pdl, a)); break;
+        default: VSR_CHECK_CUDA(launch_k(k_attend_cap<8>, grid, block, smem, st, pdl, a)); break;
+      }
     }
-    VSR_REQUIRE(smem <= 200 * 1024, VSR_EINVAL, "attention tile (R=%d x A=%d) does not fit shared memory", c->R, c->A);
-    VSR_CHECK_CUDA(launch_k(k_attend, dim3(rows), dim3(ATT_THREADS), smem, st, c->use_pdl && (c->pdl_mode & 2), a));
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // D: pre2 = WD . [att | h2_old | h1'] + b (+ U2[img]);  C: ga = att_ga . g_t rides in the same launch
@@ -965,16 +1055,18 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   }
   {
     PhaseScope ps(c, PH_SOFTMAX_TOPK, st);
-    SoftmaxArgs a{};
-    a.logits = c->logits; a.ld = c->NE; a.rows = rows; a.V = c->V; a.cur_beam = io.cur_beam; a.L = c->L;
-    a.topk = io.topk; a.ptr = c->ptr;
-    a.verbs = c->verbs; a.verbs_dtype = c->verbs_dtype; a.use_verbs = io.use_verbs; a.gt = io.gt;
-    a.vt_keys = c->vt_keys; a.vt_off = c->vt_off; a.vt_idx = c->vt_idx; a.vt_n = c->vt_n;
-    a.ha = c->hb + c->oB2_ha; a.ld_ha = c->NB2; a.ga = c->ga; a.ld_ga = c->NC; a.v_g = c->v_g; a.A = c->A;
-    a.shift = c->shift;
-    a.row_max = c->row_max; a.row_lsum = c->row_lsum; a.forced = c->forced; a.cand = c->cand;
-    a.gate_lp = c->gate_lp; a.out_logp = io.out_logp; a.out_stride = io.out_stride;
+    SoftmaxArgs a = make_softmax_args(c, rows, io.cur_beam, io.topk, io.use_verbs, io.gt);
+    a.out_logp = io.out_logp; a.out_stride = io.out_stride;
     a.gate_out = io.gate_out; a.gate_stride = io.gate_stride;
+    c->head_deferred = false;
+    if (fuse_vocab && io.defer_head && io.gate_out == nullptr) {
+      // beam search: the head is finished inside the fused tail kernel (launch_beam_step: merge + selection + reorder)
+      VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
+                  "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);
+      c->head_deferred = true; c->head_tiles = vocab_tiles; c->head_nch = vocab_bn / 16;
+      c->head_use_verbs = io.use_verbs; c->head_gt = io.gt;
+      return VSR_OK;
+    }
     if (fuse_vocab) {
       VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
                   "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);

@@ -46,6 +46,7 @@ EXPORTED_SYMBOLS = {
     "vsr_set_profiling": (ctypes.c_int, [c_vp, c_i32]),
     "vsr_get_phase_times": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_f),
                                            ctypes.POINTER(c_i32), c_i32]),
+    "vsr_get_step_times": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f), c_i32]),
 }
 
 

@@ -264,6 +264,16 @@ class DecoderEngine:
     def set_profiling(self, on: bool):
         _lib.check(self.lib, self.lib.vsr_set_profiling(self.handle, int(on)))
 
+    def step_times(self):
+        """ms of every decoder step of the last profiled beam search (CUDA events between the steps)."""
+        cap = 512
+        ms = (c_f * cap)()
+        with torch.cuda.device(self.device):
+            n = self.lib.vsr_get_step_times(self.handle, ms, cap)
+        if n < 0:
+            _lib.check(self.lib, n)
+        return [float(ms[i]) for i in range(n)]
+
     def phase_times(self):
         cap = 32
         names = (ctypes.c_char_p * cap)()
