@@ -170,6 +170,14 @@ int vsr_forward_teacher(vsr_handle h, const int64_t* captions, int32_t T,
  *   out_words,out_gates (b,T) int64. */
 int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* stream);
 
+/* Multinomial sampling decode with log-probs (CaptioningModel.sample_rl, CaptioningModel.py:54-76; caller
+ * coco_scripts/train.py:151): at every step both heads are sampled from the step's distributions (word: Gumbel-max
+ * over the vocabulary row with a Philox4x32-10 stream keyed by `seed`; gate: one uniform draw), the picks are fed
+ * back, and the log-probs of the picks are returned.  The whole loop runs on the device.
+ *   out_words,out_gates (b,T) int64;  lp_words,lp_gates (b,T) fp32.  The same seed reproduces the same draws. */
+int vsr_sample(vsr_handle h, uint64_t seed, int64_t* out_words, int64_t* out_gates,
+               float* lp_words, float* lp_gates, void* stream);
+
 /* Number of kernels this handle has launched so far (bench.py's gpu_launches). */
 int64_t vsr_launch_count(vsr_handle h);
 

@@ -49,6 +49,43 @@ def full_report(path):
                 print(f"    {k} = {r[hdr.index(k)]} {units[hdr.index(k)]}")
 
 
+def traffic_json(out_path, reps):
+    """DRAM bytes (read + write) per launch of the captured kernels -> the JSON bench.py reads for `roofline.traffic`."""
+    import json
+    import os
+    import re
+    res = {"source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch (tools/gpu_ncu_r02.sh)", "kernels": []}
+    for path in reps:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+
+        def val(r, k):
+            v = float(r[hdr.index(k)].replace(",", ""))
+            u = units[hdr.index(k)]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        tot, n = 0.0, 0
+        for r in rows[2:]:
+            by = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+            res["kernels"].append({"report": os.path.basename(path), "kernel": r[hdr.index("Kernel Name")].split("(")[0][-40:],
+                                   "grid": r[hdr.index("launch__grid_size")], "dram_bytes": by,
+                                   "time_us": float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) *
+                                   {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1)})
+            tot += by
+            n += 1
+        m = re.search(r"_(gemm|k_attend_cap|k_tail)_b(\d+)", os.path.basename(path))
+        if m and n:
+            key = ("gemm" if m.group(1) == "gemm" else "attend" if "attend" in m.group(1) else "tail") + "_bytes_per_launch_b" + m.group(2)
+            res[key] = tot / n
+    with open(out_path, "w") as f:
+        json.dump(res, f, indent=1)
+
+
 if __name__ == "__main__":
-    for p in sys.argv[1:]:
-        (launch_list if p.endswith(".csv") else full_report)(p)
+    if len(sys.argv) > 2 and sys.argv[1] == "--traffic-json":
+        traffic_json(sys.argv[2], sys.argv[3:])
+    else:
+        for p in sys.argv[1:]:
+            (launch_list if p.endswith(".csv") else full_report)(p)

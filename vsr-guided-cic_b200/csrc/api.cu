@@ -77,27 +77,45 @@ static int pad_rows(int n_valid, int bn, int alt_bn) {
   return round_up(r, 128);
 }
 
-int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, int n_valid = 0,
-               int alt_bn = 0, int alt_kb = 64, bool scaled = false) {
-  dev_free(c, b->hi); dev_free(c, b->lo);
-  b->hi = b->lo = nullptr;
+// kind of twin set: fp16 hi + fp16 residual (f16x3 GEMMs) or fp16 hi + e4m3 hi8 / lo8 (f16+f8x2 GEMMs)
+enum PairKind { PAIR_F16X3 = 0, PAIR_F8 = 1 };
+static PairKind step_kind(const Ctx* c) { return c->gemm_f8 ? PAIR_F8 : PAIR_F16X3; }
+
+int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, PairKind kind, bool weight = false, int n_valid = 0,
+               int alt_bn = 0, int alt_kb = 64) {
+  dev_free(c, b->hi); dev_free(c, b->lo); dev_free(c, b->hi8); dev_free(c, b->lo8);
+  b->hi = b->lo = b->hi8 = b->lo8 = nullptr;
   if (!c->use_tc) return VSR_OK;
   VSR_TRY(dev_alloc(c, &b->hi, (size_t)rows * ld * 2));
-  VSR_TRY(dev_alloc(c, &b->lo, (size_t)rows * ld * 2));
   b->rows = rows; b->ld = ld; b->box_rows = box_rows;
   VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box_rows));
-  VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box_rows));
   VSR_TRY(make_tmap_f16(b->map32_hi, b->hi, rows, ld, ld, box_rows, 32));
-  VSR_TRY(make_tmap_f16(b->map32_lo, b->lo, rows, ld, ld, box_rows, 32));
+  if (kind == PAIR_F16X3) {
+    VSR_TRY(dev_alloc(c, &b->lo, (size_t)rows * ld * 2));
+    VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box_rows));
+    VSR_TRY(make_tmap_f16(b->map32_lo, b->lo, rows, ld, ld, box_rows, 32));
+  } else {
+    VSR_TRY(dev_alloc(c, &b->hi8, (size_t)rows * ld));
+    VSR_TRY(dev_alloc(c, &b->lo8, (size_t)rows * ld));
+    VSR_TRY(make_tmap_u8(b->map8_hi, b->hi8, rows, ld, ld, box_rows));
+    VSR_TRY(make_tmap_u8(b->map8_lo, b->lo8, rows, ld, ld, box_rows));
+    VSR_TRY(make_tmap_u8(b->map8_32_hi, b->hi8, rows, ld, ld, box_rows, 32));
+    VSR_TRY(make_tmap_u8(b->map8_32_lo, b->lo8, rows, ld, ld, box_rows, 32));
+  }
+  b->act_scale = (!weight && kind == PAIR_F8) ? ACT_SCALE_F8 : 1.f;
   b->kb = c->gemm_kb;
   b->n_valid = n_valid > 0 ? n_valid : rows;
   b->alt_bn = 0;
   if (alt_bn > 0 && c->use_alt_tiles) {
     VSR_TRY(make_tmap_f16(b->alt_hi, b->hi, rows, ld, ld, alt_bn, alt_kb));
-    VSR_TRY(make_tmap_f16(b->alt_lo, b->lo, rows, ld, ld, alt_bn, alt_kb));
+    if (kind == PAIR_F16X3) VSR_TRY(make_tmap_f16(b->alt_lo, b->lo, rows, ld, ld, alt_bn, alt_kb));
+    else {
+      VSR_TRY(make_tmap_u8(b->alt8_hi, b->hi8, rows, ld, ld, alt_bn, alt_kb));
+      VSR_TRY(make_tmap_u8(b->alt8_lo, b->lo8, rows, ld, ld, alt_bn, alt_kb));
+    }
     b->alt_bn = alt_bn; b->alt_kb = alt_kb;
   }
-  if (scaled && b->scale == nullptr) VSR_TRY(dev_alloc(c, (void**)&b->scale, 2 * sizeof(float)));
+  if (weight && b->scale == nullptr) VSR_TRY(dev_alloc(c, (void**)&b->scale, 2 * sizeof(float)));
   return VSR_OK;
 }
 
@@ -126,10 +144,11 @@ int ensure_rows(Ctx* c, int rows) {
   VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->cand, sizeof(int32_t) * n * VSR_MAX_BEAM));
   VSR_TRY(dev_alloc(c, (void**)&c->word_in, sizeof(int64_t) * n));
-  VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD));
-  VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD));
-  VSR_TRY(alloc_pair(c, &c->h1n_b, cap, c->Hp, MPAD)); VSR_TRY(alloc_pair(c, &c->g_t_b, cap, c->Hp, MPAD));
-  VSR_TRY(alloc_pair(c, &c->att_b, cap, c->Fp, MPAD)); VSR_TRY(alloc_pair(c, &c->h2n_b, cap, c->Hp, MPAD));
+  const PairKind sk = step_kind(c);
+  VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD, sk));
+  VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD, sk));
+  VSR_TRY(alloc_pair(c, &c->h1n_b, cap, c->Hp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->g_t_b, cap, c->Hp, MPAD, sk));
+  VSR_TRY(alloc_pair(c, &c->att_b, cap, c->Fp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->h2n_b, cap, c->Hp, MPAD, sk));
   c->cap_rows = cap;
   return VSR_OK;
 }
@@ -212,8 +231,11 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   ALLOC_F(c->embed, (size_t)c->V * c->Ep);
   ALLOC_F(c->WAx, (size_t)c->NA * c->Ep); ALLOC_F(c->X, (size_t)c->V * c->NA);
   {
-    const char* mode = getenv("VSRDEC_GEMM");   // "simt": fp32 FFMA twin for A/B verification of the tcgen05 path
+    // VSRDEC_GEMM: "simt" = fp32 FFMA twin for A/B verification of the tcgen05 path; "f16x3" = all three passes of the
+    // step GEMMs in fp16 (default: the two residual passes on the fp8 tensor path, "f16+f8x2")
+    const char* mode = getenv("VSRDEC_GEMM");
     c->use_tc = !(mode != nullptr && strcmp(mode, "simt") == 0);
+    c->gemm_f8 = !(mode != nullptr && strcmp(mode, "f16x3") == 0);
   }
   // UMMA N tile per GEMM (128 or 256): 128 measured faster on B200 for every per-step shape (more CTAs
   // in flight, 3-stage ring); VSRDEC_BN=256 switches all of them for experiments
@@ -222,20 +244,26 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   // GEMM-A / GEMM-D tiles are fixed by their fused LSTM epilogues: 6 gates x 32 units = 192, 4 x 32 = 128.
   if (const char* e = getenv("VSRDEC_GRAPH")) c->use_graphs = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL")) c->use_pdl = atoi(e) != 0;
-  if (const char* e = getenv("VSRDEC_FUSE_TAIL")) c->fuse_tail = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_ZERO_STATE")) c->zero_state_opt = atoi(e) != 0;
   if (const char* e = getenv("VSRDEC_PDL_MODE")) c->pdl_mode = atoi(e);
   if (const char* e = getenv("VSRDEC_KB")) c->gemm_kb = atoi(e) == 32 ? 32 : 64;
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
   // weight pairs are power-of-two scaled per tensor (F16Pair::scale)
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, 0, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, c->NB1v, 0, 64, true));
-  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, c->NB2v, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, 0, 0, 64, true));
-  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, 0, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, c->V, 144, 64, true));
+  const PairKind sk = step_kind(c);
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, sk, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, sk, true, c->NB1v));
+  VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, sk, true, c->NB2v)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, sk, true));
+  VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, sk, true)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, sk, true, c->V, 144, 64));
+  if (const char* e = getenv("VSRDEC_PAIR")) c->use_pair = atoi(e) != 0;
+  if (c->use_pair && c->use_tc) {     // CTA-pair kernel for the large-batch launches: 256 x 192 tiles for A, 256 x 256 for B, D + C
+    VSR_TRY(make_pair_maps(&c->WA_b, 96)); VSR_TRY(make_pair_maps(&c->WB1_b, 128)); VSR_TRY(make_pair_maps(&c->WB2_b, 128));
+    VSR_TRY(make_pair_maps(&c->WC_b, 128)); VSR_TRY(make_pair_maps(&c->WD_b, 128));
+  }
   // GEMM-A's 192-wide tile only fits 2 ring stages with 64-element k-blocks; 32-element blocks give 5
   c->WA_b.kb = 32;
   if (const char* e = getenv("VSRDEC_KB_A")) c->WA_b.kb = atoi(e) == 32 ? 32 : 64;
-  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128, 0, 0, 64, true)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn, 0, 0, 64, true));
-  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128, 0, 0, 64, true));
+  // the once-per-batch prologue GEMMs (U, U2, att_va projection) keep all three passes in fp16
+  VSR_TRY(alloc_pair(c, &c->WU_b, c->NA, c->Fp, 128, PAIR_F16X3, true)); VSR_TRY(alloc_pair(c, &c->Wva_b, c->NVA, c->Fp, bn, PAIR_F16X3, true));
+  if (d->img_second_lstm) VSR_TRY(alloc_pair(c, &c->WU2_b, c->ND, c->Fp, 128, PAIR_F16X3, true));
   VSR_TRY(pack_weights(c, w, 0));
   VSR_CHECK_CUDA(cudaStreamSynchronize(0));
   return VSR_OK;
@@ -334,7 +362,7 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     c->img = c->U = c->U2 = nullptr; c->cap_img = 0;
     ALLOC_F(c->img, n_img_pad * c->Fp); ALLOC_F(c->U, n_img_pad * c->NA);
     if (c->d.img_second_lstm) ALLOC_F(c->U2, n_img_pad * c->ND);
-    VSR_TRY(alloc_pair(c, &c->img_b, (int)n_img_pad, c->Fp, MPAD));
+    VSR_TRY(alloc_pair(c, &c->img_b, (int)n_img_pad, c->Fp, MPAD, PAIR_F16X3));
     c->cap_img = n_img_pad;
   }
   // rows of the projection buffer: one per slot row (materialised form) or one per detection row plus one
@@ -352,7 +380,7 @@ static int prologue_impl(Ctx* c, const float* det, int64_t det_stride, int D, co
     VSR_TRY(dev_alloc(c, (void**)&c->slot_mask, sizeof(unsigned long long) * need_slots));
     VSR_TRY(dev_alloc(c, (void**)&c->slot_base, sizeof(int32_t) * need_slots));
     VSR_TRY(dev_alloc(c, (void**)&c->comp_valid, round_up((int)need_rows, MPAD)));
-    VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)need_rows, MPAD), c->Fp, MPAD));
+    VSR_TRY(alloc_pair(c, &c->ds_b, round_up((int)need_rows, MPAD), c->Fp, MPAD, PAIR_F16X3));
     c->cap_P = need_rows; c->cap_slots = need_slots;
   }
   c->Pmean = slot_index != nullptr ? c->P + (size_t)round_up(c->n_img * D, MPAD) * c->NVA : nullptr;
@@ -414,8 +442,8 @@ static int step_impl(Ctx* c, const float* h1, const float* c1, const float* h2, 
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   VSR_TRY(launch_words(c, word, b, st));
   if (c->use_tc) {
-    VSR_TRY(launch_split_f16(c->h1, c->h1_b.hi, c->h1_b.lo, (size_t)b * c->Hp, st));
-    VSR_TRY(launch_split_f16(c->h2, c->h2_b.hi, c->h2_b.lo, (size_t)b * c->Hp, st));
+    VSR_TRY(launch_split_pair(c->h1, c->h1_b, (size_t)b * c->Hp, st));
+    VSR_TRY(launch_split_pair(c->h2, c->h2_b, (size_t)b * c->Hp, st));
     c->launches += 2;
   }
   StepIO io{};
@@ -450,7 +478,6 @@ static int enqueue_beam_steps(Ctx* c, int k, const int64_t* eos, int use_verbs, 
     StepIO io{};
     io.rows = rows; io.cur_beam = cur; io.use_verbs = use_verbs != 0; io.gt = gt != 0; io.topk = k;
     io.zero_state = t == 0 && c->zero_state_opt;
-    io.defer_head = c->fuse_tail;
     if (tr && tr->step_out) { io.out_logp = tr->step_out + (size_t)t * b * k * c->V; io.out_stride = c->V; }
     if (tr && tr->step_gate) { io.gate_out = tr->step_gate + (size_t)t * b * k * 2; io.gate_stride = 2; }
     VSR_TRY(run_step(c, io, st));
@@ -499,12 +526,22 @@ static int beam_search_impl(Ctx* c, int k, int out_size, const int64_t* eos, int
   return VSR_OK;
 }
 
-static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, float* gate, cudaStream_t st) {
-  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_forward_teacher: call vsr_prologue first");
-  VSR_REQUIRE(captions && out && gate, VSR_EINVAL, "vsr_forward_teacher: null argument");
-  VSR_REQUIRE(T >= 1 && T <= c->L, VSR_EINVAL, "vsr_forward_teacher: T=%d exceeds the prologue's slot count L=%d", T, c->L);
+// (re)size the all-steps buffers of the batched teacher-forced forward
+static int ensure_fwd_ws(Ctx* c, int rows) {
+  if (rows <= c->cap_fwd_rows) return VSR_OK;
+  const int cap = round_up(rows, MPAD);
+  dev_free(c, c->logits_all); dev_free(c, c->gate_all);
+  c->logits_all = c->gate_all = nullptr; c->cap_fwd_rows = 0;
+  ALLOC_F(c->logits_all, (size_t)cap * c->NE); ALLOC_F(c->gate_all, (size_t)cap * 2);
+  VSR_TRY(alloc_pair(c, &c->h2all_b, cap, c->Hp, MPAD, step_kind(c)));
+  c->cap_fwd_rows = cap;
+  return VSR_OK;
+}
+
+// the recurrent part of the teacher-forced unroll: everything except the vocabulary projection, which does not feed
+// back (CaptioningModel.py:22-36) and therefore runs ONCE over all (caption, step) rows after the loop
+static int enqueue_forward_steps(Ctx* c, const int64_t* captions, int T, bool batched, float* out, float* gate, cudaStream_t st) {
   const int b = c->b;
-  VSR_TRY(ensure_rows(c, b));
   VSR_TRY(launch_state_init(c, b, st));
   // the first input token is captions[:, 0], not bos (controllable_captioning.py:131-133)
   for (int t = 0; t < T; ++t) {
@@ -517,11 +554,41 @@ static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, floa
     StepIO io{};
     io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 0;
     io.zero_state = t == 0 && c->zero_state_opt;
-    io.out_logp = out + (size_t)t * c->V; io.out_stride = (int64_t)T * c->V;
-    io.gate_out = gate + (size_t)t * 2; io.gate_stride = (int64_t)T * 2;
-    VSR_TRY(run_step(c, io, st));
+    if (batched) {
+      io.skip_vocab = true;
+      VSR_TRY(run_step(c, io, st));
+      VSR_TRY(launch_gate_head(c, b, c->gate_all + (size_t)t * 2, (int64_t)T * 2, st));      // row i -> (i, t)
+      VSR_TRY(launch_rows_to_all(c, c->h2n_b, c->h2all_b, b, T, t, st));
+    } else {
+      io.out_logp = out + (size_t)t * c->V; io.out_stride = (int64_t)T * c->V;
+      io.gate_out = gate + (size_t)t * 2; io.gate_stride = (int64_t)T * 2;
+      VSR_TRY(run_step(c, io, st));
+    }
     if (t + 1 < T) VSR_TRY(launch_commit_identity(c, b, captions + (t + 1), T, t + 1, st));
   }
+  if (batched) VSR_TRY(run_vocab_rows(c, c->h2all_b, c->logits_all, b * T, nullptr, st, false));   // M = b*T rows
+  return VSR_OK;
+}
+
+static int forward_impl(Ctx* c, const int64_t* captions, int T, float* out, float* gate, cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_forward_teacher: call vsr_prologue first");
+  VSR_REQUIRE(captions && out && gate, VSR_EINVAL, "vsr_forward_teacher: null argument");
+  VSR_REQUIRE(T >= 1 && T <= c->L, VSR_EINVAL, "vsr_forward_teacher: T=%d exceeds the prologue's slot count L=%d", T, c->L);
+  const int b = c->b;
+  VSR_TRY(ensure_rows(c, b));
+  const bool batched = c->use_tc;        // (the FFMA twin keeps the plain per-step unroll)
+  if (!batched) return enqueue_forward_steps(c, captions, T, false, out, gate, st);
+  VSR_TRY(ensure_fwd_ws(c, b * T));
+  if (graphs_usable(c, st)) {            // the loop + the batched vocabulary GEMM replay from the graph cache (kind 2)
+    Ctx::GraphKey key = graph_key(c, 2);
+    key.captions = captions; key.T = T;
+    VSR_TRY(run_graphed(c, key, st, [&](cudaStream_t s) { return enqueue_forward_steps(c, captions, T, true, nullptr, nullptr, s); }));
+  } else {
+    VSR_TRY(enqueue_forward_steps(c, captions, T, true, nullptr, nullptr, st));
+  }
+  // caller-owned outputs are written outside the graph: log-softmax of the b*T vocabulary rows, and the gate rows
+  VSR_TRY(run_vocab_rows(c, c->h2all_b, c->logits_all, b * T, out, st, true));
+  VSR_CHECK_CUDA(cudaMemcpyAsync(gate, c->gate_all, sizeof(float) * (size_t)b * T * 2, cudaMemcpyDeviceToDevice, st));
   return VSR_OK;
 }
 
@@ -538,6 +605,26 @@ static int greedy_impl(Ctx* c, int64_t* out_words, int64_t* out_gates, cudaStrea
     io.zero_state = t == 0 && c->zero_state_opt;
     VSR_TRY(run_step(c, io, st));
     VSR_TRY(launch_greedy_pick(c, b, t, T, out_words, out_gates, st));
+    if (t + 1 < T) VSR_TRY(launch_commit_identity(c, b, nullptr, 0, -1, st));
+  }
+  return VSR_OK;
+}
+
+// multinomial sampling decode: the whole loop on the device, one pick kernel per step, no host work in between
+static int sample_impl(Ctx* c, uint64_t seed, int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
+                       cudaStream_t st) {
+  VSR_REQUIRE(c->have_prologue, VSR_ESTATE, "vsr_sample: call vsr_prologue first");
+  VSR_REQUIRE(out_words && out_gates && lp_words && lp_gates, VSR_EINVAL, "vsr_sample: null argument");
+  const int b = c->b, T = c->d.seq_len;
+  VSR_TRY(ensure_rows(c, b));
+  VSR_TRY(ensure_beam_ws(c, b, T));
+  VSR_TRY(launch_state_init(c, b, st));
+  for (int t = 0; t < T; ++t) {
+    StepIO io{};
+    io.rows = b; io.cur_beam = 1; io.use_verbs = false; io.gt = false; io.topk = 0;     // statistics + gate head only
+    io.zero_state = t == 0 && c->zero_state_opt;
+    VSR_TRY(run_step(c, io, st));
+    VSR_TRY(launch_sample_pick(c, b, t, T, seed, out_words, out_gates, lp_words, lp_gates, st));
     if (t + 1 < T) VSR_TRY(launch_commit_identity(c, b, nullptr, 0, -1, st));
   }
   return VSR_OK;
@@ -682,11 +769,19 @@ int vsr_greedy(vsr_handle h, int64_t* out_words, int64_t* out_gates, void* strea
   return vsr::greedy_impl((Ctx*)h, out_words, out_gates, (cudaStream_t)stream);
 }
 
+int vsr_sample(vsr_handle h, uint64_t seed, int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates,
+               void* stream) {
+  if (!h) { vsr::set_error("vsr_sample: null handle"); return VSR_EINVAL; }
+  DeviceGuard dg((const vsr::Ctx*)h);
+  return vsr::sample_impl((Ctx*)h, seed, out_words, out_gates, lp_words, lp_gates, (cudaStream_t)stream);
+}
+
 int64_t vsr_launch_count(vsr_handle h) { return h ? ((Ctx*)h)->launches : -1; }
 
 const char* vsr_gemm_kind(vsr_handle h) {
   if (!h) return "none";
-  return ((Ctx*)h)->use_tc ? "tcgen05-f16x3" : "simt-fp32";
+  const Ctx* c = (const Ctx*)h;
+  return !c->use_tc ? "simt-fp32" : (c->gemm_f8 ? "tcgen05-f16+f8x2" : "tcgen05-f16x3");
 }
 
 int vsr_set_profiling(vsr_handle h, int32_t enabled) {

@@ -8,11 +8,14 @@
 #include <math.h>
 
 #include "common.cuh"
-#include "vocab_head.cuh"
 
 namespace vsr {
 
 namespace {
+
+__device__ __forceinline__ bool before(float v1, int i1, float v2, int i2) {
+  return v1 > v2 || (v1 == v2 && i1 < i2);
+}
 
 // log-prob of vocabulary entry `word` in row `row` as returned by the step (post verb forcing)
 __device__ __forceinline__ float row_logp(const float* logits, int ld, const float* row_max,
@@ -21,15 +24,6 @@ __device__ __forceinline__ float row_logp(const float* logits, int ld, const flo
   if (f >= 0) return word == f ? 0.f : -1e6f;
   return (logits[(size_t)row * ld + word] - row_max[row]) - row_lsum[row];
 }
-
-// Heads of a caption's rows left in shared memory by the merge warps of the fused tail kernel (k_tail): the selection
-// then needs no global round trip for the candidates, their log-probs, the gate log-probs and the row statistics.
-struct HeadSmem {
-  float mx[VSR_MAX_BEAM], ls[VSR_MAX_BEAM], gate[VSR_MAX_BEAM][2];
-  int forced[VSR_MAX_BEAM];
-  int cand[VSR_MAX_BEAM][VSR_MAX_BEAM];
-  float wlp[VSR_MAX_BEAM][VSR_MAX_BEAM];      // post-forcing word log-prob of every candidate
-};
 
 struct BeamArgs {
   int t, b, cur, k, V;
@@ -44,20 +38,7 @@ struct BeamArgs {
   int32_t *hist_parent, *hist_word, *hist_gate;    // [T][b][k] slices for step t
   float *hist_score, *hist_lpw, *hist_lpg;
   const int32_t *f_beam, *f_word, *f_gate;        // forced selections for step t or null
-  const HeadSmem* hs;                              // k_tail: the rows' heads in shared memory (else read from global)
 };
-
-// post-forcing word log-prob of `word` in beam row j (global row `row`) of the caption
-__device__ __forceinline__ float pick_logp(const BeamArgs& a, int row, int j, int word) {
-  if (a.hs == nullptr) return row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
-  const int f = a.hs->forced[j];
-  if (f >= 0) return word == f ? 0.f : -1e6f;
-  for (int i = 0; i < a.k; ++i) if (a.hs->cand[j][i] == word) return a.hs->wlp[j][i];
-  return (a.logits[(size_t)row * a.ld + word] - a.hs->mx[j]) - a.hs->ls[j];     // trajectory replay / frozen beams
-}
-__device__ __forceinline__ float gate_logp(const BeamArgs& a, int row, int j, int g) {
-  return a.hs == nullptr ? a.gate_lp[row * 2 + g] : a.hs->gate[j][g];
-}
 
 constexpr int MAXC = 2 * VSR_MAX_BEAM * VSR_MAX_BEAM;  // 128 candidates per caption
 
@@ -98,13 +79,9 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
         const int row = c * cur + j;
         int word; float sc;
         if (s_full[j]) {
-          float wl;
-          if (a.hs != nullptr) { word = a.hs->cand[j][i]; wl = a.hs->wlp[j][i]; }
-          else {
-            word = a.cand[row * VSR_MAX_BEAM + i];
-            wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
-          }
-          sc = __fadd_rn(s_seq[j], __fadd_rn(wl, gate_logp(a, row, j, g)));   // seq + (word + gate), :139
+          word = a.cand[row * VSR_MAX_BEAM + i];
+          const float wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+          sc = __fadd_rn(s_seq[j], __fadd_rn(wl, a.gate_lp[row * 2 + g]));   // seq + (word + gate), :139
         } else {
           // frozen beam: old score at word 0 (both gates), -999 elsewhere (:146-150)
           word = i;
@@ -140,8 +117,8 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
     const int row = c * cur + j;
     float sc;
     if (s_full[j]) {
-      const float wl = pick_logp(a, row, j, word);
-      sc = __fadd_rn(s_seq[j], __fadd_rn(wl, gate_logp(a, row, j, g)));
+      const float wl = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+      sc = __fadd_rn(s_seq[j], __fadd_rn(wl, a.gate_lp[row * 2 + g]));
     } else {
       sc = (word == 0) ? s_seq[j] : -999.f;
     }
@@ -154,8 +131,8 @@ __device__ __forceinline__ void beam_select_warp(const BeamArgs& a, BeamSmem& sh
     const int row = c * cur + j;
     const int o = c * k + lane;
     // per-token log-probs of the pick, in slot order, masked by the parent's sticky masks (:145,175-177)
-    float lw = pick_logp(a, row, j, word);
-    float lg = gate_logp(a, row, j, g);
+    float lw = row_logp(a.logits, a.ld, a.row_max, a.row_lsum, a.forced, row, word);
+    float lg = a.gate_lp[row * 2 + g];
     if (a.t > 0) { lw *= s_m0[j]; lg *= s_m1[j]; }
     a.sel_beam[o] = j; a.sel_word[o] = word; a.sel_gate[o] = g;
     a.seq_lp_n[o] = s_ps[lane];
@@ -178,9 +155,10 @@ struct AdvanceArgs {
   float *h1, *c1, *h2, *c2;
   const int32_t* ptr; int32_t* ptrn;
   int32_t* word_idx;
-  // fp16 hi/lo twins (null on the fp32 path): 16-byte vectors of 8 fp16
-  const uint4 *h1n_hi, *h1n_lo, *h2n_hi, *h2n_lo;
-  uint4 *h1_hi, *h1_lo, *h2_hi, *h2_lo;
+  // tensor-core twins of h1 / h2 (none on the fp32 path), moved as raw 16-byte vectors: per state up to three arrays
+  // (fp16 hi + fp16 lo, or fp16 hi + e4m3 hi8 + e4m3 lo8) of `tw_vec[i]` vectors per row
+  int n_tw;
+  const uint4* tw_src[6]; uint4* tw_dst[6]; int tw_vec[6];
 };
 
 // copy the state of parent row p into new row n, record the next input word, update the slot pointer
@@ -195,12 +173,11 @@ __device__ __forceinline__ void advance_row(const AdvanceArgs& a, int n, int p, 
     *reinterpret_cast<float4*>(a.c2 + dof + i) = *reinterpret_cast<const float4*>(a.c2n + so + i);
   }
   w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
-  if (a.h1_hi != nullptr) {
-    const size_t sv = (size_t)p * (a.Hp / 8), dv = (size_t)n * (a.Hp / 8);
-    for (int i = threadIdx.x; i < a.Hp / 8; i += blockDim.x) {
-      a.h1_hi[dv + i] = a.h1n_hi[sv + i]; a.h1_lo[dv + i] = a.h1n_lo[sv + i];
-      a.h2_hi[dv + i] = a.h2n_hi[sv + i]; a.h2_lo[dv + i] = a.h2n_lo[sv + i];
-    }
+  for (int q = 0; q < a.n_tw; ++q) {
+    const int nv = a.tw_vec[q];
+    const uint4* src = a.tw_src[q] + (size_t)p * nv;
+    uint4* dst = a.tw_dst[q] + (size_t)n * nv;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) dst[i] = src[i];
   }
   if (threadIdx.x == 0) {
     a.word_idx[n] = (int32_t)w;
@@ -236,83 +213,16 @@ __global__ void __launch_bounds__(256) k_beam_step(const BeamArgs b, const Advan
   advance_row(a, c * b.k + i, c * b.cur + sh.pb[i], (int64_t)sh.pw[i], sh.pg[i]);
 }
 
-// Fused tail of a beam-search step, one CTA per CAPTION: warp j finishes the vocabulary head of beam row j (merge_row:
-// softmax statistics, exact top-k words, gate head, verb forcing), warp 0 then selects the caption's k best (parent,
-// word, gate) candidates out of shared memory, and the whole CTA moves the k new beam rows' states.  One launch instead
-// of k_vocab_merge + k_beam_step, no global round trip between merge and selection, one merge per row.
-constexpr int TAIL_THREADS = 512;
-__global__ void __launch_bounds__(TAIL_THREADS) k_tail(const SoftmaxArgs m, const float* __restrict__ vpart, int n_tiles,
-                                                       int nch, BeamArgs b, const AdvanceArgs a, int do_advance) {
-  __shared__ BeamSmem sh;
-  __shared__ HeadSmem hs;
-  const int c = blockIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  pdl_trigger();
-  pdl_wait();
-  if (warp < b.cur) {
-    RowHead h;
-    merge_row(m, vpart, n_tiles, nch, c * b.cur + warp, lane, h);
-    if (lane == 0) {
-      hs.mx[warp] = h.mx; hs.ls[warp] = h.lsum; hs.forced[warp] = h.forced;
-      hs.gate[warp][0] = h.g0; hs.gate[warp][1] = h.g1;
-    }
-    if (lane < m.topk) {
-      hs.cand[warp][lane] = h.pick;
-      hs.wlp[warp][lane] = h.forced >= 0 ? (h.pick == h.forced ? 0.f : -1e6f) : (h.pick_logit - h.mx) - h.lsum;
-    }
-  }
-  __syncthreads();
-  b.hs = &hs;
-  if (warp == 0) beam_select_warp(b, sh, c, lane, true);
-  __syncthreads();
-  if (!do_advance) return;
-  // move the k new rows: (row i, 16-byte piece) flattened over the CTA
-  const int k = b.k, Hp = a.Hp;
-  const int p4 = Hp / 4;                      // float4 pieces of an fp32 state row
-  for (int idx = threadIdx.x; idx < k * p4; idx += TAIL_THREADS) {
-    const int i = idx / p4, e = (idx - i * p4) * 4;
-    const size_t so = (size_t)(c * b.cur + sh.pb[i]) * Hp + e, dof = (size_t)(c * k + i) * Hp + e;
-    if (a.h1n != nullptr) {
-      *reinterpret_cast<float4*>(a.h1 + dof) = *reinterpret_cast<const float4*>(a.h1n + so);
-      *reinterpret_cast<float4*>(a.h2 + dof) = *reinterpret_cast<const float4*>(a.h2n + so);
-    }
-    *reinterpret_cast<float4*>(a.c1 + dof) = *reinterpret_cast<const float4*>(a.c1n + so);
-    *reinterpret_cast<float4*>(a.c2 + dof) = *reinterpret_cast<const float4*>(a.c2n + so);
-  }
-  if (a.h1_hi != nullptr) {
-    const int p8 = Hp / 8;                    // uint4 pieces of an fp16 row
-    for (int idx = threadIdx.x; idx < k * p8; idx += TAIL_THREADS) {
-      const int i = idx / p8, e = idx - i * p8;
-      const size_t sv = (size_t)(c * b.cur + sh.pb[i]) * p8 + e, dv = (size_t)(c * k + i) * p8 + e;
-      a.h1_hi[dv] = a.h1n_hi[sv]; a.h1_lo[dv] = a.h1n_lo[sv];
-      a.h2_hi[dv] = a.h2n_hi[sv]; a.h2_lo[dv] = a.h2n_lo[sv];
-    }
-  }
-  if (threadIdx.x < k) {
-    const int i = threadIdx.x, n = c * k + i, p = c * b.cur + sh.pb[i];
-    int w = sh.pw[i];
-    w = w < 0 ? 0 : (w >= a.V ? a.V - 1 : w);
-    a.word_idx[n] = w;
-    int s = a.ptr[p] + sh.pg[i];                                   // ctrl_det_idxs + prev gate, clamped (:139-140)
-    s = s < 0 ? 0 : (s > a.L - 1 ? a.L - 1 : s);
-    a.ptrn[n] = s;
-  }
-}
-
 // zero state, slot 0, input word = bos   (init_state, controllable_captioning.py:109-115, :136)
-struct PairPtr { __half* hi; __half* lo; };
-
 __global__ void k_state_init(float* h1, float* c1, float* h2, float* c2, int32_t* word_idx, int32_t* ptr,
-                             int bos, int Hp, PairPtr h1b, PairPtr h2b) {
+                             int bos, int Hp, TwinOut h1b, TwinOut h2b) {
   const int n = blockIdx.x;
-  const __half z = __float2half_rn(0.f);
-  for (int i = threadIdx.x; i < Hp; i += blockDim.x) {
-    h1[(size_t)n * Hp + i] = 0.f; c1[(size_t)n * Hp + i] = 0.f;
-    h2[(size_t)n * Hp + i] = 0.f; c2[(size_t)n * Hp + i] = 0.f;
-    if (h1b.hi != nullptr) {
-      h1b.hi[(size_t)n * Hp + i] = z; h1b.lo[(size_t)n * Hp + i] = z;
-      h2b.hi[(size_t)n * Hp + i] = z; h2b.lo[(size_t)n * Hp + i] = z;
-    }
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x * 4; i < Hp; i += blockDim.x * 4) {
+    const size_t o = (size_t)n * Hp + i;
+    *reinterpret_cast<float4*>(h1 + o) = z; *reinterpret_cast<float4*>(c1 + o) = z;
+    *reinterpret_cast<float4*>(h2 + o) = z; *reinterpret_cast<float4*>(c2 + o) = z;
+    store_twin4(h1b, o, z); store_twin4(h2b, o, z);       // (all-zero bit patterns in fp16 and e4m3 alike)
   }
   if (threadIdx.x == 0) { ptr[n] = 0; word_idx[n] = bos; }
 }
@@ -335,6 +245,68 @@ __global__ void k_greedy_pick(const int32_t* cand, const float* gate_lp, int32_t
   const int g = gate_lp[n * 2 + 1] > gate_lp[n * 2 + 0] ? 1 : 0;
   sel_word[n] = w; sel_gate[n] = g;
   out_words[(size_t)n * T + t] = w; out_gates[(size_t)n * T + t] = g;
+}
+
+// ---------------------------------------------------------------- multinomial sampling (CaptioningModel.sample_rl)
+// Philox4x32-10 counter-based generator: the draw of (seed, row, step, vocabulary entry) never depends on launch shape.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.f / 16777216.f); }   // (0, 1)
+
+// One CTA per row: word ~ Categorical(softmax(logits)) by the Gumbel-max trick (argmax of logit + G, G = -log(-log u),
+// which draws index v with probability exp(logit_v) / sum exp), gate ~ Categorical(exp(gate_lp)); log-probs of the
+// draws as torch.distributions.Categorical(logits=out).log_prob(sample) returns them (CaptioningModel.py:66-70).
+__global__ void __launch_bounds__(256) k_sample_pick(const float* __restrict__ logits, int ld, int V, const float* __restrict__ row_max,
+                                                     const float* __restrict__ row_lsum, const float* __restrict__ gate_lp,
+                                                     unsigned long long seed, int t, int T, int32_t* sel_word, int32_t* sel_gate,
+                                                     int64_t* out_words, int64_t* out_gates, float* lp_words, float* lp_gates) {
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = logits + (size_t)n * ld;
+  const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int v0 = tid * 4; v0 < V; v0 += 256 * 4) {
+    const uint4 r = philox4x32_10(make_uint4((unsigned)(v0 >> 2), (unsigned)n, (unsigned)t, 0u), key);
+    const float4 q = *reinterpret_cast<const float4*>(x + v0);        // rows are padded to a multiple of 4 columns
+    const float xs[4] = {q.x, q.y, q.z, q.w};
+    const unsigned rs[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (v0 + e >= V) break;
+      const float g = -logf(-logf(u01(rs[e])));
+      const float sc = xs[e] + g;
+      if (sc > bv) { bv = sc; bi = v0 + e; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (before(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) if (before(s_v[w], s_i[w], bv, bi)) { bv = s_v[w]; bi = s_i[w]; }
+    const int word = bi < V ? bi : V - 1;
+    const float lw = (x[word] - row_max[n]) - row_lsum[n];
+    // gate: two categories with log-probs gate_lp[n]; counter word 1 keeps this draw apart from the vocabulary's
+    const uint4 r = philox4x32_10(make_uint4(0u, (unsigned)n, (unsigned)t, 1u), key);
+    const float g0 = gate_lp[(size_t)n * 2], g1 = gate_lp[(size_t)n * 2 + 1];
+    const int gate = u01(r.x) < expf(g0) ? 0 : 1;
+    sel_word[n] = word; sel_gate[n] = gate;
+    out_words[(size_t)n * T + t] = word; out_gates[(size_t)n * T + t] = gate;
+    lp_words[(size_t)n * T + t] = lw; lp_gates[(size_t)n * T + t] = gate == 0 ? g0 : g1;
+  }
 }
 
 // final ordering of the beams by accumulated score (stable, descending) and unroll of the
@@ -386,12 +358,7 @@ __global__ void __launch_bounds__(64) k_backtrack(int b, int k, int T, int out_s
 
 }  // namespace
 
-static PairPtr pp(const Ctx* c, const F16Pair& b) {
-  PairPtr p;
-  p.hi = c->use_tc ? (__half*)b.hi : nullptr;
-  p.lo = c->use_tc ? (__half*)b.lo : nullptr;
-  return p;
-}
+static TwinOut pp(const Ctx* c, const F16Pair& b) { return twin_out(&b, c->use_tc); }
 
 int launch_state_init(Ctx* c, int rows, cudaStream_t st) {
   k_state_init<<<rows, 256, 0, st>>>(c->h1, c->c1, c->h2, c->c2, c->word_idx, c->ptr, c->d.bos_idx, c->Hp,
@@ -411,11 +378,19 @@ static void fill_advance(Ctx* c, AdvanceArgs& a) {
   a.h1n = c->state_h32 ? c->h1n : nullptr; a.c1n = c->c1n; a.h2n = c->state_h32 ? c->h2n : nullptr; a.c2n = c->c2n;
   a.h1 = c->h1; a.c1 = c->c1; a.h2 = c->h2; a.c2 = c->c2;
   a.ptr = c->ptr; a.ptrn = c->ptrn; a.word_idx = c->word_idx;
+  a.n_tw = 0;
   if (c->use_tc) {
-    a.h1n_hi = (const uint4*)c->h1n_b.hi; a.h1n_lo = (const uint4*)c->h1n_b.lo;
-    a.h2n_hi = (const uint4*)c->h2n_b.hi; a.h2n_lo = (const uint4*)c->h2n_b.lo;
-    a.h1_hi = (uint4*)c->h1_b.hi; a.h1_lo = (uint4*)c->h1_b.lo;
-    a.h2_hi = (uint4*)c->h2_b.hi; a.h2_lo = (uint4*)c->h2_b.lo;
+    auto add = [&](const void* src, void* dst, int bytes_per_elem) {
+      if (src == nullptr || dst == nullptr) return;
+      a.tw_src[a.n_tw] = (const uint4*)src; a.tw_dst[a.n_tw] = (uint4*)dst; a.tw_vec[a.n_tw] = c->Hp * bytes_per_elem / 16;
+      ++a.n_tw;
+    };
+    const F16Pair* src[2] = {&c->h1n_b, &c->h2n_b};
+    F16Pair* dst[2] = {&c->h1_b, &c->h2_b};
+    for (int q = 0; q < 2; ++q) {
+      add(src[q]->hi, dst[q]->hi, 2); add(src[q]->lo, dst[q]->lo, 2);
+      add(src[q]->hi8, dst[q]->hi8, 1); add(src[q]->lo8, dst[q]->lo8, 1);
+    }
   }
 }
 
@@ -438,14 +413,7 @@ int launch_beam_step(Ctx* c, int t, int b, int cur, int k, int64_t eos0, int64_t
   AdvanceArgs ad{};
   ad.rows_new = b * k; ad.cur = cur; ad.k = k; ad.fixed_slot = -1;
   fill_advance(c, ad);
-  if (c->head_deferred) {      // the step left its vocabulary head to this launch (run_step, StepIO::defer_head)
-    SoftmaxArgs m = make_softmax_args(c, b * cur, cur, k, c->head_use_verbs, c->head_gt);
-    VSR_CHECK_CUDA(launch_k(k_tail, dim3(b), dim3(TAIL_THREADS), 0, st, c->use_pdl && (c->pdl_mode & 2), m, (const float*)c->vpart,
-                            c->head_tiles, c->head_nch, a, ad, advance ? 1 : 0));
-    c->head_deferred = false;
-  } else {
-    VSR_CHECK_CUDA(launch_k(k_beam_step, dim3(b, advance ? k : 1), dim3(256), 0, st, c->use_pdl && (c->pdl_mode & 2), a, ad, advance ? 1 : 0));
-  }
+  VSR_CHECK_CUDA(launch_k(k_beam_step, dim3(b, advance ? k : 1), dim3(256), 0, st, c->use_pdl && (c->pdl_mode & 2), a, ad, advance ? 1 : 0));
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   std::swap(c->sel_beam, c->sel_beam_n);
   std::swap(c->sel_word, c->sel_word_n);
@@ -482,6 +450,15 @@ int launch_greedy_pick(Ctx* c, int rows, int t, int T, int64_t* out_words, int64
   PhaseScope ps(c, PH_BEAM, st);
   k_greedy_pick<<<(rows + 127) / 128, 128, 0, st>>>(c->cand, c->gate_lp, c->sel_word, c->sel_gate,
                                                     out_words, out_gates, rows, t, T);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+int launch_sample_pick(Ctx* c, int rows, int t, int T, uint64_t seed, int64_t* out_words, int64_t* out_gates,
+                       float* lp_words, float* lp_gates, cudaStream_t st) {
+  PhaseScope ps(c, PH_BEAM, st);
+  k_sample_pick<<<rows, 256, 0, st>>>(c->logits, c->NE, c->V, c->row_max, c->row_lsum, c->gate_lp, (unsigned long long)seed, t, T,
+                                      c->sel_word, c->sel_gate, out_words, out_gates, lp_words, lp_gates);
   VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   return VSR_OK;
 }

@@ -37,6 +37,10 @@ void set_error(const char* fmt, ...);
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 #ifdef __CUDACC__
+}  // namespace vsr
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+namespace vsr {
 // Gate non-linearities on the SFU (ex2.approx + fast reciprocal): absolute error ~1e-7, i.e. fp32 rounding
 // level, at ~1/4 of the instructions of expf/tanhf.  tanh via 1 - 2/(e^{2x}+1) saturates cleanly (e^{2x} = inf
 // -> 1, = 0 -> -1); its relative error grows for |x| << 1 but the ABSOLUTE error stays ~1e-7, which is what
@@ -53,9 +57,19 @@ constexpr int MPAD = 128;   // UMMA M tile
 
 // An fp32 matrix carried as an error-compensated fp16 pair (x = hi + lo + O(2^-22 x)) with the TMA
 // tensor maps (64 x box_rows boxes, 128-byte swizzle) the tcgen05 GEMM loads it through.
+// Activation twins of the f16+f8x2 GEMM mode are stored scaled by ACT_SCALE_F8 (a power of two, exact): their
+// residuals x*s - fp16(x*s) then sit in the normal range of e4m3 for the |x| ~ 1e-2..1 of the decoder's states.
+constexpr float ACT_SCALE_F8 = 256.f;
+
 struct F16Pair {
   void* hi = nullptr;   // __half [rows][ld]
-  void* lo = nullptr;
+  void* lo = nullptr;   // __half residual (f16x3 mode), or null
+  // f16+f8x2 mode: e4m3 twins, uint8 [rows][ld].  hi8 = e4m3(hi / 32), lo8 = e4m3((x*s - hi) * 32): with these
+  // shifts hi*W_hi (fp16), hi8*W_lo8 and lo8*W_hi8 (fp8) all carry the same power-of-two scale and accumulate into
+  // ONE fp32 TMEM accumulator; both e4m3 operands stay inside the format's normal range (|hi| <= 2^13).
+  void* hi8 = nullptr;
+  void* lo8 = nullptr;
+  float act_scale = 1.f;   // activations: the constant the producer multiplied x by (1, or ACT_SCALE_F8 in f16+f8x2 mode)
   int rows = 0, ld = 0, box_rows = 0;
   // (weights only) device [2] = {s, 1/s}: the pair holds x * s with s the power of two that brings max|x| to 2^13..2^14,
   // so lo parts of small weights stay out of the fp16 subnormals; the GEMM epilogue multiplies the accumulator by 1/s
@@ -66,12 +80,61 @@ struct F16Pair {
   alignas(64) unsigned char map_lo[128];
   alignas(64) unsigned char map32_hi[128];   // 32-element k-blocks, 64-byte swizzle
   alignas(64) unsigned char map32_lo[128];
+  alignas(64) unsigned char map8_hi[128];    // e4m3 twins, 64-element k-blocks (64-byte rows, 64-byte swizzle)
+  alignas(64) unsigned char map8_lo[128];
+  alignas(64) unsigned char map8_32_hi[128]; // e4m3 twins, 32-element k-blocks (32-byte rows, 32-byte swizzle)
+  alignas(64) unsigned char map8_32_lo[128];
+  alignas(64) unsigned char alt8_hi[128];    // e4m3 twins, alternative N tile
+  alignas(64) unsigned char alt8_lo[128];
+  // (weights only) CTA-pair kernel: each CTA of the pair loads pair_rows = BN / 2 rows of a BN-wide W tile (64-element k-blocks)
+  int pair_rows = 0;
+  alignas(64) unsigned char pair_hi[128];
+  alignas(64) unsigned char pair_lo[128];    // fp16 residual (f16x3) or e4m3 residual (f16+f8x2)
+  alignas(64) unsigned char pair_h8[128];    // e4m3 copy of hi (f16+f8x2)
   // (weights only) alternative N tile, chosen per launch when it needs fewer waves over the 148 SMs
   int n_valid = 0;      // real number of output rows (<= rows)
   int alt_bn = 0, alt_kb = 64;
   alignas(64) unsigned char alt_hi[128];
   alignas(64) unsigned char alt_lo[128];
 };
+
+// Where a kernel writes the tensor-core twins of an activation it produces (any pointer may be null).
+struct TwinOut {
+  void* hi; void* lo; uint8_t* hi8; uint8_t* lo8;
+  float scale;
+};
+inline TwinOut twin_out(const F16Pair* b, bool enabled = true) {
+  TwinOut o{nullptr, nullptr, nullptr, nullptr, 1.f};
+  if (b != nullptr && enabled) { o.hi = b->hi; o.lo = b->lo; o.hi8 = (uint8_t*)b->hi8; o.lo8 = (uint8_t*)b->lo8; o.scale = b->act_scale; }
+  return o;
+}
+#ifdef __CUDACC__
+// twins of four consecutive values at element offset off (multiple of 4)
+__device__ __forceinline__ void store_twin4(const TwinOut& o, size_t off, const float4 v) {
+  if (o.hi == nullptr) return;
+  const float x[4] = {fminf(fmaxf(v.x * o.scale, -65504.f), 65504.f), fminf(fmaxf(v.y * o.scale, -65504.f), 65504.f),
+                      fminf(fmaxf(v.z * o.scale, -65504.f), 65504.f), fminf(fmaxf(v.w * o.scale, -65504.f), 65504.f)};
+  __align__(8) __half h[4];
+  float hf[4], r[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); hf[j] = __half2float(h[j]); r[j] = x[j] - hf[j]; }
+  *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(o.hi) + off) = *reinterpret_cast<const uint2*>(h);
+  if (o.lo != nullptr) {
+    __align__(8) __half l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) l[j] = __float2half_rn(r[j]);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(o.lo) + off) = *reinterpret_cast<const uint2*>(l);
+  }
+  if (o.hi8 != nullptr) {
+    const unsigned h01 = __nv_cvt_float2_to_fp8x2(make_float2(hf[0] * 0.03125f, hf[1] * 0.03125f), __NV_SATFINITE, __NV_E4M3);
+    const unsigned h23 = __nv_cvt_float2_to_fp8x2(make_float2(hf[2] * 0.03125f, hf[3] * 0.03125f), __NV_SATFINITE, __NV_E4M3);
+    const unsigned l01 = __nv_cvt_float2_to_fp8x2(make_float2(r[0] * 32.f, r[1] * 32.f), __NV_SATFINITE, __NV_E4M3);
+    const unsigned l23 = __nv_cvt_float2_to_fp8x2(make_float2(r[2] * 32.f, r[3] * 32.f), __NV_SATFINITE, __NV_E4M3);
+    *reinterpret_cast<uint32_t*>(o.hi8 + off) = h01 | (h23 << 16);
+    *reinterpret_cast<uint32_t*>(o.lo8 + off) = l01 | (l23 << 16);
+  }
+}
+#endif
 
 // ---------------------------------------------------------------- GEMM (C = sum_seg A_seg * W_seg^T + ...)
 struct GemmSeg {
@@ -116,13 +179,13 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 struct FusedCell {
   int mode = 0;                 // 0 = plain, 1 = LSTM cell 1 (+ sentinel gate, 6 gates), 2 = LSTM cell 2 (4 gates)
   const float* c_old = nullptr; float* c_new = nullptr; float* h_new = nullptr;
-  void *h_hi = nullptr, *h_lo = nullptr;
-  float* s_new = nullptr; void *s_hi = nullptr, *s_lo = nullptr;   // mode 1: s_t = sig(s) * tanh(c1')
+  const F16Pair *h_b = nullptr, *s_b = nullptr, *g_b = nullptr;     // twins of h_new / s_new / g_t to write (or null)
+  float* s_new = nullptr;                                           // mode 1: s_t = sig(s) * tanh(c1')
   float* gq = nullptr;                                              // mode 1: shift-gate pre-activation (input_1 part)
   int ld_state = 0;
   // plain mode only: on output columns [0, gt_cols) write g_t = sig(gq + acc) * tanh(c1') instead of acc
   int gt_cols = 0; const float* gt_gq = nullptr; const float* gt_c1n = nullptr;
-  float* g_t = nullptr; void *g_hi = nullptr, *g_lo = nullptr;
+  float* g_t = nullptr;
   // mode 3 (vocabulary head): besides the logits, per (row, N tile) records of VOCAB_REC floats
   // {tile max, sum exp(x - max), max of each 16-column chunk}.  *vocab_tiles_out / *vocab_bn_out = tiling of the launch.
   float* vocab_part = nullptr; int* vocab_tiles_out = nullptr; int* vocab_bn_out = nullptr;
@@ -147,6 +210,9 @@ struct GemmArgs {
   const int32_t* gather_idx = nullptr;
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
   const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
+  bool allow_pair = false;      // may run on the CTA-pair kernel when the launch is large enough (step GEMMs A, B, D+C)
+  bool no_alt = false;          // keep the weight's default N tile (whose epilogue is the coalesced shared-memory tile one)
+  bool f8 = false;              // f16+f8x2 mode: residual products on the fp8 tensor path (operand pairs need hi8 / lo8)
   bool pdl = false;             // launch with programmatic dependent launch (decoder-step GEMMs only)
   bool zero_acc = false;        // every A operand is known to be zero (h = 0 at t = 0): skip the main loop, acc := 0
   int pdl_flags = 0;            // bit 0: weight tiles before the dependency wait; bit 1: trigger after the main loop
@@ -159,7 +225,11 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t st);
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st);
 bool gemm_uses_tc(const Ctx* c, const GemmArgs& g);
 int make_tmap_f16(void* out_map, const void* base, int rows, int cols, int ld, int box_rows, int kb = 64);
-int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st, float* scale = nullptr);
+int make_tmap_u8(void* out_map, const void* base, int rows, int cols, int ld, int box_rows, int kb = 64);
+int make_pair_maps(F16Pair* b, int pair_rows);   // tensor maps of a weight for the CTA-pair kernel (after hi/lo/hi8/lo8 are set)
+// x -> pair (fp16 hi + fp16 lo and/or e4m3 hi8/lo8, whichever arrays the pair has); scale = device {s, 1/s} computed
+// here from max|x| (weights), or null: x is multiplied by p.act_scale (activations)
+int launch_split_pair(const float* x, const F16Pair& p, size_t n, cudaStream_t st, bool weight_scale = false);
 
 // ---------------------------------------------------------------- context
 struct Phase {
@@ -202,12 +272,16 @@ struct Ctx {
   int NVA;                     // padded rows of Wva
   // fp16 hi/lo twins for the tcgen05 GEMMs
   bool use_tc = true;
+  bool use_pair = true;          // CTA-pair (cta_group::2) kernel for the large-batch step GEMMs (VSRDEC_PAIR=0 disables)
+  bool gemm_f8 = true;           // step GEMMs in f16+f8x2 mode (VSRDEC_GEMM=f16x3 keeps all three passes in fp16)
   bool use_alt_tiles = true;     // per-launch choice between the default and the alternative N tile (VSRDEC_ALT_TILES=0)
   int gemm_kb = 64;              // k-block of the tensor-core GEMMs (VSRDEC_KB=32: 64-byte swizzle, deeper ring)
   F16Pair WA_b, WB1_b, WB2_b, WC_b, WD_b, WE_b;
   F16Pair WU_b, WU2_b, Wva_b;   // prologue weights
   F16Pair ds_b, img_b;          // prologue activations: slot rows [b*L*R][Fp], image descriptors [n_img][Fp]
   F16Pair h1_b, h2_b, s_t_b, h1n_b, g_t_b, att_b, h2n_b;
+  // batched teacher-forced forward: h2' of every (caption, step) [b*T][Hp] twins, their logits and gate rows
+  F16Pair h2all_b; float* logits_all = nullptr; float* gate_all = nullptr; int cap_fwd_rows = 0;
   // verb table (device CSR)
   int64_t* vt_keys = nullptr; int32_t* vt_off = nullptr; int32_t* vt_idx = nullptr; int vt_n = 0;
   // prologue products (per batch)
@@ -273,7 +347,8 @@ struct Ctx {
   // Key = every value baked into the kernels' arguments; `epoch` changes whenever a device buffer is (re)allocated.
   struct GraphKey {
     uint64_t epoch;
-    int64_t kind;                    // 0 = steps of a beam search, 1 = prologue
+    int64_t kind;                    // 0 = steps of a beam search, 1 = prologue, 2 = teacher-forced forward
+    const void* captions;
     const void *det, *det_seqs, *slot_index, *verbs;
     int64_t det_stride, eos0, eos1;
     int32_t b, D, L, R, n_img, verbs_dtype, k, use_verbs, gt, T;
@@ -284,12 +359,9 @@ struct Ctx {
   uint64_t epoch = 0, graph_clock = 0;
   cudaStream_t cap_stream = nullptr;
   bool attend_attr_set = false;
-  // the step's vocabulary head was left to the fused tail kernel of the beam search (run_step -> launch_beam_step)
-  bool head_deferred = false; int head_tiles = 0, head_nch = 0; bool head_use_verbs = false, head_gt = false;
   bool state_h32 = true;             // the last step wrote fp32 h1'/h2' (always on the FFMA twin)
   bool use_graphs = true;            // VSRDEC_GRAPH=0 disables
   bool zero_state_opt = true;        // VSRDEC_ZERO_STATE=0: run the h-dependent GEMM parts at t = 0 although h = 0
-  bool fuse_tail = true;             // VSRDEC_FUSE_TAIL=0: separate k_vocab_merge + k_beam_step launches (round-1 layout)
   bool use_pdl = true;               // VSRDEC_PDL=0: plain stream serialization between the step kernels
   // VSRDEC_PDL_MODE bits: 1 = GEMM launches, 2 = small kernels, 4 = weight prefetch before the wait, 8 = GEMMs
   // trigger after their main loop.  Measured inside the decode graph (ms per decode): off 4.07, 1: 4.02, 1|4: 4.00,
@@ -322,7 +394,7 @@ struct StepIO {
   int64_t gate_stride;
   int topk;          // number of word candidates to extract per row (0 = none)
   bool zero_state;   // h1 = h2 = 0 on entry (first step after init_state): their GEMM contributions are skipped
-  bool defer_head;   // beam search: leave the vocabulary head (softmax statistics, top-k, gate head) to the tail kernel
+  bool skip_vocab;   // stop after LSTM cell 2 (batched teacher-forced forward: out_fc + log-softmax run once after the loop)
   bool need_h32;     // the caller reads the fp32 h1'/h2' (vsr_step); the tensor-core path itself only needs the fp16 twins
 };
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st);
@@ -338,5 +410,10 @@ int launch_commit_identity(Ctx* c, int rows, const int64_t* next_words, int64_t 
                            int next_slot, cudaStream_t st);
 int launch_greedy_pick(Ctx* c, int rows, int t, int T, int64_t* out_words, int64_t* out_gates,
                        cudaStream_t st);
+int launch_sample_pick(Ctx* c, int rows, int t, int T, uint64_t seed, int64_t* out_words, int64_t* out_gates,
+                       float* lp_words, float* lp_gates, cudaStream_t st);
+int launch_gate_head(Ctx* c, int rows, float* gate_out, int64_t gate_stride, cudaStream_t st);
+int launch_rows_to_all(Ctx* c, const F16Pair& src, const F16Pair& dst, int rows, int T, int t, cudaStream_t st);
+int run_vocab_rows(Ctx* c, const F16Pair& a_b, float* logits, int M, float* out_logp, cudaStream_t st, bool softmax_only);
 
 }  // namespace vsr

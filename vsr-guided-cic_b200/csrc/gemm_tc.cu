@@ -113,6 +113,21 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 template <> __device__ __forceinline__ uint64_t make_kmajor_desc<64>(uint32_t a) { return make_sw128_desc(a); }
 template <> __device__ __forceinline__ uint64_t make_kmajor_desc<32>(uint32_t a) { return make_sw64_desc(a); }
 
+// K-major operand tile with 32-byte swizzle (rows of 32 B, 8-row groups 256 B apart)
+__device__ __forceinline__ uint64_t make_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;                      // stride byte offset: 8 rows x 32 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;                               // layout type: SWIZZLE_32B
+  return d;
+}
+// 8-bit (e4m3) operand tiles of a KB-element k-block: rows of KB bytes
+template <int KB> __device__ __forceinline__ uint64_t make_kmajor_desc8(uint32_t smem_addr);
+template <> __device__ __forceinline__ uint64_t make_kmajor_desc8<64>(uint32_t a) { return make_sw64_desc(a); }
+template <> __device__ __forceinline__ uint64_t make_kmajor_desc8<32>(uint32_t a) { return make_sw32_desc(a); }
+
 // instruction descriptor, kind::f16: D=f32 (bit 4), A=B=f16 (format 0), both K-major, M=128, N=BN
 template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc() {
   return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -124,6 +139,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// kind::f8f6f4 with e4m3 operands (format code 0 in the same descriptor fields): M=128, N=BN, K=32, twice the f16 rate
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -145,7 +169,9 @@ enum { EPI_PLAIN = 0, EPI_LSTM1 = 1, EPI_LSTM2 = 2, EPI_VOCAB = 3 };
 
 // One GEMM problem.  Up to two independent problems (same tile shape) share a launch.
 struct TcProblem {
-  CUtensorMap a_hi[3], a_lo[3], w_hi, w_lo;
+  CUtensorMap a_hi[3], a_lo[3], w_hi, w_lo;     // fp16 hi; lo = fp16 residual (f16x3) or e4m3 residual (f16+f8x2)
+  CUtensorMap a_h8[3], w_h8;                   // f16+f8x2 only: e4m3 copies of hi
+  int f8;                                      // 1 = f16+f8x2 mode
   int nseg;
   int kblocks[3];
   int n_tiles, m_tiles, M;
@@ -158,15 +184,16 @@ struct TcProblem {
   float* c; int ldc;
   // fused LSTM-cell epilogues (gate-interleaved output columns, see cell_col() in common.cuh)
   int mode;
-  const float* c_old; float* c_new; float* h_new; __half* h_hi; __half* h_lo;
-  float* s_new; __half* s_hi; __half* s_lo; float* gq;
+  const float* c_old; float* c_new; float* h_new; TwinOut h_tw;
+  float* s_new; TwinOut s_tw; float* gq;
   int ld_state;
   // fused g_t = sig(gq + acc) * tanh(c1') on the tiles with n0 < gt_cols (plain epilogue elsewhere)
-  int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; __half* g_hi; __half* g_lo;
+  int gt_cols; const float* gt_gq; const float* gt_c1n; float* g_t; TwinOut g_tw;
   // EPI_VOCAB: per (row, N tile) softmax / top-k partial records instead of (or besides, when c != null) the logits
   float* vpart; int n_valid;
   int zero_acc;     // k_gemm_tc only: no main loop, the accumulator is taken as zero
   const float* acc_scale;   // device scalar 1/s undoing the power-of-two scale of the weight's fp16 pair, or null
+  float act_inv;            // 1 / (constant scale of the activation twins): folded into the same epilogue multiply
 };
 struct TcParams {
   TcProblem pr[2];
@@ -189,19 +216,10 @@ __device__ __forceinline__ void add4(float4& a, const float4 b) { a.x += b.x; a.
 template <int BN>
 __device__ __forceinline__ int tile_slot(int r, int c4) { return r * BN + ((c4 ^ (r & 7)) << 2); }
 
-// fp32 + optional fp16 hi/lo twins of four consecutive values
-__device__ __forceinline__ void store4(float* f32, __half* hi, __half* lo, size_t off, const float4 v) {
+// fp32 + optional tensor-core twins of four consecutive values
+__device__ __forceinline__ void store4(float* f32, const TwinOut& tw, size_t off, const float4 v) {
   if (f32 != nullptr) *reinterpret_cast<float4*>(f32 + off) = v;
-  if (hi != nullptr) {
-    const float x[4] = {fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f),
-                        fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f)};
-    __align__(8) __half h[4];
-    __align__(8) __half l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { h[j] = __float2half_rn(x[j]); l[j] = __float2half_rn(x[j] - __half2float(h[j])); }
-    *reinterpret_cast<uint2*>(hi + off) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + off) = *reinterpret_cast<const uint2*>(l);
-  }
+  store_twin4(tw, off, v);
 }
 
 // TMEM -> tile: the two warps of quarter q write their 32 rows, each one half of the columns
@@ -261,7 +279,7 @@ __device__ __forceinline__ void tile_plain(const TcProblem& p, const float* tile
       // g_t = sig(gq + W1_hg.h1') * tanh(c1')      (controllable_captioning.py:181-182)
       const float4 o = make_float4(fast_sigmoid(x0[k].x + acc[k].x) * fast_tanh(x1[k].x), fast_sigmoid(x0[k].y + acc[k].y) * fast_tanh(x1[k].y),
                                    fast_sigmoid(x0[k].z + acc[k].z) * fast_tanh(x1[k].z), fast_sigmoid(x0[k].w + acc[k].w) * fast_tanh(x1[k].w));
-      store4(p.g_t, p.g_hi, p.g_lo, (size_t)row * p.ld_state + n, o);
+      store4(p.g_t, p.g_tw, (size_t)row * p.ld_state + n, o);
     } else {
       float4 o = acc[k];
       add4(o, *reinterpret_cast<const float4*>(s_bias + 4 * c4));
@@ -274,13 +292,19 @@ __device__ __forceinline__ void tile_plain(const TcProblem& p, const float* tile
 // Fused LSTM cell.  The tile's BN = NG*32 columns hold NG gates x 32 units as [gate][32 units] (cell_col()).
 // LSTM1: NG = 6 (i,f,g,o | sentinel gate s | shift gate gq), LSTM2: NG = 4.  One item = 4 units of one row:
 // pre = acc + bias + rowadd + cadd + gather, then the cell math of nn.LSTMCell.  256 items = one per epilogue thread.
+// CH = BN / (NG * 32) 32-unit chunks per tile (2 for the 256-wide LSTM2 tiles of the CTA-pair kernel): h = chunk.
 template <int BN, int NG>
-__device__ __forceinline__ void tile_cell(const TcProblem& p, const float* tile, const float* s_bias, int rowq, int n0, int n_tile,
-                                          int te) {
-  static_assert(BN == NG * 32, "one 32-unit chunk per tile");
+__device__ __forceinline__ void tile_cell(const TcProblem& p, const float* tile, const float* s_bias, int rowq, int n0_tile, int n_tile_,
+                                          int te, int h = 0) {
+  static_assert(BN % (NG * 32) == 0, "whole 32-unit chunks per tile");
+  constexpr int CH = BN / (NG * 32);
   const int r = te >> 3, uq = te & 7;
   const int row = rowq + r;
   if (row >= p.M) return;
+  const int n_tile = n_tile_ * CH + h;          // 32-unit chunk index
+  const int n0 = n0_tile + h * NG * 32;         // first output column of the chunk
+  tile += 0; s_bias += h * NG * 32;
+  const int cpiece = h * NG * 8;                // first 16-byte piece of the chunk inside the tile row
   const int unit = n_tile * 32 + uq * 4;
   const size_t so = (size_t)row * p.ld_state + unit;
   float4 pre[NG], x0[NG], x1[NG], x2[NG];
@@ -294,7 +318,7 @@ __device__ __forceinline__ void tile_cell(const TcProblem& p, const float* tile,
   const float* gath = p.gather != nullptr ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather + n0 + uq * 4 : nullptr;
 #pragma unroll
   for (int g = 0; g < NG; ++g) {
-    pre[g] = *reinterpret_cast<const float4*>(tile + tile_slot<BN>(r, g * 8 + uq));
+    pre[g] = *reinterpret_cast<const float4*>(tile + tile_slot<BN>(r, cpiece + g * 8 + uq));
     x0[g] = radd != nullptr ? __ldg(reinterpret_cast<const float4*>(radd + g * 32)) : zero;
     x1[g] = cadd != nullptr ? *reinterpret_cast<const float4*>(cadd + g * 32) : zero;
     x2[g] = gath != nullptr ? __ldg(reinterpret_cast<const float4*>(gath + g * 32)) : zero;
@@ -321,13 +345,13 @@ __device__ __forceinline__ void tile_cell(const TcProblem& p, const float* tile,
 #ifdef VSR_DBG_CLK
   const long long k2 = clock64();
 #endif
-  store4(p.c_new, nullptr, nullptr, so, make_float4(cn[0], cn[1], cn[2], cn[3]));
-  store4(p.h_new, p.h_hi, p.h_lo, so, make_float4(hn[0], hn[1], hn[2], hn[3]));
+  *reinterpret_cast<float4*>(p.c_new + so) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+  store4(p.h_new, p.h_tw, so, make_float4(hn[0], hn[1], hn[2], hn[3]));
   if constexpr (NG == 6) {
     const float ps[4] = {pre[4].x, pre[4].y, pre[4].z, pre[4].w};
-    store4(p.s_new, p.s_hi, p.s_lo, so, make_float4(fast_sigmoid(ps[0]) * tc[0], fast_sigmoid(ps[1]) * tc[1],
+    store4(p.s_new, p.s_tw, so, make_float4(fast_sigmoid(ps[0]) * tc[0], fast_sigmoid(ps[1]) * tc[1],
                                                      fast_sigmoid(ps[2]) * tc[2], fast_sigmoid(ps[3]) * tc[3]));
-    store4(p.gq, nullptr, nullptr, so, pre[5]);
+    *reinterpret_cast<float4*>(p.gq + so) = pre[5];
   }
 #ifdef VSR_DBG_CLK
   if ((te == 0 || te == 200) && blockIdx.x == 5 && p.M > 200 && (rowq & 127) == 0)
@@ -341,7 +365,7 @@ __device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_
                                               const float* s_bias, float* tile) {
   const int q = warp & 3, hsel = (warp - 2) >> 2, te = (warp - 2) * 32 + lane;
   const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-  const float sc = p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f;
+  const float sc = (p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f) * p.act_inv;
 #ifdef VSR_DBG_CLK
   long long td = 0, tb1 = 0, tp = 0, tb2 = 0;
 #endif
@@ -363,6 +387,9 @@ __device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_
     if (p.mode == EPI_PLAIN) tile_plain<BN>(p, tile, s_bias, rowq, n0, te);
     if constexpr (BN == 192) { if (p.mode == EPI_LSTM1) tile_cell<BN, 6>(p, tile, s_bias, rowq, n0, n_tile, te); }
     if constexpr (BN == 128) { if (p.mode == EPI_LSTM2) tile_cell<BN, 4>(p, tile, s_bias, rowq, n0, n_tile, te); }
+    if constexpr (BN == 256) {
+      if (p.mode == EPI_LSTM2) { tile_cell<BN, 4>(p, tile, s_bias, rowq, n0, n_tile, te, 0); tile_cell<BN, 4>(p, tile, s_bias, rowq, n0, n_tile, te, 1); }
+    }
 #ifdef VSR_DBG_CLK
     const long long c3 = clock64();
 #endif
@@ -392,7 +419,7 @@ __device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlan
 #pragma unroll
   for (int k = 0; k < VOCAB_REC - 2; ++k) cmx[k] = -INFINITY;
   float* crow = p.c + (size_t)row * p.ldc;
-  const float sc = p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f;
+  const float sc = (p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f) * p.act_inv;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
     if ((ch < H0) != (hsel == 0)) continue;
@@ -497,7 +524,7 @@ __device__ __forceinline__ void rowwise_plain(const TcProblem& p, uint32_t tmem_
   const float* gath = (p.gather != nullptr && live) ? p.gather + (size_t)p.gather_idx[row] * p.ld_gather : nullptr;
   float* crow = p.c + (size_t)row * p.ldc;
   constexpr int NCH = BN / 16;
-  const float sc = p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f;
+  const float sc = (p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f) * p.act_inv;
   const int c_lo = hsel * NCH / nsplit, c_hi = (hsel + 1) * NCH / nsplit;
 #pragma unroll 1
   for (int ch = c_lo; ch < c_hi; ++ch) {       // 16 accumulator columns per TMEM load: any BN % 16 == 0
@@ -537,6 +564,66 @@ __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_ba
   }
 }
 
+// ---------------------------------------------------------------- one ring stage: operand loads and MMA issue
+// Stage layout (same bytes in both modes): A hi16 | A second half | W hi16 | W second half, where the second half is
+// the fp16 residual tile (f16x3) or the two e4m3 tiles hi8 | lo8 (f16+f8x2).
+template <int BN, int KB>
+__device__ __forceinline__ void load_w_stage(const TcProblem& p, uint64_t* bar, uint8_t* base, int kb, int n0) {
+  using Cfg = TcCfg<BN, KB>;
+  uint8_t* w = base + 2 * Cfg::kABytes;
+  tma_load_2d(&p.w_hi, bar, w, kb * KB, n0);
+  if (p.f8) {
+    tma_load_2d(&p.w_h8, bar, w + Cfg::kWBytes, kb * KB, n0);
+    tma_load_2d(&p.w_lo, bar, w + Cfg::kWBytes + Cfg::kWBytes / 2, kb * KB, n0);
+  } else {
+    tma_load_2d(&p.w_lo, bar, w + Cfg::kWBytes, kb * KB, n0);
+  }
+}
+template <int BN, int KB>
+__device__ __forceinline__ void load_a_stage(const TcProblem& p, uint64_t* bar, uint8_t* base, int seg, int kk, int m0) {
+  using Cfg = TcCfg<BN, KB>;
+  tma_load_2d(&p.a_hi[seg], bar, base, kk * KB, m0);
+  if (p.f8) {
+    tma_load_2d(&p.a_h8[seg], bar, base + Cfg::kABytes, kk * KB, m0);
+    tma_load_2d(&p.a_lo[seg], bar, base + Cfg::kABytes + Cfg::kABytes / 2, kk * KB, m0);
+  } else {
+    tma_load_2d(&p.a_lo[seg], bar, base + Cfg::kABytes, kk * KB, m0);
+  }
+}
+// the MMAs of one k-block into the accumulator at tmem_acc (first = the k-block overwrites instead of accumulating)
+template <int BN, int KB>
+__device__ __forceinline__ void issue_stage(const TcProblem& p, uint32_t tmem_acc, uint32_t base, bool first) {
+  using Cfg = TcCfg<BN, KB>;
+  constexpr uint32_t idesc = make_idesc<BN>();
+  const uint64_t ah = make_kmajor_desc<KB>(base), wh = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes);
+  if (p.f8) {
+    // x_hi*w_hi on the fp16 path; x_hi8*w_lo8 + x_lo8*w_hi8 on the fp8 path (K = 32 per instruction, twice the rate)
+    const uint64_t a8 = make_kmajor_desc8<KB>(base + Cfg::kABytes), al = make_kmajor_desc8<KB>(base + Cfg::kABytes + Cfg::kABytes / 2);
+    const uint64_t w8 = make_kmajor_desc8<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes);
+    const uint64_t wl = make_kmajor_desc8<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes + Cfg::kWBytes / 2);
+#pragma unroll
+    for (int k = 0; k < KB / UMMA_K; ++k) {
+      const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);     // 32 bytes inside the swizzle row
+      umma_f16(tmem_acc, ah + off, wh + off, idesc, (first && k == 0) ? 0u : 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < KB / 32; ++k) {
+      const uint64_t off = (uint64_t)((k * 32) >> 4);             // 32 e4m3 = 32 bytes
+      umma_f8(tmem_acc, a8 + off, wl + off, idesc, 1u);
+      umma_f8(tmem_acc, al + off, w8 + off, idesc, 1u);
+    }
+  } else {
+    const uint64_t al = make_kmajor_desc<KB>(base + Cfg::kABytes), wl = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes);
+#pragma unroll
+    for (int k = 0; k < KB / UMMA_K; ++k) {
+      const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);     // advance inside the swizzle row
+      umma_f16(tmem_acc, ah + off, wh + off, idesc, (first && k == 0) ? 0u : 1u);
+      umma_f16(tmem_acc, ah + off, wl + off, idesc, 1u);
+      umma_f16(tmem_acc, al + off, wh + off, idesc, 1u);
+    }
+  }
+}
+
 template <int BN, int KB>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant__ TcParams params) {
   using Cfg = TcCfg<BN, KB>;
@@ -568,8 +655,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 needs 1024-B alignment
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); }
-    prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
+    for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); if (p.f8) prefetch_tmap(&p.a_h8[s]); }
+    prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); if (p.f8) prefetch_tmap(&p.w_h8);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -596,10 +683,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
       // the WEIGHT halves of the first ring pass do not depend on the previous kernel: fetch them, then wait
       const int pre = !(params.pdl_flags & 1) ? 0 : (total_kb < Cfg::kStages ? total_kb : Cfg::kStages);
       for (int kb = 0; kb < pre; ++kb) {
-        uint8_t* base = smem + kb * Cfg::kStageBytes;
         mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
-        tma_load_2d(&p.w_hi, &full_bar[kb], base + 2 * Cfg::kABytes, kb * KB, n0);
-        tma_load_2d(&p.w_lo, &full_bar[kb], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+        load_w_stage<BN, KB>(p, &full_bar[kb], smem + kb * Cfg::kStageBytes, kb, n0);
       }
       pdl_wait();
       int seg = 0, kk = 0;
@@ -610,34 +695,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tc(const __grid_constant
         if (kb >= pre) {
           mbar_wait(&empty_bar[st], ph ^ 1);
           mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
-          tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
-          tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+          load_w_stage<BN, KB>(p, &full_bar[st], base, kb, n0);
         }
-        tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
-        tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
+        load_a_stage<BN, KB>(p, &full_bar[st], base, seg, kk, m0);
         if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc<BN>();
       for (int kb = 0; kb < total_kb; ++kb) {
         const int st = kb % Cfg::kStages;
         const uint32_t ph = (kb / Cfg::kStages) & 1;
         mbar_wait(&full_bar[st], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
-        const uint64_t ah = make_kmajor_desc<KB>(base), al = make_kmajor_desc<KB>(base + Cfg::kABytes);
-        const uint64_t wh = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes);
-        const uint64_t wl = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes);
-#pragma unroll
-        for (int k = 0; k < KB / UMMA_K; ++k) {
-          const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);     // advance inside the swizzle row
-          umma_f16(tmem_base, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_f16(tmem_base, ah + off, wl + off, idesc, 1u);
-          umma_f16(tmem_base, al + off, wh + off, idesc, 1u);
-        }
+        issue_stage<BN, KB>(p, tmem_base, smem_u32(smem + st * Cfg::kStageBytes), kb == 0);
         umma_commit(&empty_bar[st]);          // frees the smem slot once these MMAs have read it
       }
       umma_commit(&tmem_full_bar);            // accumulator complete -> epilogue
@@ -711,8 +783,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
   if (warp == 0 && lane == 0) {
     for (int q = 0; q < params.nprob; ++q) {
       const TcProblem& p = params.pr[q];
-      for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); }
-      prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo);
+      for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); if (p.f8) prefetch_tmap(&p.a_h8[s]); }
+      prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); if (p.f8) prefetch_tmap(&p.w_h8);
     }
   }
   if (warp == 1) {
@@ -753,10 +825,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
         if (!pdl_waited) {
           pre = !(params.pdl_flags & 1) ? 0 : (total_kb < Cfg::kStages ? total_kb : Cfg::kStages);
           for (int kb = 0; kb < pre; ++kb) {
-            uint8_t* base = smem + kb * Cfg::kStageBytes;
             mbar_expect_tx(&full_bar[kb], Cfg::kStageBytes);
-            tma_load_2d(&p.w_hi, &full_bar[kb], base + 2 * Cfg::kABytes, kb * KB, n0);
-            tma_load_2d(&p.w_lo, &full_bar[kb], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+            load_w_stage<BN, KB>(p, &full_bar[kb], smem + kb * Cfg::kStageBytes, kb, n0);
           }
           pdl_wait();
           pdl_waited = true;
@@ -769,18 +839,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
           if (kb >= pre) {
             mbar_wait(&empty_bar[st], ph ^ 1);
             mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
-            tma_load_2d(&p.w_hi, &full_bar[st], base + 2 * Cfg::kABytes, kb * KB, n0);
-            tma_load_2d(&p.w_lo, &full_bar[st], base + 2 * Cfg::kABytes + Cfg::kWBytes, kb * KB, n0);
+            load_w_stage<BN, KB>(p, &full_bar[st], base, kb, n0);
           }
-          tma_load_2d(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
-          tma_load_2d(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
+          load_a_stage<BN, KB>(p, &full_bar[st], base, seg, kk, m0);
           if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
         }
       }
       __syncwarp();
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = make_idesc<BN>();
         mbar_wait(&tmem_empty_bar[acc], aph ^ 1);       // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < total_kb; ++kb) {
@@ -788,17 +855,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
           const uint32_t ph = ((it + kb) / Cfg::kStages) & 1;
           mbar_wait(&full_bar[st], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
-          const uint64_t ah = make_kmajor_desc<KB>(base), al = make_kmajor_desc<KB>(base + Cfg::kABytes);
-          const uint64_t wh = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes);
-          const uint64_t wl = make_kmajor_desc<KB>(base + 2 * Cfg::kABytes + Cfg::kWBytes);
-#pragma unroll
-          for (int k = 0; k < KB / UMMA_K; ++k) {
-            const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
-            umma_f16(tmem_acc, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
-            umma_f16(tmem_acc, ah + off, wl + off, idesc, 1u);
-            umma_f16(tmem_acc, al + off, wh + off, idesc, 1u);
-          }
+          issue_stage<BN, KB>(p, tmem_acc, smem_u32(smem + st * Cfg::kStageBytes), kb == 0);
           umma_commit(&empty_bar[st]);
         }
         umma_commit(&tmem_full_bar[acc]);
@@ -825,16 +882,228 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
 }
 
 // x -> (fp16 hi, fp16 lo) with lo = fp16(x - hi)
-// scale != null: x is multiplied by the power of two scale[0] first (weights, see F16Pair::scale)
-__global__ void k_split_f16(const float* __restrict__ x, __half* __restrict__ hi,
-                             __half* __restrict__ lo, size_t n, const float* __restrict__ scale) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float s = scale != nullptr ? scale[0] : 1.f;
-  const float v = fminf(fmaxf(x[i] * s, -65504.f), 65504.f);   // saturate instead of overflowing to inf
-  const __half h = __float2half_rn(v);
-  hi[i] = h;
-  lo[i] = __float2half_rn(v - __half2float(h));
+// ---------------------------------------------------------------- CTA-pair kernel (cta_group::2), persistent
+// What bounds the single-CTA kernels once the batch is large (ncu on the stacked 400-caption decode: tensor pipe 40-45 %
+// active, L2 -> SM 10-12 TB/s) is operand delivery: a 128 x 128 tile pulls (128 + 128) x KB x 4 bytes through L2 and
+// shared memory per k-block, whichever passes are issued.  Here the two CTAs of a cluster (one TPC) compute a 256 x BN
+// tile: each stages its own 128 rows of A and HALF of the W tile (BN / 2 rows); the leader issues tcgen05.mma
+// .cta_group::2 (M = 256), which reads both CTAs' shared memory, and each CTA ends up with its 128 x BN accumulator in
+// its own TMEM.  Bytes per output element halve (BN = 256), which is also what lets the e4m3 residual MMAs run near their
+// rate.  Persistent (one cluster per TPC walks the tile list), accumulators double-buffered in TMEM (2 x 256 columns), the
+// same shared-memory-tile epilogues as the single-CTA kernels (plain / g_t / LSTM cell 1 at BN = 192 / LSTM cell 2 at 256).
+template <int BN> struct PairCfg {
+  static constexpr int KB = 64;
+  static constexpr int kStages = 3;
+  static constexpr int kABytes = BM * KB * 2;                 // fp16 tile of this CTA's 128 A rows (the second half of the
+  static constexpr int kWBytes = (BN / 2) * KB * 2;           //   stage holds lo16, or hi8 | lo8); this CTA's half of the W tile
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  static constexpr int kRingBytes = kStages * kStageBytes;
+  static constexpr int kEpiBytes = 32 * BN * 4;
+  static constexpr int kSmemBytes = kRingBytes + 1024 + kEpiBytes;
+  static constexpr int kAccCols = 256, kTmemCols = 512;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (count 1) on the same mbarrier of CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// TMA load whose completion bytes are credited to the LEADER CTA's mbarrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_f8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// commit: arrive on the same mbarrier in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc_pair() {   // M = 256
+  return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gemm_pair(const __grid_constant__ TcParams params) {
+  using Cfg = PairCfg<BN>;
+  constexpr int KB = Cfg::KB;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];       // waited on in the leader CTA only
+  __shared__ __align__(8) uint64_t empty_bar[Cfg::kStages];      // per CTA, signalled by the leader's multicast commits
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];             // per CTA, likewise
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];            // leader's: 2 x 8 epilogue warps arrive (peer's remotely)
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float s_bias[BN];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                       // 0 = leader (issues the MMAs), 1 = peer
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int mp0 = (params.pr[0].m_tiles + 1) >> 1;
+  const int tiles0 = params.pr[0].n_tiles * mp0;
+  const int total_tiles = tiles0 + (params.nprob > 1 ? params.pr[1].n_tiles * ((params.pr[1].m_tiles + 1) >> 1) : 0);
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  pdl_trigger();
+  pdl_wait();                       // (no early weight prefetch here: multi-wave launches hide the set-up anyway)
+  if (warp == 0 && lane == 0) {
+    for (int q = 0; q < params.nprob; ++q) {
+      const TcProblem& p = params.pr[q];
+      for (int s = 0; s < p.nseg; ++s) { prefetch_tmap(&p.a_hi[s]); prefetch_tmap(&p.a_lo[s]); if (p.f8) prefetch_tmap(&p.a_h8[s]); }
+      prefetch_tmap(&p.w_hi); prefetch_tmap(&p.w_lo); if (p.f8) prefetch_tmap(&p.w_h8);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      // full: ONE arrival (the leader's expect_tx, which announces both CTAs' bytes); the peer's loads are accounted for
+      // by their complete_tx on the leader's barrier alone (a remote release-arrive per stage measured ~2x slower)
+      for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], 2 * TC_EPI_WARPS); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();               // barriers of both CTAs initialised, TMEM allocated in both
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_slot;
+
+  int it = 0;        // running k-block counter -> smem ring stage / phase
+  int ti = 0;        // running tile counter -> accumulator buffer / phase
+  for (int tile = cluster_id; tile < total_tiles; tile += n_clusters) {
+    const int pi = (params.nprob > 1 && tile >= tiles0) ? 1 : 0;
+    const int t = tile - pi * tiles0;
+    const TcProblem& p = params.pr[pi];
+    const int m_pairs = (p.m_tiles + 1) >> 1;
+    const int m_pair = t % m_pairs, n_tile = t / m_pairs;
+    const int m0 = (m_pair * 2 + (int)rank) * BM, n0 = n_tile * BN;
+    int total_kb = 0;
+    for (int s = 0; s < p.nseg; ++s) total_kb += p.kblocks[s];
+    const int acc = ti & 1;
+    const uint32_t aph = (ti >> 1) & 1;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * Cfg::kAccCols);
+
+    if (warp == 0) {
+      if (lane == 0) {
+        const int wrow = n0 + (int)rank * (BN / 2);     // this CTA's half of the W tile
+        int seg = 0, kk = 0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int st = (it + kb) % Cfg::kStages;
+          const uint32_t ph = ((it + kb) / Cfg::kStages) & 1;
+          mbar_wait(&empty_bar[st], ph ^ 1);
+          uint8_t* base = smem + st * Cfg::kStageBytes;
+          uint8_t* wb = base + 2 * Cfg::kABytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[st], 2 * Cfg::kStageBytes);   // both CTAs' bytes land on the leader's barrier
+          tma_load_2d_pair(&p.a_hi[seg], &full_bar[st], base, kk * KB, m0);
+          tma_load_2d_pair(&p.w_hi, &full_bar[st], wb, kb * KB, wrow);
+          if (p.f8) {
+            tma_load_2d_pair(&p.a_h8[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
+            tma_load_2d_pair(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes + Cfg::kABytes / 2, kk * KB, m0);
+            tma_load_2d_pair(&p.w_h8, &full_bar[st], wb + Cfg::kWBytes, kb * KB, wrow);
+            tma_load_2d_pair(&p.w_lo, &full_bar[st], wb + Cfg::kWBytes + Cfg::kWBytes / 2, kb * KB, wrow);
+          } else {
+            tma_load_2d_pair(&p.a_lo[seg], &full_bar[st], base + Cfg::kABytes, kk * KB, m0);
+            tma_load_2d_pair(&p.w_lo, &full_bar[st], wb + Cfg::kWBytes, kb * KB, wrow);
+          }
+          if (++kk == p.kblocks[seg]) { kk = 0; ++seg; }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0 && rank == 0) {
+        constexpr uint32_t idesc = make_idesc_pair<BN>();
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1);       // both CTAs' epilogues have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < total_kb; ++kb) {
+          const int st = (it + kb) % Cfg::kStages;
+          const uint32_t ph = ((it + kb) / Cfg::kStages) & 1;
+          mbar_wait(&full_bar[st], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
+          const uint32_t wbase = base + 2 * Cfg::kABytes;
+          const uint64_t ah = make_sw128_desc(base), wh = make_sw128_desc(wbase);
+          if (p.f8) {
+            const uint64_t a8 = make_sw64_desc(base + Cfg::kABytes), al = make_sw64_desc(base + Cfg::kABytes + Cfg::kABytes / 2);
+            const uint64_t w8 = make_sw64_desc(wbase + Cfg::kWBytes), wl = make_sw64_desc(wbase + Cfg::kWBytes + Cfg::kWBytes / 2);
+#pragma unroll
+            for (int k = 0; k < KB / UMMA_K; ++k) {
+              const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
+              umma_f16_pair(tmem_acc, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+#pragma unroll
+            for (int k = 0; k < KB / 32; ++k) {
+              const uint64_t off = (uint64_t)((k * 32) >> 4);
+              umma_f8_pair(tmem_acc, a8 + off, wl + off, idesc, 1u);
+              umma_f8_pair(tmem_acc, al + off, w8 + off, idesc, 1u);
+            }
+          } else {
+            const uint64_t al = make_sw128_desc(base + Cfg::kABytes), wl = make_sw128_desc(wbase + Cfg::kWBytes);
+#pragma unroll
+            for (int k = 0; k < KB / UMMA_K; ++k) {
+              const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
+              umma_f16_pair(tmem_acc, ah + off, wh + off, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_f16_pair(tmem_acc, ah + off, wl + off, idesc, 1u);
+              umma_f16_pair(tmem_acc, al + off, wh + off, idesc, 1u);
+            }
+          }
+          umma_commit_pair(&empty_bar[st]);     // frees this stage in BOTH CTAs
+        }
+        umma_commit_pair(&tmem_full_bar[acc]);  // accumulators complete in both CTAs -> epilogues
+      }
+      __syncwarp();
+    } else {
+      // bias of the tile -> shared memory behind the main loop
+      if (ti != 0) epi_bar(1);                  // previous tile's readers are done
+      for (int i = (warp - 2) * 32 + lane; i < BN; i += TC_EPI_THREADS) s_bias[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.f;
+      epi_bar(1);
+      mbar_wait(&tmem_full_bar[acc], aph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tile_epilogue<BN>(p, tmem_acc, m0, n0, n_tile, warp, lane, s_bias, reinterpret_cast<float*>(smem + Cfg::kRingBytes));
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {                          // every epilogue warp of both CTAs -> the leader's barrier
+        if (rank == 0) mbar_arrive(&tmem_empty_bar[acc]); else mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+      }
+    }
+    it += total_kb;
+    ++ti;
+  }
+  // neither CTA may release TMEM / exit while the pair's MMAs, remote arrivals or the other epilogue are still running
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::kTmemCols) : "memory");
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -880,24 +1149,65 @@ __global__ void k_absmax(const float* __restrict__ x, size_t n, unsigned* __rest
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
 }
-// scale[0] = 2^e with max|x| * 2^e in (2^13, 2^14]  (1 for an all-zero tensor), scale[1] = 2^-e
+// scale[0] = 2^e with max|x| * 2^e in (2^12, 2^13]  (1 for an all-zero tensor), scale[1] = 2^-e
+// (2^13: the e4m3 copy hi / 32 then stays below the format's maximum of 448)
 __global__ void k_pick_scale(float* scale) {
   const float m = __uint_as_float(*reinterpret_cast<unsigned*>(scale));
   int e = 0;
-  if (m > 0.f) { int ex; frexpf(m, &ex); e = 14 - ex; }     // m = f * 2^ex, f in [0.5, 1)
+  if (m > 0.f) { int ex; frexpf(m, &ex); e = 13 - ex; }     // m = f * 2^ex, f in [0.5, 1)
   e = e > 100 ? 100 : (e < -100 ? -100 : e);
   scale[0] = ldexpf(1.f, e);
   scale[1] = ldexpf(1.f, -e);
 }
 
-int launch_split_f16(const float* x, void* hi, void* lo, size_t n, cudaStream_t st, float* scale) {
-  if (n == 0) return VSR_OK;
+// 2-D e4m3 (uint8) tensor map over a row-major [rows][ld] buffer: box = kb (K) x box_rows, rows of kb bytes
+int make_tmap_u8(void* out_map, const void* base, int rows, int cols, int ld, int box_rows, int kb) {
+  EncodeTiledFn enc = get_encode();
+  VSR_REQUIRE(enc != nullptr, VSR_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld};
+  const cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc((CUtensorMap*)out_map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstr,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kb == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VSR_REQUIRE(r == CUDA_SUCCESS, VSR_ECUDA, "cuTensorMapEncodeTiled (u8) failed (%d) rows=%d cols=%d ld=%d", (int)r, rows, cols, ld);
+  return VSR_OK;
+}
+
+int make_pair_maps(F16Pair* b, int pair_rows) {
+  b->pair_rows = 0;
+  if (b->hi == nullptr || pair_rows <= 0) return VSR_OK;
+  VSR_TRY(make_tmap_f16(b->pair_hi, b->hi, b->rows, b->ld, b->ld, pair_rows));
+  if (b->lo != nullptr) VSR_TRY(make_tmap_f16(b->pair_lo, b->lo, b->rows, b->ld, b->ld, pair_rows));
+  if (b->hi8 != nullptr) {
+    VSR_TRY(make_tmap_u8(b->pair_h8, b->hi8, b->rows, b->ld, b->ld, pair_rows));
+    VSR_TRY(make_tmap_u8(b->pair_lo, b->lo8, b->rows, b->ld, b->ld, pair_rows));
+  }
+  b->pair_rows = pair_rows;
+  return VSR_OK;
+}
+
+namespace {
+// x -> whichever twins `o` has; s = *scale (weights) or o.scale (activations)
+__global__ void k_split_pair(const float* __restrict__ x, TwinOut o, size_t n4, const float* __restrict__ scale) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  if (scale != nullptr) o.scale = scale[0];
+  store_twin4(o, i * 4, *reinterpret_cast<const float4*>(x + i * 4));
+}
+}  // namespace
+
+int launch_split_pair(const float* x, const F16Pair& p, size_t n, cudaStream_t st, bool weight_scale) {
+  if (n == 0 || p.hi == nullptr) return VSR_OK;
+  VSR_REQUIRE(n % 4 == 0, VSR_EINVAL, "launch_split_pair: element count %zu not a multiple of 4", n);
+  float* scale = weight_scale ? p.scale : nullptr;
   if (scale != nullptr) {
     VSR_CHECK_CUDA(cudaMemsetAsync(scale, 0, 2 * sizeof(float), st));
     k_absmax<<<296, 256, 0, st>>>(x, n, reinterpret_cast<unsigned*>(scale));
     k_pick_scale<<<1, 1, 0, st>>>(scale);
   }
-  k_split_f16<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, (__half*)hi, (__half*)lo, n, scale);
+  k_split_pair<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(x, twin_out(&p), n / 4, scale);
   VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }
@@ -917,23 +1227,50 @@ int tc_gemm_init() {
   TCP_SET_SMEM(128, 64); TCP_SET_SMEM(144, 64); TCP_SET_SMEM(192, 32); TCP_SET_SMEM(192, 64); TCP_SET_SMEM(128, 32);
 #undef TCP_SET_SMEM
 #undef TC_SET_SMEM
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_pair<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<192>::kSmemBytes));
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_pair<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::kSmemBytes));
   if (dev < 64) done_mask |= 1ull << dev;
   return VSR_OK;
 }
 
-static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64) {
+static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64, bool pair = false) {
   VSR_REQUIRE(g.M > 0 && g.N >= round_up(g.wb->n_valid, BN), VSR_EINVAL, "launch_gemm_tc: N=%d too small for N tile %d", g.N, BN);
   p->nseg = g.nseg;
+  p->f8 = g.f8 ? 1 : 0;
+  VSR_REQUIRE(g.f8 ? (g.wb->hi8 != nullptr && g.wb->lo8 != nullptr) : g.wb->lo != nullptr, VSR_EINVAL,
+              "launch_gemm_tc: the weight has no %s twin", g.f8 ? "e4m3" : "fp16 residual");
   for (int s = 0; s < g.nseg; ++s) {
-    VSR_REQUIRE(g.seg[s].b != nullptr && g.seg[s].k % BK == 0, VSR_EINVAL, "launch_gemm_tc: segment %d not tensor-core ready", s);
-    memcpy(&p->a_hi[s], kb == 32 ? g.seg[s].b->map32_hi : g.seg[s].b->map_hi, sizeof(CUtensorMap));
-    memcpy(&p->a_lo[s], kb == 32 ? g.seg[s].b->map32_lo : g.seg[s].b->map_lo, sizeof(CUtensorMap));
+    const F16Pair* b = g.seg[s].b;
+    VSR_REQUIRE(b != nullptr && g.seg[s].k % BK == 0, VSR_EINVAL, "launch_gemm_tc: segment %d not tensor-core ready", s);
+    VSR_REQUIRE(g.f8 ? (b->hi8 != nullptr && b->lo8 != nullptr) : b->lo != nullptr, VSR_EINVAL,
+                "launch_gemm_tc: segment %d has no %s twin", s, g.f8 ? "e4m3" : "fp16 residual");
+    VSR_REQUIRE(b->act_scale == g.seg[0].b->act_scale, VSR_EINVAL, "launch_gemm_tc: segments with different activation scales");
+    memcpy(&p->a_hi[s], kb == 32 ? b->map32_hi : b->map_hi, sizeof(CUtensorMap));
+    if (g.f8) {
+      memcpy(&p->a_h8[s], kb == 32 ? b->map8_32_hi : b->map8_hi, sizeof(CUtensorMap));
+      memcpy(&p->a_lo[s], kb == 32 ? b->map8_32_lo : b->map8_lo, sizeof(CUtensorMap));
+    } else {
+      memcpy(&p->a_lo[s], kb == 32 ? b->map32_lo : b->map_lo, sizeof(CUtensorMap));
+    }
     p->kblocks[s] = g.seg[s].k / kb;
   }
-  const bool alt = BN == g.wb->alt_bn && BN != g.wb->box_rows;
+  const bool alt = !pair && BN == g.wb->alt_bn && BN != g.wb->box_rows;
+  if (pair) {       // CTA-pair kernel: half-tile maps (BN / 2 rows), 64-element k-blocks
+    VSR_REQUIRE(g.wb->pair_rows * 2 == BN && kb == 64, VSR_EINVAL, "launch_gemm_tc: weight has no pair maps for N tile %d", BN);
+    memcpy(&p->w_hi, g.wb->pair_hi, sizeof(CUtensorMap));
+    memcpy(&p->w_lo, g.wb->pair_lo, sizeof(CUtensorMap));
+    if (g.f8) memcpy(&p->w_h8, g.wb->pair_h8, sizeof(CUtensorMap));
+  } else {
   memcpy(&p->w_hi, alt ? g.wb->alt_hi : (kb == 32 ? g.wb->map32_hi : g.wb->map_hi), sizeof(CUtensorMap));
-  memcpy(&p->w_lo, alt ? g.wb->alt_lo : (kb == 32 ? g.wb->map32_lo : g.wb->map_lo), sizeof(CUtensorMap));
+  if (g.f8) {
+    memcpy(&p->w_h8, alt ? g.wb->alt8_hi : (kb == 32 ? g.wb->map8_32_hi : g.wb->map8_hi), sizeof(CUtensorMap));
+    memcpy(&p->w_lo, alt ? g.wb->alt8_lo : (kb == 32 ? g.wb->map8_32_lo : g.wb->map8_lo), sizeof(CUtensorMap));
+  } else {
+    memcpy(&p->w_lo, alt ? g.wb->alt_lo : (kb == 32 ? g.wb->map32_lo : g.wb->map_lo), sizeof(CUtensorMap));
+  }
+  }
   p->acc_scale = g.wb->scale != nullptr ? g.wb->scale + 1 : nullptr;
+  p->act_inv = 1.f / g.seg[0].b->act_scale;
   p->n_tiles = (g.wb->n_valid + BN - 1) / BN; p->m_tiles = (g.M + BM - 1) / BM; p->M = g.M; p->row_skip = g.row_skip;
   p->bias = g.bias; p->rowadd = g.rowadd; p->ld_rowadd = g.ld_rowadd; p->row_div = g.row_div > 0 ? g.row_div : 1;
   p->rowadd_mul = g.rowadd_mul; p->cadd = g.cadd; p->ld_cadd = g.ld_cadd; p->c = g.c; p->ldc = g.ldc;
@@ -947,22 +1284,59 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64) {
     if (f.vocab_tiles_out != nullptr) *f.vocab_tiles_out = p->n_tiles;
     if (f.vocab_bn_out != nullptr) *f.vocab_bn_out = BN;
   } else if (f.mode != 0) {
-    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && BN == 128), VSR_EINVAL,
+    VSR_REQUIRE((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && (BN == 128 || (pair && BN == 256))), VSR_EINVAL,
                 "launch_gemm_tc: fused cell mode %d does not fit N tile %d", f.mode, BN);
-    p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_hi = (__half*)f.h_hi; p->h_lo = (__half*)f.h_lo;
-    p->s_new = f.s_new; p->s_hi = (__half*)f.s_hi; p->s_lo = (__half*)f.s_lo; p->gq = f.gq;
+    p->c_old = f.c_old; p->c_new = f.c_new; p->h_new = f.h_new; p->h_tw = twin_out(f.h_b);
+    p->s_new = f.s_new; p->s_tw = twin_out(f.s_b); p->gq = f.gq;
   }
-  VSR_REQUIRE(f.gt_cols == 0 || BN == 128 || BN == 192, VSR_EINVAL, "launch_gemm_tc: g_t fusion needs a 128- or 192-wide tile");
+  VSR_REQUIRE(f.gt_cols == 0 || BN == 128 || BN == 192 || (pair && BN == 256 && f.gt_cols % 256 == 0), VSR_EINVAL,
+              "launch_gemm_tc: g_t fusion needs a 128- or 192-wide tile");
   p->zero_acc = g.zero_acc ? 1 : 0;
   p->ld_state = f.ld_state;
   p->gt_cols = f.gt_cols; p->gt_gq = f.gt_gq; p->gt_c1n = f.gt_c1n; p->g_t = f.g_t;
-  p->g_hi = (__half*)f.g_hi; p->g_lo = (__half*)f.g_lo;
+  p->g_tw = twin_out(f.g_b);
+  return VSR_OK;
+}
+
+// Can this launch run on the CTA-pair kernel?  Large row counts only (at a few hundred rows the 256-row pair tiles leave
+// most SMs idle: measured slower), pair maps present, tile-compatible epilogues, whole tiles in N.
+static bool pair_ok(const GemmArgs& g) {
+  if (!g.allow_pair || g.wb == nullptr || g.wb->pair_rows <= 0 || g.M < 1024 || g.row_skip != nullptr || g.zero_acc) return false;
+  const int BN = 2 * g.wb->pair_rows;
+  if (g.N % BN != 0 || (BN != 192 && BN != 256)) return false;
+  const int mode = g.cell.mode;
+  if (mode == EPI_VOCAB) return false;
+  if (mode == EPI_LSTM1 && BN != 192) return false;
+  if (mode == EPI_LSTM2 && BN != 256) return false;
+  if (g.cell.gt_cols % BN != 0) return false;
+  return true;
+}
+
+static int launch_gemm_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
+  const int BN = 2 * g.wb->pair_rows;
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  VSR_TRY(fill_problem(&p.pr[0], g, BN, 64, true));
+  p.nprob = 1;
+  int tiles = p.pr[0].n_tiles * ((p.pr[0].m_tiles + 1) / 2);
+  if (g2 != nullptr) {
+    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, 64, true));
+    p.nprob = 2;
+    tiles += p.pr[1].n_tiles * ((p.pr[1].m_tiles + 1) / 2);
+  }
+  static int sms = 0;
+  if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  const int clusters = tiles < sms / 2 ? tiles : sms / 2;
+  if (BN == 192) VSR_CHECK_CUDA(launch_k(k_gemm_pair<192>, dim3(2 * clusters), dim3(TC_THREADS), PairCfg<192>::kSmemBytes, st, g.pdl, p));
+  else VSR_CHECK_CUDA(launch_k(k_gemm_pair<256>, dim3(2 * clusters), dim3(TC_THREADS), PairCfg<256>::kSmemBytes, st, g.pdl, p));
+  VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }
 
 // g2 (optional) is an independent problem with the same N tile that shares the launch
 int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   VSR_TRY(tc_gemm_init());
+  if (pair_ok(g) && (g2 == nullptr || (pair_ok(*g2) && g2->wb->pair_rows == g.wb->pair_rows))) return launch_gemm_pair(g, g2, st);
   int BN = g.wb->box_rows;
   VSR_REQUIRE(BN == 128 || BN == 192 || BN == 256, VSR_EINVAL, "launch_gemm_tc: unsupported N tile %d", BN);
   VSR_REQUIRE(g2 == nullptr || g2->wb->box_rows == BN, VSR_EINVAL, "launch_gemm_tc: grouped problems need one tile shape");
@@ -972,7 +1346,7 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   VSR_REQUIRE(g2 == nullptr || g2->wb->kb == kb, VSR_EINVAL, "launch_gemm_tc: grouped problems need one k-block size");
   // Tile choice: operand delivery bounds these GEMMs, so a tile costs ~ (BM + BN) and a launch costs
   // waves(tiles / 148 SMs) * (BM + BN).  Take the alternative N tile when that is cheaper.
-  if (g.wb->alt_bn > 0 && (g.cell.mode == 0 || g.cell.mode == EPI_VOCAB) && (g2 == nullptr || (g2->wb->alt_bn == g.wb->alt_bn && g2->cell.mode == 0))) {
+  if (g.wb->alt_bn > 0 && !g.no_alt && (g.cell.mode == 0 || g.cell.mode == EPI_VOCAB) && (g2 == nullptr || (g2->wb->alt_bn == g.wb->alt_bn && g2->cell.mode == 0))) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const int mt = (g.M + BM - 1) / BM;

@@ -14,19 +14,9 @@ namespace vsr {
 
 namespace {
 
-struct PairOut { __half* hi; __half* lo; int ld; };
-__device__ __forceinline__ void store_pair4(const PairOut& o, size_t i, const float4& v) {
-  const float x[4] = {v.x, v.y, v.z, v.w};
-  __half h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float xv = fminf(fmaxf(x[j], -65504.f), 65504.f);   // fp16 range (saturate, never inf)
-    h[j] = __float2half_rn(xv);
-    l[j] = __float2half_rn(xv - __half2float(h[j]));
-  }
-  *reinterpret_cast<uint2*>(o.hi + i) = *reinterpret_cast<const uint2*>(h);
-  *reinterpret_cast<uint2*>(o.lo + i) = *reinterpret_cast<const uint2*>(l);
-}
+// the prologue's activation twins (slot rows, image descriptors): fp16 hi + fp16 residual, row stride ld
+struct PairOut { TwinOut tw; int ld; __device__ __host__ bool on() const { return tw.hi != nullptr; } };
+__device__ __forceinline__ void store_pair4(const PairOut& o, size_t i, const float4& v) { store_twin4(o.tw, i, v); }
 
 // dst[r0+r][c0+c] = src[r][sc0+c]
 __global__ void k_pack_block(float* __restrict__ dst, int ld_dst, int r0, int c0,
@@ -71,7 +61,7 @@ __global__ void k_row_valid(const float* __restrict__ x, int64_t group_stride, i
   for (int f = lane * 4; f < F; f += 128) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(p + f));
     s += (v.x + v.y) + (v.z + v.w);
-    if (split.hi != nullptr) store_pair4(split, (size_t)row * split.ld + f, v);
+    if (split.on()) store_pair4(split, (size_t)row * split.ld + f, v);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -189,7 +179,7 @@ __global__ void __launch_bounds__(128 * POOL_Y) k_pool(const float* __restrict__
   const float n = (float)s_cnt;
   const float4 o = make_float4(s.x / n, s.y / n, s.z / n, s.w / n);
   *reinterpret_cast<float4*>(img + (size_t)g * ld_img + f) = o;
-  if (split.hi != nullptr) store_pair4(split, (size_t)g * split.ld + f, o);
+  if (split.on()) store_pair4(split, (size_t)g * split.ld + f, o);
 }
 
 }  // namespace
@@ -321,7 +311,7 @@ int pack_weights(Ctx* c, const float* const* w, cudaStream_t st) {
                    {c->WD, &c->WD_b, (size_t)c->ND * c->KD}, {c->WE, &c->WE_b, (size_t)c->NE * Hp}};
   for (const Tw& t : tw) {
     if (t.b->hi == nullptr || t.f == nullptr) continue;
-    VSR_TRY(launch_split_f16(t.f, t.b->hi, t.b->lo, t.n, st, t.b->scale));
+    VSR_TRY(launch_split_pair(t.f, *t.b, t.n, st, true));
     c->launches += t.b->scale != nullptr ? 3 : 1;
   }
   return VSR_OK;
@@ -334,7 +324,7 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
   // validity of detection rows and slot rows
   {
     const int rows = n_img * D;
-    const PairOut none{nullptr, nullptr, 0};
+    const PairOut none{twin_out(nullptr), 0};
     k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, none);
     VSR_CHECK_CUDA(cudaGetLastError());
     const int srows = b * L * R;
@@ -346,7 +336,7 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
     c->launches += 3;
     if (c->p_compact) {
       // about half of the slot rows are padding: only the valid ones are split to fp16 and projected
-      const PairOut dsp{(__half*)c->ds_b.hi, (__half*)c->ds_b.lo, c->Fp};
+      const PairOut dsp{twin_out(&c->ds_b), c->Fp};
       k_slot_scan<<<1, 1024, 0, st>>>(c->slot_mask, b * L, c->slot_base, c->comp_valid, round_up(srows, MPAD));
       VSR_CHECK_CUDA(cudaGetLastError());
       k_split_compact<<<(int)(((size_t)srows * 32 + 255) / 256), 256, 0, st>>>(c->det_seqs, R, srows, F, c->slot_mask,
@@ -358,7 +348,7 @@ int run_prologue(Ctx* c, const float* det, int64_t det_stride, cudaStream_t st) 
   // image descriptor
   {
     dim3 grid((F / 4 + 127) / 128, n_img);
-    const PairOut ip{c->use_tc ? (__half*)c->img_b.hi : nullptr, (__half*)c->img_b.lo, c->Fp};
+    const PairOut ip{twin_out(&c->img_b, c->use_tc), c->Fp};
     k_pool<<<grid, dim3(128, POOL_Y), 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches++;
@@ -401,14 +391,14 @@ int run_prologue_indexed(Ctx* c, const float* det, int64_t det_stride, cudaStrea
   const int n_img = c->n_img;
   const int rows = n_img * D;
   {
-    const PairOut dsp{c->use_tc ? (__half*)c->ds_b.hi : nullptr, (__half*)c->ds_b.lo, c->Fp};
+    const PairOut dsp{twin_out(&c->ds_b, c->use_tc), c->Fp};
     k_row_valid<<<(rows * 32 + 255) / 256, 256, 0, st>>>(det, det_stride, D, rows, F, c->det_valid, dsp);
     VSR_CHECK_CUDA(cudaGetLastError());
     k_slot_masks_indexed<<<(b * L + 127) / 128, 128, 0, st>>>(c->slot_index, c->det_valid, R, L, D, b * L,
                                                               n_img == 1 ? 0 : 1, c->slot_mask);
     VSR_CHECK_CUDA(cudaGetLastError());
     dim3 grid((F / 4 + 127) / 128, n_img);
-    const PairOut ip{c->use_tc ? (__half*)c->img_b.hi : nullptr, (__half*)c->img_b.lo, c->Fp};
+    const PairOut ip{twin_out(&c->img_b, c->use_tc), c->Fp};
     k_pool<<<grid, dim3(128, POOL_Y), 0, st>>>(det, det_stride, D, F, c->det_valid, c->img, c->Fp, ip);
     VSR_CHECK_CUDA(cudaGetLastError());
     c->launches += 3;

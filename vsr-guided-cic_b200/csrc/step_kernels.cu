@@ -18,14 +18,19 @@ namespace {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// store x as fp32 and as the error-compensated fp16 pair the tcgen05 GEMMs consume
-struct PairOut { __half* hi; __half* lo; };
+// store the tensor-core twins of one value (the FFMA-twin path never has any: o.hi == null there)
+using PairOut = TwinOut;
 __device__ __forceinline__ void store_pair(const PairOut& o, size_t i, float v) {
   if (o.hi == nullptr) return;
-  v = fminf(fmaxf(v, -65504.f), 65504.f);   // fp16 range (saturate, never inf)
+  v = fminf(fmaxf(v * o.scale, -65504.f), 65504.f);   // fp16 range (saturate, never inf)
   const __half h = __float2half_rn(v);
-  o.hi[i] = h;
-  o.lo[i] = __float2half_rn(v - __half2float(h));
+  reinterpret_cast<__half*>(o.hi)[i] = h;
+  const float r = v - __half2float(h);
+  if (o.lo != nullptr) reinterpret_cast<__half*>(o.lo)[i] = __float2half_rn(r);
+  if (o.hi8 != nullptr) {
+    o.hi8[i] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h) * 0.03125f, __NV_SATFINITE, __NV_E4M3);
+    o.lo8[i] = (uint8_t)__nv_cvt_float_to_fp8(r * 32.f, __NV_SATFINITE, __NV_E4M3);
+  }
 }
 
 
@@ -94,7 +99,6 @@ __global__ void k_lstm2(const float* __restrict__ pre2, int ld_pre, const float*
 //   gate  = log_softmax([att_g . tanh(ga + ha), sum_{valid r} e_r])            :184-188
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_MAX_R = 64;
-constexpr int ATC_MAX_TR = VSR_MAX_BEAM * ATT_MAX_R;     // tile rows of a caption, worst case
 
 struct AttendArgs {
   const float* det_seqs;   // (b, L, R, F) materialised slot tiles, or null in index form
@@ -335,14 +339,10 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
       }
     }
     if (out != nullptr) *reinterpret_cast<float4*>(out + f0) = acc0;
-    const size_t o0 = (size_t)n * a.ld_att + f0;
-    store_pair(a.att_b, o0, acc0.x); store_pair(a.att_b, o0 + 1, acc0.y);
-    store_pair(a.att_b, o0 + 2, acc0.z); store_pair(a.att_b, o0 + 3, acc0.w);
+    store_twin4(a.att_b, (size_t)n * a.ld_att + f0, acc0);
     if (two) {
       if (out != nullptr) *reinterpret_cast<float4*>(out + f1) = acc1;
-      const size_t o1 = (size_t)n * a.ld_att + f1;
-      store_pair(a.att_b, o1, acc1.x); store_pair(a.att_b, o1 + 1, acc1.y);
-      store_pair(a.att_b, o1 + 2, acc1.z); store_pair(a.att_b, o1 + 3, acc1.w);
+      store_twin4(a.att_b, (size_t)n * a.ld_att + f1, acc1);
     }
   }
   TICK();
@@ -351,279 +351,6 @@ __global__ void __launch_bounds__(ATT_THREADS) k_attend(const AttendArgs a) {
     printf("attend n=%d warp=%d nv=%d: setup %lld  wait+bar %lld  scores %lld  bar+softmax+bar %lld  wsum %lld\n", n, warp, nv,
            tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4]);
 #endif
-}
-
-// ---------------------------------------------------------------- slot attention, one CTA per CAPTION
-// The k beam rows of a caption mostly sit on the same slot, so the row-per-CTA kernel above re-fetches one slot tile k
-// times through L2 behind a ptr -> mask -> P -> scores -> softmax -> features dependency chain (ncu: 13 % of HBM peak,
-// 63 % L2 hits, latency-bound).  Here a CTA owns all rows of a caption:
-//   * the rows are grouped by slot pointer; the valid regions of every distinct slot form a flat list of "tile rows";
-//   * each tile row's att_va projection is staged ONCE in shared memory (cp.async) and scored against every row of its
-//     group (one warp per (row, tile row) job: v_a . tanh(P + ha_row));
-//   * the weighted sum streams each tile row's feature row ONCE from global memory (one float4 column per thread, up to
-//     eight independent 128-bit loads in flight) and accumulates it into the K per-row accumulators with the row's
-//     softmax weight (0 for rows of another group).
-// Same math and the same per-row summation order as k_attend; outputs identical buffers.
-constexpr int ATC_THREADS = 512;
-constexpr int ATC_CAP = 24;           // tile rows whose projections are staged per scoring pass
-
-template <int K>
-__global__ void __launch_bounds__(ATC_THREADS, 1) k_attend_cap(const AttendArgs a) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int NW = ATC_THREADS / 32;
-  const int A = a.A, R = a.R, k = a.cur_beam;
-  const int max_tr = k * R;                         // worst case: every row on its own slot, all regions valid
-  const float** s_feat = reinterpret_cast<const float**>(sm);   // [max_tr] feature row of every tile row
-  const float** s_prow = s_feat + max_tr;                        // [max_tr] its att_va projection row
-  float* ha = reinterpret_cast<float*>(s_prow + max_tr);         // [K][A]   (16-byte aligned: 16 * max_tr bytes before it)
-  float* va = ha + K * A;                           // [A] att_a weights
-  float* vs = va + A;                               // [A] att_s weights
-  float* Ps = vs + A;                               // [ATC_CAP][A]
-  float* e = Ps + ATC_CAP * A;                      // [K][R + 2]: 0 = sentinel, 1 = padding score, 2 + r = region r
-  float* wmat = e + K * (R + 2);                    // [max_tr][K] softmax weight of tile row t for row j
-  __shared__ float s_red[K][NW];
-  __shared__ float s_as[K];                         // sentinel weight per row
-  __shared__ int s_slot[K], s_grp[K], s_goff[K + 1], s_gslot[K];
-  __shared__ unsigned long long s_gmask[K];
-  __shared__ unsigned char s_tgrp[ATC_MAX_TR];      // group of tile row t
-  __shared__ unsigned char s_treg[ATC_MAX_TR];      // region index of tile row t
-  __shared__ int s_ngrp;
-
-  const int cap = blockIdx.x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row0 = cap * k;
-  pdl_trigger();
-  pdl_wait();
-  const int imgi = cap * a.img_mul;
-
-  // ---- loads that depend only on the row index first: sentinel columns (registers), ha rows, attention vectors
-  float4 sent_v[K];
-  const int f0 = tid * 4;                           // F <= 4 * ATC_THREADS columns per pass (host checks the loop bound)
-#pragma unroll
-  for (int j = 0; j < K; ++j)
-    sent_v[j] = (j < k && f0 < a.F) ? *reinterpret_cast<const float4*>(a.sent + (size_t)(row0 + j) * a.ld_sent + f0)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = tid; i < k * A; i += ATC_THREADS) {
-    const int j = i / A, c = i - j * A;
-    ha[j * A + c] = a.hb[(size_t)(row0 + j) * a.ld_hb + a.o_ha + c];
-  }
-  for (int i = tid; i < A; i += ATC_THREADS) { va[i] = __ldg(a.v_a + i); vs[i] = __ldg(a.v_s + i); }
-
-  // ---- warp 0: slot pointers -> groups of rows that share a slot -> tile-row offsets
-  if (warp == 0) {
-    int slot = -1;
-    if (lane < k) slot = a.ptr[row0 + lane];
-    unsigned long long mask = 0ull;
-    if (lane < k) mask = a.slot_mask[(size_t)cap * a.L + slot];
-    const unsigned same = __match_any_sync(0xffffffffu, slot);
-    const int leader = __ffs(same) - 1;
-    const bool is_leader = lane < k && leader == lane;
-    const unsigned lead_ballot = __ballot_sync(0xffffffffu, is_leader);
-    const int my_grp = __popc(lead_ballot & ((1u << leader) - 1u));      // group id = rank of the leader lane
-    if (lane < k) { s_slot[lane] = slot; s_grp[lane] = my_grp; }
-    if (is_leader) { s_gmask[my_grp] = mask; s_gslot[my_grp] = slot; }
-    __syncwarp();
-    if (lane == 0) {
-      const int ng = __popc(lead_ballot);
-      int off = 0;
-      for (int g = 0; g < ng; ++g) { s_goff[g] = off; off += __popcll(s_gmask[g]); }
-      s_goff[ng] = off;
-      s_ngrp = ng;
-    }
-  }
-  __syncthreads();
-  const int ngrp = s_ngrp, n_tr = s_goff[ngrp];
-
-  // ---- tile-row table: (group, region) -> projection row / feature row pointers
-  for (int t = tid; t < n_tr; t += ATC_THREADS) {
-    int g = 0;
-    while (t >= s_goff[g + 1]) ++g;
-    const unsigned long long m = s_gmask[g];
-    int idx = t - s_goff[g];
-    unsigned long long mm = m;                      // region = position of the idx-th set bit of m
-    for (int q = 0; q < idx; ++q) mm &= mm - 1ull;
-    const int r = __ffsll((long long)mm) - 1;
-    const int slot = s_gslot[g];
-    const size_t tile_row0 = ((size_t)cap * a.L + slot) * R;
-    const float* prow;
-    const float* frow;
-    if (a.slot_index == nullptr) {
-      const int pbase = a.slot_base != nullptr ? a.slot_base[(size_t)cap * a.L + slot] : -1;
-      prow = a.P + (pbase >= 0 ? (size_t)(pbase + idx) : tile_row0 + r) * a.ldP;
-      frow = a.det_seqs + (tile_row0 + r) * a.F;
-    } else {
-      const int di = a.slot_index[tile_row0 + r];
-      if (di >= 0) {
-        prow = a.P + ((size_t)imgi * a.D + di) * a.ldP;
-        frow = a.det + (size_t)imgi * a.det_stride + (size_t)di * a.F;
-      } else {
-        prow = a.Pmean + (size_t)imgi * a.ldP;
-        frow = a.img + (size_t)imgi * a.ld_img;
-      }
-    }
-    s_tgrp[t] = (unsigned char)g; s_treg[t] = (unsigned char)r;
-    s_feat[t] = frow; s_prow[t] = prow;
-  }
-  // sum of every sentinel row (its validity is computed like any region row's, :159)
-  {
-    float ss[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) ss[j] = (sent_v[j].x + sent_v[j].y) + (sent_v[j].z + sent_v[j].w);
-    for (int f = f0 + ATC_THREADS * 4; f < a.F; f += ATC_THREADS * 4) {
-#pragma unroll
-      for (int j = 0; j < K; ++j) if (j < k) {
-        const float4 v = *reinterpret_cast<const float4*>(a.sent + (size_t)(row0 + j) * a.ld_sent + f);
-        ss[j] += (v.x + v.y) + (v.z + v.w);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < K; ++j) { const float w = warp_sum(ss[j]); if (lane == 0) s_red[j][warp] = w; }
-  }
-  __syncthreads();
-
-  // ---- scores.  Pass p stages the projections of tile rows [p*CAP, p*CAP+CAP) and scores them against the rows of
-  // their groups; pass 0 also does the 2k row-only jobs (sentinel: att_s . tanh(sa + ha); padding rows: att_a . tanh(ha))
-  for (int t0 = 0; t0 == 0 || t0 < n_tr; t0 += ATC_CAP) {
-    const int nt = min(ATC_CAP, n_tr - t0);
-    if (t0 > 0) __syncthreads();                      // previous pass's readers of Ps are done
-    for (int i = tid; i < nt * (A / 4); i += ATC_THREADS) {
-      const int t = i / (A / 4), ch = (i - t * (A / 4)) * 4;
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(Ps + (size_t)t * A + ch);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(s_prow[t0 + t] + ch) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    if (t0 == 0) {
-      // pull the feature rows towards L2 while the scores are computed
-      for (int i = tid; i < n_tr * (a.F / 32); i += ATC_THREADS) {
-        const int t = i / (a.F / 32), c = i - t * (a.F / 32);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(s_feat[t] + c * 32));
-      }
-      for (int job = warp; job < 2 * k; job += NW) {   // row-only jobs need no staged data
-        const int j = job >> 1;
-        const bool is_sent = (job & 1) == 0;
-        const float* sa = a.sent + (size_t)(row0 + j) * a.ld_sent + a.o_sa;
-        const float* vec = is_sent ? vs : va;
-        float acc = 0.f;
-        for (int i = lane * 4; i < A; i += 128) {
-          const float4 hv = *reinterpret_cast<const float4*>(ha + j * A + i);
-          const float4 pv = is_sent ? *reinterpret_cast<const float4*>(sa + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float4 vv = *reinterpret_cast<const float4*>(vec + i);
-          acc += vv.x * fast_tanh(pv.x + hv.x) + vv.y * fast_tanh(pv.y + hv.y) + vv.z * fast_tanh(pv.z + hv.z) + vv.w * fast_tanh(pv.w + hv.w);
-        }
-        acc = warp_sum(acc);
-        if (lane == 0) e[j * (R + 2) + (is_sent ? 0 : 1)] = acc;
-      }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    for (int job = warp; job < nt * k; job += NW) {
-      const int t = job / k, j = job - t * k;
-      if (s_grp[j] != (int)s_tgrp[t0 + t]) continue;   // warp-uniform
-      const float* pr = Ps + (size_t)t * A;
-      float acc = 0.f;
-      for (int i = lane * 4; i < A; i += 128) {
-        const float4 hv = *reinterpret_cast<const float4*>(ha + j * A + i);
-        const float4 pv = *reinterpret_cast<const float4*>(pr + i);
-        const float4 vv = *reinterpret_cast<const float4*>(va + i);
-        acc += vv.x * fast_tanh(pv.x + hv.x) + vv.y * fast_tanh(pv.y + hv.y) + vv.z * fast_tanh(pv.z + hv.z) + vv.w * fast_tanh(pv.w + hv.w);
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) e[j * (R + 2) + 2 + (int)s_treg[t0 + t]] = acc;
-    }
-  }
-  __syncthreads();
-
-  // ---- masked softmax per row (one warp per row): softmax over [sentinel, R regions] -> mask -> renormalise (:167-169)
-  for (int j = warp; j < k; j += NW) {
-    float sent_sum = 0.f;
-    for (int w = 0; w < NW; ++w) sent_sum += s_red[j][w];
-    const int g = s_grp[j];
-    const unsigned long long vmask = s_gmask[g];
-    const float* ej = e + j * (R + 2);
-    const float e_pad = ej[1];
-    // entry x in [0, R]: 0 = sentinel, x >= 1 = region x-1; lanes stride the entries
-    float m = -INFINITY;
-    for (int x = lane; x <= R; x += 32) {
-      const bool valid = x == 0 ? true : (((vmask >> (x - 1)) & 1ull) != 0);
-      m = fmaxf(m, (x == 0 || valid) ? ej[x == 0 ? 0 : x + 1] : e_pad);
-    }
-    m = warp_max(m);
-    float S = 0.f;
-    for (int x = lane; x <= R; x += 32) {
-      const bool valid = x == 0 ? true : (((vmask >> (x - 1)) & 1ull) != 0);
-      S += expf(((x == 0 || valid) ? ej[x == 0 ? 0 : x + 1] : e_pad) - m);
-    }
-    S = warp_sum(S);
-    float T = 0.f, shift = 0.f;
-    for (int x = lane; x <= R; x += 32) {
-      const bool valid = x == 0 ? (sent_sum != 0.f) : (((vmask >> (x - 1)) & 1ull) != 0);
-      if (valid) {
-        const float ev = ej[x == 0 ? 0 : x + 1];
-        T += expf(ev - m) / S;
-        if (x > 0) shift += ev;
-      }
-    }
-    T = warp_sum(T);
-    shift = warp_sum(shift);
-    // weights of this row: its group's tile rows get alpha, every other tile row 0
-    for (int t = lane; t < n_tr; t += 32) {
-      float w = 0.f;
-      if ((int)s_tgrp[t] == g) w = (expf(ej[2 + (int)s_treg[t]] - m) / S) / T;
-      wmat[(size_t)t * K + j] = w;
-    }
-    if (lane == 0) {
-      s_as[j] = (sent_sum != 0.f) ? (expf(ej[0] - m) / S) / T : 0.f;
-      a.shift[row0 + j] = shift;
-    }
-  }
-  __syncthreads();
-
-  // ---- weighted sum: att_j = alpha_s * sentinel_j + sum_t w[t][j] * feature row t; every feature row is read once
-  for (int fb = f0; fb < a.F; fb += ATC_THREADS * 4) {
-    float4 acc[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      float4 sv = sent_v[j];
-      if (fb != f0 && j < k) sv = *reinterpret_cast<const float4*>(a.sent + (size_t)(row0 + j) * a.ld_sent + fb);
-      const float as = j < k ? s_as[j] : 0.f;
-      acc[j] = make_float4(as * sv.x, as * sv.y, as * sv.z, as * sv.w);
-    }
-    constexpr int U = 8;
-    for (int t = 0; t < n_tr; t += U) {
-      float4 v[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(s_feat[min(t + u, n_tr - 1)] + fb));
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (t + u < n_tr) {
-          const float* wr = wmat + (size_t)(t + u) * K;
-#pragma unroll
-          for (int j = 0; j < K; ++j) {
-            const float w = wr[j];
-            acc[j].x += w * v[u].x; acc[j].y += w * v[u].y; acc[j].z += w * v[u].z; acc[j].w += w * v[u].w;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < K; ++j) {
-      if (j >= k) break;
-      const size_t o = (size_t)(row0 + j) * a.ld_att + fb;
-      if (a.att != nullptr) *reinterpret_cast<float4*>(a.att + o) = acc[j];
-      if (a.att_b.hi != nullptr) {
-        const float x[4] = {acc[j].x, acc[j].y, acc[j].z, acc[j].w};
-        __align__(8) __half h[4];
-        __align__(8) __half l[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float xv = fminf(fmaxf(x[q], -65504.f), 65504.f);
-          h[q] = __float2half_rn(xv); l[q] = __float2half_rn(xv - __half2float(h[q]));
-        }
-        *reinterpret_cast<uint2*>(a.att_b.hi + o) = *reinterpret_cast<const uint2*>(h);
-        *reinterpret_cast<uint2*>(a.att_b.lo + o) = *reinterpret_cast<const uint2*>(l);
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------- log-softmax + gate head + verb forcing + top-k
@@ -662,7 +389,8 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
 
   // thread 0 starts its dependent loads early (slot pointer -> verb id, shift logit)
   int64_t verb = -1; float shift_logit = 0.f;
-  if (tid == 0) {
+  const bool gate_head = a.ha != nullptr;      // null: log-softmax of the vocabulary rows only (batched forward)
+  if (tid == 0 && gate_head) {
     shift_logit = a.shift[n];
     if (a.use_verbs && a.verbs != nullptr)
       verb = load_verb(a.verbs, a.verbs_dtype, (size_t)(n / a.cur_beam) * a.L + a.ptr[n]);
@@ -670,7 +398,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
 
   // stay-gate logit att_g . tanh(ga + ha): every thread takes a slice (loads issued before the row scan)
   float stay_part = 0.f;
-  {
+  if (gate_head) {
     const float* ha = a.ha + (size_t)n * a.ld_ha;
     const float* ga = a.ga + (size_t)n * a.ld_ga;
     for (int i = tid; i < a.A; i += THREADS) stay_part += a.v_g[i] * fast_tanh(ga[i] + ha[i]);
@@ -795,6 +523,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
       forced = min(max(forced, 0), V - 1);
     }
     s_forced = forced;
+    if (gate_head) {
     a.row_max[n] = mx;
     a.row_lsum[n] = lsum;
     a.forced[n] = forced;
@@ -813,6 +542,7 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
     if (a.gate_out != nullptr) {
       a.gate_out[(size_t)n * a.gate_stride + 0] = g0;
       a.gate_out[(size_t)n * a.gate_stride + 1] = g1;
+    }
     }
   }
   if (a.out_logp == nullptr && topk <= 0) return;
@@ -888,15 +618,87 @@ __global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs
   if (lane < a.topk) a.cand[(size_t)n * VSR_MAX_BEAM + lane] = h.pick;
 }
 
+// ---------------------------------------------------------------- batched teacher-forced forward helpers
+// Gate head alone (no verb forcing), one warp per row: gate = log_softmax([att_g . tanh(ga + ha), shift])   (:184-188)
+__global__ void __launch_bounds__(128) k_gate_head(const float* __restrict__ ha, int ld_ha, const float* __restrict__ ga, int ld_ga,
+                                                   const float* __restrict__ v_g, int A, const float* __restrict__ shift,
+                                                   float* __restrict__ gate_out, int64_t gate_stride, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (n >= rows) return;
+  const float4* h4 = reinterpret_cast<const float4*>(ha + (size_t)n * ld_ha);
+  const float4* g4 = reinterpret_cast<const float4*>(ga + (size_t)n * ld_ga);
+  const float4* v4 = reinterpret_cast<const float4*>(v_g);
+  float stay = 0.f;
+  for (int i = lane; i < A / 4; i += 32) {
+    const float4 h = h4[i], g = g4[i], w = __ldg(v4 + i);
+    stay += (w.x * fast_tanh(g.x + h.x) + w.y * fast_tanh(g.y + h.y)) + (w.z * fast_tanh(g.z + h.z) + w.w * fast_tanh(g.w + h.w));
+  }
+  stay = warp_sum(stay);
+  if (lane == 0) {
+    const float sh = shift[n];
+    const float gm = fmaxf(stay, sh);
+    const float ls = logf(expf(stay - gm) + expf(sh - gm));
+    gate_out[(size_t)n * gate_stride] = (stay - gm) - ls;
+    gate_out[(size_t)n * gate_stride + 1] = (sh - gm) - ls;
+  }
+}
+
+// dst row (i * T + t) <- src row i, for up to three raw twin arrays (16-byte vectors)
+struct RowScatter { int n; const uint4* src[3]; uint4* dst[3]; int vec[3]; };
+__global__ void __launch_bounds__(128) k_rows_to_all(const RowScatter r, int T, int t) {
+  const int i = blockIdx.x;
+  for (int q = 0; q < r.n; ++q) {
+    const uint4* s = r.src[q] + (size_t)i * r.vec[q];
+    uint4* d = r.dst[q] + ((size_t)i * T + t) * r.vec[q];
+    for (int e = threadIdx.x; e < r.vec[q]; e += blockDim.x) d[e] = s[e];
+  }
+}
+
 }  // namespace
 
-// ---------------------------------------------------------------- one decoder step (host side)
-static PairOut pair_out(const Ctx* c, const F16Pair& b) {
-  PairOut o;
-  o.hi = c->use_tc ? (__half*)b.hi : nullptr;
-  o.lo = c->use_tc ? (__half*)b.lo : nullptr;
-  return o;
+int launch_gate_head(Ctx* c, int rows, float* gate_out, int64_t gate_stride, cudaStream_t st) {
+  k_gate_head<<<(rows + 3) / 4, 128, 0, st>>>(c->hb + c->oB2_ha, c->NB2, c->ga, c->NC, c->v_g, c->A, c->shift, gate_out, gate_stride, rows);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
 }
+
+// twins of h2' (rows i) -> rows i * T + t of the all-steps operand of the batched vocabulary GEMM
+int launch_rows_to_all(Ctx* c, const F16Pair& src, const F16Pair& dst, int rows, int T, int t, cudaStream_t st) {
+  RowScatter r{};
+  auto add = [&](const void* s, void* d, int bytes) {
+    if (s == nullptr || d == nullptr) return;
+    r.src[r.n] = (const uint4*)s; r.dst[r.n] = (uint4*)d; r.vec[r.n] = c->Hp * bytes / 16; ++r.n;
+  };
+  add(src.hi, dst.hi, 2); add(src.lo, dst.lo, 2); add(src.hi8, dst.hi8, 1); add(src.lo8, dst.lo8, 1);
+  k_rows_to_all<<<rows, 128, 0, st>>>(r, T, t);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+// logits[M][NE] = out_fc . h2'[M] + b for M rows of an all-steps operand, then out[M][V] = log_softmax (full rows)
+int run_vocab_rows(Ctx* c, const F16Pair& a_b, float* logits, int M, float* out_logp, cudaStream_t st, bool softmax_only) {
+  if (!softmax_only) {
+    PhaseScope ps(c, PH_GEMM_E, st);
+    GemmArgs g{};
+    g.nseg = 1; g.seg[0] = {nullptr, c->Hp, c->Hp, c->Hp, &a_b};
+    g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE; g.wb = &c->WE_b;
+    g.c = logits; g.ldc = c->NE; g.M = M; g.N = c->NE;
+    g.f8 = c->gemm_f8; g.allow_pair = true; g.no_alt = true;
+    VSR_TRY(launch_gemm(c, g, st)); c->launches++;
+    return VSR_OK;
+  }
+  PhaseScope ps(c, PH_SOFTMAX_TOPK, st);
+  SoftmaxArgs a{};
+  a.logits = logits; a.ld = c->NE; a.rows = M; a.V = c->V; a.cur_beam = 1; a.L = c->L; a.topk = 0;
+  a.out_logp = out_logp; a.out_stride = c->V;
+  k_softmax_topk<<<M, SM_THREADS, 0, st>>>(a);
+  VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
+  return VSR_OK;
+}
+
+// ---------------------------------------------------------------- one decoder step (host side)
+static PairOut pair_out(const Ctx* c, const F16Pair& b) { return twin_out(&b, c->use_tc); }
 
 int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   const int rows = io.rows, H = c->H;
@@ -919,14 +721,15 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
     g.zero_acc = io.zero_state;           // [h2 | h1] = 0 at t = 0: pre1 = U[caption] + X[bos], no main loop
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
+    g.f8 = c->gemm_f8; g.allow_pair = true;
     fused = gemm_uses_tc(c, g);
     c->state_h32 = !fused || io.need_h32;
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
       // fp32 copies of h1', s_t (and g_t, att, h2' below) feed only the FFMA twin and vsr_step's outputs: the
       // tensor-core GEMMs read the fp16 hi/lo twins, so those stores (and their reorder copies) are skipped
       g.cell.mode = 1; g.cell.c_old = c->c1; g.cell.c_new = c->c1n; g.cell.h_new = io.need_h32 ? c->h1n : nullptr;
-      g.cell.h_hi = c->h1n_b.hi; g.cell.h_lo = c->h1n_b.lo;
-      g.cell.s_new = nullptr; g.cell.s_hi = c->s_t_b.hi; g.cell.s_lo = c->s_t_b.lo;
+      g.cell.h_b = &c->h1n_b;
+      g.cell.s_new = nullptr; g.cell.s_b = &c->s_t_b;
       g.cell.gq = c->gq; g.cell.ld_state = c->Hp;
     }
     VSR_TRY(launch_gemm(c, g, st)); c->launches++;
@@ -945,13 +748,14 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->sent; g.ldc = c->NB1; g.M = rows; g.N = c->NB1;
     GemmArgs g2{};
     g2.nseg = 1; g2.seg[0] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
-    g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b;
+    g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b; g2.f8 = c->gemm_f8; g2.allow_pair = true;
     g2.c = c->hb; g2.ldc = c->NB2; g2.M = rows; g2.N = c->NB2;
     if (fused) {   // g_t = sig(gq + W1_hg.h1') * tanh(c1') on the hg column block of the h1' projection
       g2.cell.gt_cols = c->oB2_ha; g2.cell.gt_gq = c->gq; g2.cell.gt_c1n = c->c1n; g2.cell.g_t = nullptr;
-      g2.cell.g_hi = c->g_t_b.hi; g2.cell.g_lo = c->g_t_b.lo; g2.cell.ld_state = c->Hp;
+      g2.cell.g_b = &c->g_t_b; g2.cell.ld_state = c->Hp;
     }
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
+    g.f8 = c->gemm_f8; g.allow_pair = true;
     VSR_TRY(launch_gemm(c, g, st, &g2)); c->launches += fused ? 1 : 2;   // one grouped launch on tensor cores
   }
   if (!fused) {
@@ -972,39 +776,13 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.att = fused ? nullptr : c->att; a.ld_att = c->Fp; a.att_b = pair_out(c, c->att_b); a.shift = c->shift;
     a.rows = rows; a.cur_beam = io.cur_beam; a.L = c->L; a.R = c->R; a.F = c->F; a.A = c->A; a.H = H;
     a.ldP = c->NVA;
-    static const bool per_row = [] { const char* e = getenv("VSRDEC_ATTEND"); return e != nullptr && strcmp(e, "row") == 0; }();
-    if (per_row) {      // the round-1 kernel (one CTA per row), kept for A/B measurements
-      const size_t smem = sizeof(float) * ((size_t)c->A + (size_t)c->R * c->A + c->R + 1);
-      if (!c->attend_attr_set) {     // per device, hence per handle
-        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        c->attend_attr_set = true;
-      }
-      VSR_REQUIRE(smem <= 200 * 1024, VSR_EINVAL, "attention tile (R=%d x A=%d) does not fit shared memory", c->R, c->A);
-      VSR_CHECK_CUDA(launch_k(k_attend, dim3(rows), dim3(ATT_THREADS), smem, st, c->use_pdl && (c->pdl_mode & 2), a));
-    } else {            // one CTA per caption: every slot tile is fetched once for all the beams that sit on it
-      const int k = io.cur_beam, KK = k <= 1 ? 1 : k <= 2 ? 2 : k <= 4 ? 4 : k <= 6 ? 6 : 8;
-      const size_t max_tr = (size_t)k * c->R;
-      const size_t smem = 2 * sizeof(float*) * max_tr +
-                          sizeof(float) * ((size_t)KK * c->A + 2 * (size_t)c->A + (size_t)ATC_CAP * c->A + (size_t)KK * (c->R + 2) + max_tr * KK);
-      VSR_REQUIRE(smem <= 200 * 1024 && rows % k == 0, VSR_EINVAL, "attention workspace (beam %d, R=%d, A=%d) does not fit shared memory", k, c->R, c->A);
-      if (!c->attend_attr_set) {
-        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend_cap<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        c->attend_attr_set = true;
-      }
-      const bool pdl = c->use_pdl && (c->pdl_mode & 2);
-      const dim3 grid(rows / k), block(ATC_THREADS);
-      switch (KK) {
-        case 1: VSR_CHECK_CUDA(launch_k(k_attend_cap<1>, grid, block, smem, st, pdl, a)); break;
-        case 2: VSR_CHECK_CUDA(launch_k(k_attend_cap<2>, grid, block, smem, st, pdl, a)); break;
-        case 4: VSR_CHECK_CUDA(launch_k(k_attend_cap<4>, grid, block, smem, st, pdl, a)); break;
-        case 6: VSR_CHECK_CUDA(launch_k(k_attend_cap<6>, grid, block, smem, st, pdl, a)); break;
-        default: VSR_CHECK_CUDA(launch_k(k_attend_cap<8>, grid, block, smem, st, pdl, a)); break;
-      }
+    const size_t smem = sizeof(float) * ((size_t)c->A + (size_t)c->R * c->A + c->R + 1);
+    if (!c->attend_attr_set) {     // per device, hence per handle
+      VSR_CHECK_CUDA(cudaFuncSetAttribute(k_attend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      c->attend_attr_set = true;
     }
+    VSR_REQUIRE(smem <= 200 * 1024, VSR_EINVAL, "attention tile (R=%d x A=%d) does not fit shared memory", c->R, c->A);
+    VSR_CHECK_CUDA(launch_k(k_attend, dim3(rows), dim3(ATT_THREADS), smem, st, c->use_pdl && (c->pdl_mode & 2), a));
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
   {  // D: pre2 = WD . [att | h2_old | h1'] + b (+ U2[img]);  C: ga = att_ga . g_t rides in the same launch
@@ -1012,7 +790,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     PhaseScope ps(c, PH_GEMM_D, st);
     GemmArgs gc{};
     gc.nseg = 1; gc.seg[0] = {c->g_t, c->Hp, c->Hp, c->Hp, &c->g_t_b};
-    gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b;
+    gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b; gc.f8 = c->gemm_f8; gc.allow_pair = true;
     gc.c = c->ga; gc.ldc = c->NC; gc.M = rows; gc.N = c->NC;
     GemmArgs g{};
     g.nseg = io.zero_state ? 2 : 3;       // h2 = 0 at t = 0: its K segment (last in WD) is not read
@@ -1026,9 +804,10 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->pre2; g.ldc = c->ND; g.M = rows; g.N = c->ND;
     if (fused) {   // LSTM cell 2 in the epilogue
       g.cell.mode = 2; g.cell.c_old = c->c2; g.cell.c_new = c->c2n; g.cell.h_new = io.need_h32 ? c->h2n : nullptr;
-      g.cell.h_hi = c->h2n_b.hi; g.cell.h_lo = c->h2n_b.lo; g.cell.ld_state = c->Hp;
+      g.cell.h_b = &c->h2n_b; g.cell.ld_state = c->Hp;
     }
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
+    g.f8 = c->gemm_f8; g.allow_pair = true;
     VSR_TRY(launch_gemm(c, g, st, &gc)); c->launches += fused ? 1 : 2;
   }
   if (!fused) {
@@ -1036,6 +815,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     k_lstm2<<<pw_grid, 128, 0, st>>>(c->pre2, c->ND, c->c2, c->h2n, c->c2n, pair_out(c, c->h2n_b), c->Hp, H, rows);
     VSR_CHECK_CUDA(cudaGetLastError()); c->launches++;
   }
+  if (io.skip_vocab) return VSR_OK;     // batched forward: the vocabulary projection of all steps runs after the loop
   // Fused vocabulary head (tensor-core path, nobody needs full log-prob rows): the GEMM epilogue also reduces
   // every tile to a softmax record and k_vocab_merge finishes the row without scanning the logits.
   static const bool fuse_enabled = [] { const char* e = getenv("VSRDEC_FUSE_VOCAB"); return e == nullptr || atoi(e) != 0; }();
@@ -1048,6 +828,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE; g.wb = &c->WE_b;
     g.c = c->logits; g.ldc = c->NE; g.M = rows; g.N = c->NE;
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
+    g.f8 = c->gemm_f8; g.allow_pair = true;
     if (fuse_vocab) {
       g.cell.mode = 3; g.cell.vocab_part = c->vpart; g.cell.vocab_tiles_out = &vocab_tiles; g.cell.vocab_bn_out = &vocab_bn;
     }
@@ -1058,15 +839,6 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     SoftmaxArgs a = make_softmax_args(c, rows, io.cur_beam, io.topk, io.use_verbs, io.gt);
     a.out_logp = io.out_logp; a.out_stride = io.out_stride;
     a.gate_out = io.gate_out; a.gate_stride = io.gate_stride;
-    c->head_deferred = false;
-    if (fuse_vocab && io.defer_head && io.gate_out == nullptr) {
-      // beam search: the head is finished inside the fused tail kernel (launch_beam_step: merge + selection + reorder)
-      VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
-                  "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);
-      c->head_deferred = true; c->head_tiles = vocab_tiles; c->head_nch = vocab_bn / 16;
-      c->head_use_verbs = io.use_verbs; c->head_gt = io.gt;
-      return VSR_OK;
-    }
     if (fuse_vocab) {
       VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
                   "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);

@@ -2,7 +2,7 @@
 
 Same class surface as the reference's models/CaptioningModel.py:8-294 (`forward`, `test`,
 `sample_rl`, `beam_search`, `beam_search_v`, `_select_beam[_i]`), but each driver hands the
-WHOLE loop to libvsrdec (vsr_forward_teacher / vsr_greedy / vsr_beam_search): the per-step
+WHOLE loop to libvsrdec (vsr_forward_teacher / vsr_greedy / vsr_sample / vsr_beam_search): the per-step
 Python loop, the per-step statics gather, the full candidate sort and every host sync of the
 reference are gone.  Sub-classes provide `_engine_for(statics, seqs, verbs)`.
 """
@@ -40,27 +40,16 @@ class CaptioningModel(nn.Module):
         eng = self._engine_for(statics)
         return eng.greedy()
 
-    def sample_rl(self, statics, *args):
-        """Multinomial sampling with log-probs (reference CaptioningModel.py:54-76).  Uses the
-        device step kernel per step; the categorical draw stays in torch."""
-        device = statics[0].device
-        b_s = statics[0].size(0)
-        state = self.init_state(b_s, device)
-        outputs, log_probs = [], []
-        for t in range(self.seq_len):
-            prev = outputs[-1] if t > 0 else None
-            outs, state = self.step(t, state, prev, statics, None, *args, mode='feedback')
-            picks, lps = [], []
-            for o in outs:
-                distr = torch.distributions.Categorical(logits=o)
-                s = distr.sample()
-                picks.append(s)
-                lps.append(distr.log_prob(s))
-            outputs.append(picks)
-            log_probs.append(lps)
-        outputs = tuple(torch.stack(o, 1) for o in zip(*outputs))
-        log_probs = tuple(torch.stack(o, 1) for o in zip(*log_probs))
-        return outputs, log_probs
+    def sample_rl(self, statics, *args, seed=None):
+        """Multinomial sampling with log-probs (reference CaptioningModel.py:54-76): at every step both heads are
+        sampled from the step's distributions and fed back; returns ((words, gates), (lp_words, lp_gates)), each (b,T).
+        The whole loop runs on the device (vsr_sample: Gumbel-max over the vocabulary row with a Philox stream).  The
+        stream's seed is drawn from torch's CPU generator unless given, so torch.manual_seed() makes it reproducible
+        (the draws differ from torch.distributions' — another generator — but follow the same distributions)."""
+        eng = self._engine_for(statics)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return eng.sample(seed)
 
     def _select_beam(self, input, selected_beam, cur_beam_size, beam_size, b_s, reduced=True):
         """Beam-axis gather over (nested) tensors (reference CaptioningModel.py:78-94).  Kept for

@@ -186,5 +186,5 @@ class ControllableCaptioningModel(_CaptioningModel):
     def test(self, detections, ctrl_det_seqs_test):
         return super().test((detections, ctrl_det_seqs_test))
 
-    def sample_rl(self, detections, ctrl_det_seqs_test):
-        return super().sample_rl((detections, ctrl_det_seqs_test))
+    def sample_rl(self, detections, ctrl_det_seqs_test, seed=None):
+        return super().sample_rl((detections, ctrl_det_seqs_test), seed=seed)

@@ -254,6 +254,19 @@ class DecoderEngine:
                                                      _stream_ptr(self.device)))
         return words, gates
 
+    def sample(self, seed: int):
+        """Multinomial sampling decode (vsr_sample): (words, gates) int64 (b,T), (lp_words, lp_gates) fp32 (b,T)."""
+        b, T = self.b, self.dims["seq_len"]
+        words = torch.empty((b, T), device=self.device, dtype=torch.long)
+        gates = torch.empty((b, T), device=self.device, dtype=torch.long)
+        lpw = torch.empty((b, T), device=self.device, dtype=torch.float32)
+        lpg = torch.empty((b, T), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.vsr_sample(self.handle, int(seed) & 0xFFFFFFFFFFFFFFFF, words.data_ptr(),
+                                                     gates.data_ptr(), lpw.data_ptr(), lpg.data_ptr(),
+                                                     _stream_ptr(self.device)))
+        return (words, gates), (lpw, lpg)
+
     # ------------------------------------------------------------------ instrumentation
     def launch_count(self) -> int:
         return int(self.lib.vsr_launch_count(self.handle))
