@@ -220,6 +220,25 @@ def parity_check(model, dev_batch, host_batch, stacked_words, n_check=10):
             "seconds": round(time.perf_counter() - t0, 2)}
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """Pin this rank to its GPU's local CPUs (NVML cpu affinity) BEFORE the pinned host buffers are allocated and first
+    touched, so they land on the GPU-local NUMA node (8 ranks pulling 205 MB batches across the inter-socket link is what
+    collapsed the round-1 e2e scaling).  Returns a note for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        masks = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, m in enumerate(masks) for b in range(64) if (m >> b) & 1]
+        use = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if not use:
+            return "no GPU-local cpus in the allowed set"
+        os.sched_setaffinity(0, use)
+        return f"{len(use)} GPU-local cpus of {os.cpu_count()}"
+    except Exception as e:   # noqa: BLE001
+        return "unavailable: " + repr(e)[:80]
+
+
 def main_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from models import ControllableCaptioningModel
@@ -227,6 +246,9 @@ def main_ours(args, rank, world, local_rank):
     w = WORKLOAD
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    gpu_index = (local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                 int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    bind_note = bind_to_gpu_cpus(gpu_index) if not args.no_bind else "off"
     if world > 1:
         # stdout carries exactly one JSON line: NCCL logs (its version banner at NCCL_DEBUG=VERSION/WARN) go to stderr
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -289,8 +311,7 @@ def main_ours(args, rank, world, local_rank):
     for i in range(max(args.warmup, 3 * N_DISTINCT)):      # per input buffer: eager, graph capture, replay
         decode_single(i)
     eng = model._eng
-    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]))
+    sampler = ClockSampler(gpu_index)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
@@ -361,7 +382,8 @@ def main_ours(args, rank, world, local_rank):
     # ---- the same e2e loop through the index-form entry point (vsr_prologue_indexed): the slots
     # arrive as int32 indices into the detections instead of materialised (b,L,R,F) tiles
     host_i = [tuple(t.pin_memory() for t in make_inputs_indexed(rank, i)) for i in range(N_DISTINCT)]
-    e2e_idx_s = e2e_measure(host_i, True, S)
+    S_idx = max(1, args.idx_stack)
+    e2e_idx_s = e2e_measure(host_i, True, S_idx)
     h2d_idx_bytes = sum(t.numel() * t.element_size() for t in host_i[0])
     del host_i
 
@@ -435,7 +457,7 @@ def main_ours(args, rank, world, local_rank):
                     "gemm_kind": eng.gemm_kind(),
                     "describes": what, "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved_tf / peak_tf,
-                    "traffic": traffic.get("gemm_bytes_per_launch_b%d" % caps),
+                    "traffic": traffic.get("gemm_bytes_per_launch_b%d" % caps, traffic.get("gemm_bytes_per_launch_b1000" if caps > 100 else "gemm_bytes_per_launch_b100")),
                     "traffic_source": traffic.get("source"),
                     "peak_source": f"{peaks['source']} bf16_tflops_sustained (MEASURED_PEAKS.json)",
                     "passes": 3, "f16_equivalent_passes": 2 if f8 else 3,
@@ -462,13 +484,13 @@ def main_ours(args, rank, world, local_rank):
             ptr = torch.clamp(torch.gather(ptr, 1, parent[t].long()) + gate[t].long(), 0, w["L"] - 1)
         att_ms = ph1["attend_gate"][0]
         att_gbs = att_bytes / (att_ms * 1e-3) / 1e9
-        roofline_att = {"kernel": "k_attend_cap (slot attention + shift gate, one CTA per caption)", "bound": "hbm",
+        roofline_att = {"kernel": "k_attend (slot attention + shift gate, one CTA per beam row)", "bound": "hbm",
                         "describes": "one 100-caption decode (one_at_a_time)", "achieved": att_gbs,
                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": att_gbs / peaks["hbm_gbs"],
                         "traffic": traffic.get("attend_bytes_per_launch_b100"), "traffic_source": traffic.get("source"),
                         "bytes_per_decode": att_bytes, "unique_bytes_per_decode": uniq_bytes, "ms_per_decode": att_ms,
-                        "note": "achieved counts SURVEY 8d's algorithmic bytes (every beam row reads its slot tile); the kernel "
-                                "fetches a tile once per caption, so its real traffic is close to unique_bytes_per_decode"}
+                        "note": "achieved counts SURVEY 8d's algorithmic bytes (every beam row reads its slot tile); the beams of a "
+                                "caption mostly share a tile, so L2 serves the repeats and DRAM sees about unique_bytes_per_decode"}
         check = parity_check(model, dev_single[0], host[0], None)
         # the stacked decode of set 0 holds batch 0 in its first 100 rows: must equal the single decode bit for bit
         (w_st, _), _ = model.beam_search_v(dev_stacked[0], w["eos"], w["beam"], 1, gt=w["gt"])
@@ -498,12 +520,12 @@ def main_ours(args, rank, world, local_rank):
                                      f"{n_prof} eager 100-caption decodes; inside the CUDA-graph replay a step takes p50_decode_ms / {T}",
                 "e2e": {"value": e2e_value, "unit": "captions/s", "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes, "ms_per_step": 1e3 * e2e_s / K,
-                        "h2d_gbs": world * h2d_bytes * K / e2e_s / 1e9,
+                        "h2d_gbs": world * h2d_bytes * K / e2e_s / 1e9, "cpu_binding": bind_note,
                         "pipeline": f"vsrdec.DecodePipeline: stack {S_e2e}, {n_lanes} lanes, {2 * n_lanes} input buffers; H2D (copy stream), "
                                     "decodes and D2H + host read of finished results overlap; all inside the timed region"},
                 "e2e_indexed": {"value": world * b * K / e2e_idx_s, "unit": "captions/s",
                                 "h2d_bytes_per_step": h2d_idx_bytes, "d2h_bytes_per_step": d2h_bytes,
-                                "ms_per_step": 1e3 * e2e_idx_s / K, "stack": S,
+                                "ms_per_step": 1e3 * e2e_idx_s / K, "stack": S_idx,
                                 "entry": "beam_search_v_indexed / vsr_prologue_indexed: slots as int32 indices into the detections"},
                 "parity_check": check,
                 "forward_teacher": fwd,
@@ -546,7 +568,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--stack", type=int, default=4, help="batches stacked along the caption axis per decode call")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the rank to its GPU's local CPUs")
+    ap.add_argument("--stack", type=int, default=10, help="batches stacked along the caption axis per decode call")
+    ap.add_argument("--idx-stack", type=int, default=5, help="batches per decode call of the index-form e2e loop")
     ap.add_argument("--e2e-stack", type=int, default=1, help="batches per decode call of the e2e loop (materialised inputs)")
     ap.add_argument("--lanes", type=int, default=2, help="decode calls in flight per GPU (engines on their own streams)")
     args = ap.parse_args()

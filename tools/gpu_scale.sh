@@ -1,10 +1,18 @@
 #!/bin/bash
-# bench at N GPUs under torchrun, as the driver launches it
-N=${1:-2}; R=${2:-r01}
+# multi-GPU pass on one N-GPU box: aggregate H2D ceiling, the 2-GPU sharded-vs-single parity test, bench at N as the driver launches it
+N=${1:-2}; R=${2:-r02}
 mkdir -p gpurun_out
-if [ "$N" = "1" ]; then
-  timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 > gpurun_out/scale_${R}_n$N.json 2> gpurun_out/scale_${R}_n$N.err
-else
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/scale_${R}_n$N.json 2> gpurun_out/scale_${R}_n$N.err
-fi
-echo "rc=$?"; cat gpurun_out/scale_${R}_n$N.json | cut -c1-1200; tail -5 gpurun_out/scale_${R}_n$N.err
+nvidia-smi topo -m 2>&1 | head -14 > gpurun_out/topo_${R}_n$N.txt; lscpu | grep -i -E "numa|^CPU\(s\)|model name" >> gpurun_out/topo_${R}_n$N.txt
+for n in 1 2 4 8; do
+  [ $n -le $N ] || continue
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29541 tools/h2d_probe.py > gpurun_out/h2d_${R}_n$n.json 2> gpurun_out/h2d_${R}_n$n.err
+  echo "h2d n=$n rc=$?"; cat gpurun_out/h2d_${R}_n$n.json
+done
+timeout 600 python -m pytest tests -m gpu -q -k "two_gpu" > gpurun_out/pytest_2gpu_${R}.log 2>&1; echo "2gpu test rc=$?"; tail -2 gpurun_out/pytest_2gpu_${R}.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/scale_${R}_n$N.json 2> gpurun_out/scale_${R}_n$N.err
+echo "bench rc=$?"; tail -3 gpurun_out/scale_${R}_n$N.err
+python - gpurun_out/scale_${R}_n$N.json <<'PY'
+import json,sys
+d=json.load(open(sys.argv[1]))
+print({k:(round(d[k],1) if isinstance(d[k],float) else d[k]) for k in ['value','ms_per_step','n_gpus']}, 'e2e',round(d['e2e']['value']), 'h2d_gbs', round(d['e2e']['h2d_gbs'],1), 'e2e_idx', round(d['e2e_indexed']['value']), 'one', round(d['one_at_a_time']['value']), 'parity', d['parity_check'])
+PY

@@ -75,9 +75,9 @@ def traffic_json(out_path, reps):
                                    {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1)})
             tot += by
             n += 1
-        m = re.search(r"_(gemm|k_attend_cap|k_tail)_b(\d+)", os.path.basename(path))
+        m = re.search(r"_(gemm|k_attend|k_vocab_merge|k_beam_step)_b(\d+)", os.path.basename(path))
         if m and n:
-            key = ("gemm" if m.group(1) == "gemm" else "attend" if "attend" in m.group(1) else "tail") + "_bytes_per_launch_b" + m.group(2)
+            key = {"gemm": "gemm", "k_attend": "attend", "k_vocab_merge": "vocab_merge", "k_beam_step": "beam_step"}[m.group(1)] + "_bytes_per_launch_b" + m.group(2)
             res[key] = tot / n
     with open(out_path, "w") as f:
         json.dump(res, f, indent=1)

@@ -78,7 +78,7 @@ static int pad_rows(int n_valid, int bn, int alt_bn) {
 }
 
 // kind of twin set: fp16 hi + fp16 residual (f16x3 GEMMs) or fp16 hi + e4m3 hi8 / lo8 (f16+f8x2 GEMMs)
-enum PairKind { PAIR_F16X3 = 0, PAIR_F8 = 1 };
+enum PairKind { PAIR_F16X3 = 0, PAIR_F8 = 1, PAIR_BOTH = 2 };     // BOTH: operands of a GEMM that runs in either mode
 static PairKind step_kind(const Ctx* c) { return c->gemm_f8 ? PAIR_F8 : PAIR_F16X3; }
 
 int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, PairKind kind, bool weight = false, int n_valid = 0,
@@ -90,11 +90,12 @@ int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, PairKind kind
   b->rows = rows; b->ld = ld; b->box_rows = box_rows;
   VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, box_rows));
   VSR_TRY(make_tmap_f16(b->map32_hi, b->hi, rows, ld, ld, box_rows, 32));
-  if (kind == PAIR_F16X3) {
+  if (kind == PAIR_F16X3 || kind == PAIR_BOTH) {
     VSR_TRY(dev_alloc(c, &b->lo, (size_t)rows * ld * 2));
     VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, box_rows));
     VSR_TRY(make_tmap_f16(b->map32_lo, b->lo, rows, ld, ld, box_rows, 32));
-  } else {
+  }
+  if (kind == PAIR_F8 || kind == PAIR_BOTH) {
     VSR_TRY(dev_alloc(c, &b->hi8, (size_t)rows * ld));
     VSR_TRY(dev_alloc(c, &b->lo8, (size_t)rows * ld));
     VSR_TRY(make_tmap_u8(b->map8_hi, b->hi8, rows, ld, ld, box_rows));
@@ -102,14 +103,14 @@ int alloc_pair(Ctx* c, F16Pair* b, int rows, int ld, int box_rows, PairKind kind
     VSR_TRY(make_tmap_u8(b->map8_32_hi, b->hi8, rows, ld, ld, box_rows, 32));
     VSR_TRY(make_tmap_u8(b->map8_32_lo, b->lo8, rows, ld, ld, box_rows, 32));
   }
-  b->act_scale = (!weight && kind == PAIR_F8) ? ACT_SCALE_F8 : 1.f;
+  b->act_scale = (!weight && kind != PAIR_F16X3) ? ACT_SCALE_F8 : 1.f;
   b->kb = c->gemm_kb;
   b->n_valid = n_valid > 0 ? n_valid : rows;
   b->alt_bn = 0;
   if (alt_bn > 0 && c->use_alt_tiles) {
     VSR_TRY(make_tmap_f16(b->alt_hi, b->hi, rows, ld, ld, alt_bn, alt_kb));
-    if (kind == PAIR_F16X3) VSR_TRY(make_tmap_f16(b->alt_lo, b->lo, rows, ld, ld, alt_bn, alt_kb));
-    else {
+    if (kind != PAIR_F8) VSR_TRY(make_tmap_f16(b->alt_lo, b->lo, rows, ld, ld, alt_bn, alt_kb));
+    if (kind != PAIR_F16X3) {
       VSR_TRY(make_tmap_u8(b->alt8_hi, b->hi8, rows, ld, ld, alt_bn, alt_kb));
       VSR_TRY(make_tmap_u8(b->alt8_lo, b->lo8, rows, ld, ld, alt_bn, alt_kb));
     }
@@ -138,17 +139,19 @@ int ensure_rows(Ctx* c, int rows) {
   ALLOC_F(c->sent, n * c->NB1); ALLOC_F(c->hb, n * c->NB2); ALLOC_F(c->ga, n * c->NC);
   ALLOC_F(c->att, n * c->Fp); ALLOC_F(c->pre2, n * c->ND); ALLOC_F(c->logits, n * c->NE);
   ALLOC_F(c->gate_lp, n * 2); ALLOC_F(c->row_max, n); ALLOC_F(c->row_lsum, n); ALLOC_F(c->shift, n);
-  ALLOC_F(c->vpart, n * (size_t)(c->NE / 128 + 1) * VOCAB_REC);
+  ALLOC_F(c->vpart, n * (size_t)(c->NE / 16) * 2);
   VSR_TRY(dev_alloc(c, (void**)&c->ptr, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->ptrn, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->cand, sizeof(int32_t) * n * VSR_MAX_BEAM));
   VSR_TRY(dev_alloc(c, (void**)&c->word_in, sizeof(int64_t) * n));
-  const PairKind sk = step_kind(c);
-  VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD, sk));
+  // the recurrent states feed GEMM-A, which keeps all three passes in fp16 (step_kernels.cu: run_step), and GEMM-D,
+  // which runs f16+f8x2: h1 / h2 (and the h1' / h2' they are copied from) carry both residual forms
+  const PairKind sk = step_kind(c), hk = sk == PAIR_F8 ? PAIR_BOTH : sk;
+  VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD, hk)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD, hk));
   VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD, sk));
-  VSR_TRY(alloc_pair(c, &c->h1n_b, cap, c->Hp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->g_t_b, cap, c->Hp, MPAD, sk));
-  VSR_TRY(alloc_pair(c, &c->att_b, cap, c->Fp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->h2n_b, cap, c->Hp, MPAD, sk));
+  VSR_TRY(alloc_pair(c, &c->h1n_b, cap, c->Hp, MPAD, hk)); VSR_TRY(alloc_pair(c, &c->g_t_b, cap, c->Hp, MPAD, sk));
+  VSR_TRY(alloc_pair(c, &c->att_b, cap, c->Fp, MPAD, sk)); VSR_TRY(alloc_pair(c, &c->h2n_b, cap, c->Hp, MPAD, hk));
   c->cap_rows = cap;
   return VSR_OK;
 }
@@ -213,7 +216,7 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   c->NB2 = pad_rows(c->NB2v, 128, 0);
   c->NC = round_up(c->A, NPAD);
   c->ND = 4 * c->Hp;                       // gate-interleaved: 4 gates x Hp units (multiple of 256)
-  c->NE = pad_rows(c->V, 128, 144);
+  c->NE = round_up(c->V, 1152);            // whole tiles for every N tile of the vocabulary GEMM: 128, 144, 192 (lcm 1152)
   c->NVA = round_up(c->A, NPAD);
   c->KA = (d->h2_first_lstm ? c->Hp : 0) + c->Hp;
   c->KD = c->Fp + 2 * c->Hp;
@@ -250,13 +253,13 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
   // weight pairs are power-of-two scaled per tensor (F16Pair::scale)
   const PairKind sk = step_kind(c);
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, sk, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, sk, true, c->NB1v));
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, PAIR_F16X3, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, sk, true, c->NB1v));
   VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, sk, true, c->NB2v)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, sk, true));
   VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, sk, true)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, sk, true, c->V, 144, 64));
   if (const char* e = getenv("VSRDEC_PAIR")) c->use_pair = atoi(e) != 0;
   if (c->use_pair && c->use_tc) {     // CTA-pair kernel for the large-batch launches: 256 x 192 tiles for A, 256 x 256 for B, D + C
     VSR_TRY(make_pair_maps(&c->WA_b, 96)); VSR_TRY(make_pair_maps(&c->WB1_b, 128)); VSR_TRY(make_pair_maps(&c->WB2_b, 128));
-    VSR_TRY(make_pair_maps(&c->WC_b, 128)); VSR_TRY(make_pair_maps(&c->WD_b, 128));
+    VSR_TRY(make_pair_maps(&c->WC_b, 128)); VSR_TRY(make_pair_maps(&c->WD_b, 128)); VSR_TRY(make_pair_maps(&c->WE_b, 96));
   }
   // GEMM-A's 192-wide tile only fits 2 ring stages with 64-element k-blocks; 32-element blocks give 5
   c->WA_b.kb = 32;

@@ -158,7 +158,7 @@ struct AdvanceArgs {
   // tensor-core twins of h1 / h2 (none on the fp32 path), moved as raw 16-byte vectors: per state up to three arrays
   // (fp16 hi + fp16 lo, or fp16 hi + e4m3 hi8 + e4m3 lo8) of `tw_vec[i]` vectors per row
   int n_tw;
-  const uint4* tw_src[6]; uint4* tw_dst[6]; int tw_vec[6];
+  const uint4* tw_src[8]; uint4* tw_dst[8]; int tw_vec[8];
 };
 
 // copy the state of parent row p into new row n, record the next input word, update the slot pointer

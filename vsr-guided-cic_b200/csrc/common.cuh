@@ -89,7 +89,8 @@ struct F16Pair {
   // (weights only) CTA-pair kernel: each CTA of the pair loads pair_rows = BN / 2 rows of a BN-wide W tile (64-element k-blocks)
   int pair_rows = 0;
   alignas(64) unsigned char pair_hi[128];
-  alignas(64) unsigned char pair_lo[128];    // fp16 residual (f16x3) or e4m3 residual (f16+f8x2)
+  alignas(64) unsigned char pair_lo[128];    // e4m3 residual (f16+f8x2)
+  alignas(64) unsigned char pair_lo16[128];  // fp16 residual (f16x3)
   alignas(64) unsigned char pair_h8[128];    // e4m3 copy of hi (f16+f8x2)
   // (weights only) alternative N tile, chosen per launch when it needs fewer waves over the 148 SMs
   int n_valid = 0;      // real number of output rows (<= rows)
@@ -325,7 +326,7 @@ struct Ctx {
   float *row_max, *row_lsum;         // [rows]
   int32_t *forced;                   // [rows] forced vocab idx or -1
   int32_t *cand;                     // [rows][VSR_MAX_BEAM]
-  float *vpart;                      // [rows][NE / 128 + 1][VOCAB_REC] per-tile softmax records of the vocabulary GEMM
+  float *vpart;                      // [rows][NE / 16][2] per-chunk softmax records {max, sum exp} of the vocabulary GEMM
   // beam workspace
   int cap_caps = 0, cap_T = 0;
   float *seq_lp, *seq_lp_n;          // [caps][beam]

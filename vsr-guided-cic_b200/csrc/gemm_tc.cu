@@ -404,21 +404,18 @@ __device__ __forceinline__ void tile_epilogue(const TcProblem& p, uint32_t tmem_
 #endif
 }
 
-// Vocabulary-head epilogue: besides storing the logits (acc + bias) the thread that owns a row folds its BN
-// columns into one record {tile max, sum exp(x - max), max of every 16-column chunk}.  k_vocab_merge
-// (step_kernels.cu) finishes log-softmax and top-k from the records and re-reads only the few chunks that can hold
-// a top-k element, so the 20 MB logits tensor is written but never scanned.
+// Vocabulary-head epilogue: besides storing the logits (acc + bias) the thread that owns a row reduces every 16-column
+// chunk of its BN columns to a record {max, sum exp(x - max)}.  k_vocab_merge (vocab_head.cuh: merge_row) finishes
+// log-softmax and top-k from the chunk records and re-reads only the few chunks that can hold a top-k element, so the
+// 20 MB logits tensor is written but never scanned.  Records are per CHUNK, not per tile: the row's log-sum-exp (and
+// with it every returned log-prob) does not depend on the N tile of the launch, i.e. on the batch size or on which
+// kernel variant ran (bit-exact caption independence, stacked decodes).
 template <int BN>
-__device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0, int n_tile,
-                                               const float* s_bias, float (*s_vx)[8], int hsel, int lane) {
-  static_assert(BN / 16 <= VOCAB_REC - 2, "record too small for this tile");
+__device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlane, int row, bool live, int n0,
+                                               const float* s_bias, int hsel) {
   constexpr int NCH = BN / 16, H0 = (NCH + 1) / 2;      // chunks [0, H0) -> first warp of the quarter, [H0, NCH) -> second
-  static_assert(NCH - H0 <= 6, "exchange record too small");
-  float m = -INFINITY, ssum = 0.f;
-  float cmx[VOCAB_REC - 2];
-#pragma unroll
-  for (int k = 0; k < VOCAB_REC - 2; ++k) cmx[k] = -INFINITY;
   float* crow = p.c + (size_t)row * p.ldc;
+  float2* rec = reinterpret_cast<float2*>(p.vpart) + (size_t)row * (p.ldc / 16) + n0 / 16;
   const float sc = (p.acc_scale != nullptr ? __ldg(p.acc_scale) : 1.f) * p.act_inv;
 #pragma unroll
   for (int ch = 0; ch < NCH; ++ch) {
@@ -441,42 +438,18 @@ __device__ __forceinline__ void vocab_epilogue(const TcProblem& p, uint32_t tlan
       }
       float cm = fmaxf(fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3])), fmaxf(fmaxf(v[4], v[5]), fmaxf(v[6], v[7])));
       cm = fmaxf(cm, fmaxf(fmaxf(fmaxf(v[8], v[9]), fmaxf(v[10], v[11])), fmaxf(fmaxf(v[12], v[13]), fmaxf(v[14], v[15]))));
-      cmx[ch] = cm;
-      if (cm > m) { ssum *= __expf(m - cm); m = cm; }
-      if (m > -INFINITY) {
+      float cs = 0.f;
+      if (cm > -INFINITY) {
         float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;     // exp(-inf) = 0 on masked columns
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          e0 += __expf(v[j] - m); e1 += __expf(v[j + 1] - m); e2 += __expf(v[j + 2] - m); e3 += __expf(v[j + 3] - m);
+          e0 += __expf(v[j] - cm); e1 += __expf(v[j + 1] - cm); e2 += __expf(v[j + 2] - cm); e3 += __expf(v[j + 3] - cm);
         }
-        ssum += (e0 + e1) + (e2 + e3);
+        cs = (e0 + e1) + (e2 + e3);
       }
+      rec[ch] = make_float2(cm, cs);
     }
   }
-  // the quarter's second warp hands {max, sum, its chunk maxima} of the row to the first one through shared memory
-  if (hsel != 0) {
-    float* x = s_vx[lane];
-    x[0] = m; x[1] = ssum;
-#pragma unroll
-    for (int k = 0; k < NCH - H0; ++k) x[2 + k] = cmx[H0 + k];
-  }
-  epi_bar(2);
-  if (hsel != 0 || !live) return;
-  {
-    const float* x = s_vx[lane];
-    const float m2 = x[0], s2 = x[1];
-#pragma unroll
-    for (int k = 0; k < NCH - H0; ++k) cmx[H0 + k] = x[2 + k];
-    const float mm = fmaxf(m, m2);
-    float tot = 0.f;
-    if (m > -INFINITY) tot += ssum * __expf(m - mm);
-    if (m2 > -INFINITY) tot += s2 * __expf(m2 - mm);
-    m = mm; ssum = tot;
-  }
-  float4* rec = reinterpret_cast<float4*>(p.vpart + ((size_t)row * p.n_tiles + n_tile) * VOCAB_REC);
-  rec[0] = make_float4(m, ssum, cmx[0], cmx[1]);
-#pragma unroll
-  for (int q = 1; q < VOCAB_REC / 4; ++q) rec[q] = make_float4(cmx[4 * q - 2], cmx[4 * q - 1], cmx[4 * q], cmx[4 * q + 1]);
 }
 
 // Before the accumulator is complete (i.e. behind the main loop), by all epilogue warps: the tile's bias -> shared
@@ -550,13 +523,10 @@ template <int BN, int KB>
 __device__ __forceinline__ void tc_epilogue(const TcProblem& p, uint32_t tmem_base, int m0, int n0, int n_tile,
                                             int warp, int lane, const float* s_bias, float* tile) {
   using Cfg = TcCfg<BN, KB>;
-  float (*s_vx)[32][8] = reinterpret_cast<float (*)[32][8]>(tile);     // vocabulary mode: exchange buffer instead of a tile
   const int q = warp & 3, hsel = (warp - 2) >> 2;
   if (p.mode == EPI_VOCAB) {
-    if constexpr (BN / 16 <= VOCAB_REC - 2) {
-      const int row = m0 + q * 32 + lane;
-      vocab_epilogue<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16), row, row < p.M, n0, n_tile, s_bias, s_vx[q], hsel, lane);
-    }
+    const int row = m0 + q * 32 + lane;
+    vocab_epilogue<BN>(p, tmem_base + ((uint32_t)(q * 32) << 16), row, row < p.M, n0, s_bias, hsel);
   } else if constexpr (Cfg::kTileEpi) {
     tile_epilogue<BN>(p, tmem_base, m0, n0, n_tile, warp, lane, s_bias, tile);
   } else {
@@ -1087,7 +1057,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
       epi_bar(1);
       mbar_wait(&tmem_full_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tile_epilogue<BN>(p, tmem_acc, m0, n0, n_tile, warp, lane, s_bias, reinterpret_cast<float*>(smem + Cfg::kRingBytes));
+      if (p.mode == EPI_VOCAB) {
+        const int q = warp & 3, row = m0 + q * 32 + lane;
+        vocab_epilogue<BN>(p, tmem_acc + ((uint32_t)(q * 32) << 16), row, row < p.M, n0, s_bias, (warp - 2) >> 2);
+      } else {
+        tile_epilogue<BN>(p, tmem_acc, m0, n0, n_tile, warp, lane, s_bias, reinterpret_cast<float*>(smem + Cfg::kRingBytes));
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {                          // every epilogue warp of both CTAs -> the leader's barrier
@@ -1179,7 +1154,7 @@ int make_pair_maps(F16Pair* b, int pair_rows) {
   b->pair_rows = 0;
   if (b->hi == nullptr || pair_rows <= 0) return VSR_OK;
   VSR_TRY(make_tmap_f16(b->pair_hi, b->hi, b->rows, b->ld, b->ld, pair_rows));
-  if (b->lo != nullptr) VSR_TRY(make_tmap_f16(b->pair_lo, b->lo, b->rows, b->ld, b->ld, pair_rows));
+  if (b->lo != nullptr) VSR_TRY(make_tmap_f16(b->pair_lo16, b->lo, b->rows, b->ld, b->ld, pair_rows));
   if (b->hi8 != nullptr) {
     VSR_TRY(make_tmap_u8(b->pair_h8, b->hi8, b->rows, b->ld, b->ld, pair_rows));
     VSR_TRY(make_tmap_u8(b->pair_lo, b->lo8, b->rows, b->ld, b->ld, pair_rows));
@@ -1258,7 +1233,7 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64, bo
   if (pair) {       // CTA-pair kernel: half-tile maps (BN / 2 rows), 64-element k-blocks
     VSR_REQUIRE(g.wb->pair_rows * 2 == BN && kb == 64, VSR_EINVAL, "launch_gemm_tc: weight has no pair maps for N tile %d", BN);
     memcpy(&p->w_hi, g.wb->pair_hi, sizeof(CUtensorMap));
-    memcpy(&p->w_lo, g.wb->pair_lo, sizeof(CUtensorMap));
+    memcpy(&p->w_lo, g.f8 ? g.wb->pair_lo : g.wb->pair_lo16, sizeof(CUtensorMap));
     if (g.f8) memcpy(&p->w_h8, g.wb->pair_h8, sizeof(CUtensorMap));
   } else {
   memcpy(&p->w_hi, alt ? g.wb->alt_hi : (kb == 32 ? g.wb->map32_hi : g.wb->map_hi), sizeof(CUtensorMap));
@@ -1278,11 +1253,9 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64, bo
   const FusedCell& f = g.cell;
   p->mode = f.mode;
   if (f.mode == EPI_VOCAB) {
-    VSR_REQUIRE(f.vocab_part != nullptr && g.bias != nullptr && g.c != nullptr && BN / 16 <= VOCAB_REC - 2, VSR_EINVAL,
-                "launch_gemm_tc: vocabulary epilogue needs a bias, an output and a record buffer (N tile %d)", BN);
+    VSR_REQUIRE(f.vocab_part != nullptr && g.bias != nullptr && g.c != nullptr && g.ldc % 16 == 0 && g.N % BN == 0, VSR_EINVAL,
+                "launch_gemm_tc: vocabulary epilogue needs a bias, an output padded to whole tiles and a record buffer (N tile %d)", BN);
     p->vpart = f.vocab_part; p->n_valid = g.wb->n_valid;
-    if (f.vocab_tiles_out != nullptr) *f.vocab_tiles_out = p->n_tiles;
-    if (f.vocab_bn_out != nullptr) *f.vocab_bn_out = BN;
   } else if (f.mode != 0) {
     VSR_REQUIRE((f.mode == EPI_LSTM1 && BN == 192) || (f.mode == EPI_LSTM2 && (BN == 128 || (pair && BN == 256))), VSR_EINVAL,
                 "launch_gemm_tc: fused cell mode %d does not fit N tile %d", f.mode, BN);
@@ -1305,7 +1278,7 @@ static bool pair_ok(const GemmArgs& g) {
   const int BN = 2 * g.wb->pair_rows;
   if (g.N % BN != 0 || (BN != 192 && BN != 256)) return false;
   const int mode = g.cell.mode;
-  if (mode == EPI_VOCAB) return false;
+  if (mode == EPI_VOCAB && BN != 192) return false;     // row-per-thread epilogue: 12 chunks per row keep its registers in check
   if (mode == EPI_LSTM1 && BN != 192) return false;
   if (mode == EPI_LSTM2 && BN != 256) return false;
   if (g.cell.gt_cols % BN != 0) return false;
@@ -1355,9 +1328,7 @@ int launch_gemm_tc(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
       if (g2 != nullptr) tiles += ((g2->M + BM - 1) / BM) * ((g2->wb->n_valid + bn - 1) / bn);
       return ((tiles + sms - 1) / sms) * (BM + bn);
     };
-    // (the vocabulary head always takes the alternative tile: its per-tile records, and with them the summation
-    //  order of the row's log-sum-exp, must not depend on how many rows the launch has)
-    if (cost(g.wb->alt_bn) < cost(BN) || g.cell.mode == EPI_VOCAB) { BN = g.wb->alt_bn; kb = g.wb->alt_kb; }
+    if (cost(g.wb->alt_bn) < cost(BN)) { BN = g.wb->alt_bn; kb = g.wb->alt_kb; }
   }
   VSR_TRY(fill_problem(&p.pr[0], g, BN, kb));
   p.nprob = 1;

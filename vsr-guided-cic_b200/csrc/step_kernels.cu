@@ -598,15 +598,14 @@ __global__ void __launch_bounds__(SM_THREADS) k_softmax_topk(const SoftmaxArgs a
 
 constexpr int VM_WARPS = 4;
 // k_vocab_merge: vocab_head.cuh (merge_row) — one warp per row finishes the vocabulary head from the GEMM's records
-__global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs a, const float* __restrict__ vpart,
-                                                                int n_tiles, int nch) {
+__global__ void __launch_bounds__(VM_WARPS * 32) k_vocab_merge(const SoftmaxArgs a, const float* __restrict__ vpart, int n_chunks) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * VM_WARPS + (threadIdx.x >> 5);
   pdl_trigger();
   pdl_wait();
   if (n >= a.rows) return;
   RowHead h;
-  merge_row(a, vpart, n_tiles, nch, n, lane, h);
+  merge_row(a, vpart, n_chunks, n, lane, h);
   if (lane == 0) {
     a.row_max[n] = h.mx; a.row_lsum[n] = h.lsum; a.forced[n] = h.forced;
     a.gate_lp[(size_t)n * 2] = h.g0; a.gate_lp[(size_t)n * 2 + 1] = h.g1;
@@ -721,7 +720,11 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->pre1; g.ldc = c->NA; g.M = rows; g.N = c->NA;
     g.zero_acc = io.zero_state;           // [h2 | h1] = 0 at t = 0: pre1 = U[caption] + X[bos], no main loop
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
-    g.f8 = c->gemm_f8; g.allow_pair = true;
+    g.allow_pair = true;
+    // GEMM-A keeps all three passes in fp16 at every batch size: its 192-wide tile only fits 32-element k-blocks on the
+    // single-CTA kernel, whose 32-byte e4m3 rows load poorly (58 vs 46 us per launch at 500 rows), and switching modes
+    // with the batch size would make a caption's result depend on what else is in the batch
+    g.f8 = false;
     fused = gemm_uses_tc(c, g);
     c->state_h32 = !fused || io.need_h32;
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
@@ -820,7 +823,6 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
   // every tile to a softmax record and k_vocab_merge finishes the row without scanning the logits.
   static const bool fuse_enabled = [] { const char* e = getenv("VSRDEC_FUSE_VOCAB"); return e == nullptr || atoi(e) != 0; }();
   const bool fuse_vocab = fuse_enabled && fused && io.out_logp == nullptr && io.topk > 0;
-  int vocab_tiles = 0, vocab_bn = 0;
   {  // E: logits = out_fc . h2' + b
     PhaseScope ps(c, PH_GEMM_E, st);
     GemmArgs g{};
@@ -830,7 +832,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     g.f8 = c->gemm_f8; g.allow_pair = true;
     if (fuse_vocab) {
-      g.cell.mode = 3; g.cell.vocab_part = c->vpart; g.cell.vocab_tiles_out = &vocab_tiles; g.cell.vocab_bn_out = &vocab_bn;
+      g.cell.mode = 3; g.cell.vocab_part = c->vpart;
     }
     VSR_TRY(launch_gemm(c, g, st)); c->launches++;
   }
@@ -840,10 +842,8 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     a.out_logp = io.out_logp; a.out_stride = io.out_stride;
     a.gate_out = io.gate_out; a.gate_stride = io.gate_stride;
     if (fuse_vocab) {
-      VSR_REQUIRE(vocab_tiles > 0 && vocab_tiles <= c->NE / 128 + 1 && vocab_bn >= 128, VSR_EINVAL,
-                  "run_step: %d vocabulary tiles of %d", vocab_tiles, vocab_bn);
       VSR_CHECK_CUDA(launch_k(k_vocab_merge, dim3((rows + VM_WARPS - 1) / VM_WARPS), dim3(VM_WARPS * 32), 0, st, c->use_pdl && (c->pdl_mode & 2),
-                              a, (const float*)c->vpart, vocab_tiles, vocab_bn / 16));
+                              a, (const float*)c->vpart, c->NE / 16));
     } else {
       VSR_CHECK_CUDA(launch_k(k_softmax_topk, dim3(rows), dim3(SM_THREADS), 0, st, c->use_pdl && (c->pdl_mode & 2), a));
     }

@@ -120,21 +120,22 @@ struct RowHead {
   float pick_logit;     // lane j: logit of pick (unforced rows)
 };
 
-// The vocabulary GEMM's epilogue leaves, per (row, N tile), {max, sum exp, max of every 16-column chunk}.  One WARP
-// per row: row max / log-sum-exp from the records; then the topk tiles by max, the topk chunks among them by max, and
-// only those topk * 16 logits are re-read and their topk picked.
-// Exact: if an element e of group C (tile or chunk) were in the row's top-k without C being among the topk groups
-// in (max desc, position asc) order, each of the topk groups ahead of C would hold an element ordered before e
-// (larger, or equal with a smaller index).
-// Every level runs in (value desc, position asc) order with composite keys orderable(value) : ~position, so "ordered
-// before" is a plain unsigned 64-bit '>'.  The tile maxima stay in registers across the topk rounds (VM_TPL per lane).
-constexpr int VM_TPL = 12;            // tiles per lane: 32 * 12 * 128 columns >= the largest supported vocabulary
+// The vocabulary GEMM's epilogue leaves one record {max, sum exp(x - max)} per (row, 16-column chunk).  One WARP per
+// row: row max / log-sum-exp from the records (lanes stride the chunks, so the summation order depends on nothing but
+// the vocabulary size); then the topk chunks by (max desc, position asc), whose topk * 16 logits are re-read, and the
+// topk elements among them.
+// Exact: if an element e of chunk C were in the row's top-k without C being among the topk chunks in that order, each
+// of the topk chunks ahead of C would hold an element ordered before e (larger, or equal with a smaller index).
+// Composite keys orderable(value) : ~position make "ordered before" a plain unsigned 64-bit '>'.  The chunk maxima stay
+// in registers across the topk rounds when the row has at most 32 * VM_CPL chunks (V <= 12288), else they are re-read.
+constexpr int VM_CPL = 24;
 
-__device__ __forceinline__ void merge_row(const SoftmaxArgs& a, const float* __restrict__ vpart, int n_tiles, int nch,
+__device__ __forceinline__ void merge_row(const SoftmaxArgs& a, const float* __restrict__ vpart, int n_chunks,
                                           int n, int lane, RowHead& out) {
   const int V = a.V, topk = a.topk;
-  const float* rec0 = vpart + (size_t)n * n_tiles * VOCAB_REC;
+  const float2* rec = reinterpret_cast<const float2*>(vpart) + (size_t)n * n_chunks;
   const float* x = a.logits + (size_t)n * a.ld;
+  const int used = (V + 15) >> 4;               // chunks that hold vocabulary entries
 
   int64_t verb = -1; float shift_logit = 0.f;
   if (lane == 0) {
@@ -142,21 +143,27 @@ __device__ __forceinline__ void merge_row(const SoftmaxArgs& a, const float* __r
     if (a.use_verbs && a.verbs != nullptr)
       verb = load_verb(a.verbs, a.verbs_dtype, (size_t)(n / a.cur_beam) * a.L + a.ptr[n]);
   }
-  // (max, sum exp) of this lane's tiles; the maxima are kept for the selection rounds
-  float tmx[VM_TPL];
+  const bool in_regs = used <= 32 * VM_CPL;
+  float cmx[VM_CPL];
   float m = -INFINITY, ssum = 0.f;
-  {
-    float2 ms[VM_TPL];
+  if (in_regs) {
+    float2 ms[VM_CPL];
 #pragma unroll
-    for (int q = 0; q < VM_TPL; ++q) {
+    for (int q = 0; q < VM_CPL; ++q) {
       const int t = lane + 32 * q;
-      ms[q] = t < n_tiles ? *reinterpret_cast<const float2*>(rec0 + (size_t)t * VOCAB_REC) : make_float2(-INFINITY, 0.f);
+      ms[q] = t < used ? rec[t] : make_float2(-INFINITY, 0.f);
     }
 #pragma unroll
-    for (int q = 0; q < VM_TPL; ++q) {
-      tmx[q] = ms[q].x;
+    for (int q = 0; q < VM_CPL; ++q) {
+      cmx[q] = ms[q].x;
       if (ms[q].x > m) { ssum *= __expf(m - ms[q].x); m = ms[q].x; }
       if (ms[q].x > -INFINITY) ssum += ms[q].y * __expf(ms[q].x - m);
+    }
+  } else {
+    for (int t = lane; t < used; t += 32) {
+      const float2 r2 = rec[t];
+      if (r2.x > m) { ssum *= __expf(m - r2.x); m = r2.x; }
+      if (r2.x > -INFINITY) ssum += r2.y * __expf(r2.x - m);
     }
   }
   // stay-gate logit att_g . tanh(ga + ha)
@@ -175,50 +182,33 @@ __device__ __forceinline__ void merge_row(const SoftmaxArgs& a, const float* __r
   const float lsum = logf(se);
   stay = warp_sum(stay);
 
-  //   1. the topk TILES by tile max (round j: every lane's best key strictly below the previous winner, then a
-  //      warp arg-best; lane j keeps winner j),
+  //   1. the topk CHUNKS by chunk max (round j: every lane's best key strictly below the previous winner, then a warp
+  //      arg-best; lane j keeps winner j)
   unsigned long long prev = ~0ull;
-  int my_tile = -1;
+  int my_chunk = -1;
   for (int j = 0; j < topk; ++j) {
     unsigned long long best = 0ull;
+    if (in_regs) {
 #pragma unroll
-    for (int q = 0; q < VM_TPL; ++q) {
-      const int t = lane + 32 * q;
-      const unsigned long long key = ((unsigned long long)orderable(tmx[q]) << 32) | (unsigned)(~(unsigned)t);
-      if (tmx[q] > -INFINITY && key < prev && key > best) best = key;
+      for (int q = 0; q < VM_CPL; ++q) {
+        const int t = lane + 32 * q;
+        const unsigned long long key = ((unsigned long long)orderable(cmx[q]) << 32) | (unsigned)(~(unsigned)t);
+        if (cmx[q] > -INFINITY && key < prev && key > best) best = key;
+      }
+    } else {
+      for (int t = lane; t < used; t += 32) {
+        const float cm = rec[t].x;
+        const unsigned long long key = ((unsigned long long)orderable(cm) << 32) | (unsigned)(~(unsigned)t);
+        if (cm > -INFINITY && key < prev && key > best) best = key;
+      }
     }
     const unsigned hi = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32));
     const unsigned lo = __reduce_max_sync(0xffffffffu, (unsigned)(best >> 32) == hi ? (unsigned)best : 0u);
     prev = ((unsigned long long)hi << 32) | lo;
-    if (hi == 0u && lo == 0u) break;          // fewer tiles than topk (uniform)
-    if (lane == j) my_tile = (int)(~lo);
+    if (hi == 0u && lo == 0u) break;          // fewer chunks than topk (uniform)
+    if (lane == j) my_chunk = (int)(~lo);
   }
-  //   2. the topk 16-column CHUNKS among those tiles' chunk maxima,
-  constexpr int CQ = (VSR_MAX_BEAM * (VOCAB_REC - 2) + 31) / 32;
-  float kv[CQ]; int kc[CQ];
-#pragma unroll
-  for (int q = 0; q < CQ; ++q) {
-    const int e = lane + 32 * q;
-    const int tsel = e / nch, ch = e - tsel * nch;
-    const int tile = __shfl_sync(0xffffffffu, my_tile, tsel & 31);
-    kv[q] = -INFINITY; kc[q] = 0x7fffffff;
-    if (tsel < topk && tile >= 0) {
-      const float cm = rec0[(size_t)tile * VOCAB_REC + 2 + ch];
-      if (cm > -INFINITY) { kv[q] = cm; kc[q] = tile * nch + ch; }
-    }
-  }
-  int my_chunk = -1;
-  for (int j = 0; j < topk; ++j) {
-    float bv = -INFINITY; int bi = 0x7fffffff;
-#pragma unroll
-    for (int q = 0; q < CQ; ++q) if (before(kv[q], kc[q], bv, bi)) { bv = kv[q]; bi = kc[q]; }
-    unsigned kb; int ib;
-    warp_argbest_redux(bv, bi, kb, ib);
-#pragma unroll
-    for (int q = 0; q < CQ; ++q) if (kc[q] == ib) { kv[q] = -INFINITY; kc[q] = 0x7fffffff; }
-    if (lane == j && ib != 0x7fffffff) my_chunk = ib;
-  }
-  //   3. the topk ELEMENTS among those chunks' logits: lane owns elements e = lane + 32 * q of the topk * 16
+  //   2. the topk ELEMENTS among those chunks' logits: lane owns elements e = lane + 32 * q of the topk * 16
   constexpr int EQ = VSR_MAX_BEAM * 16 / 32;
   float cv[EQ]; int ci[EQ];
 #pragma unroll

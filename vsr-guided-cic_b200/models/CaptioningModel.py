@@ -101,9 +101,11 @@ class CaptioningModel(nn.Module):
         return outputs, log_probs
 
     def beam_search(self, statics, eos_idxs, beam_size, out_size=1, *args):
-        """Joint (word, gate) beam search (reference CaptioningModel.py:116-195)."""
+        """Joint (word, gate) beam search (reference CaptioningModel.py:116-195).  beam_size <= 8, out_size <= beam_size,
+        <= 64 regions per slot (see the limits in models/controllable_captioning.py)."""
         return self._beam(statics[:2], eos_idxs, beam_size, out_size, False, False)
 
     def beam_search_v(self, statics, eos_idxs, beam_size, out_size=1, *args, gt=False):
-        """Beam search with verb forcing (reference CaptioningModel.py:197-294)."""
+        """Beam search with verb forcing (reference CaptioningModel.py:197-294).  beam_size <= 8, out_size <= beam_size,
+        <= 64 regions per slot (see the limits in models/controllable_captioning.py)."""
         return self._beam(statics, eos_idxs, beam_size, out_size, True, gt)

@@ -7,6 +7,17 @@ signature, the 28-tensor state_dict (same names, shapes, dtypes, registration or
 `.to()`, `.eval()`, `load_state_dict()` work unchanged; all arithmetic of the hot path runs in
 libvsrdec's sm_100a kernels on a packed copy of the weights that is rebuilt whenever the
 parameters change.  CPU tensors raise: this path has no fallback.
+
+LIMITS the reference does not have (each raises VsrError with a message, never a silent wrong result):
+  * CUDA tensors only; parameters and inputs on one device;
+  * beam_size <= 8 (VSR_MAX_BEAM: the fused per-caption selection keeps 2*beam^2 candidates in one warp);
+  * <= 64 regions per slot (the slot validity mask is one 64-bit word);
+  * det_feat_size % 4 == 0 and att_size % 4 == 0 (128-bit loads); vocab_size <= 49152; vocab_size >= beam_size;
+  * seq_len <= 256 for beam search (back-track kernel's shared-memory history);
+  * tensor-core operands are carried as fp16 (+ fp16 / e4m3 residuals): weights are rescaled per tensor by a power of
+    two, activations are not — hidden states are in [-1, 1] by construction, region features must stay below 255 in
+    magnitude in the default "f16+f8x2" GEMM mode (65504 with VSRDEC_GEMM=f16x3); larger values saturate.
+Among candidates whose fp32 scores tie EXACTLY the order is (score desc, flat index asc); torch.sort leaves it unspecified.
 """
 import json
 import os
