@@ -196,6 +196,22 @@ int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* la
  * ms is a [host] array of capacity cap; returns the number of steps written, or a negative error. */
 int vsr_get_step_times(vsr_handle h, float* ms, int32_t cap);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * R-level SSP of the eval pre-step (first piece): SinkhornNet forward + optimal assignment, batched.
+ * Replaces models/sinkhorn_network.py:30-51 (SinkhornNet.forward / sinkhorn) and the per-role
+ * `.cpu()` + `munkres.Munkres().compute(make_cost_matrix(mx))` of coco_scripts/eval_coco.py:184-189 (flickr_scripts/
+ * eval_flickr.py likewise).  `weights` [host array of 10 device pointers] follows the state_dict order:
+ *   W1_txt.weight (128,300) .bias | W1_vis.weight (512,2048) .bias | W2_vis.weight (128,512) .bias |
+ *   W_fc_pos.weight (256,260) .bias | W_fc.weight (N,256) .bias          (sinkhorn_network.py:11-15)
+ * vsr_ssp_forward:  seq (B,N,2352) fp32 rows [txt 300 | vis 2048 | pos 4] as eval_coco.py:146 concatenates them;
+ *   matrix (B,N,N) fp32 = SinkhornNet(seq);  assign (B,N) int32 or NULL = for every row r of matrix^T (the profit matrix
+ *   of eval_coco.py:187) the column of its maximum-profit assignment (what munkres returns as pairs (r, col)). */
+typedef struct VsrSspHandle_* vsr_ssp_handle;
+int vsr_ssp_create(const float* const* weights, int32_t N, int32_t n_iters, float tau, vsr_ssp_handle* out);
+int vsr_ssp_load_weights(vsr_ssp_handle h, const float* const* weights, void* stream);
+void vsr_ssp_destroy(vsr_ssp_handle h);
+int vsr_ssp_forward(vsr_ssp_handle h, const float* seq, int32_t B, float* matrix, int32_t* assign, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -645,3 +645,55 @@ def test_decode_pipeline_matches_direct_calls(indexed, stack):
     again = list(pipe.run(iter(pinned)))
     for a, b_ in zip(again, got):
         assert all(torch.equal(x, y) for x, y in zip(a, b_))
+
+
+# ----------------------------------------------------------------------------- f2 (first piece): R-level SSP on the device
+def test_sinkhorn_net_matches_oracle_and_optimal_assignment():
+    """models.SinkhornNet (k_sinkhorn: MLP + Sinkhorn iterations + Hungarian, one CTA per problem) against the oracle
+    restatement of the reference's SinkhornNet.forward (pinned to the reference golden on the CPU side) and against
+    scipy's optimal assignment of the same profit matrices; also the reference-golden matrices themselves."""
+    from oracle import ssp_oracle as S
+    from models import SinkhornNet
+    import os
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ssp_small.pt"), weights_only=False)
+    W = S.init_weights(10, fx["seed_w"])
+    net = SinkhornNet(10, 20, 0.1)
+    net.load_state_dict(W)
+    net = net.to(DEV).eval()
+    seq = S.synth_seq(6, 10, fx["seed_x"])
+    out = net(seq.to(DEV))
+    torch.cuda.synchronize()
+    assert out.shape == (6, 10, 10)
+    assert rel_close(out.cpu(), fx["matrix"], 1e-4, 1e-6), float((out.cpu() - fx["matrix"]).abs().max())
+    # a larger batch of random problems, with ragged ones (trailing zero rows): matrix + assignment
+    g = torch.Generator().manual_seed(9)
+    big = torch.relu(torch.randn((300, 10, 2352), generator=g))
+    big[:, :, 2348:] = torch.rand((300, 10, 4), generator=g)
+    for i in range(0, 300, 3):
+        big[i, 2 + (i % 7):] = 0
+    m, a = net.assign(big.to(DEV))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = S.forward(W, big)
+    assert rel_close(m.cpu(), ref, 1e-4, 1e-6)
+    differ = 0
+    for i in range(300):
+        want = S.assign(ref[i])
+        got = a[i].cpu().numpy()
+        assert sorted(got.tolist()) == list(range(10))
+        if (want != got).any():          # only legitimate when the two assignments tie within rounding
+            mx = ref[i].double().numpy().T
+            pw, pg = mx[range(10), want].sum(), mx[range(10), got].sum()
+            assert abs(pw - pg) <= 1e-5 * max(1.0, abs(pw)), (i, pw, pg)
+            differ += 1
+    print("PARITY sinkhorn: 300 problems, matrices within 1e-4 relative, assignments identical to the optimum in %d, tied in %d" % (300 - differ, differ))
+    # weight reload is picked up
+    W2 = {k: v * 0.5 for k, v in W.items()}
+    net.load_state_dict(W2)
+    out2 = net(seq.to(DEV))
+    with torch.no_grad():
+        ref2 = S.forward(W2, seq)
+    assert rel_close(out2.cpu(), ref2, 1e-4, 1e-6)
+    from vsrdec import VsrError
+    with pytest.raises(VsrError):
+        net(seq)                          # CPU tensor: no fallback

@@ -2,7 +2,7 @@
 # compute-sanitizer over the round-2 kernels: GEMM self-test (single-CTA + CTA-pair kernels, both operand modes) and the
 # tiny-model tests (beam search on both vocabulary-head paths, edge cases, odd dimensions, sampling, teacher forcing)
 mkdir -p gpurun_out
-SEL='small_model or edge or odd_dim or sample_rl_logprobs or odd_seq_len'
+SEL="small_model or edge or odd_dim or sample_rl_logprobs or odd_seq_len or sinkhorn"
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 vsr-guided-cic_b200/csrc/build/selftest_gemm quick > gpurun_out/san_${tool}_gemm.log 2>&1
   echo "$tool gemm rc=$?: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|SELFTEST' gpurun_out/san_${tool}_gemm.log | tr '\n' ' ')"

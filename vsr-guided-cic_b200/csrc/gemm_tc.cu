@@ -964,6 +964,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();               // barriers of both CTAs initialised, TMEM allocated in both
+  __syncthreads();                  // (the cluster barrier already orders the allocator's write of tmem_base_slot; this one is
+                                    //  what compute-sanitizer's racecheck recognises)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
 

@@ -3,9 +3,10 @@
 Mirrors the import surface of the reference's models/__init__.py:1-4 so that
 coco_scripts/eval_coco.py:6,10 and flickr_scripts/eval_flickr.py:6 keep working when this
 directory's parent is placed on sys.path ahead of the reference checkout.  Only the
-captioning decoder is re-implemented (B200-native, via libvsrdec); the S-/R-level SSP
-models (`S_SSP`, `SinkhornNet`) are out of this path's scope and are
-forwarded, unmodified, to a reference checkout named by $VSR_REFERENCE_ROOT.
+captioning decoder and (first piece) the R-level SSP network `SinkhornNet`
+are re-implemented (B200-native, via libvsrdec); the S-level SSP transformer `S_SSP` is out
+of this path's scope and is forwarded, unmodified, to a reference checkout named by
+$VSR_REFERENCE_ROOT.
 """
 import importlib.util
 import os
@@ -13,8 +14,9 @@ import sys
 
 from .CaptioningModel import CaptioningModel as _CaptioningModel
 from .controllable_captioning import ControllableCaptioningModel
+from .sinkhorn_network import SinkhornNet
 
-_PASS_THROUGH = {"SinkhornNet": "sinkhorn_network", "S_SSP": "sort_model"}
+_PASS_THROUGH = {"S_SSP": "sort_model"}
 
 
 def _load_reference_module(stem):

@@ -48,6 +48,10 @@ EXPORTED_SYMBOLS = {
     "vsr_get_phase_times": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(c_f),
                                            ctypes.POINTER(c_i32), c_i32]),
     "vsr_get_step_times": (ctypes.c_int, [c_vp, ctypes.POINTER(c_f), c_i32]),
+    "vsr_ssp_create": (ctypes.c_int, [ctypes.POINTER(c_vp), c_i32, c_i32, c_f, ctypes.POINTER(c_vp)]),
+    "vsr_ssp_load_weights": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_vp]),
+    "vsr_ssp_destroy": (None, [c_vp]),
+    "vsr_ssp_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
 }
 
 
