@@ -861,14 +861,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_gemm_tcp(const __grid_constan
 // its own TMEM.  Bytes per output element halve (BN = 256), which is also what lets the e4m3 residual MMAs run near their
 // rate.  Persistent (one cluster per TPC walks the tile list), accumulators double-buffered in TMEM (2 x 256 columns), the
 // same shared-memory-tile epilogues as the single-CTA kernels (plain / g_t / LSTM cell 1 at BN = 192 / LSTM cell 2 at 256).
-template <int BN> struct PairCfg {
-  static constexpr int KB = 64;
-  static constexpr int kStages = 3;
+// VOCAB: the row-per-thread vocabulary epilogue needs no shared-memory tile, which buys one more stage (measured: -2 %).
+// (32-element k-blocks — the same ring bytes in twice as many, finer stages — were measured SLOWER for the fp16-only
+// GEMM-A: 201 vs 179 us on the M=1900, N=6144, K=3072 self-test shape; KB_ stays 64.)
+template <int BN, int KB_ = 64, bool VOCAB = false> struct PairCfg {
+  static constexpr int KB = KB_;
   static constexpr int kABytes = BM * KB * 2;                 // fp16 tile of this CTA's 128 A rows (the second half of the
   static constexpr int kWBytes = (BN / 2) * KB * 2;           //   stage holds lo16, or hi8 | lo8); this CTA's half of the W tile
   static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  static constexpr int kEpiBytes = VOCAB ? 0 : 32 * BN * 4;
+  static constexpr int kStages = (227 * 1024 - 2048 - 1024 - kEpiBytes) / kStageBytes;      // (2 KB: static shared memory)
   static constexpr int kRingBytes = kStages * kStageBytes;
-  static constexpr int kEpiBytes = 32 * BN * 4;
   static constexpr int kSmemBytes = kRingBytes + 1024 + kEpiBytes;
   static constexpr int kAccCols = 256, kTmemCols = 512;
 };
@@ -921,9 +924,9 @@ template <int BN> __device__ __forceinline__ constexpr uint32_t make_idesc_pair(
   return (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int KB_, bool VOCAB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gemm_pair(const __grid_constant__ TcParams params) {
-  using Cfg = PairCfg<BN>;
+  using Cfg = PairCfg<BN, KB_, VOCAB>;
   constexpr int KB = Cfg::KB;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[Cfg::kStages];       // waited on in the leader CTA only
@@ -1022,10 +1025,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t base = smem_u32(smem + st * Cfg::kStageBytes);
           const uint32_t wbase = base + 2 * Cfg::kABytes;
-          const uint64_t ah = make_sw128_desc(base), wh = make_sw128_desc(wbase);
+          const uint64_t ah = make_kmajor_desc<KB>(base), wh = make_kmajor_desc<KB>(wbase);
           if (p.f8) {
-            const uint64_t a8 = make_sw64_desc(base + Cfg::kABytes), al = make_sw64_desc(base + Cfg::kABytes + Cfg::kABytes / 2);
-            const uint64_t w8 = make_sw64_desc(wbase + Cfg::kWBytes), wl = make_sw64_desc(wbase + Cfg::kWBytes + Cfg::kWBytes / 2);
+            const uint64_t a8 = make_kmajor_desc8<KB>(base + Cfg::kABytes), al = make_kmajor_desc8<KB>(base + Cfg::kABytes + Cfg::kABytes / 2);
+            const uint64_t w8 = make_kmajor_desc8<KB>(wbase + Cfg::kWBytes), wl = make_kmajor_desc8<KB>(wbase + Cfg::kWBytes + Cfg::kWBytes / 2);
 #pragma unroll
             for (int k = 0; k < KB / UMMA_K; ++k) {
               const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -1038,7 +1041,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
               umma_f8_pair(tmem_acc, al + off, w8 + off, idesc, 1u);
             }
           } else {
-            const uint64_t al = make_sw128_desc(base + Cfg::kABytes), wl = make_sw128_desc(wbase + Cfg::kWBytes);
+            const uint64_t al = make_kmajor_desc<KB>(base + Cfg::kABytes), wl = make_kmajor_desc<KB>(wbase + Cfg::kWBytes);
 #pragma unroll
             for (int k = 0; k < KB / UMMA_K; ++k) {
               const uint64_t off = (uint64_t)((k * UMMA_K * 2) >> 4);
@@ -1059,7 +1062,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1) k_gem
       epi_bar(1);
       mbar_wait(&tmem_full_bar[acc], aph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (p.mode == EPI_VOCAB) {
+      if constexpr (VOCAB) {
         const int q = warp & 3, row = m0 + q * 32 + lane;
         vocab_epilogue<BN>(p, tmem_acc + ((uint32_t)(q * 32) << 16), row, row < p.M, n0, s_bias, (warp - 2) >> 2);
       } else {
@@ -1204,8 +1207,9 @@ int tc_gemm_init() {
   TCP_SET_SMEM(128, 64); TCP_SET_SMEM(144, 64); TCP_SET_SMEM(192, 32); TCP_SET_SMEM(192, 64); TCP_SET_SMEM(128, 32);
 #undef TCP_SET_SMEM
 #undef TC_SET_SMEM
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_pair<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<192>::kSmemBytes));
-  VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_pair<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<256>::kSmemBytes));
+#define PAIR_SET_SMEM(BN_, KB_, V_) VSR_CHECK_CUDA(cudaFuncSetAttribute(k_gemm_pair<BN_, KB_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<BN_, KB_, V_>::kSmemBytes))
+  PAIR_SET_SMEM(192, 64, false); PAIR_SET_SMEM(192, 64, true); PAIR_SET_SMEM(256, 64, false);
+#undef PAIR_SET_SMEM
   if (dev < 64) done_mask |= 1ull << dev;
   return VSR_OK;
 }
@@ -1289,21 +1293,26 @@ static bool pair_ok(const GemmArgs& g) {
 
 static int launch_gemm_pair(const GemmArgs& g, const GemmArgs* g2, cudaStream_t st) {
   const int BN = 2 * g.wb->pair_rows;
+  const bool vocab = g.cell.mode == EPI_VOCAB;
+  const int kb = 64;
   TcParams p;
   memset(&p, 0, sizeof(p));
-  VSR_TRY(fill_problem(&p.pr[0], g, BN, 64, true));
+  VSR_TRY(fill_problem(&p.pr[0], g, BN, kb, true));
   p.nprob = 1;
   int tiles = p.pr[0].n_tiles * ((p.pr[0].m_tiles + 1) / 2);
   if (g2 != nullptr) {
-    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, 64, true));
+    VSR_TRY(fill_problem(&p.pr[1], *g2, BN, kb, true));
     p.nprob = 2;
     tiles += p.pr[1].n_tiles * ((p.pr[1].m_tiles + 1) / 2);
   }
   static int sms = 0;
   if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   const int clusters = tiles < sms / 2 ? tiles : sms / 2;
-  if (BN == 192) VSR_CHECK_CUDA(launch_k(k_gemm_pair<192>, dim3(2 * clusters), dim3(TC_THREADS), PairCfg<192>::kSmemBytes, st, g.pdl, p));
-  else VSR_CHECK_CUDA(launch_k(k_gemm_pair<256>, dim3(2 * clusters), dim3(TC_THREADS), PairCfg<256>::kSmemBytes, st, g.pdl, p));
+#define PAIR_LAUNCH(BN_, KB_, V_) VSR_CHECK_CUDA(launch_k(k_gemm_pair<BN_, KB_, V_>, dim3(2 * clusters), dim3(TC_THREADS), PairCfg<BN_, KB_, V_>::kSmemBytes, st, g.pdl, p))
+  if (BN == 192 && vocab) PAIR_LAUNCH(192, 64, true);
+  else if (BN == 192) PAIR_LAUNCH(192, 64, false);
+  else PAIR_LAUNCH(256, 64, false);
+#undef PAIR_LAUNCH
   VSR_CHECK_CUDA(cudaGetLastError());
   return VSR_OK;
 }
