@@ -145,8 +145,8 @@ int ensure_rows(Ctx* c, int rows) {
   VSR_TRY(dev_alloc(c, (void**)&c->forced, sizeof(int32_t) * n));
   VSR_TRY(dev_alloc(c, (void**)&c->cand, sizeof(int32_t) * n * VSR_MAX_BEAM));
   VSR_TRY(dev_alloc(c, (void**)&c->word_in, sizeof(int64_t) * n));
-  // the recurrent states feed GEMM-A, which keeps all three passes in fp16 (step_kernels.cu: run_step), and GEMM-D,
-  // which runs f16+f8x2: h1 / h2 (and the h1' / h2' they are copied from) carry both residual forms
+  // the recurrent states feed GEMM-A, which runs f16x3 when the CTA-pair kernel is disabled (step_kernels.cu: run_step),
+  // and GEMM-D, which runs f16+f8x2: h1 / h2 (and the h1' / h2' they are copied from) carry both residual forms
   const PairKind sk = step_kind(c), hk = sk == PAIR_F8 ? PAIR_BOTH : sk;
   VSR_TRY(alloc_pair(c, &c->h1_b, cap, c->Hp, MPAD, hk)); VSR_TRY(alloc_pair(c, &c->h2_b, cap, c->Hp, MPAD, hk));
   VSR_TRY(alloc_pair(c, &c->s_t_b, cap, c->Hp, MPAD, sk));
@@ -253,10 +253,11 @@ static int create_impl(const VsrDims* d, const float* const* w, Ctx** out) {
   if (const char* e = getenv("VSRDEC_ALT_TILES")) c->use_alt_tiles = atoi(e) != 0;
   // weight pairs are power-of-two scaled per tensor (F16Pair::scale)
   const PairKind sk = step_kind(c);
-  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, PAIR_F16X3, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, sk, true, c->NB1v));
+  VSR_TRY(alloc_pair(c, &c->WA_b, c->NA, c->KA, 192, sk == PAIR_F8 ? PAIR_BOTH : sk, true)); VSR_TRY(alloc_pair(c, &c->WB1_b, c->NB1, c->Hp, bn, sk, true, c->NB1v));
   VSR_TRY(alloc_pair(c, &c->WB2_b, c->NB2, c->Hp, bn, sk, true, c->NB2v)); VSR_TRY(alloc_pair(c, &c->WC_b, c->NC, c->Hp, 128, sk, true));
   VSR_TRY(alloc_pair(c, &c->WD_b, c->ND, c->KD, 128, sk, true)); VSR_TRY(alloc_pair(c, &c->WE_b, c->NE, c->Hp, bn, sk, true, c->V, 144, 64));
   if (const char* e = getenv("VSRDEC_PAIR")) c->use_pair = atoi(e) != 0;
+  if (const char* e = getenv("VSRDEC_PAIR_MIN_ROWS")) c->pair_min_rows = atoi(e);
   if (c->use_pair && c->use_tc) {     // CTA-pair kernel for the large-batch launches: 256 x 192 tiles for A, 256 x 256 for B, D + C
     VSR_TRY(make_pair_maps(&c->WA_b, 96)); VSR_TRY(make_pair_maps(&c->WB1_b, 128)); VSR_TRY(make_pair_maps(&c->WB2_b, 128));
     VSR_TRY(make_pair_maps(&c->WC_b, 128)); VSR_TRY(make_pair_maps(&c->WD_b, 128)); VSR_TRY(make_pair_maps(&c->WE_b, 96));

@@ -211,7 +211,8 @@ struct GemmArgs {
   const int32_t* gather_idx = nullptr;
   const uint8_t* row_skip;  // optional [M]: a row tile whose flags are all 0 is skipped
   const F16Pair* wb = nullptr;  // fp16 hi/lo twin of w (tensor-core path), or null
-  bool allow_pair = false;      // may run on the CTA-pair kernel when the launch is large enough (step GEMMs A, B, D+C)
+  bool allow_pair = false;      // may run on the CTA-pair kernel when the launch is large enough (step GEMMs A, B, D+C, E)
+  int pair_min_rows = 1024;     //   ... i.e. has at least this many rows
   bool no_alt = false;          // keep the weight's default N tile (whose epilogue is the coalesced shared-memory tile one)
   bool f8 = false;              // f16+f8x2 mode: residual products on the fp8 tensor path (operand pairs need hi8 / lo8)
   bool pdl = false;             // launch with programmatic dependent launch (decoder-step GEMMs only)
@@ -273,6 +274,8 @@ struct Ctx {
   int NVA;                     // padded rows of Wva
   // fp16 hi/lo twins for the tcgen05 GEMMs
   bool use_tc = true;
+  int pair_min_rows = 640;       // B, D + C, E take the CTA-pair kernel from this many rows (VSRDEC_PAIR_MIN_ROWS; measured:
+                                 //   slower at 500 rows, 6 % faster at 1000)
   bool use_pair = true;          // CTA-pair (cta_group::2) kernel for the large-batch step GEMMs (VSRDEC_PAIR=0 disables)
   bool gemm_f8 = true;           // step GEMMs in f16+f8x2 mode (VSRDEC_GEMM=f16x3 keeps all three passes in fp16)
   bool use_alt_tiles = true;     // per-launch choice between the default and the alternative N tile (VSRDEC_ALT_TILES=0)

@@ -1280,7 +1280,7 @@ static int fill_problem(TcProblem* p, const GemmArgs& g, int BN, int kb = 64, bo
 // Can this launch run on the CTA-pair kernel?  Large row counts only (at a few hundred rows the 256-row pair tiles leave
 // most SMs idle: measured slower), pair maps present, tile-compatible epilogues, whole tiles in N.
 static bool pair_ok(const GemmArgs& g) {
-  if (!g.allow_pair || g.wb == nullptr || g.wb->pair_rows <= 0 || g.M < 1024 || g.row_skip != nullptr || g.zero_acc) return false;
+  if (!g.allow_pair || g.wb == nullptr || g.wb->pair_rows <= 0 || g.M < g.pair_min_rows || g.row_skip != nullptr || g.zero_acc) return false;
   const int BN = 2 * g.wb->pair_rows;
   if (g.N % BN != 0 || (BN != 192 && BN != 256)) return false;
   const int mode = g.cell.mode;

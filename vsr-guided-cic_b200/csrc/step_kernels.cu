@@ -721,10 +721,12 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.zero_acc = io.zero_state;           // [h2 | h1] = 0 at t = 0: pre1 = U[caption] + X[bos], no main loop
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
     g.allow_pair = true;
-    // GEMM-A keeps all three passes in fp16 at every batch size: its 192-wide tile only fits 32-element k-blocks on the
-    // single-CTA kernel, whose 32-byte e4m3 rows load poorly (58 vs 46 us per launch at 500 rows), and switching modes
-    // with the batch size would make a caption's result depend on what else is in the batch
-    g.f8 = false;
+    // GEMM-A runs on the CTA-pair kernel at EVERY row count (its 32 N tiles fill the machine from 2 row tiles on, and
+    // below that the pair splits the weight stream over two SMs: faster than the single-CTA kernel at 100, 500 and 5000
+    // rows alike), with the residual passes in fp8.  One kernel and one operand mode at every batch size keeps a
+    // caption's result independent of what else is in the batch.  (On the single-CTA kernel its 192-wide tile only fits
+    // 32-element k-blocks, whose 32-byte e4m3 rows load poorly: that path keeps three fp16 passes, VSRDEC_PAIR=0.)
+    g.f8 = c->gemm_f8 && c->use_pair; g.pair_min_rows = 1;
     fused = gemm_uses_tc(c, g);
     c->state_h32 = !fused || io.need_h32;
     if (fused) {   // LSTM cell 1 + sentinel gate in the epilogue: pre1 is never written
@@ -751,14 +753,14 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.c = c->sent; g.ldc = c->NB1; g.M = rows; g.N = c->NB1;
     GemmArgs g2{};
     g2.nseg = 1; g2.seg[0] = {c->h1n, c->Hp, c->Hp, c->Hp, &c->h1n_b};
-    g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b; g2.f8 = c->gemm_f8; g2.allow_pair = true;
+    g2.w = c->WB2; g2.ldw = c->Hp; g2.wb = &c->WB2_b; g2.f8 = c->gemm_f8; g2.allow_pair = true; g2.pair_min_rows = c->pair_min_rows;
     g2.c = c->hb; g2.ldc = c->NB2; g2.M = rows; g2.N = c->NB2;
     if (fused) {   // g_t = sig(gq + W1_hg.h1') * tanh(c1') on the hg column block of the h1' projection
       g2.cell.gt_cols = c->oB2_ha; g2.cell.gt_gq = c->gq; g2.cell.gt_c1n = c->c1n; g2.cell.g_t = nullptr;
       g2.cell.g_b = &c->g_t_b; g2.cell.ld_state = c->Hp;
     }
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
-    g.f8 = c->gemm_f8; g.allow_pair = true;
+    g.f8 = c->gemm_f8; g.allow_pair = true; g.pair_min_rows = c->pair_min_rows;
     VSR_TRY(launch_gemm(c, g, st, &g2)); c->launches += fused ? 1 : 2;   // one grouped launch on tensor cores
   }
   if (!fused) {
@@ -793,7 +795,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     PhaseScope ps(c, PH_GEMM_D, st);
     GemmArgs gc{};
     gc.nseg = 1; gc.seg[0] = {c->g_t, c->Hp, c->Hp, c->Hp, &c->g_t_b};
-    gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b; gc.f8 = c->gemm_f8; gc.allow_pair = true;
+    gc.w = c->WC; gc.ldw = c->Hp; gc.wb = &c->WC_b; gc.f8 = c->gemm_f8; gc.allow_pair = true; gc.pair_min_rows = c->pair_min_rows;
     gc.c = c->ga; gc.ldc = c->NC; gc.M = rows; gc.N = c->NC;
     GemmArgs g{};
     g.nseg = io.zero_state ? 2 : 3;       // h2 = 0 at t = 0: its K segment (last in WD) is not read
@@ -810,7 +812,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
       g.cell.h_b = &c->h2n_b; g.cell.ld_state = c->Hp;
     }
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
-    g.f8 = c->gemm_f8; g.allow_pair = true;
+    g.f8 = c->gemm_f8; g.allow_pair = true; g.pair_min_rows = c->pair_min_rows;
     VSR_TRY(launch_gemm(c, g, st, &gc)); c->launches += fused ? 1 : 2;
   }
   if (!fused) {
@@ -830,7 +832,7 @@ int run_step(Ctx* c, const StepIO& io, cudaStream_t st) {
     g.w = c->WE; g.ldw = c->Hp; g.bias = c->bE; g.wb = &c->WE_b;
     g.c = c->logits; g.ldc = c->NE; g.M = rows; g.N = c->NE;
     g.pdl = c->use_pdl && (c->pdl_mode & 1); g.pdl_flags = ((c->pdl_mode & 4) ? 1 : 0) | ((c->pdl_mode & 8) ? 2 : 0);
-    g.f8 = c->gemm_f8; g.allow_pair = true;
+    g.f8 = c->gemm_f8; g.allow_pair = true; g.pair_min_rows = c->pair_min_rows;
     if (fuse_vocab) {
       g.cell.mode = 3; g.cell.vocab_part = c->vpart;
     }
