@@ -182,3 +182,21 @@ def test_decode_pipeline_refuses_cpu_models():
         DecodePipeline([m], [3, -1], 3)
     with pytest.raises(ValueError):
         DecodePipeline([], [3, -1], 3)
+
+
+def test_sinkhorn_net_surface_and_no_cpu_fallback():
+    """models.SinkhornNet keeps the reference's constructor, parameter names / shapes and initialiser stream
+    (sinkhorn_network.py:5-28); on CPU tensors it raises instead of falling back."""
+    import torch
+    from models import SinkhornNet
+    from oracle import ssp_oracle as S
+    from vsrdec import VsrError
+    torch.manual_seed(1234)
+    net = SinkhornNet(10, 20, 0.1)
+    sd = net.state_dict()
+    assert tuple(sd.keys()) == S.PARAMS
+    W = S.init_weights(10, 1234)
+    for k in S.PARAMS:
+        assert torch.equal(sd[k], W[k]), k
+    with pytest.raises(VsrError):
+        net(torch.zeros(1, 10, 2352))
