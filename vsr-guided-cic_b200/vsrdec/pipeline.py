@@ -21,11 +21,12 @@ import torch
 
 class DecodePipeline:
     def __init__(self, models: Sequence, eos_idxs, beam_size: int, out_size: int = 1, gt: bool = False,
-                 indexed: bool = False, buffers: Optional[int] = None, stack: int = 1,
+                 indexed: bool = False, buffers: Optional[int] = None, stack: int = 1, ramp: bool = True,
                  post: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
         """models: one drop-in model per lane (same weights, same device).  `stack` host batches (of equal shapes) are
-        decoded per call.  `post` is applied to each batch's words tensor on the lane's stream (e.g. the all-gather of
-        a caption-sharded job)."""
+        decoded per call; with `ramp` the first group of a run holds a single batch, so that the first decode starts after
+        one batch's host->device copy instead of `stack` of them (the un-overlapped pipeline fill of a short run).  `post` is
+        applied to each batch's words tensor on the lane's stream (e.g. the all-gather of a caption-sharded job)."""
         if not models:
             raise ValueError("DecodePipeline needs at least one model")
         self.models = list(models)
@@ -35,6 +36,7 @@ class DecodePipeline:
         self.eos_idxs, self.beam_size, self.out_size, self.gt, self.indexed = eos_idxs, beam_size, out_size, gt, indexed
         self.post = post
         self.stack = max(1, int(stack))
+        self.ramp = bool(ramp)
         self.n_lanes = len(self.models)
         self.n_buf = buffers if buffers is not None else 2 * self.n_lanes
         # results are staged per input slot and collected one decode late: with a single slot decode s+1 would overwrite
@@ -120,7 +122,8 @@ class DecodePipeline:
             if exhausted:
                 return False
             group = []
-            while len(group) < self.stack:
+            want = 1 if (self.ramp and staged == 0) else self.stack
+            while len(group) < want:
                 try:
                     group.append(next(it))
                 except StopIteration:
