@@ -212,6 +212,42 @@ int vsr_ssp_load_weights(vsr_ssp_handle h, const float* const* weights, void* st
 void vsr_ssp_destroy(vsr_ssp_handle h);
 int vsr_ssp_forward(vsr_ssp_handle h, const float* seq, int32_t B, float* matrix, int32_t* assign, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * S-level SSP of the eval pre-step: the semantic-role sorter, batched.
+ * Replaces models/sort_model.py:105-119, 149-183 (S_SSP.generate(mode='not-normal')) with its encoder / decoder stacks
+ * (models/sort_modules.py:52-63, 79-99, 120-135; models/transformer_modules.py:36-54, 104-134, 188-212, 325-346) as
+ * coco_scripts/eval_coco.py:170-174 calls them once per (caption, verb) with batch 1.
+ * `weights` [host array of n_weights = 10 + 34 * n_layers device pointers], in this order (state_dict names):
+ *   sr_embed_layer.weight (n_roles,d) | v_embed_layer.weight (n_verbs,d) | encoder.fc_feat.weight (d,d) .bias (both NULL when
+ *   add_fc = 0) | encoder.layer_norm.weight .bias |
+ *   per encoder layer l: attention.linear_{Q,K,V,O}.{weight,bias} | ff_layer.w_1.{weight,bias} | ff_layer.w_2.{weight,bias} |
+ *                        layer_norm1.{weight,bias} | layer_norm2.{weight,bias}                                    (16 pointers)
+ *   decoder.layer_norm.weight .bias |
+ *   per decoder layer l: attention.linear_{Q,K,V,O}.{weight,bias} | ff_layer.w_1 | ff_layer.w_2 | layer_norm1..3  (18 pointers;
+ *                        the checkpoint's cross_attention.* tensors are never used by the reference, sort_modules.py:88)
+ *   expander_nn.weight (n_roles,d) .bias
+ * vsr_sort_generate: P independent problems.  verbs (P) int64 (already taken modulo 10000, sort_model.py:108), roles (P,max_len)
+ *   int64 = the problem's distinct non-zero role ids, zero padded (ids outside [0,n_roles) / [0,n_verbs) are clamped);
+ *   n_steps decoder steps are run (the largest role count of the batch is enough; <= max_len);  pred (P,max_len) int64 = role
+ *   ids in generated order, logp (P,max_len) fp32 = log-prob of each choice, both zero after a problem's last role;
+ *   step_rows (P,n_steps,n_roles) fp32 or NULL = the log-softmax row of every step.  No host synchronisation. */
+typedef struct VsrSortDims {
+  int32_t n_roles;   /* 26 */
+  int32_t n_verbs;   /* rows of v_embed_layer: 2663 (coco) / 2927 (flickr) */
+  int32_t d_model;   /* 512 */
+  int32_t d_ff;      /* 2048 */
+  int32_t n_heads;   /* 8 */
+  int32_t n_layers;  /* 3 encoder + 3 decoder layers */
+  int32_t max_len;   /* 10 */
+  int32_t add_fc;    /* encoder.fc_feat present */
+} VsrSortDims;
+typedef struct VsrSortHandle_* vsr_sort_handle;
+int vsr_sort_create(const VsrSortDims* dims, const float* const* weights, int32_t n_weights, vsr_sort_handle* out);
+int vsr_sort_load_weights(vsr_sort_handle h, const float* const* weights, int32_t n_weights, void* stream);
+void vsr_sort_destroy(vsr_sort_handle h);
+int vsr_sort_generate(vsr_sort_handle h, const int64_t* verbs, const int64_t* roles, int32_t P, int32_t n_steps,
+                      int64_t* pred, float* logp, float* step_rows, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

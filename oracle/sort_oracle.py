@@ -185,3 +185,17 @@ def permute_slots(final_rank: Sequence[int], n_slots: int, slot_valid: Sequence[
     for j, r in enumerate(placed):
         verbs[j] = float(verb_list[r])
     return src, verbs
+
+
+def replay(W, verb: int, roles: Sequence[int], chosen: Sequence[int]) -> List[torch.Tensor]:
+    """Log-prob rows of every step along a GIVEN order `chosen` (the device's): what a tie-aware comparison needs — after a
+    near-tie resolved the other way the free-running order is a different, equally valid trajectory."""
+    roles = list(roles) + [0] * (MAX_LEN - len(roles))
+    prior = encode(W, torch.tensor([[int(verb) % 10000]], dtype=torch.long), torch.tensor([roles], dtype=torch.long))
+    rows, tokens = [], [0]
+    for r in chosen:
+        if r == 0:
+            break
+        rows.append(step_logprobs(W, torch.tensor([tokens], dtype=torch.long), prior)[0])
+        tokens.append(int(r))
+    return rows

@@ -697,3 +697,70 @@ def test_sinkhorn_net_matches_oracle_and_optimal_assignment():
     from vsrdec import VsrError
     with pytest.raises(VsrError):
         net(seq)                          # CPU tensor: no fallback
+
+
+# ----------------------------------------------------------------------------- f2: S-level SSP (role sorter) on the device
+def _sort_problems(n, seed):
+    import random
+    rnd = random.Random(seed)
+    out = []
+    for i in range(n):
+        k = 1 + i % 10
+        roles = rnd.sample(range(1, 26), k)
+        out.append((rnd.randint(1, 2662), roles + [0] * (10 - k)))
+    return out
+
+
+def test_s_ssp_generate_matches_oracle_and_reference_golden():
+    """models.S_SSP.generate_batch (csrc/sort.cu: batched encoder, key/value-cached decoder, constrained greedy choice) against
+    (a) the golden orders of the unmodified reference's generate(mode='not-normal'), (b) the oracle replayed along the device's
+    own order: every step's 26 log-probs within 1e-4 and every choice within 2e-4 of the best role still to be placed."""
+    import os
+    from oracle import sort_oracle as O
+    from models import S_SSP
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sort_small.pt"), weights_only=False)
+    net = S_SSP()
+    W = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.to(DEV).eval()
+    probs = list(fx["problems"]) + _sort_problems(120, 3)
+    verbs = torch.tensor([p[0] for p in probs], device=DEV)
+    roles = torch.tensor([p[1] for p in probs], device=DEV)
+    pred, logp, rows = net.generate_batch(verbs, roles, trace=True)
+    torch.cuda.synchronize()
+    pred, logp, rows = pred.cpu(), logp.cpu(), rows.cpu()
+    n_gold = len(fx["problems"])
+    same_as_ref = sum(int(torch.equal(pred[i], fx["pred"][i])) for i in range(n_gold))
+    worst_row, worst_gap, tied = 0.0, 0.0, 0
+    with torch.no_grad():
+        for i, (verb, rl) in enumerate(probs):
+            n = sum(r != 0 for r in rl)
+            chosen = pred[i].tolist()
+            assert sorted(chosen[:n]) == sorted(r for r in rl if r) and all(c == 0 for c in chosen[n:]), (i, chosen)
+            want = O.replay(W, verb, rl, chosen)
+            left = [r for r in rl if r]
+            for t, row in enumerate(want):
+                worst_row = max(worst_row, float((rows[i, t] - row).abs().max()))
+                best = max(float(row[r]) for r in left)
+                gap = best - float(row[chosen[t]])
+                worst_gap = max(worst_gap, gap)
+                tied += int(gap > 0)
+                assert abs(float(logp[i, t]) - float(row[chosen[t]])) <= 1e-4
+                left.remove(chosen[t])
+    assert worst_row <= 1e-4, worst_row
+    assert worst_gap <= 2e-4, worst_gap
+    assert same_as_ref == n_gold or tied > 0
+    print("PARITY s_ssp: %d problems, orders identical to the reference golden %d/%d, step log-probs within %.1e of the oracle, "
+          "choices off the oracle's best by at most %.1e (%d near-tie decisions)" % (len(probs), same_as_ref, n_gold, worst_row, worst_gap, tied))
+    # the reference's one-problem call (eval_coco.py:174)
+    p1, l1, _ = net.generate(verbs[5:6], roles[5:6], mode='not-normal')
+    assert p1.shape == (1, 10) and torch.equal(p1.cpu()[0], pred[5])
+    # fewer decoder steps than max_len when the batch's largest role count is known
+    p2, _ = net.generate_batch(verbs[:4], roles[:4], n_steps=4)
+    assert torch.equal(p2.cpu(), pred[:4])
+    # timing of a batch the size of an eval batch's (caption, verb) problems
+    big = _sort_problems(300, 5)
+    bv = torch.tensor([p[0] for p in big], device=DEV); br = torch.tensor([p[1] for p in big], device=DEV)
+    net.generate_batch(bv, br)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); net.generate_batch(bv, br); e1.record(); torch.cuda.synchronize()
+    print("TIMING s_ssp: 300 problems (1..10 roles) in %.2f ms" % e0.elapsed_time(e1))

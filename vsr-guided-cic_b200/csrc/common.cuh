@@ -216,6 +216,7 @@ struct GemmArgs {
   bool no_alt = false;          // keep the weight's default N tile (whose epilogue is the coalesced shared-memory tile one)
   bool f8 = false;              // f16+f8x2 mode: residual products on the fp8 tensor path (operand pairs need hi8 / lo8)
   bool pdl = false;             // launch with programmatic dependent launch (decoder-step GEMMs only)
+  bool relu = false;            // FFMA twin only: max(0, .) on the output (feed-forward layers of the S-level SSP sorter)
   bool zero_acc = false;        // every A operand is known to be zero (h = 0 at t = 0): skip the main loop, acc := 0
   int pdl_flags = 0;            // bit 0: weight tiles before the dependency wait; bit 1: trigger after the main loop
   FusedCell cell;               // epilogue fusion (tensor-core path only)

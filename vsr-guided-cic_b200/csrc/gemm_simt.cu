@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(THREADS) k_gemm_simt(const GemmArgs g) {
       const float4 r = *reinterpret_cast<const float4*>(g.gather + (size_t)g.gather_idx[row] * g.ld_gather + n);
       o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
     }
+    if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     *reinterpret_cast<float4*>(g.c + (size_t)row * g.ldc + n) = o;
   }
 }

@@ -19,6 +19,10 @@ class VsrDims(ctypes.Structure):
                                       "h2_first_lstm", "img_second_lstm")]
 
 
+class VsrSortDims(ctypes.Structure):
+    _fields_ = [(n, c_i32) for n in ("n_roles", "n_verbs", "d_model", "d_ff", "n_heads", "n_layers", "max_len", "add_fc")]
+
+
 class VsrTrace(ctypes.Structure):
     _fields_ = [("step_out", c_vp), ("step_gate", c_vp), ("forced_beam", c_vp),
                 ("forced_word", c_vp), ("forced_gate", c_vp)]
@@ -52,6 +56,10 @@ EXPORTED_SYMBOLS = {
     "vsr_ssp_load_weights": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_vp]),
     "vsr_ssp_destroy": (None, [c_vp]),
     "vsr_ssp_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "vsr_sort_create": (ctypes.c_int, [ctypes.POINTER(VsrSortDims), ctypes.POINTER(c_vp), c_i32, ctypes.POINTER(c_vp)]),
+    "vsr_sort_load_weights": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_i32, c_vp]),
+    "vsr_sort_destroy": (None, [c_vp]),
+    "vsr_sort_generate": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
 }
 
 
