@@ -199,3 +199,23 @@ def replay(W, verb: int, roles: Sequence[int], chosen: Sequence[int]) -> List[to
         rows.append(step_logprobs(W, torch.tensor([tokens], dtype=torch.long), prior)[0])
         tokens.append(int(r))
     return rows
+
+
+def reconstruct_tiles(final_rank: Sequence[int], tiles: np.ndarray, verb_list: np.ndarray):
+    """eval_coco.py:217-237 literally, on one caption's materialised slot tiles (fixed_len, R, F) and verb list (fixed_len, 1):
+    permutation matrix, matrix product, rows with a zero sum dropped, tail filled with the last kept row; the verb list goes
+    through the same matrix, -1 on the rows nothing was placed in."""
+    fixed_len = tiles.shape[0]
+    perm_matrix = np.zeros((fixed_len, fixed_len))
+    for j, rk in enumerate(final_rank):
+        if j < fixed_len:
+            perm_matrix[j, int(rk)] = 1
+    recons = np.dot(perm_matrix, tiles.reshape(fixed_len, -1)).reshape(tiles.shape)
+    recons = recons[np.sum(recons, (1, 2)) != 0]
+    out = np.zeros(tiles.shape)
+    last = recons.shape[0] - 1
+    out[:recons.shape[0]] = recons
+    out[last + 1:] = recons[last:last + 1]
+    perm_mask = (np.sum(perm_matrix, -1) == 0).astype(int)
+    verbs = -1 * perm_mask[:, np.newaxis] + np.dot(perm_matrix, verb_list.reshape(fixed_len, 1))
+    return out, verbs[:, 0]

@@ -200,3 +200,43 @@ def test_sinkhorn_net_surface_and_no_cpu_fallback():
         assert torch.equal(sd[k], W[k]), k
     with pytest.raises(VsrError):
         net(torch.zeros(1, 10, 2352))
+
+
+def test_preorder_host_logic_matches_oracle_and_reference_golden():
+    """vsrdec.preorder's integer bookkeeping (no device work): merge_verb_ranks against the golden merges of the reference's
+    verb_rank_merge; roles_of_verb / permutation_from_rank against the oracle restatement of the eval loop, incl. its literal
+    permutation-matrix form."""
+    import os
+    import random
+    import numpy as np
+    from oracle import sort_oracle as O
+    from vsrdec import preorder as P
+    from common import synth_eval_captions
+    fx = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ssp_small.pt"), weights_only=False)
+    for la, lb, want in fx["merges"]:
+        assert P.merge_verb_ranks(la, lb) == want, (la, lb)
+    d = synth_eval_captions(C=60, seed=4)
+    n_rep = 0
+    for c in range(60):
+        for verb in d["control_verb"][c]:
+            if verb == 0:
+                break
+            got = P.roles_of_verb(int(verb), d["det_seqs_v"][c], d["det_seqs_sr"][c])
+            assert got == O.verb_roles(int(verb), d["det_seqs_v"][c], d["det_seqs_sr"][c])
+            n_rep += len(got[2])
+    assert n_rep > 10                                  # the synthetic captions do exercise repeated roles
+    rnd = random.Random(1)
+    for c in range(60):
+        n_valid = int(d["slot_valid"][c].sum())
+        rank = rnd.sample(range(10), rnd.randint(1, 10))
+        src, verbs = P.permutation_from_rank(rank, 10, d["slot_valid"][c], d["verb_list"][c, :, 0])
+        kept = [r for r in rank if r < n_valid]
+        if not kept:
+            continue                                   # the reference itself fails on a caption with no filled slot placed
+        assert (src, verbs) == O.permute_slots(rank, 10, d["slot_valid"][c], d["verb_list"][c, :, 0])
+        tiles, vl = O.reconstruct_tiles(rank, d["tiles"][c].double().numpy(), d["verb_list"][c])
+        assert np.array_equal(d["tiles"][c].double().numpy()[src], tiles)
+        assert np.array_equal(np.array(verbs), vl)
+        assert torch.equal(P.permute_slot_tiles(d["tiles"][c:c + 1], torch.tensor([src]))[0].double(), torch.from_numpy(tiles))
+        si = P.permute_slot_index(d["slot_index"][c:c + 1], torch.tensor([src]))[0]
+        assert torch.equal(si, d["slot_index"][c][torch.tensor(src)])

@@ -764,3 +764,66 @@ def test_s_ssp_generate_matches_oracle_and_reference_golden():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net.generate_batch(bv, br); e1.record(); torch.cuda.synchronize()
     print("TIMING s_ssp: 300 problems (1..10 roles) in %.2f ms" % e0.elapsed_time(e1))
+
+
+def test_role_orderer_matches_oracle_eval_loop():
+    """vsrdec.preorder.RoleOrderer (one S_SSP.generate_batch + one SinkhornNet.assign per batch of captions, host bookkeeping)
+    against the oracle restatement of the reference's per-caption loop (eval_coco.py:127-237) driven by the oracle networks:
+    same final rank for every caption, same re-ordered slot tiles / verb lists as the reference's permutation-matrix form."""
+    import numpy as np
+    from oracle import sort_oracle as O
+    from oracle import ssp_oracle as S
+    from models import S_SSP, SinkhornNet
+    from vsrdec.preorder import RoleOrderer, permute_slot_index, permute_slot_tiles
+    from common import synth_eval_captions
+    C = 40
+    d = synth_eval_captions(C=C, seed=21)
+    sort_net = S_SSP()
+    Wsort = {k: v.clone() for k, v in sort_net.state_dict().items()}
+    sort_net = sort_net.to(DEV).eval()
+    Wsk = S.init_weights(10, 1234)
+    sk = SinkhornNet(10, 20, 0.1)
+    sk.load_state_dict(Wsk)
+    sk = sk.to(DEV).eval()
+    ro = RoleOrderer(sort_net, sk, sinkhorn_len=10, fixed_len=10)
+    ranks = ro.ranks(d["control_verb"], d["det_seqs_v"], d["det_seqs_sr"], d["seqs_perm"].to(DEV))
+    torch.cuda.synchronize()
+    n_s, n_r = 0, 0
+    with torch.no_grad():
+        for c in range(C):
+            def order_roles(verb, roles):
+                nonlocal n_s
+                n_s += 1
+                return O.generate_not_normal(Wsort, verb, roles)[0]
+
+            def order_regions(role, slots):
+                nonlocal n_r
+                n_r += 1
+                rows = torch.zeros((10, 2352))
+                for j, loc in enumerate(slots):
+                    rows[j] = d["seqs_perm"][c, loc]
+                return S.region_order(S.forward(Wsk, rows[None])[0], slots)
+
+            want = O.caption_rank(d["control_verb"][c], d["det_seqs_v"][c], d["det_seqs_sr"][c], order_roles, order_regions,
+                                  S.verb_rank_merge)
+            assert ranks[c] == want, (c, ranks[c], want)
+    assert n_s >= C and n_r >= 10
+    src, verbs = ro.order(d["control_verb"], d["det_seqs_v"], d["det_seqs_sr"], d["verb_list"], d["seqs_perm"].to(DEV), d["slot_valid"])
+    tiles = permute_slot_tiles(d["tiles"].to(DEV), src).cpu()
+    sidx = permute_slot_index(d["slot_index"].to(DEV), src).cpu()
+    for c in range(C):
+        want_tiles, want_verbs = O.reconstruct_tiles(ranks[c], d["tiles"][c].double().numpy(), d["verb_list"][c])
+        assert np.array_equal(tiles[c].double().numpy(), want_tiles), c
+        assert np.array_equal(verbs[c].double().numpy(), want_verbs), c
+        assert torch.equal(sidx[c], d["slot_index"][c][src[c]]), c
+    print("PARITY eval pre-step: %d captions, %d S-level and %d R-level problems, final ranks, re-ordered tiles and verb lists "
+          "identical to the oracle's eval loop" % (C, n_s, n_r))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import time
+    big = synth_eval_captions(C=100, seed=5)
+    sp = big["seqs_perm"].to(DEV)
+    ro.order(big["control_verb"], big["det_seqs_v"], big["det_seqs_sr"], big["verb_list"], sp, big["slot_valid"])
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    ro.order(big["control_verb"], big["det_seqs_v"], big["det_seqs_sr"], big["verb_list"], sp, big["slot_valid"])
+    torch.cuda.synchronize()
+    print("TIMING eval pre-step: 100 captions ordered in %.1f ms wall (host bookkeeping + 2 device calls)" % ((time.perf_counter() - t0) * 1e3))

@@ -1,0 +1,177 @@
+"""Eval pre-step: the per-caption role ordering of coco_scripts/eval_coco.py:127-237, batched.
+
+The reference walks every caption of a batch in Python and, per (caption, verb), calls `S_SSP.generate` on the GPU with batch 1,
+per repeated role calls `SinkhornNet` with batch 1, copies the matrix to the host for munkres, and finally permutes the caption's
+(10, R, F) slot tiles with an `np.dot` against a permutation matrix.  Here the integer bookkeeping stays on the host (it is a few
+comparisons per caption), but
+
+  * every (caption, verb) problem of the batch goes through ONE `S_SSP.generate_batch` call (csrc/sort.cu),
+  * every repeated role of the batch goes through ONE `SinkhornNet.assign` call (csrc/ssp.cu: MLP + Sinkhorn + Hungarian),
+  * the permutation is returned as slot indices: `src_slot (C, L)` — row j of the re-ordered caption is slot src_slot[c, j] —
+    which `permute_slot_index` applies to the index-form input of `beam_search_v_indexed` (a (C, L, R) int32 gather) and
+    `permute_slot_tiles` to the reference's materialised tiles (a device gather instead of the reference's matmul).
+
+`RoleOrderer.order(...)` mirrors the names of the eval loop: control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm."""
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def merge_verb_ranks(first: Sequence[int], second: Sequence[int]) -> List[int]:
+    """Slot order of a further verb merged into the order so far (utils/tools.py:35-71, `verb_rank_merge`): slots in both lists
+    keep the first list's relative order (the second list is re-labelled to agree), and every slot only the second list has is
+    inserted in front of the nearest shared slot on its right in the second list, or appended when there is none."""
+    first, second = [int(x) for x in first], [int(x) for x in second]
+    shared = [s for s in first if s in second]
+    where = [second.index(s) for s in shared]
+    if where != sorted(where):
+        for s, p in zip(shared, sorted(where)):
+            second[p] = s
+    anchor, nearest = {}, None
+    for s in reversed(second):
+        if s in shared:
+            nearest = s
+        else:
+            anchor[s] = nearest
+    merged = list(first)
+    for s in second:
+        if s in shared:
+            continue
+        if anchor[s] is None:
+            merged.append(s)
+        elif anchor[s] in merged:
+            merged.insert(merged.index(anchor[s]), s)
+    return merged
+
+
+def roles_of_verb(verb: int, det_seqs_v: np.ndarray, det_seqs_sr: np.ndarray, limit: int = 10):
+    """(eval_coco.py:152-169) distinct roles of `verb` in first-seen order (at most `limit`; once that many are known every later
+    match is ignored), the slots holding each role, and the roles held by several slots."""
+    roles: List[int] = []
+    slots: Dict[int, List[int]] = {}
+    repeated: List[int] = []
+    js, ks = np.nonzero(det_seqs_v == verb)           # row-major: slot by slot, then the slot's verb columns
+    for j, k in zip(js.tolist(), ks.tolist()):
+        if len(roles) >= limit:
+            break
+        sr = int(det_seqs_sr[j, k])
+        if sr not in slots:
+            slots[sr] = [j]
+            roles.append(sr)
+        else:
+            slots[sr].append(j)
+            if sr not in repeated:
+                repeated.append(sr)
+    return roles, slots, repeated
+
+
+def permutation_from_rank(final_rank: Sequence[int], n_slots: int, slot_valid: Sequence[bool], verb_list: Sequence[float]):
+    """(eval_coco.py:217-237) row j of the re-ordered caption is slot final_rank[j]; rows whose tile is empty are dropped and the
+    tail repeats the last kept slot; the verb ids follow their slots un-compacted, -1 where nothing was placed."""
+    placed = [int(r) for r in list(final_rank)[:n_slots]]
+    kept = [r for r in placed if slot_valid[r]]
+    src = kept + [kept[-1] if kept else -1] * (n_slots - len(kept))
+    verbs = [float(verb_list[r]) for r in placed] + [-1.0] * (n_slots - len(placed))
+    return src, verbs
+
+
+class RoleOrderer:
+    def __init__(self, sort_net, sinkhorn_net, sinkhorn_len: int = 10, fixed_len: int = 10):
+        """sort_net: models.S_SSP, sinkhorn_net: models.SinkhornNet(sinkhorn_len, ...), both on the CUDA device
+        (eval_coco.py:94-103)."""
+        self.sort_net, self.sinkhorn_net = sort_net, sinkhorn_net
+        self.sinkhorn_len, self.fixed_len = int(sinkhorn_len), int(fixed_len)
+
+    def ranks(self, control_verb, det_seqs_v, det_seqs_sr, seqs_perm) -> List[List[int]]:
+        """final_rank of every caption (eval_coco.py:148-215).
+        control_verb (C, max_verb), det_seqs_v / det_seqs_sr (C, fixed_len, max_verb): host arrays / tensors;
+        seqs_perm (C, fixed_len, 2352): the concatenated (vis, txt, pos) rows of eval_coco.py:146, on the CUDA device."""
+        cv = np.asarray(control_verb.cpu() if isinstance(control_verb, torch.Tensor) else control_verb)
+        dv = np.asarray(det_seqs_v.cpu() if isinstance(det_seqs_v, torch.Tensor) else det_seqs_v)
+        ds = np.asarray(det_seqs_sr.cpu() if isinstance(det_seqs_sr, torch.Tensor) else det_seqs_sr)
+        C = cv.shape[0]
+        dev = seqs_perm.device
+        problems = []          # (caption, verb, roles, slots-by-role, repeated roles)
+        for c in range(C):
+            for verb in cv[c].tolist():
+                if verb == 0:
+                    break
+                roles, slots, repeated = roles_of_verb(verb, dv[c], ds[c])
+                if roles:
+                    problems.append((c, int(verb), roles, slots, repeated))
+        if not problems:
+            return [[] for _ in range(C)]
+        # ---- S level: the order of every problem's roles, one device call
+        L = self.sort_net.max_len
+        roles_t = torch.zeros((len(problems), L), dtype=torch.long)
+        for i, p in enumerate(problems):
+            roles_t[i, :len(p[2])] = torch.tensor(p[2])
+        verbs_t = torch.tensor([p[1] for p in problems], dtype=torch.long)
+        n_steps = max(len(p[2]) for p in problems)
+        pred, _ = self.sort_net.generate_batch(verbs_t.to(dev), roles_t.to(dev), n_steps=n_steps)
+        # ---- R level: the order of the slots of every repeated role, one device call
+        rep = [(i, sr) for i, p in enumerate(problems) for sr in p[4]]
+        assign = None
+        if rep:
+            N = self.sinkhorn_len
+            gather = torch.full((len(rep), N), -1, dtype=torch.long)
+            for n, (i, sr) in enumerate(rep):
+                c, locs = problems[i][0], problems[i][3][sr][:N]
+                gather[n, :len(locs)] = torch.tensor([c * self.fixed_len + l for l in locs])
+            gather = gather.to(dev)
+            rows = seqs_perm.reshape(-1, seqs_perm.shape[-1]).float()
+            seq = rows[gather.clamp(min=0)] * (gather >= 0).unsqueeze(-1).to(rows.dtype)      # zero rows pad a role's problem
+            _, assign = self.sinkhorn_net.assign(seq.contiguous())
+            assign = assign.cpu().numpy()
+        pred = pred.cpu().numpy()
+        region_rank = {}
+        for n, (i, sr) in enumerate(rep):
+            locs = problems[i][3][sr]
+            cols = assign[n, :len(locs)]
+            region_rank[(i, sr)] = [locs[int(a)] for a in np.argsort(cols, kind="stable")]
+        # ---- assemble per verb, merge over a caption's verbs
+        per_caption: List[List[List[int]]] = [[] for _ in range(C)]
+        for i, (c, verb, roles, slots, repeated) in enumerate(problems):
+            rank: List[int] = []
+            for sr in pred[i].tolist():
+                if sr == 0:
+                    break
+                rank += region_rank[(i, sr)] if len(slots[sr]) != 1 else slots[sr]
+            per_caption[c].append(rank)
+        out = []
+        for ranks in per_caption:
+            final = ranks[0] if ranks else []
+            for nxt in ranks[1:]:
+                final = merge_verb_ranks(final, nxt)
+            out.append([int(x) for x in final])
+        return out
+
+    def order(self, control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (src_slot (C, fixed_len) long, verbs (C, fixed_len) float), host tensors.  slot_valid (C, fixed_len) bool: slots whose
+        tile is not empty (`np.sum(tile) != 0`, eval_coco.py:226).  verb_list (C, fixed_len[, 1])."""
+        ranks = self.ranks(control_verb, det_seqs_v, det_seqs_sr, seqs_perm)
+        sv = np.asarray(slot_valid.cpu() if isinstance(slot_valid, torch.Tensor) else slot_valid).astype(bool)
+        vl = np.asarray(verb_list.cpu() if isinstance(verb_list, torch.Tensor) else verb_list).reshape(sv.shape[0], -1)
+        src = torch.empty((len(ranks), self.fixed_len), dtype=torch.long)
+        verbs = torch.empty((len(ranks), self.fixed_len), dtype=torch.float32)
+        for c, rank in enumerate(ranks):
+            s, v = permutation_from_rank(rank, self.fixed_len, sv[c], vl[c])
+            src[c], verbs[c] = torch.tensor(s), torch.tensor(v)
+        return src, verbs
+
+
+def permute_slot_index(slot_index: torch.Tensor, src_slot: torch.Tensor) -> torch.Tensor:
+    """Index-form slots (C, L, R) int32 re-ordered: out[c, j] = slot_index[c, src_slot[c, j]], all padding (-1) where
+    src_slot is -1.  The result feeds beam_search_v_indexed / vsr_prologue_indexed."""
+    src = src_slot.to(slot_index.device)
+    out = torch.gather(slot_index, 1, src.clamp(min=0).unsqueeze(-1).expand(-1, -1, slot_index.size(2)))
+    return torch.where((src >= 0).unsqueeze(-1), out, torch.full_like(out, -1)).contiguous()
+
+
+def permute_slot_tiles(det_seqs_all: torch.Tensor, src_slot: torch.Tensor) -> torch.Tensor:
+    """The reference's materialised (C, L, R, F) slot tiles re-ordered the same way (`det_seqs_recons`, eval_coco.py:222-231)."""
+    src = src_slot.to(det_seqs_all.device)
+    idx = src.clamp(min=0).view(src.size(0), src.size(1), 1, 1).expand(-1, -1, det_seqs_all.size(2), det_seqs_all.size(3))
+    out = torch.gather(det_seqs_all, 1, idx)
+    return out * (src >= 0).view(src.size(0), src.size(1), 1, 1).to(out.dtype)
