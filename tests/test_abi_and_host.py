@@ -240,3 +240,24 @@ def test_preorder_host_logic_matches_oracle_and_reference_golden():
         assert torch.equal(P.permute_slot_tiles(d["tiles"][c:c + 1], torch.tensor([src]))[0].double(), torch.from_numpy(tiles))
         si = P.permute_slot_index(d["slot_index"][c:c + 1], torch.tensor([src]))[0]
         assert torch.equal(si, d["slot_index"][c][torch.tensor(src)])
+
+
+def test_s_ssp_surface_and_no_cpu_fallback():
+    """models.S_SSP keeps the reference's constructor and call surface (sort_model.py:13-50, 105); CPU tensors, the training
+    forward and the unconstrained mode raise instead of falling back; the ABI weight list has 10 + 34 * 3 entries, all state_dict
+    names, none of them a cross_attention tensor (never used by the reference's forward, sort_modules.py:88)."""
+    import torch
+    from models import S_SSP
+    from vsrdec import VsrError
+    net = S_SSP(dataset='flickr')
+    assert net.v_embed_layer.weight.shape == (2927, 512) and net.max_len == 10 and net.beam_size == 1
+    names = net._weight_names()
+    sd = net.state_dict()
+    assert len(names) == 112 and all(n in sd for n in names) and not any("cross_attention" in n for n in names)
+    assert len(set(names)) == len(names)
+    with pytest.raises(VsrError):
+        net.generate(torch.tensor([3]), torch.tensor([[1, 2, 0, 0, 0, 0, 0, 0, 0, 0]]), mode='not-normal')
+    with pytest.raises(VsrError):
+        net.generate(torch.tensor([3]), torch.tensor([[1, 2, 0, 0, 0, 0, 0, 0, 0, 0]]), mode='normal')
+    with pytest.raises(VsrError):
+        net(torch.tensor([3]), torch.zeros(1, 10), torch.zeros(1, 10))
