@@ -827,3 +827,35 @@ def test_role_orderer_matches_oracle_eval_loop():
     ro.order(big["control_verb"], big["det_seqs_v"], big["det_seqs_sr"], big["verb_list"], sp, big["slot_valid"])
     torch.cuda.synchronize()
     print("TIMING eval pre-step: 100 captions ordered in %.1f ms wall (host bookkeeping + 2 device calls)" % ((time.perf_counter() - t0) * 1e3))
+
+
+# ----------------------------------------------------------------------------- operand range (unscaled fp16 split)
+@pytest.mark.parametrize("scale_seed", [0, 1])
+def test_steps_with_small_magnitude_weights(scale_seed):
+    """Trained checkpoints hold many weights far below the Xavier range the other tests use.  Every weight matrix of the small
+    golden model is rescaled by its own factor in {1e-3, 1e-2, 0.1, 1} (biases untouched): the operand split rescales each
+    tensor by a power of two before taking the fp16 / e4m3 parts, so two feedback steps must still match the fp32 oracle to
+    the contract's 1e-3 relative."""
+    from gpu_common import make_model
+    fx = load_golden("small_a.pt")
+    d = fx["dims_obj"]
+    g = torch.Generator().manual_seed(100 + scale_seed)
+    W = {}
+    for k, v in fx["weights"].items():
+        s = [1e-3, 1e-2, 0.1, 1.0][int(torch.randint(0, 4, (1,), generator=g))] if v.dim() > 1 else 1.0
+        W[k] = (v * s).contiguous()
+    m = make_model(d, W, fx["verb_table"])
+    det, ds, vg = fx["det"], fx["det_seqs"], fx["verbs_gt"]
+    statics = _cuda(det, ds, vg)
+    st = m.init_state(det.size(0), DEV)
+    ost = O.init_state(d, det.size(0))
+    prev = oprev = None
+    with torch.no_grad():
+        for t in range(3):
+            (o, gt_), st = m.step_v(t, st, prev, statics, None, mode="feedback", gt=True)
+            (oo, og), ost = O.decoder_step(W, d, t, ost, oprev, (det, ds, vg), None, "feedback", use_verbs=True, gt=True)
+            torch.cuda.synchronize()
+            assert rel_close(o.cpu(), oo, REL, ABS), (t, max_rel_err(o.cpu(), oo))
+            assert rel_close(gt_.cpu(), og, REL, ABS), (t, max_rel_err(gt_.cpu(), og))
+            w, gsel = oo.argmax(1), og.argmax(1)
+            prev, oprev = [w.to(DEV), gsel.to(DEV)], (w, gsel)
