@@ -11,8 +11,11 @@
 //   S_SSP.generate 'not-normal'     sort_model.py:149-183         k_sort_select: log-softmax over the role ids, first maximum among the
 //                                                                 roles still to be placed, in slot order
 // The reference runs this per (caption, verb) with batch 1, re-running the decoder over the whole prefix at every step
-// (eval_coco.py:170-174).  All arithmetic is fp32 (FFMA GEMM twin + warp-level kernels): the choice is an argmax over
-// log-probs, and the work is 0.45 GFLOP per problem.
+// (eval_coco.py:170-174).  The projections (M = 10 P rows in the encoder, P rows per decoder step; 0.45 GFLOP per problem) run
+// on the tcgen05 GEMM kernels of the decoder path in f16x3 mode (gemm_tc.cu: fp16 value + fp16 residual operands, three MMAs
+// into one fp32 TMEM accumulator; fused bias / residual epilogue): the layer-norm, attention and ReLU kernels write the
+// operand twins of what they produce.  The two tiny projections (fc_feat, the 512 -> 26 role head) and everything else are
+// fp32 warp-level kernels.  VSRDEC_GEMM=simt switches every projection to the fp32 FFMA twin.
 #include "common.cuh"
 
 namespace vsr {
@@ -24,6 +27,8 @@ constexpr int SORT_NPAD = 64;       // N padding of the FFMA GEMM
 
 struct SortLayer {
   float *qkv_w, *qkv_b, *o_w, *o_b, *w1_w, *w1_b, *w2_w, *w2_b, *ln_w[3], *ln_b[3];
+  // tensor-core twins of the weights; q_v / kv_v are row-range views of qkv_p ([0, d) and [d, 3d)) sharing its arrays and scale
+  F16Pair qkv_p, q_v, kv_v, o_p, w1_p, w2_p;
 };
 
 struct SortCtx {
@@ -40,6 +45,8 @@ struct SortCtx {
   float *ckv[SORT_MAXL] = {}, *kc[SORT_MAXL] = {}, *vc[SORT_MAXL] = {};
   int32_t* token = nullptr;
   uint32_t* remain = nullptr;
+  bool use_tc = true;
+  F16Pair y_b, ctx_b, ff_b, prior_b;        // operand twins of the activations that feed a projection
 };
 
 // ---------------------------------------------------------------- kernels
@@ -93,9 +100,18 @@ __global__ void k_sort_embed_dec(const int32_t* __restrict__ token, const float*
   }
 }
 
-// LayerNorm over the last dimension (eps 1e-5, biased variance), one warp per row
+// fp16 value + fp16 residual of one activation element (the f16x3 operand form of gemm_tc.cu)
+__device__ __forceinline__ void put_twin(const TwinOut& o, size_t off, float v) {
+  if (o.hi == nullptr) return;
+  v = fminf(fmaxf(v, -65504.f), 65504.f);
+  const __half h = __float2half_rn(v);
+  reinterpret_cast<__half*>(o.hi)[off] = h;
+  reinterpret_cast<__half*>(o.lo)[off] = __float2half_rn(v - __half2float(h));
+}
+
+// LayerNorm over the last dimension (eps 1e-5, biased variance), one warp per row; y and / or its operand twins
 __global__ void k_sort_ln(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows, int d,
-                          float* __restrict__ y) {
+                          float* __restrict__ y, const TwinOut tw) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const float* xr = x + (size_t)row * d;
@@ -105,8 +121,19 @@ __global__ void k_sort_ln(const float* __restrict__ x, const float* __restrict__
   float q = 0.f;
   for (int c = lane; c < d; c += 32) { const float t = xr[c] - mean; q += t * t; }
   const float rstd = rsqrtf(wsum(q) / (float)d + 1e-5f);
-  float* yr = y + (size_t)row * d;
-  for (int c = lane; c < d; c += 32) yr[c] = (xr[c] - mean) * rstd * w[c] + b[c];
+  for (int c = lane; c < d; c += 32) {
+    const float v = (xr[c] - mean) * rstd * w[c] + b[c];
+    if (y != nullptr) y[(size_t)row * d + c] = v;
+    put_twin(tw, (size_t)row * d + c, v);
+  }
+}
+
+// operand twins of max(0, x): the feed-forward activation between its two tensor-core projections
+__global__ void k_sort_relu_twin(const float* __restrict__ x, size_t n4, const TwinOut tw) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  store_twin4(tw, i * 4, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
 }
 
 // Multi-head attention of nq queries per problem over the keys [k0, k1) of that problem; one warp per head
@@ -117,7 +144,8 @@ struct SortAttn {
   const float* k; const float* v; int ldkv; // key row of (problem p, j): k + (p * kv_rows + j) * ldkv
   int kv_rows; int k0, k1;
   float* kc; float* vc; int store_pos;      // cache append (decoder self-attention) or store_pos < 0
-  float* out; int ldo;                      // context row of (p, i): out + (p * nq + i) * ldo
+  float* out; int ldo;                      // context row of (p, i): out + (p * nq + i) * ldo (fp32, or null)
+  TwinOut out_tw;                           //   ... and / or its operand twins, same layout
   int hd; float inv_sqrt_hd;
 };
 __global__ void k_sort_attn(const SortAttn a) {
@@ -152,13 +180,14 @@ __global__ void k_sort_attn(const SortAttn a) {
 #pragma unroll
     for (int j = 0; j < SORT_MAXK; ++j) { logit[j] = j < nk ? expf(logit[j] - m) : 0.f; den += logit[j]; }
     const float inv = 1.f / den;
-    float* o = a.out + ((size_t)p * a.nq + i) * a.ldo + col0;
+    const size_t o_off = ((size_t)p * a.nq + i) * a.ldo + col0;
     for (int e = lane; e < hd; e += 32) {
       float acc = 0.f;
 #pragma unroll
       for (int j = 0; j < SORT_MAXK; ++j)
         if (j < nk) acc = fmaf(logit[j] * inv, a.v[((size_t)p * a.kv_rows + a.k0 + j) * a.ldkv + col0 + e], acc);
-      o[e] = acc;
+      if (a.out != nullptr) a.out[o_off + e] = acc;
+      put_twin(a.out_tw, o_off + e, acc);
     }
   }
 }
@@ -195,20 +224,52 @@ __global__ void k_sort_select(const float* __restrict__ logits, int ld, int n_ro
 }
 
 // ---------------------------------------------------------------- host side
-int lin(const float* a, int lda, int K, const float* w, const float* bias, float* c, int ldc, int M, int N, const float* residual,
-        bool relu, cudaStream_t st) {
+// c = act(a . w^T + bias) (+ residual): tcgen05 f16x3 when the operand twins are given, else the fp32 FFMA twin
+int lin(SortCtx* c, const float* a, const F16Pair* a_b, int lda, int K, const float* w, const F16Pair* w_b, const float* bias, float* out,
+        int ldc, int M, int N, const float* residual, bool relu, cudaStream_t st) {
   GemmArgs g{};
-  g.nseg = 1; g.seg[0] = {a, lda, K, K, nullptr};
-  g.w = w; g.ldw = K; g.bias = bias;
-  g.c = c; g.ldc = ldc; g.M = M; g.N = N;
+  g.nseg = 1; g.seg[0] = {a, lda, K, K, a_b};
+  g.w = w; g.ldw = K; g.bias = bias; g.wb = w_b;
+  g.c = out; g.ldc = ldc; g.M = M; g.N = N;
   g.cadd = residual; g.ld_cadd = ldc;
+  if (c->use_tc && a_b != nullptr && w_b != nullptr && !relu) return launch_gemm_tc(g, nullptr, st);
   g.relu = relu;
   return launch_gemm_simt(g, st);
 }
 
-int ln(const float* x, const float* w, const float* b, int rows, int d, float* y, cudaStream_t st) {
-  k_sort_ln<<<(rows + 3) / 4, 128, 0, st>>>(x, w, b, rows, d, y);
+int ln(const float* x, const float* w, const float* b, int rows, int d, float* y, const F16Pair* y_b, cudaStream_t st) {
+  k_sort_ln<<<(rows + 3) / 4, 128, 0, st>>>(x, w, b, rows, d, y, twin_out(y_b, y_b != nullptr));
   VSR_CHECK_CUDA(cudaGetLastError());
+  return VSR_OK;
+}
+
+void free_pair(F16Pair* b, bool view = false) {
+  if (!view) { if (b->hi) cudaFree(b->hi); if (b->lo) cudaFree(b->lo); if (b->scale) cudaFree(b->scale); }
+  b->hi = b->lo = nullptr; b->scale = nullptr;
+}
+
+// fp16 value / residual arrays + tensor maps of a [rows][ld] operand (rows a multiple of 128); weights also get their scale pair
+int make_pair(F16Pair* b, int rows, int ld, bool weight) {
+  free_pair(b);
+  VSR_CHECK_CUDA(cudaMalloc(&b->hi, (size_t)rows * ld * 2));
+  VSR_CHECK_CUDA(cudaMalloc(&b->lo, (size_t)rows * ld * 2));
+  VSR_CHECK_CUDA(cudaMemset(b->hi, 0, (size_t)rows * ld * 2));
+  VSR_CHECK_CUDA(cudaMemset(b->lo, 0, (size_t)rows * ld * 2));
+  if (weight) VSR_CHECK_CUDA(cudaMalloc((void**)&b->scale, 2 * sizeof(float)));
+  b->rows = rows; b->ld = ld; b->box_rows = 128; b->kb = 64; b->n_valid = rows; b->act_scale = 1.f; b->alt_bn = 0; b->pair_rows = 0;
+  VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, 128));
+  VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, 128));
+  return VSR_OK;
+}
+
+// rows [r0, r0 + rows) of a weight pair as a pair of its own (same arrays, same scale)
+int make_view(F16Pair* v, const F16Pair& of, int r0, int rows) {
+  *v = of;
+  v->hi = reinterpret_cast<__half*>(of.hi) + (size_t)r0 * of.ld;
+  v->lo = reinterpret_cast<__half*>(of.lo) + (size_t)r0 * of.ld;
+  v->rows = rows; v->n_valid = rows;
+  VSR_TRY(make_tmap_f16(v->map_hi, v->hi, rows, of.ld, of.ld, 128));
+  VSR_TRY(make_tmap_f16(v->map_lo, v->lo, rows, of.ld, of.ld, 128));
   return VSR_OK;
 }
 
@@ -252,7 +313,33 @@ int ensure_ws(SortCtx* c, int P) {
   for (size_t l = 0; l < nl; ++l) { c->ckv[l] = take(rows * 2 * D); c->kc[l] = take(KV * D); c->vc[l] = take(KV * D); }
   c->token = reinterpret_cast<int32_t*>(p);
   c->remain = reinterpret_cast<uint32_t*>(p) + P;
+  if (c->use_tc) {
+    const int rp = (int)((rows + 127) / 128 * 128);
+    VSR_TRY(make_pair(&c->y_b, rp, (int)D, false)); VSR_TRY(make_pair(&c->ctx_b, rp, (int)D, false));
+    VSR_TRY(make_pair(&c->ff_b, rp, (int)F, false)); VSR_TRY(make_pair(&c->prior_b, rp, (int)D, false));
+  }
   c->cap_P = P;
+  return VSR_OK;
+}
+
+// operand twins of the packed projection weights (after every weight load)
+int split_weights(SortCtx* c, cudaStream_t st) {
+  if (!c->use_tc) return VSR_OK;
+  const VsrSortDims& d = c->d;
+  const int D = d.d_model, F = d.d_ff;
+  for (int s = 0; s < 2; ++s)
+    for (int l = 0; l < d.n_layers; ++l) {
+      SortLayer& L = s == 0 ? c->enc[l] : c->dec[l];
+      if (L.qkv_p.hi == nullptr) {
+        VSR_TRY(make_pair(&L.qkv_p, 3 * D, D, true)); VSR_TRY(make_pair(&L.o_p, D, D, true));
+        VSR_TRY(make_pair(&L.w1_p, F, D, true)); VSR_TRY(make_pair(&L.w2_p, D, F, true));
+        VSR_TRY(make_view(&L.q_v, L.qkv_p, 0, D)); VSR_TRY(make_view(&L.kv_v, L.qkv_p, D, 2 * D));
+      }
+      VSR_TRY(launch_split_pair(L.qkv_w, L.qkv_p, (size_t)3 * D * D, st, true));
+      VSR_TRY(launch_split_pair(L.o_w, L.o_p, (size_t)D * D, st, true));
+      VSR_TRY(launch_split_pair(L.w1_w, L.w1_p, (size_t)F * D, st, true));
+      VSR_TRY(launch_split_pair(L.w2_w, L.w2_p, (size_t)D * F, st, true));
+    }
   return VSR_OK;
 }
 
@@ -262,10 +349,14 @@ int run_layer(SortCtx* c, const SortLayer& W, bool decoder, int l, int P, int t,
   const int D = d.d_model, F = d.d_ff, L = d.max_len, H = d.n_heads, hd = D / H;
   const int rows = decoder ? P : P * L;
   const float isq = 1.f / sqrtf((float)hd);
-  VSR_TRY(ln(c->x, W.ln_w[0], W.ln_b[0], rows, D, c->y, st));
-  VSR_TRY(lin(c->y, D, D, W.qkv_w, W.qkv_b, c->qkv, 3 * D, rows, 3 * D, nullptr, false, st));
+  const bool tc = c->use_tc;
+  const F16Pair *y_b = tc ? &c->y_b : nullptr, *ctx_b = tc ? &c->ctx_b : nullptr, *ff_b = tc ? &c->ff_b : nullptr;
+  float* y32 = tc ? nullptr : c->y;             // fp32 copies of the projection inputs only for the FFMA twin
+  float* ctx32 = tc ? nullptr : c->ctx;
+  VSR_TRY(ln(c->x, W.ln_w[0], W.ln_b[0], rows, D, y32, y_b, st));
+  VSR_TRY(lin(c, c->y, y_b, D, D, W.qkv_w, &W.qkv_p, W.qkv_b, c->qkv, 3 * D, rows, 3 * D, nullptr, false, st));
   SortAttn a{};
-  a.q = c->qkv; a.ldq = 3 * D; a.out = c->ctx; a.ldo = D; a.hd = hd; a.inv_sqrt_hd = isq; a.store_pos = -1;
+  a.q = c->qkv; a.ldq = 3 * D; a.out = ctx32; a.out_tw = twin_out(ctx_b, tc); a.ldo = D; a.hd = hd; a.inv_sqrt_hd = isq; a.store_pos = -1;
   if (!decoder) {
     a.nq = L; a.k = c->qkv + D; a.v = c->qkv + 2 * D; a.ldkv = 3 * D; a.kv_rows = L; a.k0 = 0; a.k1 = L;
   } else {
@@ -274,22 +365,29 @@ int run_layer(SortCtx* c, const SortLayer& W, bool decoder, int l, int P, int t,
   }
   k_sort_attn<<<P, 32 * H, 0, st>>>(a);
   VSR_CHECK_CUDA(cudaGetLastError());
-  VSR_TRY(lin(c->ctx, D, D, W.o_w, W.o_b, c->x, D, rows, D, c->x, false, st));
+  VSR_TRY(lin(c, c->ctx, ctx_b, D, D, W.o_w, &W.o_p, W.o_b, c->x, D, rows, D, c->x, false, st));
   int nln = 1;
   if (decoder) {   // "cross" attention through the SAME attention module (sort_modules.py:88) over the encoder states
-    VSR_TRY(ln(c->x, W.ln_w[1], W.ln_b[1], rows, D, c->y, st));
-    VSR_TRY(lin(c->y, D, D, W.qkv_w, W.qkv_b, c->qkv, 3 * D, rows, D, nullptr, false, st));
+    VSR_TRY(ln(c->x, W.ln_w[1], W.ln_b[1], rows, D, y32, y_b, st));
+    VSR_TRY(lin(c, c->y, y_b, D, D, W.qkv_w, &W.q_v, W.qkv_b, c->qkv, 3 * D, rows, D, nullptr, false, st));
     SortAttn x{};
     x.q = c->qkv; x.ldq = 3 * D; x.nq = 1; x.k = c->ckv[l]; x.v = c->ckv[l] + D; x.ldkv = 2 * D; x.kv_rows = L; x.k0 = 0; x.k1 = L;
-    x.store_pos = -1; x.out = c->ctx; x.ldo = D; x.hd = hd; x.inv_sqrt_hd = isq;
+    x.store_pos = -1; x.out = ctx32; x.out_tw = twin_out(ctx_b, tc); x.ldo = D; x.hd = hd; x.inv_sqrt_hd = isq;
     k_sort_attn<<<P, 32 * H, 0, st>>>(x);
     VSR_CHECK_CUDA(cudaGetLastError());
-    VSR_TRY(lin(c->ctx, D, D, W.o_w, W.o_b, c->x, D, rows, D, c->x, false, st));
+    VSR_TRY(lin(c, c->ctx, ctx_b, D, D, W.o_w, &W.o_p, W.o_b, c->x, D, rows, D, c->x, false, st));
     nln = 2;
   }
-  VSR_TRY(ln(c->x, W.ln_w[nln], W.ln_b[nln], rows, D, c->y, st));
-  VSR_TRY(lin(c->y, D, D, W.w1_w, W.w1_b, c->ff, F, rows, F, nullptr, true, st));
-  VSR_TRY(lin(c->ff, F, F, W.w2_w, W.w2_b, c->x, D, rows, D, c->x, false, st));
+  VSR_TRY(ln(c->x, W.ln_w[nln], W.ln_b[nln], rows, D, y32, y_b, st));
+  if (tc) {       // the ReLU sits between two tensor-core projections: its kernel writes the second one's operand twins
+    VSR_TRY(lin(c, c->y, y_b, D, D, W.w1_w, &W.w1_p, W.w1_b, c->ff, F, rows, F, nullptr, false, st));
+    const size_t n4 = (size_t)rows * F / 4;
+    k_sort_relu_twin<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(c->ff, n4, twin_out(ff_b));
+    VSR_CHECK_CUDA(cudaGetLastError());
+  } else {
+    VSR_TRY(lin(c, c->y, nullptr, D, D, W.w1_w, nullptr, W.w1_b, c->ff, F, rows, F, nullptr, true, st));
+  }
+  VSR_TRY(lin(c, c->ff, ff_b, F, F, W.w2_w, &W.w2_p, W.w2_b, c->x, D, rows, D, c->x, false, st));
   return VSR_OK;
 }
 
@@ -307,21 +405,22 @@ int generate_impl(SortCtx* c, const int64_t* verbs, const int64_t* roles, int P,
   k_sort_embed_enc<<<P * L, 128, 0, st>>>(verbs, roles, c->v_emb, c->sr_emb, L, D, d.n_verbs, d.n_roles, scale, c->x);
   VSR_CHECK_CUDA(cudaGetLastError());
   if (d.add_fc) {
-    VSR_TRY(lin(c->x, D, D, c->fc_w, c->fc_b, c->y, D, P * L, D, nullptr, false, st));
+    VSR_TRY(lin(c, c->x, nullptr, D, D, c->fc_w, nullptr, c->fc_b, c->y, D, P * L, D, nullptr, false, st));
     VSR_CHECK_CUDA(cudaMemcpyAsync(c->x, c->y, sizeof(float) * (size_t)P * L * D, cudaMemcpyDeviceToDevice, st));
   }
   for (int l = 0; l < d.n_layers; ++l) VSR_TRY(run_layer(c, c->enc[l], false, l, P, 0, st));
-  VSR_TRY(ln(c->x, c->enc_ln_w, c->enc_ln_b, P * L, D, c->prior, st));
+  VSR_TRY(ln(c->x, c->enc_ln_w, c->enc_ln_b, P * L, D, c->use_tc ? nullptr : c->prior, c->use_tc ? &c->prior_b : nullptr, st));
   // keys / values of the encoder states under each decoder layer's attention module
   for (int l = 0; l < d.n_layers; ++l)
-    VSR_TRY(lin(c->prior, D, D, c->dec[l].qkv_w + (size_t)D * D, c->dec[l].qkv_b + D, c->ckv[l], 2 * D, P * L, 2 * D, nullptr, false, st));
+    VSR_TRY(lin(c, c->prior, c->use_tc ? &c->prior_b : nullptr, D, D, c->dec[l].qkv_w + (size_t)D * D, &c->dec[l].kv_v, c->dec[l].qkv_b + D,
+                c->ckv[l], 2 * D, P * L, 2 * D, nullptr, false, st));
   // ---- decoder: one position per step, greedy over the roles still to be placed
   for (int t = 0; t < n_steps; ++t) {
     k_sort_embed_dec<<<P, 128, 0, st>>>(c->token, c->sr_emb, D, scale, c->x);
     VSR_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < d.n_layers; ++l) VSR_TRY(run_layer(c, c->dec[l], true, l, P, t, st));
-    VSR_TRY(ln(c->x, c->dec_ln_w, c->dec_ln_b, P, D, c->y, st));
-    VSR_TRY(lin(c->y, D, D, c->exp_w, c->exp_b, c->logits, SORT_NPAD, P, SORT_NPAD, nullptr, false, st));
+    VSR_TRY(ln(c->x, c->dec_ln_w, c->dec_ln_b, P, D, c->y, nullptr, st));
+    VSR_TRY(lin(c, c->y, nullptr, D, D, c->exp_w, nullptr, c->exp_b, c->logits, SORT_NPAD, P, SORT_NPAD, nullptr, false, st));
     k_sort_select<<<(P + 3) / 4, 128, 0, st>>>(c->logits, SORT_NPAD, d.n_roles, roles, L, P, t, n_steps, c->remain, c->token, pred, logp,
                                                step_rows);
     VSR_CHECK_CUDA(cudaGetLastError());
@@ -370,7 +469,8 @@ int vsr_sort_load_weights(vsr_sort_handle h, const float* const* weights, int32_
     }
   }
   cp(c->exp_w, (size_t)d.n_roles * D); cp(c->exp_b, d.n_roles);      // rows n_roles..63 stay zero
-  return rc;
+  if (rc != VSR_OK) return rc;
+  return vsr::split_weights(c, st);
 }
 
 int vsr_sort_create(const VsrSortDims* dims, const float* const* weights, int32_t n_weights, vsr_sort_handle* out) {
@@ -386,6 +486,7 @@ int vsr_sort_create(const VsrSortDims* dims, const float* const* weights, int32_
   VSR_REQUIRE(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, VSR_ECUDA, "vsr_sort_create: no CUDA device (no CPU fallback)");
   SortCtx* c = new SortCtx();
   c->d = d;
+  if (const char* e = getenv("VSRDEC_GEMM")) c->use_tc = strcmp(e, "simt") != 0;
   VSR_CHECK_CUDA(cudaGetDevice(&c->device));
   const size_t n = vsr::weight_floats(d);
   if (cudaMalloc((void**)&c->wbuf, n * sizeof(float)) != cudaSuccess) { vsr::set_error("vsr_sort_create: cudaMalloc failed"); delete c; return VSR_ENOMEM; }
@@ -404,6 +505,13 @@ void vsr_sort_destroy(vsr_sort_handle h) {
   cudaDeviceSynchronize();
   cudaFree(c->wbuf);
   if (c->ws) cudaFree(c->ws);
+  for (int s = 0; s < 2; ++s)
+    for (int l = 0; l < vsr::SORT_MAXL; ++l) {
+      vsr::SortLayer& L = s == 0 ? c->enc[l] : c->dec[l];
+      vsr::free_pair(&L.q_v, true); vsr::free_pair(&L.kv_v, true);
+      vsr::free_pair(&L.qkv_p); vsr::free_pair(&L.o_p); vsr::free_pair(&L.w1_p); vsr::free_pair(&L.w2_p);
+    }
+  vsr::free_pair(&c->y_b); vsr::free_pair(&c->ctx_b); vsr::free_pair(&c->ff_b); vsr::free_pair(&c->prior_b);
   delete c;
 }
 
