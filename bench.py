@@ -410,6 +410,34 @@ def main_ours(args, rank, world, local_rank):
         fwd = {"workload": "xe_forward(config5): B=100, T=20, D=100, full (B,T,V) log-prob output", "ms_per_forward": f_ms,
                "row_steps_per_s": 100 * T / (f_ms * 1e-3), "n_gpus": 1}
         del f_det, f_caps, f_ctrl
+    # ---- eval pre-step: role ordering of 100 synthetic captions (S-level sorter + R-level network + host
+    # bookkeeping, vsrdec.preorder.RoleOrderer), wall clock around the call incl. its two device calls and host reads
+    prestep = None
+    if rank == 0:
+        from models import S_SSP, SinkhornNet
+        from tools.synth import synth_eval_captions
+        from vsrdec.preorder import RoleOrderer
+        sort_net, sk_net = S_SSP().to(dev).eval(), SinkhornNet(10, 20, 0.1).to(dev).eval()
+        orderer = RoleOrderer(sort_net, sk_net, sinkhorn_len=10, fixed_len=10)
+        caps = synth_eval_captions(C=100, seed=5)
+        sp = caps["seqs_perm"].to(dev)
+        a_ = (caps["control_verb"], caps["det_seqs_v"], caps["det_seqs_sr"], caps["verb_list"], sp, caps["slot_valid"])
+        for _ in range(2):
+            orderer.order(*a_)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        n_pre = 5
+        for _ in range(n_pre):
+            orderer.order(*a_)
+        torch.cuda.synchronize(dev)
+        pre_ms = (time.perf_counter() - t0) * 1e3 / n_pre
+        n_s = int(sum((cv != 0).sum() for cv in caps["control_verb"]))
+        prestep = {"workload": "role ordering of 100 synthetic captions (1-3 verbs, 3-8 slots each; eval_coco.py:127-237)",
+                   "ms_per_100_captions": pre_ms, "s_level_problems": n_s,
+                   "how": "wall clock around vsrdec.preorder.RoleOrderer.order: host bookkeeping + one S_SSP.generate_batch + one "
+                          "SinkhornNet.assign + host reads of their results"}
+        sort_net.close(); sk_net.close()
+        del sort_net, sk_net, orderer, sp
     barrier()
 
     # ---- per-kernel times: profiled (eager, CUDA events around every phase and every step) repeats of a decode, once
@@ -529,6 +557,7 @@ def main_ours(args, rank, world, local_rank):
                                 "entry": "beam_search_v_indexed / vsr_prologue_indexed: slots as int32 indices into the detections"},
                 "parity_check": check,
                 "forward_teacher": fwd,
+                "eval_prestep": prestep,
                 "roofline": roofline, "roofline_b100": roofline_b100, "roofline_attend": roofline_att,
                 "phases_ms_per_decode": {n: v[0] for n, v in ph1.items()},
                 "phases_ms_per_stacked_decode": {n: v[0] for n, v in phS.items()} if S > 1 else None,

@@ -167,37 +167,4 @@ def check_returned_beams(tag, d, hist, out_size, dev, o_outs, o_lps, rel=1e-3, a
     return swapped
 
 
-def synth_eval_captions(C=40, seed=21, R=4, F=32):
-    """Synthetic inputs of the eval pre-step (coco_scripts/eval_coco.py:127-147): per caption 1-3 control verbs, 3-8 filled slots,
-    each slot carrying 1-2 (verb, role) pairs — with repeated roles, so that the R-level network is needed — a verb list, the
-    (vis, txt, pos) rows, small slot tiles and their index form."""
-    import numpy as np
-    import random
-    rnd = random.Random(seed)
-    g = torch.Generator().manual_seed(seed)
-    control_verb = np.zeros((C, 8), dtype=np.int64)
-    det_seqs_v = np.zeros((C, 10, 8), dtype=np.int64)
-    det_seqs_sr = np.zeros((C, 10, 8), dtype=np.int64)
-    verb_list = -np.ones((C, 10, 1), dtype=np.float64)
-    slot_valid = np.zeros((C, 10), dtype=bool)
-    for c in range(C):
-        verbs = rnd.sample(range(1, 2663), rnd.randint(1, 3))
-        control_verb[c, :len(verbs)] = verbs
-        n_slots = rnd.randint(3, 8)
-        slot_valid[c, :n_slots] = True
-        role_pool = {v: rnd.sample(range(1, 26), rnd.randint(2, 4)) for v in verbs}
-        for j in range(n_slots):
-            pairs = rnd.sample(verbs, min(len(verbs), rnd.randint(1, 2)))
-            for k, v in enumerate(pairs):
-                det_seqs_v[c, j, k] = v
-                det_seqs_sr[c, j, k] = rnd.choice(role_pool[v])
-            if rnd.random() < 0.25:
-                verb_list[c, j, 0] = rnd.choice(verbs)
-    seqs_perm = torch.relu(torch.randn((C, 10, 2352), generator=g))
-    seqs_perm[:, :, 2348:] = torch.rand((C, 10, 4), generator=g)
-    tiles = torch.relu(torch.randn((C, 10, R, F), generator=g)) + 0.1
-    tiles = tiles * torch.from_numpy(slot_valid).view(C, 10, 1, 1)
-    slot_index = torch.randint(0, 50, (C, 10, R), generator=g, dtype=torch.int32)
-    slot_index = torch.where(torch.from_numpy(slot_valid).view(C, 10, 1), slot_index, torch.full_like(slot_index, -1))
-    return dict(control_verb=control_verb, det_seqs_v=det_seqs_v, det_seqs_sr=det_seqs_sr, verb_list=verb_list, slot_valid=slot_valid,
-                seqs_perm=seqs_perm, tiles=tiles, slot_index=slot_index)
+from tools.synth import synth_eval_captions  # noqa: E402,F401  (shared with bench.py)
