@@ -117,6 +117,13 @@ int main(int argc, char** argv) {
     return 0;
   }
   const int k1[] = {64}, k2[] = {1024}, k3[] = {1024, 1024, 1024}, k4[] = {2048, 1024}, k5[] = {64, 64, 64};
+  if (argc > 1 && strcmp(argv[1], "epi") == 0) {   // CTA-pair kernel at the 1000-caption step shapes (B-, D-like): timing; with
+    g_pair = true; g_f8 = true;                     // -DVSR_DBG_CLK the epilogue's cycle breakdown is printed by the kernel
+    const int k6[] = {2048, 1024, 1024};
+    bad += run_case(5000, 4096, 1, k2, false, 256);
+    bad += run_case(5000, 4096, 3, k6, false, 256);
+    return bad ? 1 : 0;
+  }
   if (argc > 1 && strcmp(argv[1], "quick") == 0) {   // one launch per kernel variant, no timing loops (compute-sanitizer)
     g_time = false;
     for (int pass = 0; pass < 2; ++pass) {
