@@ -231,7 +231,9 @@ int vsr_ssp_forward(vsr_ssp_handle h, const float* seq, int32_t B, float* matrix
  *   int64 = the problem's distinct non-zero role ids, zero padded (ids outside [0,n_roles) / [0,n_verbs) are clamped);
  *   n_steps decoder steps are run (the largest role count of the batch is enough; <= max_len);  pred (P,max_len) int64 = role
  *   ids in generated order, logp (P,max_len) fp32 = log-prob of each choice, both zero after a problem's last role;
- *   step_rows (P,n_steps,n_roles) fp32 or NULL = the log-softmax row of every step.  No host synchronisation. */
+ *   step_rows (P,n_steps,n_roles) fp32 or NULL = the log-softmax row of every step.  n_active [host, n_steps] or NULL: when the
+ *   caller has sorted the problems by falling role count, n_active[t] = number of problems with more than t roles — the
+ *   decoder steps then run on the first n_active[t] problems only.  No host synchronisation. */
 typedef struct VsrSortDims {
   int32_t n_roles;   /* 26 */
   int32_t n_verbs;   /* rows of v_embed_layer: 2663 (coco) / 2927 (flickr) */
@@ -247,7 +249,7 @@ int vsr_sort_create(const VsrSortDims* dims, const float* const* weights, int32_
 int vsr_sort_load_weights(vsr_sort_handle h, const float* const* weights, int32_t n_weights, void* stream);
 void vsr_sort_destroy(vsr_sort_handle h);
 int vsr_sort_generate(vsr_sort_handle h, const int64_t* verbs, const int64_t* roles, int32_t P, int32_t n_steps,
-                      int64_t* pred, float* logp, float* step_rows, void* stream);
+                      const int32_t* n_active, int64_t* pred, float* logp, float* step_rows, void* stream);
 
 #ifdef __cplusplus
 }

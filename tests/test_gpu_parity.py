@@ -757,13 +757,21 @@ def test_s_ssp_generate_matches_oracle_and_reference_golden():
     # fewer decoder steps than max_len when the batch's largest role count is known
     p2, _ = net.generate_batch(verbs[:4], roles[:4], n_steps=4)
     assert torch.equal(p2.cpu(), pred[:4])
+    # role counts known on the host: problems decoded in order of falling count, finished ones dropped from the later steps
+    cnt = [sum(r != 0 for r in p[1]) for p in probs]
+    p3, l3 = net.generate_batch(verbs, roles, counts=cnt)
+    assert torch.equal(p3.cpu(), pred) and torch.equal(l3.cpu(), logp)
     # timing of a batch the size of an eval batch's (caption, verb) problems
     big = _sort_problems(300, 5)
     bv = torch.tensor([p[0] for p in big], device=DEV); br = torch.tensor([p[1] for p in big], device=DEV)
     net.generate_batch(bv, br)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); net.generate_batch(bv, br); e1.record(); torch.cuda.synchronize()
-    print("TIMING s_ssp: 300 problems (1..10 roles) in %.2f ms" % e0.elapsed_time(e1))
+    bc = [sum(r != 0 for r in p[1]) for p in big]
+    net.generate_batch(bv, br, counts=bc)
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(); net.generate_batch(bv, br, counts=bc); e3.record(); torch.cuda.synchronize()
+    print("TIMING s_ssp: 300 problems (1..10 roles) in %.2f ms; %.2f ms with the role counts given" % (e0.elapsed_time(e1), e2.elapsed_time(e3)))
 
 
 def test_role_orderer_matches_oracle_eval_loop():

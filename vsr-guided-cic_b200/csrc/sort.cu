@@ -391,8 +391,8 @@ int run_layer(SortCtx* c, const SortLayer& W, bool decoder, int l, int P, int t,
   return VSR_OK;
 }
 
-int generate_impl(SortCtx* c, const int64_t* verbs, const int64_t* roles, int P, int n_steps, int64_t* pred, float* logp,
-                  float* step_rows, cudaStream_t st) {
+int generate_impl(SortCtx* c, const int64_t* verbs, const int64_t* roles, int P, int n_steps, const int32_t* n_active, int64_t* pred,
+                  float* logp, float* step_rows, cudaStream_t st) {
   const VsrSortDims& d = c->d;
   const int D = d.d_model, L = d.max_len;
   const float scale = sqrtf((float)D);
@@ -416,13 +416,16 @@ int generate_impl(SortCtx* c, const int64_t* verbs, const int64_t* roles, int P,
                 c->ckv[l], 2 * D, P * L, 2 * D, nullptr, false, st));
   // ---- decoder: one position per step, greedy over the roles still to be placed
   for (int t = 0; t < n_steps; ++t) {
-    k_sort_embed_dec<<<P, 128, 0, st>>>(c->token, c->sr_emb, D, scale, c->x);
+    // problems sorted by falling role count: only the first n_active[t] still have a role to place at step t
+    const int Pt = n_active != nullptr ? n_active[t] : P;
+    if (Pt <= 0) break;
+    k_sort_embed_dec<<<Pt, 128, 0, st>>>(c->token, c->sr_emb, D, scale, c->x);
     VSR_CHECK_CUDA(cudaGetLastError());
-    for (int l = 0; l < d.n_layers; ++l) VSR_TRY(run_layer(c, c->dec[l], true, l, P, t, st));
-    VSR_TRY(ln(c->x, c->dec_ln_w, c->dec_ln_b, P, D, c->y, nullptr, st));
-    VSR_TRY(lin(c, c->y, nullptr, D, D, c->exp_w, nullptr, c->exp_b, c->logits, SORT_NPAD, P, SORT_NPAD, nullptr, false, st));
-    k_sort_select<<<(P + 3) / 4, 128, 0, st>>>(c->logits, SORT_NPAD, d.n_roles, roles, L, P, t, n_steps, c->remain, c->token, pred, logp,
-                                               step_rows);
+    for (int l = 0; l < d.n_layers; ++l) VSR_TRY(run_layer(c, c->dec[l], true, l, Pt, t, st));
+    VSR_TRY(ln(c->x, c->dec_ln_w, c->dec_ln_b, Pt, D, c->y, nullptr, st));
+    VSR_TRY(lin(c, c->y, nullptr, D, D, c->exp_w, nullptr, c->exp_b, c->logits, SORT_NPAD, Pt, SORT_NPAD, nullptr, false, st));
+    k_sort_select<<<(Pt + 3) / 4, 128, 0, st>>>(c->logits, SORT_NPAD, d.n_roles, roles, L, Pt, t, n_steps, c->remain, c->token, pred, logp,
+                                                step_rows);
     VSR_CHECK_CUDA(cudaGetLastError());
   }
   return VSR_OK;
@@ -515,17 +518,21 @@ void vsr_sort_destroy(vsr_sort_handle h) {
   delete c;
 }
 
-int vsr_sort_generate(vsr_sort_handle h, const int64_t* verbs, const int64_t* roles, int32_t P, int32_t n_steps, int64_t* pred,
-                      float* logp, float* step_rows, void* stream) {
+int vsr_sort_generate(vsr_sort_handle h, const int64_t* verbs, const int64_t* roles, int32_t P, int32_t n_steps,
+                      const int32_t* n_active, int64_t* pred, float* logp, float* step_rows, void* stream) {
   if (!h) { vsr::set_error("vsr_sort_generate: null handle"); return VSR_EINVAL; }
   SortCtx* c = (SortCtx*)h;
   VSR_REQUIRE(verbs && roles && pred && logp && P >= 0, VSR_EINVAL, "vsr_sort_generate: null argument");
   VSR_REQUIRE(n_steps >= 0 && n_steps <= c->d.max_len, VSR_EINVAL, "vsr_sort_generate: n_steps=%d not in [0,%d]", n_steps, c->d.max_len);
   if (P == 0) return VSR_OK;
+  if (n_active != nullptr)
+    for (int t = 0; t < n_steps; ++t)
+      VSR_REQUIRE(n_active[t] >= 0 && n_active[t] <= P && (t == 0 || n_active[t] <= n_active[t - 1]), VSR_EINVAL,
+                  "vsr_sort_generate: n_active must be non-increasing and within [0, P] (problems sorted by falling role count)");
   int prev = -1;
   cudaGetDevice(&prev);
   if (prev != c->device) cudaSetDevice(c->device);
-  const int rc = vsr::generate_impl(c, verbs, roles, P, n_steps, pred, logp, step_rows, (cudaStream_t)stream);
+  const int rc = vsr::generate_impl(c, verbs, roles, P, n_steps, n_active, pred, logp, step_rows, (cudaStream_t)stream);
   if (prev != c->device && prev >= 0) cudaSetDevice(prev);
   return rc;
 }

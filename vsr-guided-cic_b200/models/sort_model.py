@@ -197,12 +197,14 @@ class S_SSP(nn.Module):
             pass
 
     # ------------------------------------------------------------------ generation
-    def generate_batch(self, verbs, roles, n_steps=None, trace=False):
+    def generate_batch(self, verbs, roles, n_steps=None, trace=False, counts=None):
         """P independent problems in one call.  verbs (P,) and roles (P, max_len): CUDA integer tensors; a problem's roles are
         its distinct non-zero role ids, zero-padded.  Returns (pred (P, max_len) long, seqLogprobs (P, max_len) float) — the
         role ids in generated order and the log-prob of each choice, zero after the last role — and, with trace=True, the
         (P, n_steps, 26) log-prob rows of every step.  n_steps: number of decoder steps to run (default max_len; the largest
-        role count of the batch is enough)."""
+        role count of the batch is enough).  counts: host sequence of the P role counts, if the caller knows them: the problems
+        are then decoded in order of falling count and every decoder step runs only on the problems that still have a role to
+        place (results are returned in the caller's order)."""
         from vsrdec import _lib
         if not (isinstance(verbs, torch.Tensor) and isinstance(roles, torch.Tensor) and verbs.is_cuda and roles.is_cuda):
             raise _lib.VsrError("S_SSP: verbs and roles must be CUDA tensors (no CPU fallback on this path)")
@@ -211,17 +213,32 @@ class S_SSP(nn.Module):
                                 f"{tuple(roles.shape)}")
         lib = self._engine()
         P = roles.size(0)
-        n_steps = self.max_len if n_steps is None else int(n_steps)
         verbs = (verbs.reshape(-1) % 10000).long().contiguous()       # sort_model.py:108
         roles = roles.long().contiguous()
+        order = active = None
+        if counts is not None and P:
+            counts = [int(x) for x in counts]
+            if len(counts) != P:
+                raise _lib.VsrError(f"S_SSP: counts has {len(counts)} entries for {P} problems")
+            idx = sorted(range(P), key=lambda i: -counts[i])
+            order = torch.tensor(idx, dtype=torch.long, device=roles.device)
+            verbs, roles = verbs[order].contiguous(), roles[order].contiguous()
+            n_steps = min(self.max_len, max(counts)) if n_steps is None else int(n_steps)
+            active = (ctypes.c_int32 * max(n_steps, 1))(*[sum(1 for c in counts if c > t) for t in range(n_steps)])
+        n_steps = self.max_len if n_steps is None else int(n_steps)
         pred = torch.zeros((P, self.max_len), dtype=torch.long, device=roles.device)
         logp = torch.zeros((P, self.max_len), dtype=torch.float32, device=roles.device)
         rows = torch.zeros((P, n_steps, self.N_ROLES), dtype=torch.float32, device=roles.device) if trace else None
         if P:
             with torch.cuda.device(roles.device):
                 st = torch.cuda.current_stream(roles.device).cuda_stream
-                _lib.check(lib, lib.vsr_sort_generate(self._handle, verbs.data_ptr(), roles.data_ptr(), P, n_steps, pred.data_ptr(),
+                _lib.check(lib, lib.vsr_sort_generate(self._handle, verbs.data_ptr(), roles.data_ptr(), P, n_steps, active, pred.data_ptr(),
                                                       logp.data_ptr(), None if rows is None else rows.data_ptr(), st))
+        if order is not None:
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(P, device=order.device)
+            pred, logp = pred[inv], logp[inv]
+            rows = rows[inv] if rows is not None else None
         return (pred, logp, rows) if trace else (pred, logp)
 
     def generate(self, this_verb, det_seqs_sr, mode='normal'):

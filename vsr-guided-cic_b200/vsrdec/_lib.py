@@ -59,7 +59,7 @@ EXPORTED_SYMBOLS = {
     "vsr_sort_create": (ctypes.c_int, [ctypes.POINTER(VsrSortDims), ctypes.POINTER(c_vp), c_i32, ctypes.POINTER(c_vp)]),
     "vsr_sort_load_weights": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_i32, c_vp]),
     "vsr_sort_destroy": (None, [c_vp]),
-    "vsr_sort_generate": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "vsr_sort_generate": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(c_i32), c_vp, c_vp, c_vp, c_vp]),
 }
 
 

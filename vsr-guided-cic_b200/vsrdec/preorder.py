@@ -108,8 +108,7 @@ class RoleOrderer:
         for i, p in enumerate(problems):
             roles_t[i, :len(p[2])] = torch.tensor(p[2])
         verbs_t = torch.tensor([p[1] for p in problems], dtype=torch.long)
-        n_steps = max(len(p[2]) for p in problems)
-        pred, _ = self.sort_net.generate_batch(verbs_t.to(dev), roles_t.to(dev), n_steps=n_steps)
+        pred, _ = self.sort_net.generate_batch(verbs_t.to(dev), roles_t.to(dev), counts=[len(p[2]) for p in problems])
         # ---- R level: the order of the slots of every repeated role, one device call
         rep = [(i, sr) for i, p in enumerate(problems) for sr in p[4]]
         assign = None
