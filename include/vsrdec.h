@@ -197,7 +197,7 @@ int vsr_get_phase_times(vsr_handle h, const char** names, float* ms, int32_t* la
 int vsr_get_step_times(vsr_handle h, float* ms, int32_t cap);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * R-level SSP of the eval pre-step (first piece): SinkhornNet forward + optimal assignment, batched.
+ * R-level SSP of the eval pre-step: SinkhornNet forward + optimal assignment, batched.
  * Replaces models/sinkhorn_network.py:30-51 (SinkhornNet.forward / sinkhorn) and the per-role
  * `.cpu()` + `munkres.Munkres().compute(make_cost_matrix(mx))` of coco_scripts/eval_coco.py:184-189 (flickr_scripts/
  * eval_flickr.py likewise).  `weights` [host array of 10 device pointers] follows the state_dict order:

@@ -647,7 +647,7 @@ def test_decode_pipeline_matches_direct_calls(indexed, stack):
         assert all(torch.equal(x, y) for x, y in zip(a, b_))
 
 
-# ----------------------------------------------------------------------------- f2 (first piece): R-level SSP on the device
+# ----------------------------------------------------------------------------- f2: R-level SSP on the device
 def test_sinkhorn_net_matches_oracle_and_optimal_assignment():
     """models.SinkhornNet (k_sinkhorn: MLP + Sinkhorn iterations + Hungarian, one CTA per problem) against the oracle
     restatement of the reference's SinkhornNet.forward (pinned to the reference golden on the CPU side) and against
