@@ -225,6 +225,16 @@ def test_preorder_host_logic_matches_oracle_and_reference_golden():
             assert got == O.verb_roles(int(verb), d["det_seqs_v"][c], d["det_seqs_sr"][c])
             n_rep += len(got[2])
     assert n_rep > 10                                  # the synthetic captions do exercise repeated roles
+    # the vectorised search over the whole batch finds the same problems, in the same order, as the one-by-one search
+    want = []
+    for c in range(60):
+        for verb in d["control_verb"][c]:
+            if verb == 0:
+                break
+            roles, slots, rep = P.roles_of_verb(int(verb), d["det_seqs_v"][c], d["det_seqs_sr"][c])
+            if roles:
+                want.append((c, int(verb), roles, slots, rep))
+    assert P.problems_of_batch(d["control_verb"], d["det_seqs_v"], d["det_seqs_sr"]) == want
     rnd = random.Random(1)
     for c in range(60):
         n_valid = int(d["slot_valid"][c].sum())

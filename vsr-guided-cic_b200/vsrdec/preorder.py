@@ -76,6 +76,32 @@ def permutation_from_rank(final_rank: Sequence[int], n_slots: int, slot_valid: S
     return src, verbs
 
 
+def problems_of_batch(control_verb: np.ndarray, det_seqs_v: np.ndarray, det_seqs_sr: np.ndarray, limit: int = 10):
+    """Every (caption, verb) problem of a batch, as `roles_of_verb` finds them one by one, from ONE vectorised match search:
+    -> list of (caption, verb, roles, slots-by-role, repeated roles) in (caption, verb position) order; verbs after a
+    caption's first 0 are ignored and verbs without a role are skipped (eval_coco.py:149-171)."""
+    live = np.cumprod(control_verb != 0, axis=1).astype(bool)                       # (C, max_verb)
+    hit = (det_seqs_v[:, None, :, :] == control_verb[:, :, None, None]) & live[:, :, None, None]   # (C, max_verb, L, max_verb)
+    cs, vs, js, ks = np.nonzero(hit)                                               # row-major: caption, verb position, slot, column
+    sr_all = det_seqs_sr[cs, js, ks].astype(np.int64).tolist()
+    problems, cur = [], None
+    for c, v, j, sr in zip(cs.tolist(), vs.tolist(), js.tolist(), sr_all):
+        if cur is None or cur[0] != c or cur[1] != v:
+            cur = [c, v, [], {}, []]
+            problems.append(cur)
+        roles, slots, repeated = cur[2], cur[3], cur[4]
+        if len(roles) >= limit:
+            continue
+        if sr not in slots:
+            slots[sr] = [j]
+            roles.append(sr)
+        else:
+            slots[sr].append(j)
+            if sr not in repeated:
+                repeated.append(sr)
+    return [(c, int(control_verb[c, v]), roles, slots, repeated) for c, v, roles, slots, repeated in problems]
+
+
 class RoleOrderer:
     def __init__(self, sort_net, sinkhorn_net, sinkhorn_len: int = 10, fixed_len: int = 10):
         """sort_net: models.S_SSP, sinkhorn_net: models.SinkhornNet(sinkhorn_len, ...), both on the CUDA device
@@ -92,48 +118,43 @@ class RoleOrderer:
         ds = np.asarray(det_seqs_sr.cpu() if isinstance(det_seqs_sr, torch.Tensor) else det_seqs_sr)
         C = cv.shape[0]
         dev = seqs_perm.device
-        problems = []          # (caption, verb, roles, slots-by-role, repeated roles)
-        for c in range(C):
-            for verb in cv[c].tolist():
-                if verb == 0:
-                    break
-                roles, slots, repeated = roles_of_verb(verb, dv[c], ds[c])
-                if roles:
-                    problems.append((c, int(verb), roles, slots, repeated))
+        problems = problems_of_batch(cv, dv, ds)
         if not problems:
             return [[] for _ in range(C)]
-        # ---- S level: the order of every problem's roles, one device call
+        # ---- S level: the order of every problem's roles, one device call (enqueued; read back after the R level is enqueued too)
         L = self.sort_net.max_len
-        roles_t = torch.zeros((len(problems), L), dtype=torch.long)
+        roles_np = np.zeros((len(problems), L), dtype=np.int64)
         for i, p in enumerate(problems):
-            roles_t[i, :len(p[2])] = torch.tensor(p[2])
-        verbs_t = torch.tensor([p[1] for p in problems], dtype=torch.long)
-        pred, _ = self.sort_net.generate_batch(verbs_t.to(dev), roles_t.to(dev), counts=[len(p[2]) for p in problems])
+            roles_np[i, :len(p[2])] = p[2]
+        verbs_np = np.fromiter((p[1] for p in problems), dtype=np.int64, count=len(problems))
+        pred, _ = self.sort_net.generate_batch(torch.from_numpy(verbs_np).to(dev), torch.from_numpy(roles_np).to(dev),
+                                               counts=[len(p[2]) for p in problems])
         # ---- R level: the order of the slots of every repeated role, one device call
         rep = [(i, sr) for i, p in enumerate(problems) for sr in p[4]]
         assign = None
         if rep:
             N = self.sinkhorn_len
-            gather = torch.full((len(rep), N), -1, dtype=torch.long)
+            gather = np.full((len(rep), N), -1, dtype=np.int64)
             for n, (i, sr) in enumerate(rep):
-                c, locs = problems[i][0], problems[i][3][sr][:N]
-                gather[n, :len(locs)] = torch.tensor([c * self.fixed_len + l for l in locs])
-            gather = gather.to(dev)
+                locs = problems[i][3][sr][:N]
+                gather[n, :len(locs)] = locs
+                gather[n, :len(locs)] += problems[i][0] * self.fixed_len
+            gather = torch.from_numpy(gather).to(dev)
             rows = seqs_perm.reshape(-1, seqs_perm.shape[-1]).float()
             seq = rows[gather.clamp(min=0)] * (gather >= 0).unsqueeze(-1).to(rows.dtype)      # zero rows pad a role's problem
             _, assign = self.sinkhorn_net.assign(seq.contiguous())
             assign = assign.cpu().numpy()
-        pred = pred.cpu().numpy()
+        pred = pred.cpu().numpy().tolist()
         region_rank = {}
         for n, (i, sr) in enumerate(rep):
             locs = problems[i][3][sr]
             cols = assign[n, :len(locs)]
-            region_rank[(i, sr)] = [locs[int(a)] for a in np.argsort(cols, kind="stable")]
+            region_rank[(i, sr)] = [locs[a] for a in np.argsort(cols, kind="stable").tolist()]
         # ---- assemble per verb, merge over a caption's verbs
         per_caption: List[List[List[int]]] = [[] for _ in range(C)]
         for i, (c, verb, roles, slots, repeated) in enumerate(problems):
             rank: List[int] = []
-            for sr in pred[i].tolist():
+            for sr in pred[i]:
                 if sr == 0:
                     break
                 rank += region_rank[(i, sr)] if len(slots[sr]) != 1 else slots[sr]
@@ -150,14 +171,13 @@ class RoleOrderer:
         """-> (src_slot (C, fixed_len) long, verbs (C, fixed_len) float), host tensors.  slot_valid (C, fixed_len) bool: slots whose
         tile is not empty (`np.sum(tile) != 0`, eval_coco.py:226).  verb_list (C, fixed_len[, 1])."""
         ranks = self.ranks(control_verb, det_seqs_v, det_seqs_sr, seqs_perm)
-        sv = np.asarray(slot_valid.cpu() if isinstance(slot_valid, torch.Tensor) else slot_valid).astype(bool)
-        vl = np.asarray(verb_list.cpu() if isinstance(verb_list, torch.Tensor) else verb_list).reshape(sv.shape[0], -1)
-        src = torch.empty((len(ranks), self.fixed_len), dtype=torch.long)
-        verbs = torch.empty((len(ranks), self.fixed_len), dtype=torch.float32)
+        sv = np.asarray(slot_valid.cpu() if isinstance(slot_valid, torch.Tensor) else slot_valid).astype(bool).tolist()
+        vl = np.asarray(verb_list.cpu() if isinstance(verb_list, torch.Tensor) else verb_list).reshape(len(sv), -1).tolist()
+        src = np.empty((len(ranks), self.fixed_len), dtype=np.int64)
+        verbs = np.empty((len(ranks), self.fixed_len), dtype=np.float32)
         for c, rank in enumerate(ranks):
-            s, v = permutation_from_rank(rank, self.fixed_len, sv[c], vl[c])
-            src[c], verbs[c] = torch.tensor(s), torch.tensor(v)
-        return src, verbs
+            src[c], verbs[c] = permutation_from_rank(rank, self.fixed_len, sv[c], vl[c])
+        return torch.from_numpy(src), torch.from_numpy(verbs)
 
 
 def permute_slot_index(slot_index: torch.Tensor, src_slot: torch.Tensor) -> torch.Tensor:
