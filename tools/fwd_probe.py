@@ -32,3 +32,12 @@ def timeit(fn, n=8):
 print("forward_teacher ms:", round(timeit(lambda: m((det,), (caps, ctrl))), 3))
 print("greedy ms:", round(timeit(lambda: m.test(det, ds)), 3))
 print("sample_rl ms:", round(timeit(lambda: m.sample_rl(det, ds, seed=1)), 3))
+
+# per-phase breakdown of one forward (eager, CUDA events around every phase)
+eng = m._eng
+eng.set_profiling(True)
+for _ in range(3):
+    m((det,), (caps, ctrl))
+torch.cuda.synchronize()
+print("forward phases (3 eager forwards):", eng.phase_times())
+eng.set_profiling(False)
