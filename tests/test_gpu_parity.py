@@ -824,6 +824,12 @@ def test_role_orderer_matches_oracle_eval_loop():
         assert np.array_equal(tiles[c].double().numpy(), want_tiles), c
         assert np.array_equal(verbs[c].double().numpy(), want_verbs), c
         assert torch.equal(sidx[c], d["slot_index"][c][src[c]]), c
+    # the two-phase form (device work enqueued on a side stream, results collected later) gives the same permutation
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        st = ro.order_begin(d["control_verb"], d["det_seqs_v"], d["det_seqs_sr"], d["verb_list"], d["seqs_perm"].to(DEV), d["slot_valid"])
+        src2, verbs2 = ro.order_end(st)
+    assert torch.equal(src2, src) and torch.equal(verbs2, verbs)
     print("PARITY eval pre-step: %d captions, %d S-level and %d R-level problems, final ranks, re-ordered tiles and verb lists "
           "identical to the oracle's eval loop" % (C, n_s, n_r))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

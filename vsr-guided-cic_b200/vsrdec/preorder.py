@@ -109,9 +109,12 @@ class RoleOrderer:
         self.sort_net, self.sinkhorn_net = sort_net, sinkhorn_net
         self.sinkhorn_len, self.fixed_len = int(sinkhorn_len), int(fixed_len)
 
-    def ranks(self, control_verb, det_seqs_v, det_seqs_sr, seqs_perm) -> List[List[int]]:
-        """final_rank of every caption (eval_coco.py:148-215).
-        control_verb (C, max_verb), det_seqs_v / det_seqs_sr (C, fixed_len, max_verb): host arrays / tensors;
+    # The work splits at the only point where the host needs device results: `begin` does the host search and ENQUEUES the two
+    # device calls (on the current stream), `end` reads their results back and assembles the ranks.  A loop that calls
+    # begin(batch i + 1) under a side stream, enqueues the decode of batch i, then end(...) hides the pre-step's device time
+    # behind the decode.
+    def ranks_begin(self, control_verb, det_seqs_v, det_seqs_sr, seqs_perm):
+        """control_verb (C, max_verb), det_seqs_v / det_seqs_sr (C, fixed_len, max_verb): host arrays / tensors;
         seqs_perm (C, fixed_len, 2352): the concatenated (vis, txt, pos) rows of eval_coco.py:146, on the CUDA device."""
         cv = np.asarray(control_verb.cpu() if isinstance(control_verb, torch.Tensor) else control_verb)
         dv = np.asarray(det_seqs_v.cpu() if isinstance(det_seqs_v, torch.Tensor) else det_seqs_v)
@@ -120,8 +123,8 @@ class RoleOrderer:
         dev = seqs_perm.device
         problems = problems_of_batch(cv, dv, ds)
         if not problems:
-            return [[] for _ in range(C)]
-        # ---- S level: the order of every problem's roles, one device call (enqueued; read back after the R level is enqueued too)
+            return (C, problems, [], None, None)
+        # ---- S level: the order of every problem's roles, one device call
         L = self.sort_net.max_len
         roles_np = np.zeros((len(problems), L), dtype=np.int64)
         for i, p in enumerate(problems):
@@ -143,8 +146,15 @@ class RoleOrderer:
             rows = seqs_perm.reshape(-1, seqs_perm.shape[-1]).float()
             seq = rows[gather.clamp(min=0)] * (gather >= 0).unsqueeze(-1).to(rows.dtype)      # zero rows pad a role's problem
             _, assign = self.sinkhorn_net.assign(seq.contiguous())
-            assign = assign.cpu().numpy()
+        return (C, problems, rep, pred, assign)
+
+    def ranks_end(self, state) -> List[List[int]]:
+        """final_rank of every caption (eval_coco.py:148-215) from the state `ranks_begin` returned."""
+        C, problems, rep, pred, assign = state
+        if not problems:
+            return [[] for _ in range(C)]
         pred = pred.cpu().numpy().tolist()
+        assign = assign.cpu().numpy() if assign is not None else None
         region_rank = {}
         for n, (i, sr) in enumerate(rep):
             locs = problems[i][3][sr]
@@ -167,10 +177,16 @@ class RoleOrderer:
             out.append([int(x) for x in final])
         return out
 
-    def order(self, control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid) -> Tuple[torch.Tensor, torch.Tensor]:
-        """-> (src_slot (C, fixed_len) long, verbs (C, fixed_len) float), host tensors.  slot_valid (C, fixed_len) bool: slots whose
-        tile is not empty (`np.sum(tile) != 0`, eval_coco.py:226).  verb_list (C, fixed_len[, 1])."""
-        ranks = self.ranks(control_verb, det_seqs_v, det_seqs_sr, seqs_perm)
+    def ranks(self, control_verb, det_seqs_v, det_seqs_sr, seqs_perm) -> List[List[int]]:
+        return self.ranks_end(self.ranks_begin(control_verb, det_seqs_v, det_seqs_sr, seqs_perm))
+
+    def order_begin(self, control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid):
+        return (self.ranks_begin(control_verb, det_seqs_v, det_seqs_sr, seqs_perm), verb_list, slot_valid)
+
+    def order_end(self, state) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (src_slot (C, fixed_len) long, verbs (C, fixed_len) float), host tensors."""
+        rstate, verb_list, slot_valid = state
+        ranks = self.ranks_end(rstate)
         sv = np.asarray(slot_valid.cpu() if isinstance(slot_valid, torch.Tensor) else slot_valid).astype(bool).tolist()
         vl = np.asarray(verb_list.cpu() if isinstance(verb_list, torch.Tensor) else verb_list).reshape(len(sv), -1).tolist()
         src = np.empty((len(ranks), self.fixed_len), dtype=np.int64)
@@ -178,6 +194,11 @@ class RoleOrderer:
         for c, rank in enumerate(ranks):
             src[c], verbs[c] = permutation_from_rank(rank, self.fixed_len, sv[c], vl[c])
         return torch.from_numpy(src), torch.from_numpy(verbs)
+
+    def order(self, control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (src_slot (C, fixed_len) long, verbs (C, fixed_len) float), host tensors.  slot_valid (C, fixed_len) bool: slots whose
+        tile is not empty (`np.sum(tile) != 0`, eval_coco.py:226).  verb_list (C, fixed_len[, 1])."""
+        return self.order_end(self.order_begin(control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid))
 
 
 def permute_slot_index(slot_index: torch.Tensor, src_slot: torch.Tensor) -> torch.Tensor:
