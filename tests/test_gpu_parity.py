@@ -694,6 +694,16 @@ def test_sinkhorn_net_matches_oracle_and_optimal_assignment():
     with torch.no_grad():
         ref2 = S.forward(W2, seq)
     assert rel_close(out2.cpu(), ref2, 1e-4, 1e-6)
+    # ... also by the batched GEMM path (its operand twins of the weights are rebuilt on load)
+    out3 = net(big[:64].to(DEV))
+    with torch.no_grad():
+        ref3 = S.forward(W2, big[:64])
+    assert rel_close(out3.cpu(), ref3, 1e-4, 1e-6)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    bd = big[:200].to(DEV)
+    net.assign(bd)
+    e0.record(); net.assign(bd); e1.record(); torch.cuda.synchronize()
+    print("TIMING sinkhorn: 200 problems (matrix + assignment) in %.3f ms" % e0.elapsed_time(e1))
     from vsrdec import VsrError
     with pytest.raises(VsrError):
         net(seq)                          # CPU tensor: no fallback

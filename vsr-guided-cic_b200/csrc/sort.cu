@@ -17,6 +17,7 @@
 // operand twins of what they produce.  The two tiny projections (fc_feat, the 512 -> 26 role head) and everything else are
 // fp32 warp-level kernels.  VSRDEC_GEMM=simt switches every projection to the fp32 FFMA twin.
 #include "common.cuh"
+#include "twin_util.cuh"
 
 namespace vsr {
 namespace {
@@ -100,15 +101,6 @@ __global__ void k_sort_embed_dec(const int32_t* __restrict__ token, const float*
   }
 }
 
-// fp16 value + fp16 residual of one activation element (the f16x3 operand form of gemm_tc.cu)
-__device__ __forceinline__ void put_twin(const TwinOut& o, size_t off, float v) {
-  if (o.hi == nullptr) return;
-  v = fminf(fmaxf(v, -65504.f), 65504.f);
-  const __half h = __float2half_rn(v);
-  reinterpret_cast<__half*>(o.hi)[off] = h;
-  reinterpret_cast<__half*>(o.lo)[off] = __float2half_rn(v - __half2float(h));
-}
-
 // LayerNorm over the last dimension (eps 1e-5, biased variance), one warp per row; y and / or its operand twins
 __global__ void k_sort_ln(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, int rows, int d,
                           float* __restrict__ y, const TwinOut tw) {
@@ -126,14 +118,6 @@ __global__ void k_sort_ln(const float* __restrict__ x, const float* __restrict__
     if (y != nullptr) y[(size_t)row * d + c] = v;
     put_twin(tw, (size_t)row * d + c, v);
   }
-}
-
-// operand twins of max(0, x): the feed-forward activation between its two tensor-core projections
-__global__ void k_sort_relu_twin(const float* __restrict__ x, size_t n4, const TwinOut tw) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const float4 v = reinterpret_cast<const float4*>(x)[i];
-  store_twin4(tw, i * 4, make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f)));
 }
 
 // Multi-head attention of nq queries per problem over the keys [k0, k1) of that problem; one warp per head
@@ -240,36 +224,6 @@ int lin(SortCtx* c, const float* a, const F16Pair* a_b, int lda, int K, const fl
 int ln(const float* x, const float* w, const float* b, int rows, int d, float* y, const F16Pair* y_b, cudaStream_t st) {
   k_sort_ln<<<(rows + 3) / 4, 128, 0, st>>>(x, w, b, rows, d, y, twin_out(y_b, y_b != nullptr));
   VSR_CHECK_CUDA(cudaGetLastError());
-  return VSR_OK;
-}
-
-void free_pair(F16Pair* b, bool view = false) {
-  if (!view) { if (b->hi) cudaFree(b->hi); if (b->lo) cudaFree(b->lo); if (b->scale) cudaFree(b->scale); }
-  b->hi = b->lo = nullptr; b->scale = nullptr;
-}
-
-// fp16 value / residual arrays + tensor maps of a [rows][ld] operand (rows a multiple of 128); weights also get their scale pair
-int make_pair(F16Pair* b, int rows, int ld, bool weight) {
-  free_pair(b);
-  VSR_CHECK_CUDA(cudaMalloc(&b->hi, (size_t)rows * ld * 2));
-  VSR_CHECK_CUDA(cudaMalloc(&b->lo, (size_t)rows * ld * 2));
-  VSR_CHECK_CUDA(cudaMemset(b->hi, 0, (size_t)rows * ld * 2));
-  VSR_CHECK_CUDA(cudaMemset(b->lo, 0, (size_t)rows * ld * 2));
-  if (weight) VSR_CHECK_CUDA(cudaMalloc((void**)&b->scale, 2 * sizeof(float)));
-  b->rows = rows; b->ld = ld; b->box_rows = 128; b->kb = 64; b->n_valid = rows; b->act_scale = 1.f; b->alt_bn = 0; b->pair_rows = 0;
-  VSR_TRY(make_tmap_f16(b->map_hi, b->hi, rows, ld, ld, 128));
-  VSR_TRY(make_tmap_f16(b->map_lo, b->lo, rows, ld, ld, 128));
-  return VSR_OK;
-}
-
-// rows [r0, r0 + rows) of a weight pair as a pair of its own (same arrays, same scale)
-int make_view(F16Pair* v, const F16Pair& of, int r0, int rows) {
-  *v = of;
-  v->hi = reinterpret_cast<__half*>(of.hi) + (size_t)r0 * of.ld;
-  v->lo = reinterpret_cast<__half*>(of.lo) + (size_t)r0 * of.ld;
-  v->rows = rows; v->n_valid = rows;
-  VSR_TRY(make_tmap_f16(v->map_hi, v->hi, rows, of.ld, of.ld, 128));
-  VSR_TRY(make_tmap_f16(v->map_lo, v->lo, rows, of.ld, of.ld, 128));
   return VSR_OK;
 }
 
@@ -382,7 +336,7 @@ int run_layer(SortCtx* c, const SortLayer& W, bool decoder, int l, int P, int t,
   if (tc) {       // the ReLU sits between two tensor-core projections: its kernel writes the second one's operand twins
     VSR_TRY(lin(c, c->y, y_b, D, D, W.w1_w, &W.w1_p, W.w1_b, c->ff, F, rows, F, nullptr, false, st));
     const size_t n4 = (size_t)rows * F / 4;
-    k_sort_relu_twin<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(c->ff, n4, twin_out(ff_b));
+    k_relu_twin<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(c->ff, n4, twin_out(ff_b));
     VSR_CHECK_CUDA(cudaGetLastError());
   } else {
     VSR_TRY(lin(c, c->y, nullptr, D, D, W.w1_w, nullptr, W.w1_b, c->ff, F, rows, F, nullptr, true, st));
