@@ -251,6 +251,30 @@ void vsr_sort_destroy(vsr_sort_handle h);
 int vsr_sort_generate(vsr_sort_handle h, const int64_t* verbs, const int64_t* roles, int32_t P, int32_t n_steps,
                       const int32_t* n_active, int64_t* pred, float* logp, float* step_rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Host bookkeeping of the eval pre-step, for a whole batch of captions: the integer logic of
+ * coco_scripts/eval_coco.py:148-237 around the two device networks.  HOST pointers throughout; no CUDA call inside.
+ * vsr_preorder_begin: control_verb (C,n_verb), det_seqs_v / det_seqs_sr (C,L,n_verb) int64 -> the (caption, verb) problems
+ *   (eval_coco.py:148-171: distinct roles in first-seen order, at most `limit`; the slots holding each; roles held by several
+ *   slots); N = sinkhorn_len, fixed_len = slots per caption.  Returns the number of S-level problems, of R-level problems
+ *   (repeated roles) and the largest role count.
+ * vsr_preorder_fill: inputs of the two batched device calls — verbs (P), roles (P,roles_ld) zero padded, counts (P), and for
+ *   every repeated role the rows of its slots in the (C*fixed_len, 2352) row matrix: gather (n_repeated,N), -1 = zero row
+ *   (eval_coco.py:176-182).  Any output may be NULL.
+ * vsr_preorder_end: pred (P,pred_ld) = vsr_sort_generate's orders, assign (n_repeated,N) = vsr_ssp_forward's assignments,
+ *   slot_valid (C,fixed_len) u8 = slots whose tile is not empty (:226), verb_list (C,fixed_len) f64 -> src_slot (C,fixed_len)
+ *   int64 (row j of the re-ordered caption is slot src_slot[c][j]; empty tiles dropped, tail repeating the last kept slot,
+ *   :217-231) and verbs_out (C,fixed_len) f32 (:234-235); region order (:190-200), rank assembly (:202-209) and
+ *   verb_rank_merge (utils/tools.py:35-71) happen here.  Frees the handle (vsr_preorder_free: for an abandoned one). */
+typedef struct VsrPreorderHandle_* vsr_preorder_handle;
+int vsr_preorder_begin(const int64_t* control_verb, const int64_t* det_seqs_v, const int64_t* det_seqs_sr, int32_t C,
+                       int32_t n_verb, int32_t L, int32_t limit, int32_t N, int32_t fixed_len, vsr_preorder_handle* out,
+                       int32_t* n_problems, int32_t* n_repeated, int32_t* max_roles);
+int vsr_preorder_fill(vsr_preorder_handle h, int64_t* verbs, int64_t* roles, int32_t roles_ld, int32_t* counts, int64_t* gather);
+int vsr_preorder_end(vsr_preorder_handle h, const int64_t* pred, int32_t pred_ld, const int32_t* assign,
+                     const uint8_t* slot_valid, const double* verb_list, int64_t* src_slot, float* verbs_out);
+void vsr_preorder_free(vsr_preorder_handle h);
+
 #ifdef __cplusplus
 }
 #endif

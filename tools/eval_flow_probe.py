@@ -17,7 +17,8 @@ def main():
     from tools.synth import synth_eval_captions
     from vsrdec.preorder import RoleOrderer, permute_slot_index
     dev = "cuda:0"
-    K, C, D, R = 20, 100, 50, 20
+    C = int(sys.argv[1]) if len(sys.argv) > 1 else 100          # captions per batch (pre-step call and decode call)
+    K, D, R = max(8, 2000 // C), 50, 20
     torch.manual_seed(1234)
     model = ControllableCaptioningModel(20, 10000, 2, verb_tables=({}, {})).to(dev).eval()
     ro = RoleOrderer(S_SSP().to(dev).eval(), SinkhornNet(10, 20, 0.1).to(dev).eval())
@@ -60,14 +61,14 @@ def main():
         torch.cuda.synchronize()
         return out
 
-    res = {}
+    res = {"captions_per_batch": C, "batches": K}
     for name, fn in (("serial", serial), ("overlapped", overlapped)):
         for _ in range(2):
             fn()
         t0 = time.perf_counter()
         out = fn()
         dt = time.perf_counter() - t0
-        res[name] = {"captions_per_s": K * C / dt, "ms_per_100_captions": dt * 1e3 / K}
+        res[name] = {"captions_per_s": K * C / dt, "ms_per_batch": dt * 1e3 / K}
     # same captions either way
     a = serial()[0][0].cpu()
     b = overlapped()[0][0].cpu()

@@ -56,6 +56,11 @@ EXPORTED_SYMBOLS = {
     "vsr_ssp_load_weights": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_vp]),
     "vsr_ssp_destroy": (None, [c_vp]),
     "vsr_ssp_forward": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "vsr_preorder_begin": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, ctypes.POINTER(c_vp),
+                                          ctypes.POINTER(c_i32), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
+    "vsr_preorder_fill": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "vsr_preorder_end": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "vsr_preorder_free": (None, [c_vp]),
     "vsr_sort_create": (ctypes.c_int, [ctypes.POINTER(VsrSortDims), ctypes.POINTER(c_vp), c_i32, ctypes.POINTER(c_vp)]),
     "vsr_sort_load_weights": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), c_i32, c_vp]),
     "vsr_sort_destroy": (None, [c_vp]),

@@ -1,5 +1,9 @@
 """Eval pre-step: the per-caption role ordering of coco_scripts/eval_coco.py:127-237, batched.
 
+(The integer bookkeeping exists twice: as the Python functions of this module — the readable statement, used with
+`RoleOrderer(native=False)` and as the test twin — and as host code in libvsrdec, `vsr_preorder_*` (csrc/preorder.cu), which
+`RoleOrderer` uses by default: at a thousand captions per call the Python form costs more than the device work it feeds.)
+
 The reference walks every caption of a batch in Python and, per (caption, verb), calls `S_SSP.generate` on the GPU with batch 1,
 per repeated role calls `SinkhornNet` with batch 1, copies the matrix to the host for munkres, and finally permutes the caption's
 (10, R, F) slot tiles with an `np.dot` against a permutation matrix.  Here the integer bookkeeping stays on the host (it is a few
@@ -13,6 +17,8 @@ comparisons per caption), but
 
 `RoleOrderer.order(...)` mirrors the names of the eval loop: control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm."""
 from typing import Dict, List, Sequence, Tuple
+
+import ctypes
 
 import numpy as np
 import torch
@@ -103,11 +109,69 @@ def problems_of_batch(control_verb: np.ndarray, det_seqs_v: np.ndarray, det_seqs
 
 
 class RoleOrderer:
-    def __init__(self, sort_net, sinkhorn_net, sinkhorn_len: int = 10, fixed_len: int = 10):
+    def __init__(self, sort_net, sinkhorn_net, sinkhorn_len: int = 10, fixed_len: int = 10, native: bool = True):
         """sort_net: models.S_SSP, sinkhorn_net: models.SinkhornNet(sinkhorn_len, ...), both on the CUDA device
-        (eval_coco.py:94-103)."""
+        (eval_coco.py:94-103).  native: host bookkeeping in libvsrdec (vsr_preorder_*) instead of this module's Python."""
         self.sort_net, self.sinkhorn_net = sort_net, sinkhorn_net
         self.sinkhorn_len, self.fixed_len = int(sinkhorn_len), int(fixed_len)
+        self.native = bool(native)
+
+    # ------------------------------------------------------------------ native host path (csrc/preorder.cu)
+    @staticmethod
+    def _i64(x):
+        a = x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+        return np.ascontiguousarray(a, dtype=np.int64)
+
+    def _native_begin(self, control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid):
+        from . import _lib
+        lib = _lib.load_library()
+        cv, dv, ds = self._i64(control_verb), self._i64(det_seqs_v), self._i64(det_seqs_sr)
+        C, n_verb, L = cv.shape[0], cv.shape[1], dv.shape[1]
+        h, P, n_rep, max_roles = _lib.c_vp(), _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
+        ml = self.sort_net.max_len
+        _lib.check(lib, lib.vsr_preorder_begin(cv.ctypes.data, dv.ctypes.data, ds.ctypes.data, C, n_verb, L, ml, self.sinkhorn_len,
+                                               self.fixed_len, ctypes.byref(h), ctypes.byref(P), ctypes.byref(n_rep),
+                                               ctypes.byref(max_roles)))
+        P, n_rep = P.value, n_rep.value
+        pred = assign = None
+        try:
+            if P:
+                verbs = np.empty(P, dtype=np.int64)
+                roles = np.empty((P, ml), dtype=np.int64)
+                counts = np.empty(P, dtype=np.int32)
+                gather = np.empty((n_rep, self.sinkhorn_len), dtype=np.int64)
+                _lib.check(lib, lib.vsr_preorder_fill(h, verbs.ctypes.data, roles.ctypes.data, ml, counts.ctypes.data,
+                                                      gather.ctypes.data if n_rep else None))
+                dev = seqs_perm.device
+                pred, _ = self.sort_net.generate_batch(torch.from_numpy(verbs).to(dev), torch.from_numpy(roles).to(dev),
+                                                       counts=counts.tolist())
+                if n_rep:
+                    g = torch.from_numpy(gather).to(dev)
+                    rows = seqs_perm.reshape(-1, seqs_perm.shape[-1]).float()
+                    seq = rows[g.clamp(min=0)] * (g >= 0).unsqueeze(-1).to(rows.dtype)
+                    _, assign = self.sinkhorn_net.assign(seq.contiguous())
+        except Exception:
+            lib.vsr_preorder_free(h)
+            raise
+        return ("native", h, C, pred, assign, verb_list, slot_valid)
+
+    def _native_end(self, state):
+        from . import _lib
+        lib = _lib.load_library()
+        _, h, C, pred, assign, verb_list, slot_valid = state
+        pred_np = np.ascontiguousarray(pred.cpu().numpy(), dtype=np.int64) if pred is not None else None
+        asg_np = np.ascontiguousarray(assign.cpu().numpy(), dtype=np.int32) if assign is not None else None
+        sv = slot_valid.cpu().numpy() if isinstance(slot_valid, torch.Tensor) else np.asarray(slot_valid)
+        sv = np.ascontiguousarray(sv.astype(bool), dtype=np.uint8).reshape(C, self.fixed_len)
+        vl = verb_list.cpu().numpy() if isinstance(verb_list, torch.Tensor) else np.asarray(verb_list)
+        vl = np.ascontiguousarray(vl, dtype=np.float64).reshape(C, self.fixed_len)
+        src = np.empty((C, self.fixed_len), dtype=np.int64)
+        verbs = np.empty((C, self.fixed_len), dtype=np.float32)
+        _lib.check(lib, lib.vsr_preorder_end(h, None if pred_np is None else pred_np.ctypes.data,
+                                             0 if pred_np is None else pred_np.shape[1],
+                                             None if asg_np is None else asg_np.ctypes.data, sv.ctypes.data, vl.ctypes.data,
+                                             src.ctypes.data, verbs.ctypes.data))
+        return torch.from_numpy(src), torch.from_numpy(verbs)
 
     # The work splits at the only point where the host needs device results: `begin` does the host search and ENQUEUES the two
     # device calls (on the current stream), `end` reads their results back and assembles the ranks.  A loop that calls
@@ -181,10 +245,14 @@ class RoleOrderer:
         return self.ranks_end(self.ranks_begin(control_verb, det_seqs_v, det_seqs_sr, seqs_perm))
 
     def order_begin(self, control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid):
+        if self.native:
+            return self._native_begin(control_verb, det_seqs_v, det_seqs_sr, verb_list, seqs_perm, slot_valid)
         return (self.ranks_begin(control_verb, det_seqs_v, det_seqs_sr, seqs_perm), verb_list, slot_valid)
 
     def order_end(self, state) -> Tuple[torch.Tensor, torch.Tensor]:
         """-> (src_slot (C, fixed_len) long, verbs (C, fixed_len) float), host tensors."""
+        if state[0] == "native":
+            return self._native_end(state)
         rstate, verb_list, slot_valid = state
         ranks = self.ranks_end(rstate)
         sv = np.asarray(slot_valid.cpu() if isinstance(slot_valid, torch.Tensor) else slot_valid).astype(bool).tolist()
