@@ -167,10 +167,12 @@ class RoleOrderer:
         vl = np.ascontiguousarray(vl, dtype=np.float64).reshape(C, self.fixed_len)
         src = np.empty((C, self.fixed_len), dtype=np.int64)
         verbs = np.empty((C, self.fixed_len), dtype=np.float32)
-        _lib.check(lib, lib.vsr_preorder_end(h, None if pred_np is None else pred_np.ctypes.data,
-                                             0 if pred_np is None else pred_np.shape[1],
-                                             None if asg_np is None else asg_np.ctypes.data, sv.ctypes.data, vl.ctypes.data,
-                                             src.ctypes.data, verbs.ctypes.data))
+        rc = lib.vsr_preorder_end(h, None if pred_np is None else pred_np.ctypes.data, 0 if pred_np is None else pred_np.shape[1],
+                                  None if asg_np is None else asg_np.ctypes.data, sv.ctypes.data, vl.ctypes.data,
+                                  src.ctypes.data, verbs.ctypes.data)
+        if rc != 0:
+            lib.vsr_preorder_free(h)          # the library frees the state only on success
+        _lib.check(lib, rc)
         return torch.from_numpy(src), torch.from_numpy(verbs)
 
     # The work splits at the only point where the host needs device results: `begin` does the host search and ENQUEUES the two
