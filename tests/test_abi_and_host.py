@@ -311,3 +311,53 @@ def test_preorder_native_host_code_matches_python():
     e = P.RoleOrderer(FakeSort(), FakeSk()).order(cv[:0], d["det_seqs_v"][:0], d["det_seqs_sr"][:0], d["verb_list"][:0],
                                                   d["seqs_perm"][:0, :, :8], d["slot_valid"][:0])
     assert e[0].shape == (0, 10)
+
+
+def test_preorder_native_host_code_fuzz():
+    """Random small batches with everything the bookkeeping can meet — verbs listed twice, few role ids (many repeated roles),
+    role id 0, empty tiles in the middle of the slot list, captions without verbs: native and Python forms agree exactly."""
+    import random
+    import numpy as np
+    from vsrdec import preorder as P
+
+    class FakeSort:
+        max_len = 10
+
+        def generate_batch(self, verbs, roles, counts=None, **kw):
+            g = torch.Generator().manual_seed(int(verbs.sum()) % 1000)
+            out = torch.zeros_like(roles)
+            for i in range(roles.size(0)):
+                n = int((roles[i] != 0).sum())
+                out[i, :n] = roles[i, torch.randperm(n, generator=g)]
+            return out, None
+
+    class FakeSk:
+        def assign(self, seq):
+            g = torch.Generator().manual_seed(seq.shape[0])
+            return None, torch.stack([torch.randperm(seq.shape[1], generator=g) for _ in range(seq.shape[0])]).int()
+
+    for seed in range(30):
+        rnd = random.Random(seed)
+        C = rnd.randint(1, 12)
+        cv = np.zeros((C, 8), dtype=np.int64)
+        dv = np.zeros((C, 10, 8), dtype=np.int64)
+        ds = np.zeros((C, 10, 8), dtype=np.int64)
+        vl = -np.ones((C, 10, 1))
+        sv = np.zeros((C, 10), dtype=bool)
+        for c in range(C):
+            nv = rnd.randint(0, 4)
+            cv[c, :nv] = [rnd.randint(1, 6) for _ in range(nv)]
+            ns = rnd.randint(1, 10)
+            sv[c, :ns] = True
+            if rnd.random() < 0.2:
+                sv[c, rnd.randrange(ns)] = False
+            for j in range(10):
+                for k in range(rnd.randint(0, 4)):
+                    dv[c, j, k] = rnd.randint(1, 6)
+                    ds[c, j, k] = rnd.randint(0 if rnd.random() < 0.1 else 1, 5)
+                if rnd.random() < 0.3:
+                    vl[c, j, 0] = rnd.randint(1, 6)
+        sp = torch.zeros((C, 10, 8))
+        a = P.RoleOrderer(FakeSort(), FakeSk(), native=False).order(cv, dv, ds, vl, sp, sv)
+        b = P.RoleOrderer(FakeSort(), FakeSk(), native=True).order(cv, dv, ds, vl, sp, sv)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), seed
