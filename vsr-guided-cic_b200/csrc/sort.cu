@@ -24,6 +24,8 @@ namespace {
 
 constexpr int SORT_MAXL = 4;        // layers per stack
 constexpr int SORT_MAXK = 16;       // keys an attention query can see (max_len + 1 <= 16)
+constexpr int SORT_DPL = 32;        // d_model / 32 values per lane in the head kernel (d_model <= 1024)
+constexpr int SORT_HD4 = 16;        // head dimension / 4 that fits the attention kernel's registers (head_dim <= 64)
 constexpr int SORT_NPAD = 64;       // N padding of the FFMA GEMM
 
 struct SortLayer {
@@ -132,44 +134,52 @@ struct SortAttn {
   TwinOut out_tw;                           //   ... and / or its operand twins, same layout
   int hd; float inv_sqrt_hd;
 };
+// lane j owns key j (all hd values in registers, loaded once per problem and head); per query: hd FMAs per lane, two warp
+// reductions for the softmax, then lanes run along the head dimension for the weighted values (weights broadcast by shuffle)
 __global__ void k_sort_attn(const SortAttn a) {
   const int p = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hd = a.hd, col0 = h * hd;
+  const int hd = a.hd, col0 = h * hd, hd4 = hd >> 2;
   const int d = hd * (blockDim.x >> 5);
+  const int nk = a.k1 - a.k0;
+  const float* fresh = nullptr;         // decoder self-attention: the q row also carries the new key / value of position store_pos
+  int jnew = -1;
   if (a.store_pos >= 0) {
-    const float* src = a.q + (size_t)p * a.ldq;
+    fresh = a.q + (size_t)p * a.ldq;
+    jnew = a.store_pos - a.k0;
     float* kd = a.kc + ((size_t)p * a.kv_rows + a.store_pos) * a.ldkv;
     float* vd = a.vc + ((size_t)p * a.kv_rows + a.store_pos) * a.ldkv;
-    for (int e = lane; e < hd; e += 32) { kd[col0 + e] = src[d + col0 + e]; vd[col0 + e] = src[2 * d + col0 + e]; }
-    __syncwarp();
+    for (int e = lane; e < hd; e += 32) { kd[col0 + e] = fresh[d + col0 + e]; vd[col0 + e] = fresh[2 * d + col0 + e]; }
   }
-  const int nk = a.k1 - a.k0;
+  float4 kreg[SORT_HD4];
+  if (lane < nk) {
+    const float* kr = lane == jnew ? fresh + d + col0 : a.k + ((size_t)p * a.kv_rows + a.k0 + lane) * a.ldkv + col0;
+#pragma unroll
+    for (int c = 0; c < SORT_HD4; ++c) kreg[c] = c < hd4 ? *reinterpret_cast<const float4*>(kr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int i = 0; i < a.nq; ++i) {
     const float* qr = a.q + ((size_t)p * a.nq + i) * a.ldq + col0;
-    float logit[SORT_MAXK];
+    float logit = -INFINITY;
+    if (lane < nk) {
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < SORT_MAXK; ++j) {
-      logit[j] = -INFINITY;
-      if (j < nk) {
-        const float* kr = a.k + ((size_t)p * a.kv_rows + a.k0 + j) * a.ldkv + col0;
-        float s = 0.f;
-        for (int e = lane; e < hd; e += 32) s = fmaf(qr[e], kr[e], s);
-        logit[j] = wsum(s) * a.inv_sqrt_hd;
+      for (int c = 0; c < SORT_HD4; ++c) {
+        if (c < hd4) {
+          const float4 qv = *reinterpret_cast<const float4*>(qr + 4 * c);       // same address in every lane: one broadcast
+          s = fmaf(qv.x, kreg[c].x, fmaf(qv.y, kreg[c].y, fmaf(qv.z, kreg[c].z, fmaf(qv.w, kreg[c].w, s))));
+        }
       }
+      logit = s * a.inv_sqrt_hd;
     }
-    float m = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < SORT_MAXK; ++j) m = fmaxf(m, logit[j]);
-    float den = 0.f;
-#pragma unroll
-    for (int j = 0; j < SORT_MAXK; ++j) { logit[j] = j < nk ? expf(logit[j] - m) : 0.f; den += logit[j]; }
-    const float inv = 1.f / den;
+    const float m = wmax(logit);
+    const float ex = lane < nk ? expf(logit - m) : 0.f;
+    const float wgt = ex / wsum(ex);
     const size_t o_off = ((size_t)p * a.nq + i) * a.ldo + col0;
     for (int e = lane; e < hd; e += 32) {
       float acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < SORT_MAXK; ++j)
-        if (j < nk) acc = fmaf(logit[j] * inv, a.v[((size_t)p * a.kv_rows + a.k0 + j) * a.ldkv + col0 + e], acc);
+      for (int j = 0; j < nk; ++j) {
+        const float* vr = j == jnew ? fresh + 2 * d + col0 : a.v + ((size_t)p * a.kv_rows + a.k0 + j) * a.ldkv + col0;
+        acc = fmaf(__shfl_sync(0xffffffffu, wgt, j), vr[e], acc);
+      }
       if (a.out != nullptr) a.out[o_off + e] = acc;
       put_twin(a.out_tw, o_off + e, acc);
     }
@@ -178,12 +188,39 @@ __global__ void k_sort_attn(const SortAttn a) {
 
 // log-softmax over the role ids of the last position and the constrained greedy choice (sort_model.py:158-180): the first
 // maximum among the roles still to be placed, scanned in slot order; one warp per problem
-__global__ void k_sort_select(const float* __restrict__ logits, int ld, int n_roles, const int64_t* __restrict__ roles, int L, int P,
+// The whole head of a decoder step in the same warp: final layer norm of the new position's state (sort_modules.py:134), the
+// d -> n_roles projection (sort_model.py:159; each role's weight row read coalesced, one warp reduction per role), then the choice.
+__global__ void k_sort_select(const float* __restrict__ x, int d, const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                              const float* __restrict__ exp_w, const float* __restrict__ exp_b, int n_roles,
+                              const int64_t* __restrict__ roles, int L, int P,
                               int t, int n_steps, uint32_t* __restrict__ remain, int32_t* __restrict__ token, int64_t* __restrict__ pred,
                               float* __restrict__ logp, float* __restrict__ rows) {
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (p >= P) return;
-  const float v = lane < n_roles ? logits[(size_t)p * ld + lane] : -INFINITY;
+  const float* xr = x + (size_t)p * d;
+  float yv[SORT_DPL];                                    // this lane's normalised values: columns lane, lane + 32, ...
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < SORT_DPL; ++i) { yv[i] = lane + 32 * i < d ? xr[lane + 32 * i] : 0.f; s += yv[i]; }
+  const float mean = wsum(s) / (float)d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < SORT_DPL; ++i) { const float u = lane + 32 * i < d ? yv[i] - mean : 0.f; q += u * u; }
+  const float rstd = rsqrtf(wsum(q) / (float)d + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < SORT_DPL; ++i) {
+    const int c = lane + 32 * i;
+    yv[i] = c < d ? (yv[i] - mean) * rstd * ln_w[c] + ln_b[c] : 0.f;
+  }
+  float v = -INFINITY;
+  for (int r = 0; r < n_roles; ++r) {
+    const float* w = exp_w + (size_t)r * d;
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < SORT_DPL; ++i) if (lane + 32 * i < d) acc = fmaf(yv[i], __ldg(w + lane + 32 * i), acc);
+    acc = wsum(acc) + exp_b[r];
+    if (lane == r) v = acc;
+  }
   const float m = wmax(v);
   const float lse = logf(wsum(lane < n_roles ? expf(v - m) : 0.f));
   const float lp = v - m - lse;
@@ -376,10 +413,8 @@ int generate_impl(SortCtx* c, const int64_t* verbs, const int64_t* roles, int P,
     k_sort_embed_dec<<<Pt, 128, 0, st>>>(c->token, c->sr_emb, D, scale, c->x);
     VSR_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < d.n_layers; ++l) VSR_TRY(run_layer(c, c->dec[l], true, l, Pt, t, st));
-    VSR_TRY(ln(c->x, c->dec_ln_w, c->dec_ln_b, Pt, D, c->y, nullptr, st));
-    VSR_TRY(lin(c, c->y, nullptr, D, D, c->exp_w, nullptr, c->exp_b, c->logits, SORT_NPAD, Pt, SORT_NPAD, nullptr, false, st));
-    k_sort_select<<<(Pt + 3) / 4, 128, 0, st>>>(c->logits, SORT_NPAD, d.n_roles, roles, L, Pt, t, n_steps, c->remain, c->token, pred, logp,
-                                                step_rows);
+    k_sort_select<<<(Pt + 3) / 4, 128, 0, st>>>(c->x, D, c->dec_ln_w, c->dec_ln_b, c->exp_w, c->exp_b, d.n_roles, roles, L, Pt, t, n_steps,
+                                                c->remain, c->token, pred, logp, step_rows);
     VSR_CHECK_CUDA(cudaGetLastError());
   }
   return VSR_OK;
@@ -439,6 +474,9 @@ int vsr_sort_create(const VsrSortDims* dims, const float* const* weights, int32_
   VSR_REQUIRE(d.n_roles >= 1 && d.n_roles <= 32 && d.n_verbs >= 1, VSR_EINVAL, "vsr_sort_create: n_roles=%d must be <= 32", d.n_roles);
   VSR_REQUIRE(d.n_heads >= 1 && d.n_heads <= 32 && d.d_model % d.n_heads == 0 && d.d_model % 64 == 0 && d.d_ff % 64 == 0, VSR_EINVAL,
               "vsr_sort_create: d_model=%d / d_ff=%d must be multiples of 64 and d_model of n_heads=%d", d.d_model, d.d_ff, d.n_heads);
+  VSR_REQUIRE(d.d_model <= 32 * vsr::SORT_DPL, VSR_EINVAL, "vsr_sort_create: d_model=%d > %d", d.d_model, 32 * vsr::SORT_DPL);
+  VSR_REQUIRE((d.d_model / d.n_heads) % 4 == 0 && d.d_model / d.n_heads <= 4 * vsr::SORT_HD4, VSR_EINVAL,
+              "vsr_sort_create: head dimension %d must be a multiple of 4 and at most %d", d.d_model / d.n_heads, 4 * vsr::SORT_HD4);
   int ndev = 0;
   VSR_REQUIRE(cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0, VSR_ECUDA, "vsr_sort_create: no CUDA device (no CPU fallback)");
   SortCtx* c = new SortCtx();
