@@ -24,7 +24,7 @@ namespace {
 
 constexpr int SORT_MAXL = 4;        // layers per stack
 constexpr int SORT_MAXK = 16;       // keys an attention query can see (max_len + 1 <= 16)
-constexpr int SORT_DPL = 32;        // d_model / 32 values per lane in the head kernel (d_model <= 1024)
+constexpr int SORT_DPL = 16;        // d_model / 32 values per lane in the head kernel (d_model <= 512)
 constexpr int SORT_HD4 = 16;        // head dimension / 4 that fits the attention kernel's registers (head_dim <= 64)
 constexpr int SORT_NPAD = 64;       // N padding of the FFMA GEMM
 
@@ -195,6 +195,10 @@ __global__ void k_sort_select(const float* __restrict__ x, int d, const float* _
                               const int64_t* __restrict__ roles, int L, int P,
                               int t, int n_steps, uint32_t* __restrict__ remain, int32_t* __restrict__ token, int64_t* __restrict__ pred,
                               float* __restrict__ logp, float* __restrict__ rows) {
+  extern __shared__ __align__(16) float s_w[];           // [n_roles][d]: the projection, staged once per block
+  for (int i = threadIdx.x * 4; i < n_roles * d; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(s_w + i) = __ldg(reinterpret_cast<const float4*>(exp_w + i));
+  __syncthreads();
   const int p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (p >= P) return;
   const float* xr = x + (size_t)p * d;
@@ -214,10 +218,10 @@ __global__ void k_sort_select(const float* __restrict__ x, int d, const float* _
   }
   float v = -INFINITY;
   for (int r = 0; r < n_roles; ++r) {
-    const float* w = exp_w + (size_t)r * d;
+    const float* w = s_w + r * d;
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < SORT_DPL; ++i) if (lane + 32 * i < d) acc = fmaf(yv[i], __ldg(w + lane + 32 * i), acc);
+    for (int i = 0; i < SORT_DPL; ++i) if (lane + 32 * i < d) acc = fmaf(yv[i], w[lane + 32 * i], acc);
     acc = wsum(acc) + exp_b[r];
     if (lane == r) v = acc;
   }
@@ -413,8 +417,9 @@ int generate_impl(SortCtx* c, const int64_t* verbs, const int64_t* roles, int P,
     k_sort_embed_dec<<<Pt, 128, 0, st>>>(c->token, c->sr_emb, D, scale, c->x);
     VSR_CHECK_CUDA(cudaGetLastError());
     for (int l = 0; l < d.n_layers; ++l) VSR_TRY(run_layer(c, c->dec[l], true, l, Pt, t, st));
-    k_sort_select<<<(Pt + 3) / 4, 128, 0, st>>>(c->x, D, c->dec_ln_w, c->dec_ln_b, c->exp_w, c->exp_b, d.n_roles, roles, L, Pt, t, n_steps,
-                                                c->remain, c->token, pred, logp, step_rows);
+    k_sort_select<<<(Pt + 7) / 8, 256, sizeof(float) * d.n_roles * D, st>>>(c->x, D, c->dec_ln_w, c->dec_ln_b, c->exp_w, c->exp_b, d.n_roles,
+                                                                            roles, L, Pt, t, n_steps, c->remain, c->token, pred, logp,
+                                                                            step_rows);
     VSR_CHECK_CUDA(cudaGetLastError());
   }
   return VSR_OK;
@@ -483,6 +488,8 @@ int vsr_sort_create(const VsrSortDims* dims, const float* const* weights, int32_
   c->d = d;
   if (const char* e = getenv("VSRDEC_GEMM")) c->use_tc = strcmp(e, "simt") != 0;
   VSR_CHECK_CUDA(cudaGetDevice(&c->device));
+  VSR_REQUIRE(sizeof(float) * d.n_roles * d.d_model <= 200 * 1024, VSR_EINVAL, "vsr_sort_create: role projection does not fit shared memory");
+  VSR_CHECK_CUDA(cudaFuncSetAttribute(vsr::k_sort_select, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const size_t n = vsr::weight_floats(d);
   if (cudaMalloc((void**)&c->wbuf, n * sizeof(float)) != cudaSuccess) { vsr::set_error("vsr_sort_create: cudaMalloc failed"); delete c; return VSR_ENOMEM; }
   cudaMemset(c->wbuf, 0, n * sizeof(float));
