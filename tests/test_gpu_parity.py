@@ -883,3 +883,39 @@ def test_steps_with_small_magnitude_weights(scale_seed):
             assert rel_close(gt_.cpu(), og, REL, ABS), (t, max_rel_err(gt_.cpu(), og))
             w, gsel = oo.argmax(1), og.argmax(1)
             prev, oprev = [w.to(DEV), gsel.to(DEV)], (w, gsel)
+
+
+def test_eval_flow_matches_step_by_step_composition():
+    """vsrdec.EvalFlow (pre-step of batch i + 1 on a side stream beside the decode of batch i) returns exactly what the explicit
+    composition RoleOrderer.order -> permute_slot_index -> beam_search_v_indexed returns, batch by batch, with and without overlap."""
+    from gpu_common import make_model
+    from models import S_SSP, SinkhornNet
+    from vsrdec import EvalFlow, RoleOrderer, permute_slot_index
+    from common import synth_eval_captions
+    fx = load_golden("small_a.pt")
+    d = fx["dims_obj"]
+    m = make_model(d, fx["weights"], fx["verb_table"])
+    ro = RoleOrderer(S_SSP().to(DEV).eval(), SinkhornNet(10, 20, 0.1).to(DEV).eval())
+    batches = []
+    for i in range(4):
+        s = synth_eval_captions(C=9 + i, seed=200 + i, R=5, F=8)
+        g = torch.Generator().manual_seed(300 + i)
+        C = 9 + i
+        det = torch.relu(torch.randn((C, 50, d.det_feat_size), generator=g))
+        batches.append(dict(control_verb=s["control_verb"], det_seqs_v=s["det_seqs_v"], det_seqs_sr=s["det_seqs_sr"],
+                            verb_list=s["verb_list"], detections=det.to(DEV), slot_index=s["slot_index"].to(DEV),
+                            seqs_perm=s["seqs_perm"].to(DEV)))
+    want = []
+    for b in batches:
+        sv = (b["slot_index"] != -1).any(-1).cpu()
+        src, verbs = ro.order(b["control_verb"], b["det_seqs_v"], b["det_seqs_sr"], b["verb_list"], b["seqs_perm"], sv)
+        (w, g_), (lw, lg) = m.beam_search_v_indexed((b["detections"], permute_slot_index(b["slot_index"], src), verbs.to(DEV).double()),
+                                                    [3, -1], 3, 1, gt=True)
+        want.append((w.cpu(), g_.cpu(), lw.cpu()))
+    for overlap in (True, False):
+        flow = EvalFlow(m, ro, eos_idxs=[3, -1], beam_size=3, out_size=1, gt=True, overlap=overlap)
+        got = [(o[0].cpu(), o[1].cpu(), lp[0].cpu()) for o, lp in flow.run(batches)]
+        assert len(got) == len(want)
+        for a, b_ in zip(got, want):
+            assert torch.equal(a[0], b_[0]) and torch.equal(a[1], b_[1]) and torch.equal(a[2], b_[2])
+    assert list(EvalFlow(m, ro, eos_idxs=[3, -1]).run([])) == []
